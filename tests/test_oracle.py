@@ -1,0 +1,526 @@
+"""Pins the CPU oracle (oracle/gcb_oracle.c) before anything trusts it.
+
+1. Golden vectors the reference's own tests hold for this path
+   (ot/mitccrh_test.go:22-31, ot/label_test.go:38-91,
+   circuit/circuit_test.go:14-19, the sha2pc final digest
+   sha2pc/sha2pc_test.go:124 and the shipped circuits' functional KATs).
+2. The public standard vectors of the arithmetic that lives in the Go stdlib
+   (FIPS-197 App. C, SP 800-38A CTR semantics through OpenSSL).
+3. An independent Python restatement (tests/pyref.py, OpenSSL AES), byte for
+   byte, on every gate type / key size / wire-mapping / chunk-size case.
+"""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import bits_of, int_of, load_circuit, millionaire_circuit, mixed_circuit
+from mpc_b200.circuit_io import GATE_DTYPE, LABEL_DTYPE, WIRE_DTYPE, parse_bristol, parse_mpclc
+from mpc_b200.drbg import DRBG
+from oracle import pyoracle as O
+import pyref as P
+
+
+def V(l):  # numpy label -> int
+    return (int(l["d0"]) << 64) | int(l["d1"])
+
+
+def labels_to_ints(arr):
+    return [(int(a) << 64) | int(b) for a, b in zip(arr["d0"].tolist(), arr["d1"].tolist())]
+
+
+def ints_to_labels(vals):
+    out = np.zeros(len(vals), LABEL_DTYPE)
+    out["d0"] = [v >> 64 for v in vals]
+    out["d1"] = [v & (2**64 - 1) for v in vals]
+    return out
+
+
+# --------------------------------------------------------------------------- AES
+FIPS197 = [  # FIPS-197 Appendix C.1-C.3
+    (16, "69c4e0d86a7b0430d8cdb78070b4c55a"),
+    (24, "dda97ca4864cdfe06eaf70a0ec0d7191"),
+    (32, "8ea2b7ca516745bfeafc49904b496089"),
+]
+
+
+@pytest.mark.parametrize("aesni", [0, 1])
+@pytest.mark.parametrize("klen,expect", FIPS197)
+def test_fips197(aesni, klen, expect):
+    O.lib().orc_set_aesni(aesni)
+    try:
+        pt = bytes.fromhex("00112233445566778899aabbccddeeff")
+        assert O.aes_encrypt_block(bytes(range(klen)), pt).hex() == expect
+    finally:
+        O.lib().orc_set_aesni(1)
+
+
+def test_aes_portable_equals_aesni_and_openssl():
+    rng = np.random.default_rng(7)
+    for klen in (16, 24, 32):
+        for _ in range(20):
+            key, blk = rng.bytes(klen), rng.bytes(16)
+            want = P.Aes(key)._e.update(blk)
+            O.lib().orc_set_aesni(0)
+            a = O.aes_encrypt_block(key, blk)
+            O.lib().orc_set_aesni(1)
+            b = O.aes_encrypt_block(key, blk)
+            assert a == b == want
+
+
+def test_bad_key_length():
+    with pytest.raises(O.OracleError):
+        O.aes_encrypt_block(b"x" * 15, b"\0" * 16)
+
+
+def test_sp800_38a_ctr_block_semantics():
+    # SP 800-38A F.5.1 CTR-AES128: keystream block = AES_k(counter block);
+    # with Go's zero IV the counter block j is j as a 128-bit big-endian int.
+    key = bytes.fromhex("2b7e151628aed2a6abf7158809cf4f3c")
+    ctr = bytes.fromhex("f0f1f2f3f4f5f6f7f8f9fafbfcfdfeff")
+    pt = bytes.fromhex("6bc1bee22e409f96e93d7e117393172a")
+    ks = O.aes_encrypt_block(key, ctr)
+    assert bytes(a ^ b for a, b in zip(ks, pt)).hex() == "874d6191b620e3261bef6864990db6ce"
+    k = (int.from_bytes(key[:8], "big"), int.from_bytes(key[8:], "big"))
+    stream = O.prg(k, 0, 100)
+    for j in range(6):
+        assert stream[16 * j:16 * j + 16] == O.aes_encrypt_block(key, j.to_bytes(16, "big"))
+    # stateful / byte granular: resuming at any position continues the same stream
+    for pos in (1, 15, 16, 17, 33):
+        assert O.prg(k, pos, 40) == stream[pos:pos + 40]
+    # and equals OpenSSL's CTR with a zero IV
+    assert P.Prg((k[0] << 64) | k[1]).read(100) == stream
+
+
+# ------------------------------------------------------------------------ labels
+def test_label_vectors_from_reference():
+    # ot/label_test.go:52-76
+    assert O.mul2((0, 0xFFFFFFFFFFFFFFFF)) == (0x1, 0xFFFFFFFFFFFFFFFE)
+    assert O.mul4((0, 0xFFFFFFFFFFFFFFFF)) == (0x3, 0xFFFFFFFFFFFFFFFC)
+    # top bits fall off (no reduction)
+    assert O.mul2((0x8000000000000000, 0)) == (0, 0)
+    assert O.mul4((0xC000000000000001, 0x4000000000000000)) == (0x5, 0)
+
+
+def test_gate_layout_is_20_bytes():
+    # circuit/circuit_test.go:14-19
+    assert GATE_DTYPE.itemsize == 20
+    assert [GATE_DTYPE.fields[n][1] for n in ("in0", "in1", "out", "op", "level")] == [0, 4, 8, 12, 16]
+    assert LABEL_DTYPE.itemsize == 16 and WIRE_DTYPE.itemsize == 32
+
+
+def test_hashes_against_openssl():
+    rng = np.random.default_rng(3)
+    for klen in (16, 24, 32):
+        key = rng.bytes(klen)
+        alg = P.Aes(key)
+        for _ in range(25):
+            a, b, c = (int.from_bytes(rng.bytes(16), "big") for _ in range(3))
+            t = int(rng.integers(0, 2**32))
+            assert O.encrypt_half(key, P.from_v(a), t) == P.from_v(P.h1(alg, a, t))
+            e = O.encrypt(key, P.from_v(a), P.from_v(b), P.from_v(c), t)
+            assert e == P.from_v(P.h2(alg, a, b, t) ^ c)
+            # TestEnc (circuit/enc_test.go:19-44): decrypt(encrypt(c)) == c
+            assert O.decrypt(key, P.from_v(a), P.from_v(b), t, e) == P.from_v(c)
+
+
+# ----------------------------------------------------------------------- MiTCCRH
+MITCCRH_BLOCKS = [  # ot/mitccrh_test.go:22-31
+    "66e94bd4ef8a2c3b884cfa59ca342b2e", "f6b7bdd1caeebab574683893c4475484",
+    "5c76002bc7206560efe550c80b8f12cc", "ec331f5dd1c5f40e28ea541caec913f6",
+    "932c6dbf69255cf13edcdb72233acea3", "6d5c3e022e5a6f7be663b9e69bcea443",
+    "e013d7f4fa7abd93a7b85db9cfff9b14", "f0a2a65d245dd6199dc70951c2478b65",
+]
+
+
+def test_mitccrh_golden_blocks():
+    m = O.MITCCRH((0, 0), 8)
+    blks = np.zeros(16, LABEL_DTYPE)
+    m.hash(blks, 8, 2)
+    for i in range(8):
+        for j in range(2):
+            got = V(blks[2 * i + j]).to_bytes(16, "big").hex()
+            assert got == MITCCRH_BLOCKS[i]
+
+
+def test_mitccrh_against_pyref_and_renewal():
+    rng = np.random.default_rng(11)
+    seed = int.from_bytes(rng.bytes(16), "big")
+    m = O.MITCCRH(P.from_v(seed), 8)
+    gid = 0
+    for k, h in ((8, 2), (4, 1), (4, 2), (8, 1), (2, 2), (2, 1), (4, 1), (8, 2)):
+        vals = [int.from_bytes(rng.bytes(16), "big") for _ in range(k * h)]
+        blks = ints_to_labels(vals)
+        m.hash(blks, k, h)
+        assert labels_to_ints(blks) == P.mitccrh_hash(seed, gid, vals, h)
+        gid += k
+    with pytest.raises(O.OracleError):
+        m.hash(np.zeros(3, LABEL_DTYPE), 3, 1)      # batchSize % k != 0 (mitccrh.go:97-99)
+
+
+# ------------------------------------------------------------------ garble / eval
+def _rand_for(circ, tag):
+    return DRBG(tag).read(16 * (1 + circ.num_inputs))
+
+
+def _select(wires, bits):
+    out = np.zeros(len(bits), LABEL_DTYPE)
+    for i, b in enumerate(bits):
+        out[i] = wires[i]["l1"] if b else wires[i]["l0"]
+    return out
+
+
+def _decode(circ, wires_g, wires_e):
+    start = circ.num_wires - circ.num_outputs
+    bits = []
+    for i in range(circ.num_outputs):
+        w, l = wires_g[start + i], wires_e[start + i]
+        if l == w["l0"]:
+            bits.append(0)
+        elif l == w["l1"]:
+            bits.append(1)
+        else:
+            raise AssertionError(f"unknown label for output {i}")
+    return bits
+
+
+@pytest.mark.parametrize("klen", [16, 24, 32])
+@pytest.mark.parametrize("name", ["and", "not", "add64", "sub64", "mixed1", "mixed2", "millionaire"])
+def test_garble_eval_against_pyref(name, klen):
+    circ = {"mixed1": lambda: mixed_circuit(1), "mixed2": lambda: mixed_circuit(2, 500, 30, 12),
+            "millionaire": millionaire_circuit}.get(name, lambda: load_circuit(name))()
+    key = DRBG(f"key/{name}/{klen}").read(klen)
+    rand = _rand_for(circ, f"garble/{name}")
+    r, wires, slab, off = O.garble(circ, key, rand)
+    pr, pw, ptab = P.garble(circ, key, rand)
+    assert V(r) == pr and V(r) >> 127 == 1
+    assert labels_to_ints(wires["l0"]) == [w[0] for w in pw]
+    assert labels_to_ints(wires["l1"]) == [w[1] for w in pw]
+    assert labels_to_ints(slab) == [x for rows in ptab for x in rows]
+    assert off[-1] == circ.num_rows and np.array_equal(off, circ.row_offsets())
+    # evaluate on random inputs, decode, compare with the plaintext circuit
+    rng = np.random.default_rng(klen)
+    bits = rng.integers(0, 2, circ.num_inputs).tolist()
+    ew = O.eval_(circ, key, _select(wires, bits), slab, off)
+    pe = P.evaluate(circ, key, [pw[i][b] for i, b in enumerate(bits)], ptab)
+    assert labels_to_ints(ew) == pe
+    assert _decode(circ, wires, ew) == circ.compute_bits(bits).tolist()
+    # without explicit offsets the static per-op row counts are used
+    assert np.array_equal(O.eval_(circ, key, _select(wires, bits), slab), ew)
+
+
+def test_millionaire_readme_pairs():
+    # README.md:76-107: 750000 vs 800000 -> false; 900000 vs 800000 -> true
+    circ = millionaire_circuit()
+    key = bytes(32)
+    r, wires, slab, off = O.garble(circ, key, _rand_for(circ, "millionaire"))
+    for a, b, want in [(750000, 800000, 0), (900000, 800000, 1), (-1, 0, 0), (0, -1, 1), (-7, -5, 0), (-5, -7, 1)]:
+        bits = bits_of(a % 2**64, 64) + bits_of(b % 2**64, 64)
+        ew = O.eval_(circ, key, _select(wires, bits), slab, off)
+        assert _decode(circ, wires, ew) == [want]
+
+
+def test_eval_error_paths():
+    circ = load_circuit("sub64")
+    key = bytes(16)
+    r, wires, slab, off = O.garble(circ, key, _rand_for(circ, "err"))
+    ins = _select(wires, [1] * circ.num_inputs)
+    bad = off.copy()
+    and_gate = int(np.argmax(circ.gates["op"] == 2))
+    bad[and_gate + 1:] += 1                       # AND gate now "has" 3 rows
+    with pytest.raises(O.OracleError) as e:
+        O.eval_(circ, key, ins, np.concatenate([slab, slab[:4]]), bad)
+    assert e.value.rc == -3                       # corrupted ciruit: AND row length (eval.go:55)
+    bad = off.copy()
+    inv_gate = int(np.argmax(circ.gates["op"] == 4))
+    bad[inv_gate + 1:] -= 1                       # INV gate lost its row
+    with pytest.raises(O.OracleError) as e:
+        O.eval_(circ, key, ins, slab, bad)
+    assert e.value.rc in (-3, -4)
+    g = circ.gates.copy()
+    g["op"][0] = 9
+    from mpc_b200.circuit_io import Circuit
+    broken = Circuit(circ.num_gates, circ.num_wires, circ.inputs, circ.outputs, g)
+    with pytest.raises(O.OracleError) as e:
+        O.garble(broken, key, _rand_for(circ, "err"))
+    assert e.value.rc == -2
+    with pytest.raises(O.OracleError) as e:
+        O.garble(circ, b"short", _rand_for(circ, "err"))
+    assert e.value.rc == -1
+
+
+def _garble_eval_decode(circ, key, tag, bits):
+    r, wires, slab, off = O.garble(circ, key, _rand_for(circ, tag))
+    ew = O.eval_(circ, key, _select(wires, bits), slab, off)
+    return _decode(circ, wires, ew), slab
+
+
+def test_kat_aes128_circuit_fips197():
+    # pkg/crypto/aes/circuit.mpcl:10-31: key and block are big-endian integers,
+    # wire i = bit i (LSB first)
+    circ = load_circuit("aes_128")
+    assert (circ.num_gates, circ.num_wires, circ.count(2), circ.count(4), circ.num_rows) == \
+        (36663, 36919, 6400, 2087, 14887)
+    k = int.from_bytes(bytes(range(16)), "big")
+    d = int.from_bytes(bytes.fromhex("00112233445566778899aabbccddeeff"), "big")
+    out, _ = _garble_eval_decode(circ, b"0123456789abcdef", "kat/aes128", bits_of(k, 128) + bits_of(d, 128))
+    assert int_of(out).to_bytes(16, "big").hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+
+
+def test_kat_sha256_circuit_abc():
+    # pkg/crypto/sha256/sum.mpcl:66-69: Block(block uint512, state uint256)
+    circ = load_circuit("sha256")
+    assert (circ.num_gates, circ.count(2), circ.count(4), circ.num_rows) == (135073, 22573, 1856, 47002)
+    block = b"abc" + b"\x80" + bytes(52) + struct.pack(">Q", 24)
+    iv = bytes.fromhex("6a09e667bb67ae853c6ef372a54ff53a510e527f9b05688c1f83d9ab5be0cd19")
+    bits = bits_of(int.from_bytes(block, "big"), 512) + bits_of(int.from_bytes(iv, "big"), 256)
+    out, _ = _garble_eval_decode(circ, bytes(32), "kat/sha256", bits)
+    assert int_of(out).to_bytes(32, "big").hex() == hashlib.sha256(b"abc").hexdigest()
+
+
+def test_kat_sha2pc_digest_and_table_count():
+    # sha2pc/sha2pc_test.go:78-83,124: a[i]=i, b[i]=32-i -> 4b2f7457...bf2e;
+    # sha2pc/params.go:26: 42,914 table labels.  Input bits are little-endian
+    # per byte (sha2pc/bits.go:4-15), garbler first (sha2pc/evaluator.go:81-84).
+    circ = load_circuit("sha256xor")
+    a = bytes(range(32))
+    b = bytes(32 - i for i in range(32))
+    bits = []
+    for blob in (a, b):
+        for byte in blob:
+            bits += bits_of(byte, 8)
+    for klen in (16, 32):
+        out, slab = _garble_eval_decode(circ, DRBG(f"sha2pc/{klen}").read(klen), "kat/sha2pc", bits)
+        assert len(slab) == 42914
+        digest = bytes(int_of(out[8 * i:8 * i + 8]) for i in range(32))
+        assert digest.hex() == "4b2f74579fc7c778745121996f604371a326dc5174f9851706032626668abf2e"
+        assert digest == hashlib.sha256(bytes(x ^ y for x, y in zip(a, b))).digest()
+
+
+def test_batch_driver_equals_single_calls():
+    circ = load_circuit("sub64")
+    from mpc_b200.drbg import garble_inputs
+    keys, rand = garble_inputs("batch", 9, circ.num_inputs, 32)
+    for threads in (1, 4):
+        r, tables, io = O.garble_batch(circ, keys, rand, threads)
+        for i in range(9):
+            r1, w1, s1, _ = O.garble(circ, keys[i].tobytes(), rand[i].tobytes())
+            assert r[i] == r1 and np.array_equal(tables[i], s1)
+            assert np.array_equal(io[i][: circ.num_inputs], w1[: circ.num_inputs])
+            assert np.array_equal(io[i][circ.num_inputs:], w1[-circ.num_outputs:])
+        ins = io[:, : circ.num_inputs]["l1"].copy()
+        outs = O.eval_batch(circ, keys, tables, ins, threads)
+        want = circ.compute_bits([1] * circ.num_inputs)
+        for i in range(9):
+            ow = io[i][circ.num_inputs:]
+            got = [0 if outs[i][k] == ow[k]["l0"] else 1 for k in range(circ.num_outputs)]
+            assert got == want.tolist()
+    shared = O.garble_batch(circ, b"0123456789abcdef", rand, 2)
+    assert np.array_equal(shared[1][3], O.garble(circ, b"0123456789abcdef", rand[3].tobytes())[2])
+
+
+# --------------------------------------------------------------------- streaming
+def _plain_stream(circ, plain, ins, outs):
+    """Plaintext run with the streaming wire mapping (stream_garble.go:131-157):
+    aliased in/out ids read and write the same permanent wire, in gate order."""
+    nin, first_out = len(ins), circ.num_wires - len(outs)
+    tmp = {}
+
+    def loc(w):
+        if w < nin:
+            return plain, ins[w]
+        if w >= first_out:
+            return plain, outs[w - first_out]
+        return tmp, w
+
+    g = circ.gates
+    for a, b, c, op in zip(g["in0"].tolist(), g["in1"].tolist(), g["out"].tolist(), g["op"].tolist()):
+        da, ia = loc(a)
+        va = da[ia]
+        vb = 0
+        if op != 4:
+            db, ib = loc(b)
+            vb = db[ib]
+        v = [va ^ vb, 1 ^ va ^ vb, va & vb, va | vb, 1 ^ va][op]
+        dc, ic = loc(c)
+        dc[ic] = v
+
+
+@pytest.mark.parametrize("klen", [16, 32])
+def test_stream_garble_against_pyref_and_stream_eval(klen):
+    key = DRBG(f"stream/{klen}").read(klen)
+    prog_inputs = list(range(10, 138))                     # 128 permanent input wires
+    rand = DRBG("stream/rand").read(16 * (1 + len(prog_inputs)))
+    s = O.Streaming(key, rand, prog_inputs)
+    r = int.from_bytes(rand[:16], "big") | P.SBIT
+    assert s.r == P.from_v(r)
+    perm = {}
+    for i, wid in enumerate(prog_inputs):
+        l0 = int.from_bytes(rand[16 * (i + 1):16 * (i + 2)], "big")
+        perm[wid] = (l0, l0 ^ r)
+    alg = P.Aes(key)
+    add, sub, mix = load_circuit("add64"), load_circuit("sub64"), mixed_circuit(5, 200, 128, 64)
+    steps = [
+        (add, prog_inputs, list(range(200, 264))),                               # short ids
+        (sub, list(range(200, 264)) + prog_inputs[:64], list(range(70000, 70064))),   # long ids
+        (mix, list(range(70000, 70064)) + list(range(200, 264)), list(range(300, 364))),
+        (add, list(range(300, 364)) + list(range(300, 364)), list(range(300, 364))),  # in/out alias
+    ]
+    se = O.StreamEval(key)
+    pbits = np.random.default_rng(5).integers(0, 2, len(prog_inputs)).tolist()
+    for wid, b in zip(prog_inputs, pbits):
+        se.set(wid, P.from_v(perm[wid][b]))
+    plain = dict(zip(prog_inputs, pbits))
+    for circ, ins, outs in steps:
+        got = s.garble(circ, ins, outs)
+        want = P.stream_garble(alg, r, perm, circ, ins, outs)
+        assert got == want
+        for wid in outs:
+            assert s.get_input(wid) == (P.from_v(perm[wid][0]), P.from_v(perm[wid][1]))
+        used = se.circuit(got, circ.num_gates, circ.num_wires, max(max(ins), max(outs)) + 1)
+        assert used == len(got)
+        _plain_stream(circ, plain, ins, outs)
+        for wid in outs:
+            assert se.get(wid) == P.from_v(perm[wid][plain[wid]])
+
+
+def test_stream_record_sizes():
+    # circuit/stream_garble.go:391-446: 7/13-byte headers for binary gates,
+    # 5/9 for INV, plus 16 bytes per row
+    key, rand = bytes(16), DRBG("rec").read(16 * 3)
+    and_c = parse_bristol("1 3\n2 1 1\n1 1\n\n2 1 0 1 2 AND\n")
+    inv_c = parse_bristol("1 2\n1 1\n1 1\n\n1 1 0 1 INV\n")
+    s = O.Streaming(key, rand, [0, 1])
+    assert len(s.garble(and_c, [0, 1], [2])) == 7 + 32
+    assert len(s.garble(and_c, [0, 1], [65536])) == 13 + 32
+    assert len(s.garble(inv_c, [0], [3])) == 5 + 16
+    assert len(s.garble(inv_c, [0], [65537])) == 9 + 16
+    b = s.garble(and_c, [0, 1], [2])
+    assert b[0] == 0x12 and b[1:7] == bytes([0, 0, 0, 1, 0, 2])
+
+
+# -------------------------------------------------------------------------- IKNP
+def _iknp_keys(tag):
+    d = DRBG(tag)
+    k0 = np.frombuffer(d.read(128 * 16), dtype=">u8").reshape(128, 2)
+    k1 = np.frombuffer(d.read(128 * 16), dtype=">u8").reshape(128, 2)
+    mk = lambda k: np.array([(int(a), int(b)) for a, b in k], dtype=LABEL_DTYPE)
+    delta = (int.from_bytes(d.read(8), "big"), int.from_bytes(d.read(8), "big"))
+    return mk(k0), mk(k1), delta
+
+
+def test_create_labels_matches_bit_definition():
+    rng = np.random.default_rng(2)
+    for w, nl in ((1, 8), (1, 5), (17, 130), (64, 512)):
+        buf = rng.bytes(128 * w)
+        got = labels_to_ints(O.create_labels(nl, buf, w))
+        assert got == P.create_labels(nl, buf, w)
+        # Go-memory image of label j is row j of the bit matrix, little endian
+        lab = O.create_labels(nl, buf, w)
+        m = np.frombuffer(buf, np.uint8).reshape(128, w)
+        for j in (0, nl - 1):
+            row_bits = (m[:, j // 8] >> (j % 8)) & 1
+            assert np.array_equal(np.unpackbits(np.frombuffer(lab[j].tobytes(), np.uint8), bitorder="little"), row_bits)
+
+
+@pytest.mark.parametrize("sizes", [[1], [129], [511, 512, 513], [17, 1100, 8, 2000]])
+def test_iknp_against_pyref_with_persistent_streams(sizes):
+    k0, k1, delta = _iknp_keys("iknp/" + "-".join(map(str, sizes)))
+    dv = (delta[0] << 64) | delta[1]
+    # sender keys: base-OT outcome k_i = delta.Bit(i) ? k1_i : k0_i  (iknp.go:106-122)
+    ks = np.array([k1[i] if P.label_bit(dv, i) else k0[i] for i in range(128)], dtype=LABEL_DTYPE)
+    pg0 = [P.Prg(V(k)) for k in k0]
+    pg1 = [P.Prg(V(k)) for k in k1]
+    pgs = [P.Prg(V(k)) for k in ks]
+    rpos = spos = 0
+    rng = np.random.default_rng(len(sizes))
+    for n in sizes:
+        choice = rng.integers(0, 2, n).astype(np.uint8)
+        u, t, rpos2 = O.iknp_receive(k0, k1, rpos, choice)
+        chunks, pt = P.iknp_receive(pg0, pg1, choice.tolist())
+        assert u.tobytes() == b"".join(chunks) and len(u) == O.u_size(n)
+        assert labels_to_ints(t) == pt
+        q, spos2 = O.iknp_send(ks, delta, spos, u, n)
+        assert labels_to_ints(q) == P.iknp_send(pgs, dv, chunks, n)
+        # correlation checked by ot/iknp_test.go:17-116: t_j = q_j ^ b_j * delta
+        for j in range(n):
+            assert V(t[j]) == V(q[j]) ^ (dv if choice[j] else 0)
+        assert rpos2 == spos2 == rpos + sum(min(512, n - o) + 7 >> 3 for o in range(0, n, 512))
+        rpos, spos = rpos2, spos2
+
+
+def test_iknp_bit_cot():
+    k0, k1, delta = _iknp_keys("bitcot")
+    dv = (delta[0] << 64) | delta[1]
+    ks = np.array([k1[i] if P.label_bit(dv, i) else k0[i] for i in range(128)], dtype=LABEL_DTYPE)
+    pos = 0
+    for n in (64, 512, 1024 + 128):          # byteRows multiple of 8 (bitcot_test.go sizes)
+        rng = np.random.default_rng(n)
+        choices = rng.integers(0, 2**63, (n + 63) // 64).astype(np.uint64)
+        u, rb, p2 = O.iknp_receive_bits(k0, k1, pos, choices, n)
+        sb, p3 = O.iknp_send_bits(ks, delta, pos, u, n)
+        assert p2 == p3
+        d0 = P.label_bit(dv, 0)
+        for i in range(n):
+            b = (int(choices[i // 64]) >> (i % 64)) & 1
+            r_i = (int(rb[i // 64]) >> (i % 64)) & 1
+            s_i = (int(sb[i // 64]) >> (i % 64)) & 1
+            assert r_i == s_i ^ (b & d0)
+        pos = p2
+
+
+def test_cot_rot_end_to_end():
+    k0, k1, delta = _iknp_keys("cot")
+    dv = (delta[0] << 64) | delta[1]
+    ks = np.array([k1[i] if P.label_bit(dv, i) else k0[i] for i in range(128)], dtype=LABEL_DTYPE)
+    rng = np.random.default_rng(1)
+    for n in (1, 8, 13, 64):                  # ot/ot_test.go uses 64 wires
+        flags = rng.integers(0, 2, n).astype(np.uint8)
+        u, t, _ = O.iknp_receive(k0, k1, 0, flags)
+        q, _ = O.iknp_send(ks, delta, 0, u, n)
+        seed = (int(rng.integers(0, 2**63)), int(rng.integers(0, 2**63)))
+        wires = np.zeros(n, WIRE_DTYPE)
+        wires["l0"]["d0"], wires["l0"]["d1"] = rng.integers(0, 2**63, n), rng.integers(0, 2**63, n)
+        wires["l1"]["d0"], wires["l1"]["d1"] = rng.integers(0, 2**63, n), rng.integers(0, 2**63, n)
+        msgs = O.cot_send(q, delta, seed, wires)
+        got = O.cot_receive(t, flags, seed, msgs)
+        for j in range(n):
+            assert got[j] == (wires[j]["l1"] if flags[j] else wires[j]["l0"])
+        # pads are MiTCCRH with key n (batch 8): check one against pyref
+        sv = (seed[0] << 64) | seed[1]
+        j = n - 1
+        pad = P.mitccrh_hash(sv, j, [V(q[j]), V(q[j]) ^ dv], 2)
+        assert V(msgs[2 * j]) == pad[0] ^ V(wires[j]["l0"]) and V(msgs[2 * j + 1]) == pad[1] ^ V(wires[j]["l1"])
+        rw = O.rot_send(q, delta, seed)
+        rr = O.rot_receive(t, seed)
+        for j in range(n):
+            assert rr[j] == (rw[j]["l1"] if flags[j] else rw[j]["l0"])
+
+
+# ------------------------------------------------------------------------ GF(2^128)
+def test_mul128_identities():
+    # ot/mul128_test.go:14-77: identities, x^63*x^63, all ones
+    one = (1, 0)                                # Bit(0) lives in D0
+    a = (0x0123456789ABCDEF, 0xFEDCBA9876543210)
+    assert O.mul128(a, one) == (a, (0, 0))
+    assert O.mul128(a, (0, 0)) == ((0, 0), (0, 0))
+    lo, hi = O.mul128((1 << 63, 0), (1 << 63, 0))     # x^63 * x^63 = x^126
+    assert lo == (0, 1 << 62) and hi == (0, 0)
+    ones = (2**64 - 1, 2**64 - 1)
+    lo, hi = O.mul128(ones, ones)                     # (sum x^i)^2 = sum x^(2i) over GF(2)
+    pat = 0x5555555555555555
+    assert lo == (pat, pat) and hi == (pat, pat)
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        x, y = (tuple(int(v) for v in rng.integers(0, 2**63, 2)) for _ in range(2))
+        # reference bit-array definition (ot/mul128_ref.go)
+        px = x[0] | (x[1] << 64)
+        py = y[0] | (y[1] << 64)
+        acc = 0
+        for i in range(128):
+            if (px >> i) & 1:
+                acc ^= py << i
+        lo, hi = O.mul128(x, y)
+        assert lo[0] | (lo[1] << 64) | (hi[0] << 128) | (hi[1] << 192) == acc
+        assert O.mul128(y, x) == (lo, hi)
