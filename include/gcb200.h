@@ -1,0 +1,219 @@
+/*
+ * gcb200.h -- C ABI of the B200 garbled-circuit / OT-extension engine.
+ *
+ * This is the drop-in boundary: exactly the entry points a cgo shim behind the
+ * reference's unchanged Go API (packages circuit and ot of markkurossi/mpc)
+ * binds.  Each entry point cites the reference interface it replaces; the Go
+ * bindings are shown in INTEGRATION.md and kept under go/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer of the host entry points is a
+ *     HOST pointer valid for the duration of the call (cgo rule: nothing is
+ *     retained).  The *_dev entry points take DEVICE pointers and a CUDA stream
+ *     (cudaStream_t passed as void*) and only enqueue work.
+ *   - labels are 16 bytes in Go memory order: {uint64 D0; uint64 D1}, D0 the
+ *     high half (ot/label.go:28-31); wires are {L0, L1} (ot/label.go:18-21);
+ *     gates are the 20-byte circuit.Gate (circuit/circuit.go:260-266).
+ *   - every function returns 0 on success or a negative gcb_status;
+ *     gcb_last_error() gives the thread-local message.
+ *   - all entry points are re-entrant; plans are immutable after creation and
+ *     may be shared by concurrent callers (circuit.Circuit is shared by
+ *     goroutines, sha2pc/sha256xor_circuit.go:16-23).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with GCB_E_CUDA.
+ */
+#ifndef GCB200_H
+#define GCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t d0, d1; } gcb_label;          /* ot.Label */
+typedef struct { gcb_label l0, l1; } gcb_wire;          /* ot.Wire  */
+typedef struct {                                        /* circuit.Gate, 20 bytes */
+    uint32_t in0, in1, out;
+    uint8_t op;                                         /* 0 XOR 1 XNOR 2 AND 3 OR 4 INV */
+    uint8_t pad[3];
+    uint32_t level;
+} gcb_gate;
+
+typedef enum {
+    GCB_OK = 0,
+    GCB_E_ARG = -1,          /* bad argument (null pointer, zero size, ...) */
+    GCB_E_KEYLEN = -2,       /* aes.NewCipher: key must be 16, 24 or 32 bytes */
+    GCB_E_BADOP = -3,        /* "invalid gate type" (circuit/garble.go:325) */
+    GCB_E_WIRE = -4,         /* wire index out of range / read before assignment */
+    GCB_E_CUDA = -5,         /* no device, launch or memory failure */
+    GCB_E_TOO_LARGE = -6,    /* live wire set does not fit on chip */
+    GCB_E_BUFFER = -7,       /* output buffer too small */
+    GCB_E_CHUNK = -8,        /* "invalid chunk size" (ot/iknp.go:207) */
+    GCB_E_CORRUPT = -9       /* "corrupted circuit" (circuit/eval.go:55,87,103) */
+} gcb_status;
+
+const char *gcb_last_error(void);
+const char *gcb_version(void);
+
+/* Device selection.  cgo calls may arrive on any OS thread, so every entry point
+ * re-selects its device; gcb_set_device changes the calling thread's choice
+ * (default: device 0, or LOCAL_RANK when set). */
+int gcb_set_device(int device);
+int gcb_device_count(void);
+
+/* ------------------------------------------------------------------ plans --- */
+/* A plan is the compiled, immutable form of one circuit.Circuit: gates grouped
+ * into dependency steps, with the static per-gate tweak ids (the `id` counter of
+ * circuit/garble.go:357-359,419-420,451-452), slab row offsets
+ * (circuit/garble.go:292-298) and on-chip wire slots assigned from liveness. */
+typedef struct gcb_plan gcb_plan;
+
+typedef struct {
+    uint32_t num_gates, num_wires, num_inputs, num_outputs;
+    uint32_t num_rows;        /* garbled-table labels per instance (slab size) */
+    uint32_t num_tweaks;
+    uint32_t num_steps;       /* dependency steps (barriers per instance) */
+    uint32_t num_slots;       /* peak live wire labels held on chip per instance */
+    uint32_t num_and, num_or, num_inv, num_free;
+    uint32_t teams_per_sm;    /* instances resident per SM with this plan */
+    uint32_t team_threads;
+    uint32_t garble_hashes;   /* AES blocks per garbled instance (4/AND, 4/OR, 2/INV) */
+    uint32_t eval_hashes;     /* AES blocks per evaluated instance (2/AND, 1/OR, 1/INV) */
+} gcb_plan_info;
+
+/* Replaces: the per-circuit preparation Circuit.Garble does lazily
+ * (garbleScratchPool, circuit/garble.go:193-224).  Input is Circuit.Gates as is. */
+int gcb_plan_create(const gcb_gate *gates, uint32_t num_gates, uint32_t num_wires,
+                    uint32_t num_inputs, uint32_t num_outputs, gcb_plan **out);
+void gcb_plan_destroy(gcb_plan *plan);
+int gcb_plan_get_info(const gcb_plan *plan, gcb_plan_info *info);
+/* Static slab offset of every gate's first row (num_gates+1 entries): lets the
+ * Go side rebuild Garbled.Gates [][]ot.Label slice headers over the slab. */
+int gcb_plan_row_offsets(const gcb_plan *plan, uint32_t *row_off);
+
+/* ----------------------------------------------------------- garble / eval --- */
+#define GCB_FLAG_NONE 0u
+
+/* Replaces (*Circuit).Garble(rand, key) (circuit/garble.go:248-308), batched.
+ *   keys       : key bytes; key_stride 0 = one key shared by the batch, else
+ *                instance i uses keys + i*key_stride.  keylen 16/24/32.
+ *   r          : [batch] the 16 bytes read for R per instance, as a label;
+ *                the S bit is forced to 1 inside (garble.go:258).
+ *   in_l0      : [batch][num_inputs] the L0 label read for each input wire
+ *                (garble.go:271-278); L1 = L0 ^ R is derived.
+ *   tables     : [batch][num_rows] out, the slab: rows of gate g at
+ *                row_off[g] in original gate order.
+ *   io_wires   : [batch][num_inputs+num_outputs] out (may be NULL): Wires[0..in)
+ *                then Wires[NumWires-out..NumWires) -- what the callers read
+ *                (circuit/garbler.go:85-102,153; sha2pc/garbler.go:113-126).
+ *   wires_full : [batch][num_wires] out (may be NULL): the complete Garbled.Wires.
+ * batch = 1 reproduces one Go call exactly. */
+int gcb_garble(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
+               uint32_t batch, const gcb_label *r, const gcb_label *in_l0, gcb_label *tables,
+               gcb_wire *io_wires, gcb_wire *wires_full, uint32_t flags);
+
+/* Replaces (*Circuit).Eval(key, wires, garbled) (circuit/eval.go:17-115), batched.
+ *   tables     : [batch][num_rows] the slab (row counts per gate are static, so
+ *                the "corrupted circuit" length checks are done by the caller
+ *                against gcb_plan_row_offsets before the call).
+ *   in_labels  : [batch][num_inputs]   wires[0..Inputs.Size())
+ *   out_labels : [batch][num_outputs]  wires[NumWires-Outputs.Size()..)
+ *   wires_full : [batch][num_wires] out (may be NULL): every wire label. */
+int gcb_eval(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
+             uint32_t batch, const gcb_label *tables, const gcb_label *in_labels,
+             gcb_label *out_labels, gcb_label *wires_full, uint32_t flags);
+
+/* Device-resident variants (all pointers are device pointers; asynchronous on
+ * `stream`).  Used for throughput measurement and multi-stage pipelines. */
+int gcb_garble_dev(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
+                   uint32_t batch, const gcb_label *r, const gcb_label *in_l0, gcb_label *tables,
+                   gcb_wire *io_wires, gcb_wire *wires_full, uint32_t flags, void *stream);
+int gcb_eval_dev(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
+                 uint32_t batch, const gcb_label *tables, const gcb_label *in_labels,
+                 gcb_label *out_labels, gcb_label *wires_full, uint32_t flags, void *stream);
+
+/* Input selection and output decoding on the device, the label plumbing either
+ * side of Garble/Eval: LabelForBit / BitFromLabel (circuit/helpers.go:10-27).
+ *   bits: one byte (0/1) per wire.  gcb_decode_bits_dev writes 0/1, or 2 for
+ *   "unknown label". */
+int gcb_select_labels_dev(const gcb_wire *wires, size_t wire_stride, const uint8_t *bits,
+                          gcb_label *out, uint32_t batch, uint32_t n, void *stream);
+int gcb_decode_bits_dev(const gcb_wire *wires, size_t wire_stride, const gcb_label *labels,
+                        uint8_t *bits, uint32_t batch, uint32_t n, void *stream);
+
+/* ------------------------------------------------------------- gate hashes --- */
+/* Replaces the hash micro-benchmarks: encryptHalf (circuit/garble.go:104-136,
+ * BenchmarkEncHalf circuit/enc_test.go:73) and the stand-alone AES-NI benchmark
+ * circuit/aesni/c/aesni.c.  out[i] = H(x[i], tweak0 + i) = AES_k(K) ^ K,
+ * K = 2*x[i] ^ (tweak0+i). */
+int gcb_hash_half(const uint8_t *key, uint32_t keylen, const gcb_label *x, uint32_t tweak0,
+                  gcb_label *out, uint64_t n);
+int gcb_hash_half_dev(const uint8_t *key, uint32_t keylen, const gcb_label *x, uint32_t tweak0,
+                      gcb_label *out, uint64_t n, void *stream);
+
+/* --------------------------------------------------------------- streaming --- */
+/* Replaces circuit.Streaming (circuit/stream_garble.go): NewStreaming, Get/Set,
+ * GetInput(s) and Streaming.Garble, for `batch` independent program instances
+ * garbled in lock step (batch = 1 is the Go object). */
+typedef struct gcb_stream gcb_stream;
+
+/* NewStreaming (stream_garble.go:41-76): r [batch] raw R labels (S forced),
+ * input_ids [ninputs] permanent wire ids, in_l0 [batch][ninputs]. */
+int gcb_stream_create(const uint8_t *keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                      const gcb_label *r, const uint32_t *input_ids, uint32_t ninputs,
+                      const gcb_label *in_l0, gcb_stream **out);
+void gcb_stream_destroy(gcb_stream *s);
+/* GetInput / GetInputs (stream_garble.go:117-128): wires [batch][n]. */
+int gcb_stream_get_wires(gcb_stream *s, const uint32_t *ids, uint32_t n, gcb_wire *wires);
+/* Size in bytes of the record stream Streaming.Garble emits for this step. */
+int gcb_stream_step_size(gcb_stream *s, const gcb_plan *plan, const uint32_t *in, uint32_t nin,
+                         const uint32_t *out, uint32_t nout, size_t *bytes);
+/* Streaming.Garble (stream_garble.go:161-191) + garbleGate (:195-449): garbles
+ * the sub-circuit for every instance and writes, per instance, the exact byte
+ * stream the reference puts into conn.WriteBuf (gate records: op|flags byte,
+ * BE u16/u32 wire ids, BE rows).  dst: [batch][dst_stride] host bytes.
+ * ns_init / ns_garble mirror the two durations the Go method returns. */
+int gcb_stream_garble(gcb_stream *s, const gcb_plan *plan, const uint32_t *in, uint32_t nin,
+                      const uint32_t *out, uint32_t nout, uint8_t *dst, size_t dst_stride,
+                      size_t *written, uint64_t *ns_init, uint64_t *ns_garble);
+
+/* ------------------------------------------------------------------- IKNP --- */
+/* Replaces the inner loops of IKNPReceiver.receive (ot/iknp.go:468-511) and
+ * IKNPSender.send (ot/iknp.go:197-226): AES-128-CTR column expansion
+ * (newPrg/prg :622-637), the U = T0 ^ T1 ^ b matrix, and the 128-wide bit
+ * transpose createLabels (:647-683).  Base OTs, framing and I/O stay in Go;
+ * `stream_pos` is the number of keystream bytes every column PRG has already
+ * produced (the Go streams are stateful and byte granular); the new position
+ * is stream_pos + gcb_iknp_stream_advance(n).
+ *   u layout: the concatenation of the chunks the receiver passes to SendData:
+ *   chunk c covers rows [512c, 512c+rows), byteRows = ceil(rows/8), column i at
+ *   u[chunk_off + i*byteRows ...]; total gcb_iknp_u_size(n) bytes.
+ *   choice: n bytes of 0/1.  labels: [n] in Go memory order. */
+size_t gcb_iknp_u_size(uint64_t n);
+uint64_t gcb_iknp_stream_advance(uint64_t n);
+int gcb_iknp_receiver_expand(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
+                             const uint8_t *choice, uint64_t n, uint8_t *u_out, gcb_label *labels);
+int gcb_iknp_sender_expand(const gcb_label k[128], const gcb_label *delta, uint64_t stream_pos,
+                           const uint8_t *u, size_t u_len, uint64_t n, gcb_label *labels);
+int gcb_iknp_receiver_expand_dev(const gcb_label *k0, const gcb_label *k1, uint64_t stream_pos,
+                                 const uint8_t *choice, uint64_t n, uint8_t *u_out,
+                                 gcb_label *labels, void *stream);
+int gcb_iknp_sender_expand_dev(const gcb_label *k, const gcb_label *delta, uint64_t stream_pos,
+                               const uint8_t *u, size_t u_len, uint64_t n, gcb_label *labels,
+                               void *stream);
+
+/* ----------------------------------------------------------------- MiTCCRH --- */
+/* Replaces MITCCRH.Hash (ot/mitccrh.go:93-128) over many keys at once: key
+ * number g (renewKeys :70-89) is BE64(seed.D0 ^ g) || BE64(seed.D1); key
+ * gid_start + i hashes blks[i*h .. i*h+h), in place: AES(x) ^ x. */
+int gcb_mitccrh_hash(const gcb_label *seed, uint64_t gid_start, gcb_label *blks, uint64_t nkeys,
+                     uint32_t h);
+int gcb_mitccrh_hash_dev(const gcb_label *seed_host, uint64_t gid_start, gcb_label *blks,
+                         uint64_t nkeys, uint32_t h, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCB200_H */

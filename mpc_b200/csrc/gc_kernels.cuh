@@ -1,0 +1,347 @@
+// gc_kernels.cuh -- batch garble / eval kernels (K1, K2) for sm_100a.
+//
+// Replaces the gate loops of Circuit.Garble (circuit/garble.go:285-299 with
+// Gate.garbleInto :311-482) and Circuit.Eval (circuit/eval.go:28-112).
+//
+// Execution model.  One persistent CTA per SM.  The CTA is split into TEAMS; a
+// team owns one circuit instance at a time and keeps that instance's live wire
+// labels in its slice of shared memory (slots assigned by the plan compiler), so
+// intermediate labels never touch HBM: per instance HBM sees the input labels
+// once, the garbled rows once (written by the garbler, read by the evaluator)
+// and the output labels once.  A team walks the plan's dependency steps with a
+// team-local named barrier between steps.  Inside a step every AES block is one
+// lane: an AND gate is a quad of lanes hashing (a0,j0) (a1,j0) (b0,j1) (b1,j1)
+// and combining with warp shuffles, INV a pair, OR a quad; XOR/XNOR gates are
+// one lane and no AES (Free-XOR).  All teams share the 128 KiB of replicated AES
+// T-tables (aes_core.cuh).
+#pragma once
+#include "aes_core.cuh"
+#include "plan.hpp"
+
+namespace gcb {
+
+constexpr int GC_MAX_TEAMS = 32;
+constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
+
+struct GcParams {
+    const uint4* recs;                    // GateRec[]
+    const uint4* steps;                   // StepRec[]
+    const uint32_t* out_wire;
+    const uint2* live_in;                 // SlotRef[]
+    const uint2* live_out;
+    uint32_t n_steps, n_in, n_out, n_slots, n_rows, n_wires;
+    const uint8_t* keys;
+    uint32_t keylen, key_stride;
+    uint32_t batch;
+    const uint4* r;                       // garble: raw R per instance
+    const uint4* in_labels;               // garble: L0 per input; eval: active input labels
+    uint4* tables;                        // garble: out; eval: in
+    uint4* io;                            // garble: io_wires (2 labels per wire); eval: out labels
+    uint4* wires_full;                    // optional
+    uint32_t* counter;                    // next instance to claim
+    uint32_t team_threads, n_teams;
+};
+
+__device__ __forceinline__ void team_barrier(uint32_t team, uint32_t team_threads) {
+    if (team_threads == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_threads) : "memory");
+}
+
+__device__ __forceinline__ Label lds_label(const uint4* slots, uint32_t s) { return label_from_mem(slots[s]); }
+__device__ __forceinline__ void sts_label(uint4* slots, uint32_t s, Label l) { slots[s] = label_to_mem(l); }
+
+__device__ __forceinline__ Label shfl_xor_label(Label h, int m) {
+    return Label{__shfl_xor_sync(0xffffffffu, h.w0, m), __shfl_xor_sync(0xffffffffu, h.w1, m),
+                 __shfl_xor_sync(0xffffffffu, h.w2, m), __shfl_xor_sync(0xffffffffu, h.w3, m)};
+}
+__device__ __forceinline__ Label shfl_label(Label h, int src) {
+    return Label{__shfl_sync(0xffffffffu, h.w0, src), __shfl_sync(0xffffffffu, h.w1, src),
+                 __shfl_sync(0xffffffffu, h.w2, src), __shfl_sync(0xffffffffu, h.w3, src)};
+}
+__device__ __forceinline__ uint32_t mask_of(uint32_t bit) { return 0u - (bit & 1u); }
+
+// Shared-memory carve-up common to both kernels.
+struct TeamCtx {
+    uint8_t* tables;
+    uint32_t* rk;          // this team's round keys
+    uint4* slots;          // this team's wire labels
+    volatile uint32_t* claim;
+    uint32_t team, ttid;
+};
+
+__device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
+    TeamCtx c;
+    c.tables = smem;
+    c.team = threadIdx.x / p.team_threads;
+    c.ttid = threadIdx.x - c.team * p.team_threads;
+    uint8_t* q = smem + AES_TABLE_BYTES;
+    c.rk = reinterpret_cast<uint32_t*>(q + c.team * GC_RK_BYTES);
+    q += p.n_teams * GC_RK_BYTES;
+    c.slots = reinterpret_cast<uint4*>(q + (size_t)c.team * p.n_slots * 16);
+    q += (size_t)p.n_teams * p.n_slots * 16;
+    c.claim = reinterpret_cast<volatile uint32_t*>(q) + c.team;
+    return c;
+}
+
+// ------------------------------------------------------------------ garble ----
+template <bool FULL>
+__global__ void __launch_bounds__(1024, 1) garble_kernel(const GcParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const TeamCtx tc = team_ctx(smem, p);
+    aes_tables_to_smem(tc.tables);
+    __syncthreads();
+    const AesLane lane = aes_lane(tc.tables);
+    const uint32_t TT = p.team_threads, ttid = tc.ttid;
+    int nr = (int)(p.keylen >> 2) + 6;
+    if (p.key_stride == 0) {
+        if (ttid == 0) aes_expand_key(tc.tables, p.keys, (int)p.keylen, tc.rk);
+        team_barrier(tc.team, TT);
+    }
+    uint4* const slots = tc.slots;
+    const uint32_t* const rk = tc.rk;
+
+    for (;;) {
+        if (ttid == 0) *tc.claim = atomicAdd(p.counter, 1u);
+        team_barrier(tc.team, TT);
+        const uint32_t inst = *tc.claim;
+        if (inst >= p.batch) break;
+        if (p.key_stride != 0 && ttid == 0)
+            aes_expand_key(tc.tables, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+        Label R = label_from_mem(__ldg(p.r + inst));
+        R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
+        // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
+        for (uint32_t k = ttid; k < p.n_in; k += TT) {
+            const uint2 ref = __ldg(p.live_in + k);
+            const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
+            slots[ref.x] = m;
+            if (p.io) {
+                uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + ref.y) * 2;
+                w[0] = m;
+                w[1] = label_to_mem(label_from_mem(m) ^ R);
+            }
+            if (FULL) {
+                uint4* w = p.wires_full + ((size_t)inst * p.n_wires + ref.y) * 2;
+                w[0] = m;
+                w[1] = label_to_mem(label_from_mem(m) ^ R);
+            }
+        }
+        team_barrier(tc.team, TT);
+        uint4* const tab = p.tables + (size_t)inst * p.n_rows;
+
+        for (uint32_t s = 0; s < p.n_steps; s++) {
+            const uint4 st = __ldg(p.steps + s);               // first, n_free, n_quad, n_inv
+            // ---- Free-XOR gates (garble.go:331-351): one lane each, no AES
+            for (uint32_t j = ttid; j < st.y; j += TT) {
+                const uint4 g = __ldg(p.recs + st.x + j);
+                const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff, op = (g.y >> 16) & 0xff;
+                Label c0 = lds_label(slots, sa) ^ lds_label(slots, sb);
+                if (op == OP_XNOR) c0 = c0 ^ R;                // XNOR swaps (L0, L1)
+                sts_label(slots, sc, c0);
+                if (FULL) {
+                    uint4* w = p.wires_full + ((size_t)inst * p.n_wires + __ldg(p.out_wire + st.x + j)) * 2;
+                    w[0] = label_to_mem(c0);
+                    w[1] = label_to_mem(c0 ^ R);
+                }
+            }
+            // ---- ciphered gates: one AES block per lane
+            const uint32_t nq4 = 4 * st.z;
+            const uint32_t ntask = nq4 + 2 * st.w;
+            const uint32_t nloop = (ntask + 31u) & ~31u;
+            const uint32_t cbase = st.x + st.y;
+            for (uint32_t t = ttid; t < nloop; t += TT) {
+                const bool active = t < ntask;
+                uint32_t gi, k;
+                if (t < nq4) { gi = cbase + (t >> 2); k = t & 3; }
+                else { const uint32_t u = t - nq4; gi = cbase + st.z + (u >> 1); k = u & 1; }
+                uint4 g = make_uint4(0, 0, 0, 0);
+                if (active) g = __ldg(p.recs + gi);
+                const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff;
+                const uint32_t op = active ? ((g.y >> 16) & 0xff) : 0xffu;
+                const Label a0 = lds_label(slots, sa);
+                const Label b0 = lds_label(slots, sb);
+                const uint32_t pa = label_s(a0), pb = label_s(b0);
+                // the hash input of this lane
+                Label K;
+                uint32_t tw = g.z;
+                if (op == OP_OR) {                             // K = 2a ^ 4b ^ t, lane k = (a_i, b_j), k = 2i+j
+                    const Label xa = a0 ^ label_and_mask(R, mask_of(k >> 1));
+                    const Label xb = b0 ^ label_and_mask(R, mask_of(k));
+                    K = label_shl(xa, 1) ^ label_shl(xb, 2);
+                } else {                                       // AND: (a0,j0)(a1,j0)(b0,j1)(b1,j1); INV: a0, a1
+                    const bool use_b = (op == OP_AND) && (k & 2);
+                    Label x = use_b ? b0 : a0;
+                    x = x ^ label_and_mask(R, mask_of(k));
+                    K = label_shl(x, 1);
+                    if (op == OP_AND) tw += k >> 1;
+                }
+                K.w3 ^= tw;
+                const Label h = aes_hash_k(lane, rk, nr, K);
+                // ---- combine
+                const Label u = h ^ shfl_xor_label(h, 1);
+                Label v = Label{0, 0, 0, 0};
+                if (op == OP_AND) {
+                    if (k == 0) {                              // generator half (garble.go:361-369)
+                        const Label tg = u ^ label_and_mask(R, mask_of(pb));
+                        v = h ^ label_and_mask(tg, mask_of(pa));
+                        tab[g.w] = label_to_mem(tg);
+                    } else if (k == 2) {                       // evaluator half (garble.go:372-380)
+                        const Label te = u ^ a0;
+                        v = h ^ label_and_mask(u, mask_of(pb));
+                        tab[g.w + 1] = label_to_mem(te);
+                    }
+                } else if (op == OP_INV) {                     // garble.go:446-474, row-reduced
+                    if (k == 0) {
+                        const Label c0 = pa ? (u ^ h) : (h ^ R);
+                        tab[g.w] = label_to_mem(u ^ R);
+                        sts_label(slots, sc, c0);
+                        if (FULL) {
+                            uint4* w = p.wires_full + ((size_t)inst * p.n_wires + __ldg(p.out_wire + gi)) * 2;
+                            w[0] = label_to_mem(c0);
+                            w[1] = label_to_mem(c0 ^ R);
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, op == OP_OR)) {    // garble.go:412-444, row-reduced
+                    const uint32_t l0i = 2 * pa + pb;
+                    const Label t0 = shfl_label(h, (int)((threadIdx.x & 28u) + l0i));
+                    if (op == OP_OR) {
+                        const Label c0 = (l0i == 0) ? t0 : (t0 ^ R);
+                        const Label c1 = c0 ^ R;
+                        const uint32_t pos = k ^ l0i;          // table position of this lane's row
+                        if (pos != 0) tab[g.w + pos - 1] = label_to_mem(h ^ ((pos == l0i) ? c0 : c1));
+                        if (k == 0) {
+                            sts_label(slots, sc, c0);
+                            if (FULL) {
+                                uint4* w = p.wires_full + ((size_t)inst * p.n_wires + __ldg(p.out_wire + gi)) * 2;
+                                w[0] = label_to_mem(c0);
+                                w[1] = label_to_mem(c1);
+                            }
+                        }
+                    }
+                }
+                const Label w2 = v ^ shfl_xor_label(v, 2);
+                if (op == OP_AND && k == 0) {                  // combine halves (garble.go:383-392)
+                    sts_label(slots, sc, w2);
+                    if (FULL) {
+                        uint4* w = p.wires_full + ((size_t)inst * p.n_wires + __ldg(p.out_wire + gi)) * 2;
+                        w[0] = label_to_mem(w2);
+                        w[1] = label_to_mem(w2 ^ R);
+                    }
+                }
+            }
+            team_barrier(tc.team, TT);
+        }
+        // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
+        if (p.io) {
+            for (uint32_t k = ttid; k < p.n_out; k += TT) {
+                const uint2 ref = __ldg(p.live_out + k);
+                const Label l0 = lds_label(slots, ref.x);
+                uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + p.n_in + ref.y) * 2;
+                w[0] = label_to_mem(l0);
+                w[1] = label_to_mem(l0 ^ R);
+            }
+        }
+        team_barrier(tc.team, TT);
+    }
+}
+
+// -------------------------------------------------------------------- eval ----
+template <bool FULL>
+__global__ void __launch_bounds__(1024, 1) eval_kernel(const GcParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const TeamCtx tc = team_ctx(smem, p);
+    aes_tables_to_smem(tc.tables);
+    __syncthreads();
+    const AesLane lane = aes_lane(tc.tables);
+    const uint32_t TT = p.team_threads, ttid = tc.ttid;
+    const int nr = (int)(p.keylen >> 2) + 6;
+    if (p.key_stride == 0) {
+        if (ttid == 0) aes_expand_key(tc.tables, p.keys, (int)p.keylen, tc.rk);
+        team_barrier(tc.team, TT);
+    }
+    uint4* const slots = tc.slots;
+    const uint32_t* const rk = tc.rk;
+
+    for (;;) {
+        if (ttid == 0) *tc.claim = atomicAdd(p.counter, 1u);
+        team_barrier(tc.team, TT);
+        const uint32_t inst = *tc.claim;
+        if (inst >= p.batch) break;
+        if (p.key_stride != 0 && ttid == 0)
+            aes_expand_key(tc.tables, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+        for (uint32_t k = ttid; k < p.n_in; k += TT) {
+            const uint2 ref = __ldg(p.live_in + k);
+            const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
+            slots[ref.x] = m;
+            if (FULL) p.wires_full[(size_t)inst * p.n_wires + ref.y] = m;
+        }
+        team_barrier(tc.team, TT);
+        const uint4* const tab = p.tables + (size_t)inst * p.n_rows;
+
+        for (uint32_t s = 0; s < p.n_steps; s++) {
+            const uint4 st = __ldg(p.steps + s);
+            // XOR and XNOR are both a plain XOR on the evaluator side (eval.go:48-50)
+            for (uint32_t j = ttid; j < st.y; j += TT) {
+                const uint4 g = __ldg(p.recs + st.x + j);
+                const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff;
+                const Label c = lds_label(slots, sa) ^ lds_label(slots, sb);
+                sts_label(slots, sc, c);
+                if (FULL) p.wires_full[(size_t)inst * p.n_wires + __ldg(p.out_wire + st.x + j)] = label_to_mem(c);
+            }
+            // ciphered gates: AND = 2 lanes (a with j0, b with j1); OR/INV = 1 hash.
+            // OR shares the 2-lane slot of its class (second lane idle).
+            const uint32_t nq2 = 2 * st.z;
+            const uint32_t ntask = nq2 + st.w;
+            const uint32_t nloop = (ntask + 31u) & ~31u;
+            const uint32_t cbase = st.x + st.y;
+            for (uint32_t t = ttid; t < nloop; t += TT) {
+                bool active = t < ntask;
+                uint32_t gi, k;
+                if (t < nq2) { gi = cbase + (t >> 1); k = t & 1; }
+                else { gi = cbase + st.z + (t - nq2); k = 0; }
+                uint4 g = make_uint4(0, 0, 0, 0);
+                if (active) g = __ldg(p.recs + gi);
+                const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff;
+                const uint32_t op = active ? ((g.y >> 16) & 0xff) : 0xffu;
+                const Label a = lds_label(slots, sa);
+                const Label b = lds_label(slots, sb);
+                const uint32_t sA = label_s(a), sB = label_s(b);
+                // the garbled row this lane may need, fetched before the AES so the
+                // HBM latency hides behind the rounds
+                uint32_t ridx = g.w;
+                bool need = false;
+                if (op == OP_AND) { ridx += k; need = k ? sB : sA; }
+                else if (op == OP_INV) { need = sA; }
+                else if (op == OP_OR) { const uint32_t ix = 2 * sA + sB; need = (ix > 0) && (k == 0); ridx += ix - 1; }
+                Label row = Label{0, 0, 0, 0};
+                if (need) row = label_from_mem(__ldg(tab + ridx));
+                Label K;
+                uint32_t tw = g.z;
+                if (op == OP_OR) {
+                    K = label_shl(a, 1) ^ label_shl(b, 2);     // makeK, garble.go:75-83
+                } else {
+                    K = label_shl((op == OP_AND && k) ? b : a, 1);
+                    if (op == OP_AND) tw += k;
+                }
+                K.w3 ^= tw;
+                const Label h = aes_hash_k(lane, rk, nr, K);
+                Label v = h ^ row;                             // decrypt (garble.go:58-73) / half-gate
+                if (op == OP_AND && k == 1) v = v ^ label_and_mask(a, mask_of(sB));   // we ^= a (eval.go:72-75)
+                const Label o = v ^ shfl_xor_label(v, 1);
+                if (active && (k == 0)) {
+                    const Label res = (op == OP_AND) ? o : v;
+                    sts_label(slots, sc, res);
+                    if (FULL) p.wires_full[(size_t)inst * p.n_wires + __ldg(p.out_wire + gi)] = label_to_mem(res);
+                }
+            }
+            team_barrier(tc.team, TT);
+        }
+        for (uint32_t k = ttid; k < p.n_out; k += TT) {
+            const uint2 ref = __ldg(p.live_out + k);
+            p.io[(size_t)inst * p.n_out + ref.y] = slots[ref.x];
+        }
+        team_barrier(tc.team, TT);
+    }
+}
+
+}  // namespace gcb

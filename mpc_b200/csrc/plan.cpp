@@ -1,0 +1,211 @@
+// plan.cpp -- host-side circuit plan compiler (see plan.hpp).
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <functional>
+#include <limits>
+#include <queue>
+
+namespace gcb {
+
+namespace {
+constexpr uint32_t kCipherSub = 0xffffffffu;   // sub-level of the cipher gates of a level
+constexpr int64_t kForever = std::numeric_limits<int64_t>::max();
+
+inline int op_class(uint8_t op) { return op <= OP_XNOR ? 0 : (op == OP_INV ? 2 : 1); }
+}  // namespace
+
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
+    char msg[160];
+    const uint32_t ng = spec.num_gates, nw = spec.num_wires;
+    const bool identity = spec.loc.empty();
+    const uint32_t nloc = identity ? nw : spec.num_locs;
+    if (!identity && spec.loc.size() != nw) { err = "location map size mismatch"; return GCB_E_ARG; }
+    auto loc_of = [&](uint32_t w) { return identity ? w : spec.loc[w]; };
+
+    const size_t ninit = spec.live_in.size();
+    const size_t ndefs = ninit + ng;
+    // A definition is one value of one location: the initial value of a live-in
+    // location, or the output of one gate.  Re-assigned locations (legal in the
+    // file formats, and the norm for aliased streaming wires) get a new
+    // definition each time, which makes every hazard a plain RAW dependency.
+    std::vector<int64_t> cur_def(nloc, -1);
+    std::vector<uint32_t> cd(ndefs, 0), xd(ndefs, 0);       // cipher depth, free sub-depth
+    std::vector<int64_t> born(ndefs, -1), last(ndefs, -1);
+    for (size_t k = 0; k < ninit; k++) {
+        const uint32_t l = spec.live_in[k];
+        if (l >= nloc) { err = "live-in location out of range"; return GCB_E_WIRE; }
+        if (cur_def[l] >= 0) { err = "duplicate live-in location"; return GCB_E_ARG; }
+        cur_def[l] = (int64_t)k;
+    }
+
+    std::vector<uint64_t> key(ng);
+    std::vector<int64_t> def_a(ng), def_b(ng);
+    uint32_t n_and = 0, n_or = 0, n_inv = 0, n_free = 0;
+    plan.row_off.assign(ng + 1, 0);
+    plan.ops.resize(ng);
+    std::vector<uint32_t> tweak_of(ng);
+    uint32_t tweak = 0, row = 0;
+    for (uint32_t i = 0; i < ng; i++) {
+        const gcb_gate& g = spec.gates[i];
+        if (g.op > OP_INV) {
+            snprintf(msg, sizeof msg, "invalid gate type %u (gate %u)", g.op, i);
+            err = msg;
+            return GCB_E_BADOP;
+        }
+        const bool unary = g.op == OP_INV;
+        if (g.in0 >= nw || (!unary && g.in1 >= nw) || g.out >= nw) {
+            snprintf(msg, sizeof msg, "invalid wire in gate %u [0...%u[", i, nw);
+            err = msg;
+            return GCB_E_WIRE;
+        }
+        const int64_t da = cur_def[loc_of(g.in0)];
+        const int64_t db = unary ? da : cur_def[loc_of(g.in1)];
+        if (da < 0 || db < 0) {
+            snprintf(msg, sizeof msg, "input %u of gate %u not set", da < 0 ? g.in0 : g.in1, i);
+            err = msg;
+            return GCB_E_WIRE;
+        }
+        uint32_t d, x;
+        if (cd[da] > cd[db]) { d = cd[da]; x = xd[da]; }
+        else if (cd[db] > cd[da]) { d = cd[db]; x = xd[db]; }
+        else { d = cd[da]; x = std::max(xd[da], xd[db]); }
+        const size_t dout = ninit + i;
+        if (g.op >= OP_AND) {
+            key[i] = ((uint64_t)d << 32) | kCipherSub;
+            cd[dout] = d + 1; xd[dout] = 0;
+        } else {
+            key[i] = ((uint64_t)d << 32) | x;
+            cd[dout] = d; xd[dout] = x + 1;
+        }
+        def_a[i] = da; def_b[i] = db;
+        cur_def[loc_of(g.out)] = (int64_t)dout;
+        plan.ops[i] = g.op;
+        plan.row_off[i] = row;
+        tweak_of[i] = tweak;
+        switch (g.op) {
+            case OP_AND: tweak += 2; row += 2; n_and++; break;
+            case OP_OR: tweak += 1; row += 3; n_or++; break;
+            case OP_INV: tweak += 1; row += 1; n_inv++; break;
+            default: n_free++; break;
+        }
+    }
+    plan.row_off[ng] = row;
+
+    // ---- steps: sort gates by (level key, class, original index)
+    std::vector<uint32_t> order(ng);
+    for (uint32_t i = 0; i < ng; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t p, uint32_t q) {
+        if (key[p] != key[q]) return key[p] < key[q];
+        const int cp = op_class(spec.gates[p].op), cq = op_class(spec.gates[q].op);
+        if (cp != cq) return cp < cq;
+        return p < q;
+    });
+    std::vector<int64_t> step_of(ng);
+    plan.steps.clear();
+    for (uint32_t pos = 0; pos < ng;) {
+        uint32_t end = pos;
+        StepRec st{pos, 0, 0, 0};
+        while (end < ng && key[order[end]] == key[order[pos]]) {
+            const int c = op_class(spec.gates[order[end]].op);
+            (c == 0 ? st.n_free : c == 1 ? st.n_quad : st.n_inv)++;
+            step_of[order[end]] = (int64_t)plan.steps.size();
+            end++;
+        }
+        plan.steps.push_back(st);
+        pos = end;
+    }
+    const int64_t nsteps = (int64_t)plan.steps.size();
+
+    // ---- liveness
+    for (uint32_t i = 0; i < ng; i++) {
+        const int64_t s = step_of[i];
+        born[ninit + i] = s;
+        last[def_a[i]] = std::max(last[def_a[i]], s);
+        last[def_b[i]] = std::max(last[def_b[i]], s);
+    }
+    plan.live_out.clear();
+    for (size_t k = 0; k < spec.live_out.size(); k++) {
+        const uint32_t l = spec.live_out[k];
+        if (l >= nloc || cur_def[l] < 0) {
+            snprintf(msg, sizeof msg, "wire %u not assigned", l);
+            err = msg;
+            return GCB_E_WIRE;
+        }
+        last[cur_def[l]] = kForever;
+    }
+    for (size_t d = 0; d < ndefs; d++) last[d] = std::max(last[d], born[d]);
+
+    // ---- slots: lowest free index first; a slot whose value was last read in
+    // step s may be rewritten from step s+1 on (reads and writes of one step are
+    // unordered).
+    std::vector<std::vector<size_t>> expire((size_t)nsteps + 1);
+    std::vector<uint32_t> slot(ndefs, 0);
+    std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_slots;
+    uint32_t next_slot = 0;
+    plan.live_in.clear();
+    for (size_t k = 0; k < ninit; k++) {
+        slot[k] = next_slot++;
+        plan.live_in.push_back(SlotRef{slot[k], (uint32_t)k});
+        if (last[k] < 0) free_slots.push(slot[k]);                 // never read, not live-out
+        else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
+    }
+    for (int64_t s = 0; s < nsteps; s++) {
+        if (s > 0) {
+            for (size_t d : expire[(size_t)s - 1]) free_slots.push(slot[d]);
+            expire[(size_t)s - 1].clear();
+        }
+        const StepRec& st = plan.steps[(size_t)s];
+        const uint32_t n = st.n_free + st.n_quad + st.n_inv;
+        for (uint32_t j = 0; j < n; j++) {
+            const size_t d = ninit + order[st.first + j];
+            if (free_slots.empty()) slot[d] = next_slot++;
+            else { slot[d] = free_slots.top(); free_slots.pop(); }
+            if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+        }
+    }
+    if (next_slot > 65535) {
+        snprintf(msg, sizeof msg, "circuit needs %u live wire slots (limit 65535)", next_slot);
+        err = msg;
+        return GCB_E_TOO_LARGE;
+    }
+    for (size_t k = 0; k < spec.live_out.size(); k++)
+        plan.live_out.push_back(SlotRef{slot[(size_t)cur_def[spec.live_out[k]]], (uint32_t)k});
+
+    // ---- gate records in schedule order
+    plan.recs.resize(ng);
+    plan.out_wire.resize(ng);
+    plan.orig_index.resize(ng);
+    for (uint32_t pos = 0; pos < ng; pos++) {
+        const uint32_t i = order[pos];
+        GateRec r;
+        r.a = (uint16_t)slot[(size_t)def_a[i]];
+        r.b = (uint16_t)slot[(size_t)def_b[i]];
+        r.c = (uint16_t)slot[ninit + i];
+        r.op = spec.gates[i].op;
+        r.pad = 0;
+        r.tweak = tweak_of[i];
+        r.row = plan.row_off[i];
+        plan.recs[pos] = r;
+        plan.out_wire[pos] = spec.gates[i].out;
+        plan.orig_index[pos] = i;
+    }
+
+    gcb_plan_info& in = plan.info;
+    in = gcb_plan_info{};
+    in.num_gates = ng;
+    in.num_wires = nw;
+    in.num_inputs = (uint32_t)ninit;
+    in.num_outputs = (uint32_t)spec.live_out.size();
+    in.num_rows = row;
+    in.num_tweaks = tweak;
+    in.num_steps = (uint32_t)nsteps;
+    in.num_slots = next_slot;
+    in.num_and = n_and; in.num_or = n_or; in.num_inv = n_inv; in.num_free = n_free;
+    in.garble_hashes = 4 * n_and + 4 * n_or + 2 * n_inv;
+    in.eval_hashes = 2 * n_and + n_or + n_inv;
+    return GCB_OK;
+}
+
+}  // namespace gcb
