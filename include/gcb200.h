@@ -63,6 +63,14 @@ const char *gcb_version(void);
 int gcb_set_device(int device);
 int gcb_device_count(void);
 
+/* Page-locked host memory.  Replaces the per-circuit scratch pool of
+ * Circuit.Garble (garbleScratchPool, circuit/garble.go:193-224; Garbled.Release
+ * :232-244 returns to it): slabs allocated here are DMA'd in place by the host
+ * entry points; any other host memory is staged through an internal pinned
+ * buffer with one extra copy.  Returns NULL on failure. */
+void *gcb_host_alloc(size_t bytes);
+void gcb_host_free(void *p);
+
 /* ------------------------------------------------------------------ plans --- */
 /* A plan is the compiled, immutable form of one circuit.Circuit: gates grouped
  * into dependency steps, with the static per-gate tweak ids (the `id` counter of

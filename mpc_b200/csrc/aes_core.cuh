@@ -5,41 +5,91 @@
 // circuit/eval.go:20, ot/iknp.go:624, ot/mitccrh.go:82,117) is computed with
 // four T-tables held in shared memory.  Each table is replicated 32x so that
 // lane l of a warp only ever touches bank l: a warp-wide lookup is exactly one
-// conflict-free shared-memory wavefront whatever the 32 indices are.  The
-// kernels that use this core are bound by that wavefront rate (16 per round per
-// 32 blocks), not by HBM; see DESIGN.md.
+// conflict-free shared-memory wavefront whatever the 32 indices are.  One
+// lookup costs one PRMT (address = byte k of the state word in bits 8..15, the
+// lane's bank offset in bits 0..7) and one LDS [R + UR + imm]; one round is
+// 16 PRMT + 16 LDS + 8 LOP3.  The kernels built on this core are bound by the
+// shared-memory wavefront rate (16 per round per 32 blocks), not by HBM; see
+// DESIGN.md.
 //
 // State convention: four big-endian column words s0..s3 of the 16-byte block.
 // A label {D0,D1} (ot/label.go:28-31, D0 = high half) serialises big-endian
 // (GetData, ot/label.go:105-108), so s0 = D0>>32, s1 = (u32)D0, s2 = D1>>32,
-// s3 = (u32)D1 -- no byte swaps anywhere on the device.
+// s3 = (u32)D1 -- no byte swaps anywhere on the garble / eval path.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace gcb {
 
+// ---- FIPS-197 tables, generated at compile time ------------------------------
+struct AesConstTables {
+    uint8_t sbox[256];
+    uint32_t te0[256];     // (02*S, S, S, 03*S) from MSB to LSB
+};
+
+constexpr uint8_t gf_mul(uint8_t a, uint8_t b) {
+    uint8_t r = 0;
+    for (int i = 0; i < 8; i++) {
+        if (b & 1) r ^= a;
+        const bool hi = a & 0x80;
+        a = (uint8_t)(a << 1);
+        if (hi) a ^= 0x1b;
+        b >>= 1;
+    }
+    return r;
+}
+
+constexpr AesConstTables make_aes_tables() {
+    AesConstTables t{};
+    // multiplicative inverse by walking the generator 3 and its inverse 0xf6
+    uint8_t p = 1, q = 1;
+    do {
+        p = (uint8_t)(p ^ (uint8_t)(p << 1) ^ ((p & 0x80) ? 0x1b : 0));   // p *= 3
+        q ^= (uint8_t)(q << 1);                                         // q /= 3
+        q ^= (uint8_t)(q << 2);
+        q ^= (uint8_t)(q << 4);
+        if (q & 0x80) q ^= 0x09;
+        const uint8_t x = (uint8_t)(q ^ (uint8_t)((q << 1) | (q >> 7)) ^ (uint8_t)((q << 2) | (q >> 6)) ^
+                                    (uint8_t)((q << 3) | (q >> 5)) ^ (uint8_t)((q << 4) | (q >> 4)));
+        t.sbox[p] = (uint8_t)(x ^ 0x63);
+    } while (p != 1);
+    t.sbox[0] = 0x63;
+    for (int i = 0; i < 256; i++) {
+        const uint8_t s = t.sbox[i];
+        t.te0[i] = ((uint32_t)gf_mul(s, 2) << 24) | ((uint32_t)s << 16) | ((uint32_t)s << 8) | gf_mul(s, 3);
+    }
+    return t;
+}
+
+constexpr AesConstTables kAesTables = make_aes_tables();
+static_assert(kAesTables.sbox[0x00] == 0x63 && kAesTables.sbox[0x01] == 0x7c &&
+              kAesTables.sbox[0x53] == 0xed && kAesTables.sbox[0xff] == 0x16, "S-box generation");
+static_assert(kAesTables.te0[0] == 0xc66363a5u && kAesTables.te0[1] == 0xf87c7c84u, "Te0 generation");
+
+struct Te0Array { uint32_t v[256]; };
+constexpr Te0Array make_te0() {
+    Te0Array a{};
+    for (int i = 0; i < 256; i++) a.v[i] = kAesTables.te0[i];
+    return a;
+}
+__device__ const Te0Array g_te0 = make_te0();
+
 // ---- shared-memory table layout ----------------------------------------------
 // Entry x of table t for lane l lives at byte offset
 //     (t >> 1) * 65536 + x * 256 + (t & 1) * 128 + l * 4
-// i.e. two tables interleaved per 64 KiB region with a 256-byte entry stride, so
-// that "x * 256 + l * 4" is a single PRMT of the state word with the lane base.
+// (two tables interleaved per 64 KiB region with a 256-byte entry stride).
 constexpr int AES_TABLE_BYTES = 4 * 256 * 32 * 4;   // 131072
 constexpr int AES_MAX_RK_WORDS = 60;                 // AES-256: 15 round keys
 
-// Te0 for the 256 byte values, big-endian column convention:
-// Te0[x] = (02*S[x], S[x], S[x], 03*S[x]) from MSB to LSB.  Filled by the host
-// at library initialisation (aes_tables_init) from the FIPS-197 definition.
-extern __device__ uint32_t g_te0[256];
-
 __device__ __forceinline__ uint32_t ror8(uint32_t x) { return __funnelshift_r(x, x, 8); }
 
-// Cooperative fill of the replicated tables; call with all threads of the CTA,
+// Cooperative fill of the replicated tables; all threads of the CTA call it,
 // then __syncthreads().
 __device__ __forceinline__ void aes_tables_to_smem(uint8_t* smem_tables) {
     for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
         const int x = i >> 5, l = i & 31;
-        const uint32_t t0 = g_te0[x];
+        const uint32_t t0 = g_te0.v[x];
         const uint32_t t1 = ror8(t0), t2 = ror8(t1), t3 = ror8(t2);
         uint8_t* e = smem_tables + x * 256 + l * 4;
         *reinterpret_cast<uint32_t*>(e) = t0;
@@ -49,91 +99,100 @@ __device__ __forceinline__ void aes_tables_to_smem(uint8_t* smem_tables) {
     }
 }
 
-// Per-thread lookup context: 32-bit shared-window address of this lane's column
-// in region A, entry 0.
+// Per-thread lookup context.
 struct AesLane {
-    uint32_t base;      // smem address of tables + lane*4
+    uint32_t tb;        // shared-window address of the tables (warp-uniform)
+    uint32_t lane4;     // (lane id) * 4: this lane's bank
 };
 
 __device__ __forceinline__ AesLane aes_lane(const uint8_t* smem_tables) {
     AesLane a;
-    a.base = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tables)) + (threadIdx.x & 31) * 4;
+    a.tb = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tables));
+    a.lane4 = (threadIdx.x & 31u) * 4u;
     return a;
 }
 
-template <int OFF>
-__device__ __forceinline__ uint32_t lds_off(uint32_t addr) {
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 
-// byte k (0 = LSB) of s, scaled by the 256-byte entry stride
-template <int K>
-__device__ __forceinline__ uint32_t entry_off(uint32_t s) {
-    // PRMT: result byte1 = byte K of s, other bytes zero
-    return __byte_perm(s, 0, 0x4404 | (K << 4));
-}
-
+// Table T lookup of byte K (0 = LSB) of s.
 template <int T, int K>
 __device__ __forceinline__ uint32_t te(const AesLane& a, uint32_t s) {
     constexpr int OFF = (T >> 1) * 65536 + (T & 1) * 128;
-    return lds_off<OFF>(a.base + entry_off<K>(s));
+    // PRMT: byte0 = lane4, byte1 = byte K of s, bytes 2,3 = 0
+    const uint32_t e = __byte_perm(s, a.lane4, 0x5504 | (K << 4));
+    return lds_u32(a.tb + OFF + e);
 }
 
-// One full round on (s0..s3) with round-key words k0..k3.
+// One full round on (s0..s3) with round-key words k.
 __device__ __forceinline__ void aes_round(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2,
-                                          uint32_t& s3, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
-    const uint32_t t0 = te<0, 3>(a, s0) ^ te<1, 2>(a, s1) ^ te<2, 1>(a, s2) ^ te<3, 0>(a, s3) ^ k0;
-    const uint32_t t1 = te<0, 3>(a, s1) ^ te<1, 2>(a, s2) ^ te<2, 1>(a, s3) ^ te<3, 0>(a, s0) ^ k1;
-    const uint32_t t2 = te<0, 3>(a, s2) ^ te<1, 2>(a, s3) ^ te<2, 1>(a, s0) ^ te<3, 0>(a, s1) ^ k2;
-    const uint32_t t3 = te<0, 3>(a, s3) ^ te<1, 2>(a, s0) ^ te<2, 1>(a, s1) ^ te<3, 0>(a, s2) ^ k3;
+                                          uint32_t& s3, const uint4 k) {
+    const uint32_t t0 = te<0, 3>(a, s0) ^ te<1, 2>(a, s1) ^ te<2, 1>(a, s2) ^ te<3, 0>(a, s3) ^ k.x;
+    const uint32_t t1 = te<0, 3>(a, s1) ^ te<1, 2>(a, s2) ^ te<2, 1>(a, s3) ^ te<3, 0>(a, s0) ^ k.y;
+    const uint32_t t2 = te<0, 3>(a, s2) ^ te<1, 2>(a, s3) ^ te<2, 1>(a, s0) ^ te<3, 0>(a, s1) ^ k.z;
+    const uint32_t t3 = te<0, 3>(a, s3) ^ te<1, 2>(a, s0) ^ te<2, 1>(a, s1) ^ te<3, 0>(a, s2) ^ k.w;
     s0 = t0; s1 = t1; s2 = t2; s3 = t3;
 }
 
-// Final round (SubBytes + ShiftRows + AddRoundKey): S[x] is picked out of the
-// T-table entry whose byte at the wanted position is S[x].
+// Final round (SubBytes + ShiftRows + AddRoundKey).  S[x] sits in two byte lanes
+// of every T-table entry; T2 = (S,3S,2S,S) and T3 = (S,S,3S,2S) have it in the
+// top and bottom bytes, so two PRMTs gather the four S-box bytes of a column.
+__device__ __forceinline__ uint32_t last_col(const AesLane& a, uint32_t x3, uint32_t x2, uint32_t x1,
+                                             uint32_t x0, uint32_t k) {
+    const uint32_t b3 = te<2, 3>(a, x3);        // S in byte 3 (and byte 0)
+    const uint32_t b2 = te<3, 2>(a, x2);        // S in bytes 3, 2
+    const uint32_t b1 = te<0, 1>(a, x1);        // (2S,S,S,3S): S in bytes 2, 1
+    const uint32_t b0 = te<1, 0>(a, x0);        // (3S,2S,S,S): S in bytes 1, 0
+    const uint32_t hi = __byte_perm(b3, b2, 0x3600);   // byte3 = b3.3, byte2 = b2.2
+    const uint32_t lo = __byte_perm(b1, b0, 0x0014);   // byte1 = b1.1, byte0 = b0.0
+    return __byte_perm(hi, lo, 0x3254) ^ k;            // (hi.3, hi.2, lo.1, lo.0)
+}
 __device__ __forceinline__ void aes_last_round(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2,
-                                               uint32_t& s3, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3) {
-    const uint32_t t0 = (te<2, 3>(a, s0) & 0xff000000u) ^ (te<3, 2>(a, s1) & 0x00ff0000u) ^
-                        (te<0, 1>(a, s2) & 0x0000ff00u) ^ (te<1, 0>(a, s3) & 0x000000ffu) ^ k0;
-    const uint32_t t1 = (te<2, 3>(a, s1) & 0xff000000u) ^ (te<3, 2>(a, s2) & 0x00ff0000u) ^
-                        (te<0, 1>(a, s3) & 0x0000ff00u) ^ (te<1, 0>(a, s0) & 0x000000ffu) ^ k1;
-    const uint32_t t2 = (te<2, 3>(a, s2) & 0xff000000u) ^ (te<3, 2>(a, s3) & 0x00ff0000u) ^
-                        (te<0, 1>(a, s0) & 0x0000ff00u) ^ (te<1, 0>(a, s1) & 0x000000ffu) ^ k2;
-    const uint32_t t3 = (te<2, 3>(a, s3) & 0xff000000u) ^ (te<3, 2>(a, s0) & 0x00ff0000u) ^
-                        (te<0, 1>(a, s1) & 0x0000ff00u) ^ (te<1, 0>(a, s2) & 0x000000ffu) ^ k3;
+                                               uint32_t& s3, const uint4 k) {
+    const uint32_t t0 = last_col(a, s0, s1, s2, s3, k.x);
+    const uint32_t t1 = last_col(a, s1, s2, s3, s0, k.y);
+    const uint32_t t2 = last_col(a, s2, s3, s0, s1, k.z);
+    const uint32_t t3 = last_col(a, s3, s0, s1, s2, k.w);
     s0 = t0; s1 = t1; s2 = t2; s3 = t3;
 }
 
-// Encrypt one block in place.  rk: round-key words in shared memory (uniform
-// address across the warp -> broadcast loads), nr = 10/12/14.
-__device__ __forceinline__ void aes_encrypt(const AesLane& a, const uint32_t* __restrict__ rk, int nr,
-                                            uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
-    uint4 k = *reinterpret_cast<const uint4*>(rk);
+// Encrypt one block in place with round keys in shared memory (warp-uniform
+// address -> one broadcast LDS.128 per round).  NR = 10/12/14.
+template <int NR>
+__device__ __forceinline__ void aes_encrypt_smem(const AesLane& a, const uint32_t* __restrict__ rk,
+                                                 uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(rk);
+    uint4 k = k4[0];
     s0 ^= k.x; s1 ^= k.y; s2 ^= k.z; s3 ^= k.w;
-#pragma unroll 1
-    for (int r = 1; r < nr; r++) {
-        k = *reinterpret_cast<const uint4*>(rk + 4 * r);
-        aes_round(a, s0, s1, s2, s3, k.x, k.y, k.z, k.w);
-    }
-    k = *reinterpret_cast<const uint4*>(rk + 4 * nr);
-    aes_last_round(a, s0, s1, s2, s3, k.x, k.y, k.z, k.w);
+#pragma unroll
+    for (int r = 1; r < NR; r++) aes_round(a, s0, s1, s2, s3, k4[r]);
+    aes_last_round(a, s0, s1, s2, s3, k4[NR]);
 }
 
-// S-box byte through the tables (Te0 = (2s, s, s, 3s): bits 8..15 hold S[x]).
-__device__ __forceinline__ uint32_t sbox_byte(const uint8_t* smem_tables, uint32_t x) {
-    return (*reinterpret_cast<const uint32_t*>(smem_tables + (x & 0xff) * 256) >> 8) & 0xff;
-}
-__device__ __forceinline__ uint32_t sub_word(const uint8_t* t, uint32_t w) {
-    return (sbox_byte(t, w >> 24) << 24) | (sbox_byte(t, w >> 16) << 16) | (sbox_byte(t, w >> 8) << 8) |
-           sbox_byte(t, w);
+// Same with AES-128 round keys held in registers (IKNP: one key per thread).
+__device__ __forceinline__ void aes128_encrypt_regs(const AesLane& a, const uint32_t (&rk)[44],
+                                                    uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
+    s0 ^= rk[0]; s1 ^= rk[1]; s2 ^= rk[2]; s3 ^= rk[3];
+#pragma unroll
+    for (int r = 1; r < 10; r++)
+        aes_round(a, s0, s1, s2, s3, make_uint4(rk[4 * r], rk[4 * r + 1], rk[4 * r + 2], rk[4 * r + 3]));
+    aes_last_round(a, s0, s1, s2, s3, make_uint4(rk[40], rk[41], rk[42], rk[43]));
 }
 
-// FIPS-197 key expansion into big-endian words.  key: raw key bytes (global or
-// shared), keylen 16/24/32.  One thread; 4*(nr+1) words written.  Returns nr.
-__device__ __forceinline__ int aes_expand_key(const uint8_t* smem_tables, const uint8_t* key, int keylen,
-                                              uint32_t* rk) {
+// SubWord through this lane's table column (Te0 = (2s, s, s, 3s): bits 8..15).
+__device__ __forceinline__ uint32_t sub_word(const AesLane& a, uint32_t w) {
+    const uint32_t b3 = te<2, 3>(a, w), b2 = te<3, 2>(a, w), b1 = te<0, 1>(a, w), b0 = te<1, 0>(a, w);
+    const uint32_t hi = __byte_perm(b3, b2, 0x3600);
+    const uint32_t lo = __byte_perm(b1, b0, 0x0014);
+    return __byte_perm(hi, lo, 0x3254);
+}
+
+// FIPS-197 key expansion into big-endian words.  key: raw key bytes, keylen
+// 16/24/32.  One thread; 4*(nr+1) words written to rk (shared or local).
+__device__ __forceinline__ void aes_expand_key(const AesLane& a, const uint8_t* key, int keylen, uint32_t* rk) {
     const int nk = keylen >> 2, nr = nk + 6;
     for (int i = 0; i < nk; i++)
         rk[i] = (uint32_t(key[4 * i]) << 24) | (uint32_t(key[4 * i + 1]) << 16) |
@@ -142,14 +201,29 @@ __device__ __forceinline__ int aes_expand_key(const uint8_t* smem_tables, const 
     for (int i = nk; i < 4 * (nr + 1); i++) {
         uint32_t t = rk[i - 1];
         if (i % nk == 0) {
-            t = sub_word(smem_tables, (t << 8) | (t >> 24)) ^ rcon;
+            t = sub_word(a, (t << 8) | (t >> 24)) ^ rcon;
             rcon = (rcon << 1) ^ ((rcon & 0x80000000u) ? 0x1b000000u : 0u);
         } else if (nk > 6 && i % nk == 4) {
-            t = sub_word(smem_tables, t);
+            t = sub_word(a, t);
         }
         rk[i] = rk[i - nk] ^ t;
     }
-    return nr;
+}
+
+// AES-128 key expansion from four big-endian key words into registers.
+__device__ __forceinline__ void aes128_expand_regs(const AesLane& a, uint32_t k0, uint32_t k1, uint32_t k2,
+                                                   uint32_t k3, uint32_t (&rk)[44]) {
+    rk[0] = k0; rk[1] = k1; rk[2] = k2; rk[3] = k3;
+    uint32_t rcon = 0x01000000u;
+#pragma unroll
+    for (int r = 1; r <= 10; r++) {
+        const uint32_t t = rk[4 * r - 1];
+        rk[4 * r] = rk[4 * r - 4] ^ sub_word(a, (t << 8) | (t >> 24)) ^ rcon;
+        rk[4 * r + 1] = rk[4 * r - 3] ^ rk[4 * r];
+        rk[4 * r + 2] = rk[4 * r - 2] ^ rk[4 * r + 1];
+        rk[4 * r + 3] = rk[4 * r - 1] ^ rk[4 * r + 2];
+        rcon = (r == 8) ? 0x1b000000u : (rcon << 1);
+    }
 }
 
 // ---- label <-> state -----------------------------------------------------------
@@ -175,9 +249,10 @@ __device__ __forceinline__ Label label_shl(Label a, int n) {
 
 // H(K) = AES(K) ^ K  -- the tail shared by encryptHalf (circuit/garble.go:104-136)
 // and encrypt/decrypt (circuit/garble.go:40-73).
-__device__ __forceinline__ Label aes_hash_k(const AesLane& a, const uint32_t* rk, int nr, Label k) {
+template <int NR>
+__device__ __forceinline__ Label aes_hash_k(const AesLane& a, const uint32_t* rk, Label k) {
     uint32_t s0 = k.w0, s1 = k.w1, s2 = k.w2, s3 = k.w3;
-    aes_encrypt(a, rk, nr, s0, s1, s2, s3);
+    aes_encrypt_smem<NR>(a, rk, s0, s1, s2, s3);
     return Label{s0 ^ k.w0, s1 ^ k.w1, s2 ^ k.w2, s3 ^ k.w3};
 }
 

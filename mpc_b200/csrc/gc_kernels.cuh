@@ -20,7 +20,7 @@
 
 namespace gcb {
 
-constexpr int GC_MAX_TEAMS = 32;
+constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-barrier teams
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
 
 struct GcParams {
@@ -40,11 +40,28 @@ struct GcParams {
     uint4* wires_full;                    // optional
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
+    // streaming mode (GC_STREAM): live-in / live-out labels come from and go to
+    // the permanent wire file instead of in_labels / io
+    const uint32_t* in_ids;               // [n_in] permanent wire id of live-in k
+    const uint32_t* out_ids;              // [n_out] permanent wire id of live-out k
+    uint4* const* pages;                  // wire-file page table
 };
+
+enum : int { GC_PLAIN = 0, GC_FULL = 1, GC_STREAM = 2 };
+
+// Permanent wire file of the streaming garbler (circuit/stream_garble.go:78-114:
+// wires[w>>16][w&0xffff] pages of ot.Wire).  Here a page covers WF_PAGE_IDS ids
+// and holds the L0 label of each id for every instance, [instance][id]; L1 is
+// always L0 ^ R.
+constexpr uint32_t WF_PAGE_SHIFT = 12;
+constexpr uint32_t WF_PAGE_IDS = 1u << WF_PAGE_SHIFT;
+__device__ __forceinline__ uint4* wf_slot(uint4* const* pages, uint32_t id, uint32_t inst) {
+    return pages[id >> WF_PAGE_SHIFT] + ((size_t)inst << WF_PAGE_SHIFT) + (id & (WF_PAGE_IDS - 1));
+}
 
 __device__ __forceinline__ void team_barrier(uint32_t team, uint32_t team_threads) {
     if (team_threads == 32) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_threads) : "memory");
+    else asm volatile("bar.sync %0, %1;" ::"r"(team), "r"(team_threads) : "memory");
 }
 
 __device__ __forceinline__ Label lds_label(const uint4* slots, uint32_t s) { return label_from_mem(slots[s]); }
@@ -84,17 +101,18 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
 }
 
 // ------------------------------------------------------------------ garble ----
-template <bool FULL>
+template <int NR, int MODE>
 __global__ void __launch_bounds__(1024, 1) garble_kernel(const GcParams p) {
+    constexpr bool FULL = MODE == GC_FULL;
+    constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
     aes_tables_to_smem(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
-    int nr = (int)(p.keylen >> 2) + 6;
     if (p.key_stride == 0) {
-        if (ttid == 0) aes_expand_key(tc.tables, p.keys, (int)p.keylen, tc.rk);
+        if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
     uint4* const slots = tc.slots;
@@ -106,15 +124,17 @@ __global__ void __launch_bounds__(1024, 1) garble_kernel(const GcParams p) {
         const uint32_t inst = *tc.claim;
         if (inst >= p.batch) break;
         if (p.key_stride != 0 && ttid == 0)
-            aes_expand_key(tc.tables, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+            aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Label R = label_from_mem(__ldg(p.r + inst));
         R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
-            const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
+            uint4 m;
+            if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + ref.y), inst);
+            else m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
             slots[ref.x] = m;
-            if (p.io) {
+            if (!STREAM && p.io) {
                 uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + ref.y) * 2;
                 w[0] = m;
                 w[1] = label_to_mem(label_from_mem(m) ^ R);
@@ -175,7 +195,7 @@ __global__ void __launch_bounds__(1024, 1) garble_kernel(const GcParams p) {
                     if (op == OP_AND) tw += k >> 1;
                 }
                 K.w3 ^= tw;
-                const Label h = aes_hash_k(lane, rk, nr, K);
+                const Label h = aes_hash_k<NR>(lane, rk, K);
                 // ---- combine
                 const Label u = h ^ shfl_xor_label(h, 1);
                 Label v = Label{0, 0, 0, 0};
@@ -232,7 +252,12 @@ __global__ void __launch_bounds__(1024, 1) garble_kernel(const GcParams p) {
             team_barrier(tc.team, TT);
         }
         // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
-        if (p.io) {
+        if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
+            for (uint32_t k = ttid; k < p.n_out; k += TT) {
+                const uint2 ref = __ldg(p.live_out + k);
+                *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots[ref.x];
+            }
+        } else if (p.io) {
             for (uint32_t k = ttid; k < p.n_out; k += TT) {
                 const uint2 ref = __ldg(p.live_out + k);
                 const Label l0 = lds_label(slots, ref.x);
@@ -246,17 +271,17 @@ __global__ void __launch_bounds__(1024, 1) garble_kernel(const GcParams p) {
 }
 
 // -------------------------------------------------------------------- eval ----
-template <bool FULL>
+template <int NR, int MODE>
 __global__ void __launch_bounds__(1024, 1) eval_kernel(const GcParams p) {
+    constexpr bool FULL = MODE == GC_FULL;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
     aes_tables_to_smem(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
-    const int nr = (int)(p.keylen >> 2) + 6;
     if (p.key_stride == 0) {
-        if (ttid == 0) aes_expand_key(tc.tables, p.keys, (int)p.keylen, tc.rk);
+        if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
     uint4* const slots = tc.slots;
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(1024, 1) eval_kernel(const GcParams p) {
         const uint32_t inst = *tc.claim;
         if (inst >= p.batch) break;
         if (p.key_stride != 0 && ttid == 0)
-            aes_expand_key(tc.tables, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+            aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
             const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(1024, 1) eval_kernel(const GcParams p) {
                     if (op == OP_AND) tw += k;
                 }
                 K.w3 ^= tw;
-                const Label h = aes_hash_k(lane, rk, nr, K);
+                const Label h = aes_hash_k<NR>(lane, rk, K);
                 Label v = h ^ row;                             // decrypt (garble.go:58-73) / half-gate
                 if (op == OP_AND && k == 1) v = v ^ label_and_mask(a, mask_of(sB));   // we ^= a (eval.go:72-75)
                 const Label o = v ^ shfl_xor_label(v, 1);

@@ -1,0 +1,906 @@
+// gcb200.cu -- the C ABI of include/gcb200.h: argument checking, device
+// selection, plan upload, kernel launches and the host-buffer staging paths.
+// There is no CPU fallback in this file: without a CUDA device every compute
+// entry point fails with GCB_E_CUDA.
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/gcb200.h"
+#include "gc_kernels.cuh"
+#include "ot_kernels.cuh"
+#include "stream_kernels.cuh"
+#include "plan.hpp"
+#include "hostpipe.hpp"
+
+namespace gcb {
+
+// ------------------------------------------------------------------ errors ----
+static thread_local std::string tl_err;
+static thread_local int tl_device = -1;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    tl_err = buf;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(GCB_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+
+// ----------------------------------------------------------------- devices ----
+constexpr size_t kSmemOptin = 232448;           // 227 KiB per CTA on sm_100
+constexpr uint32_t kCounterRing = 1024;
+
+struct DeviceInfo {
+    int sm_count = 0;
+    uint32_t* counters = nullptr;               // ring of work-claim counters
+    std::atomic<uint32_t> next{0};
+};
+static std::mutex g_dev_mu;
+static std::map<int, std::unique_ptr<DeviceInfo>> g_devs;
+
+template <class K>
+static cudaError_t opt_in(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptin);
+}
+
+int select_device(DeviceInfo** out) {
+    if (tl_device < 0) {
+        const char* lr = getenv("LOCAL_RANK");
+        tl_device = lr ? atoi(lr) : 0;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(GCB_E_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (tl_device >= count) return fail(GCB_E_CUDA, "device %d out of range (%d devices)", tl_device, count);
+    CK(cudaSetDevice(tl_device));
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    auto& slot = g_devs[tl_device];
+    if (!slot) {
+        auto di = std::make_unique<DeviceInfo>();
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, tl_device));
+        if (prop.major < 10)
+            return fail(GCB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", tl_device,
+                        prop.major, prop.minor);
+        di->sm_count = prop.multiProcessorCount;
+        CK(cudaMalloc(&di->counters, kCounterRing * sizeof(uint32_t)));
+        CK(cudaMemset(di->counters, 0, kCounterRing * sizeof(uint32_t)));
+        CK(opt_in(garble_kernel<10, GC_PLAIN>)); CK(opt_in(garble_kernel<10, GC_FULL>)); CK(opt_in(garble_kernel<10, GC_STREAM>));
+        CK(opt_in(garble_kernel<12, GC_PLAIN>)); CK(opt_in(garble_kernel<12, GC_FULL>)); CK(opt_in(garble_kernel<12, GC_STREAM>));
+        CK(opt_in(garble_kernel<14, GC_PLAIN>)); CK(opt_in(garble_kernel<14, GC_FULL>)); CK(opt_in(garble_kernel<14, GC_STREAM>));
+        CK(opt_in(eval_kernel<10, GC_PLAIN>)); CK(opt_in(eval_kernel<10, GC_FULL>));
+        CK(opt_in(eval_kernel<12, GC_PLAIN>)); CK(opt_in(eval_kernel<12, GC_FULL>));
+        CK(opt_in(eval_kernel<14, GC_PLAIN>)); CK(opt_in(eval_kernel<14, GC_FULL>));
+        CK(opt_in(hash_half_kernel<10>)); CK(opt_in(hash_half_kernel<12>)); CK(opt_in(hash_half_kernel<14>));
+        CK(opt_in(mitccrh_kernel));
+        CK(opt_in(iknp_kernel<false>)); CK(opt_in(iknp_kernel<true>));
+        slot = std::move(di);
+    }
+    if (out) *out = slot.get();
+    return GCB_OK;
+}
+
+// A zeroed claim counter for one launch on `stream`.
+static int fresh_counter(DeviceInfo* di, cudaStream_t stream, uint32_t** out) {
+    uint32_t* c = di->counters + (di->next.fetch_add(1) % kCounterRing);
+    CK(cudaMemsetAsync(c, 0, sizeof(uint32_t), stream));
+    *out = c;
+    return GCB_OK;
+}
+
+// ------------------------------------------------------------- plan upload ----
+DevicePlan::~DevicePlan() {
+    // best effort: the context may already be gone at process exit
+    if (recs) cudaFree(recs);
+    if (steps) cudaFree(steps);
+    if (out_wire) cudaFree(out_wire);
+    if (live_in) cudaFree(live_in);
+    if (live_out) cudaFree(live_out);
+}
+
+template <class T>
+static cudaError_t upload(T** dst, const std::vector<T>& v) {
+    const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* out) {
+    std::lock_guard<std::mutex> lk(plan.mu);
+    auto it = plan.dev.find(device);
+    if (it != plan.dev.end()) { *out = it->second; return GCB_OK; }
+    auto dp = std::make_shared<DevicePlan>();
+    dp->device = device;
+    CK(upload(&dp->recs, plan.recs));
+    CK(upload(&dp->steps, plan.steps));
+    CK(upload(&dp->out_wire, plan.out_wire));
+    CK(upload(&dp->live_in, plan.live_in));
+    CK(upload(&dp->live_out, plan.live_out));
+    plan.dev[device] = dp;
+    *out = dp;
+    return GCB_OK;
+}
+
+// Team geometry for a plan: how many instances one SM keeps resident.
+void team_geometry(uint32_t num_slots, uint32_t* n_teams, uint32_t* team_threads) {
+    const size_t avail = kSmemOptin - AES_TABLE_BYTES - 128;
+    const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES;
+    size_t n = avail / per_team;
+    if (n >= 32) { *n_teams = 32; *team_threads = 32; }
+    else if (n >= 16) { *n_teams = 16; *team_threads = 64; }
+    else if (n == 0) { *n_teams = 0; *team_threads = 0; }
+    else { *n_teams = (uint32_t)n; *team_threads = 32u * (32u / (uint32_t)n); }
+}
+size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams) {
+    return AES_TABLE_BYTES + (size_t)n_teams * GC_RK_BYTES + (size_t)n_teams * num_slots * 16 + 128;
+}
+
+static int check_keylen(uint32_t keylen) {
+    if (keylen != 16 && keylen != 24 && keylen != 32)
+        return fail(GCB_E_KEYLEN, "crypto/aes: invalid key size %u", keylen);
+    return GCB_OK;
+}
+
+static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, const uint8_t* keys,
+                     uint32_t keylen, uint32_t key_stride, uint32_t batch, const gcb_label* r,
+                     const gcb_label* in_labels, gcb_label* tables, void* io, void* wires_full,
+                     cudaStream_t stream, const uint32_t* in_ids = nullptr, const uint32_t* out_ids = nullptr,
+                     uint4* const* pages = nullptr) {
+    std::shared_ptr<DevicePlan> dp;
+    int rc = plan_on_device(plan, device, &dp);
+    if (rc) return rc;
+    const gcb_plan_info& in = plan.info;
+    GcParams p{};
+    p.recs = reinterpret_cast<const uint4*>(dp->recs);
+    p.steps = reinterpret_cast<const uint4*>(dp->steps);
+    p.out_wire = dp->out_wire;
+    p.live_in = reinterpret_cast<const uint2*>(dp->live_in);
+    p.live_out = reinterpret_cast<const uint2*>(dp->live_out);
+    p.n_steps = in.num_steps; p.n_in = in.num_inputs; p.n_out = in.num_outputs;
+    p.n_slots = in.num_slots; p.n_rows = in.num_rows; p.n_wires = in.num_wires;
+    p.keys = keys; p.keylen = keylen; p.key_stride = key_stride; p.batch = batch;
+    p.r = reinterpret_cast<const uint4*>(r);
+    p.in_labels = reinterpret_cast<const uint4*>(in_labels);
+    p.tables = reinterpret_cast<uint4*>(tables);
+    p.io = reinterpret_cast<uint4*>(io);
+    p.wires_full = reinterpret_cast<uint4*>(wires_full);
+    p.team_threads = in.team_threads; p.n_teams = in.teams_per_sm;
+    p.in_ids = in_ids; p.out_ids = out_ids; p.pages = pages;
+    rc = fresh_counter(di, stream, &p.counter);
+    if (rc) return rc;
+    const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;
+    const dim3 grid(want < (uint32_t)di->sm_count ? want : (uint32_t)di->sm_count);
+    const dim3 block(p.n_teams * p.team_threads);
+    const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams);
+    const bool full = wires_full != nullptr;
+#define GC_LAUNCH(K, NR)                                                         \
+    do {                                                                         \
+        if (full) K<NR, GC_FULL><<<grid, block, smem, stream>>>(p);              \
+        else K<NR, GC_PLAIN><<<grid, block, smem, stream>>>(p);                  \
+    } while (0)
+    if (pages) {
+        if (keylen == 16) garble_kernel<10, GC_STREAM><<<grid, block, smem, stream>>>(p);
+        else if (keylen == 24) garble_kernel<12, GC_STREAM><<<grid, block, smem, stream>>>(p);
+        else garble_kernel<14, GC_STREAM><<<grid, block, smem, stream>>>(p);
+    } else if (garble) {
+        if (keylen == 16) GC_LAUNCH(garble_kernel, 10);
+        else if (keylen == 24) GC_LAUNCH(garble_kernel, 12);
+        else GC_LAUNCH(garble_kernel, 14);
+    } else {
+        if (keylen == 16) GC_LAUNCH(eval_kernel, 10);
+        else if (keylen == 24) GC_LAUNCH(eval_kernel, 12);
+        else GC_LAUNCH(eval_kernel, 14);
+    }
+#undef GC_LAUNCH
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+
+// ---- small label-plumbing kernels (circuit/helpers.go:10-27) -------------------
+__global__ void select_labels_kernel(const uint4* wires, size_t wire_stride, const uint8_t* bits, uint4* out,
+                                     uint32_t batch, uint32_t n) {
+    const size_t total = (size_t)batch * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t inst = i / n, k = i % n;
+        const uint4* w = wires + (inst * wire_stride + k) * 2;
+        out[i] = __ldg(w + (bits[i] ? 1 : 0));            // LabelForBit
+    }
+}
+__global__ void decode_bits_kernel(const uint4* wires, size_t wire_stride, const uint4* labels, uint8_t* bits,
+                                   uint32_t batch, uint32_t n) {
+    const size_t total = (size_t)batch * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t inst = i / n, k = i % n;
+        const uint4* w = wires + (inst * wire_stride + k) * 2;
+        const uint4 l = __ldg(labels + i), l0 = __ldg(w), l1 = __ldg(w + 1);
+        const bool is0 = l.x == l0.x && l.y == l0.y && l.z == l0.z && l.w == l0.w;
+        const bool is1 = l.x == l1.x && l.y == l1.y && l.z == l1.z && l.w == l1.w;
+        bits[i] = is0 ? 0 : is1 ? 1 : 2;                  // BitFromLabel: 2 = "unknown label"
+    }
+}
+
+// ---- host staging helpers -------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct StreamGuard {
+    cudaStream_t s = nullptr;
+    ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+};
+
+// ------------------------------------------------------- streaming garbler ----
+}  // namespace gcb
+
+struct gcb_stream {
+    int device = 0;
+    uint32_t batch = 0, keylen = 0, key_stride = 0;
+    gcb::DevBuf keys, r;
+    std::vector<uint4*> pages;              // host copy of the page table
+    gcb::DevBuf page_table;
+    size_t page_table_cap = 0;
+    cudaStream_t cs = nullptr;
+    gcb::DevBuf slab, ser, ids, tmpl, row_pos, wires;
+    size_t slab_cap = 0, ser_cap = 0, ids_cap = 0, tmpl_cap = 0, row_pos_cap = 0, wires_cap = 0;
+    std::mutex mu;
+    ~gcb_stream() {
+        for (uint4* p : pages) if (p) cudaFree(p);
+        if (cs) cudaStreamDestroy(cs);
+    }
+};
+
+namespace gcb {
+
+static int grow(DevBuf& b, size_t& cap, size_t bytes) {
+    if (bytes <= cap) return GCB_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; cap = 0; }
+    bytes += bytes / 4;
+    CK(b.alloc(bytes));
+    cap = bytes;
+    return GCB_OK;
+}
+
+// ensureWires (stream_garble.go:78-100): pages up to max_id exist, zero-filled.
+static int ensure_wires(gcb_stream* s, uint32_t max_id) {
+    const size_t need = ((size_t)max_id >> WF_PAGE_SHIFT) + 1;
+    if (need <= s->pages.size()) return GCB_OK;
+    const size_t page_bytes = (size_t)s->batch * WF_PAGE_IDS * 16;
+    while (s->pages.size() < need) {
+        uint4* p = nullptr;
+        CK(cudaMalloc(&p, page_bytes));
+        s->pages.push_back(p);
+        CK(cudaMemsetAsync(p, 0, page_bytes, s->cs));
+    }
+    if (s->pages.size() > s->page_table_cap) {
+        CK(cudaStreamSynchronize(s->cs));               // kernels may still read the old table
+        int rc = grow(s->page_table, s->page_table_cap, s->pages.size() * 2 * sizeof(uint4*));
+        if (rc) return rc;
+        s->page_table_cap /= sizeof(uint4*);
+    }
+    CK(cudaMemcpyAsync(s->page_table.p, s->pages.data(), s->pages.size() * sizeof(uint4*), cudaMemcpyHostToDevice,
+                       s->cs));
+    return GCB_OK;
+}
+
+// One staging pipe per (host thread, device), kept across calls so that repeated
+// Garble / Eval calls do not re-allocate their arenas.
+static HostPipe& thread_pipe(int device) {
+    static thread_local std::map<int, std::unique_ptr<HostPipe>> pipes;
+    auto& p = pipes[device];
+    if (!p) p = std::make_unique<HostPipe>();
+    return *p;
+}
+
+}  // namespace gcb
+
+using namespace gcb;
+
+// ======================================================================= C ABI ==
+extern "C" {
+
+const char* gcb_last_error(void) { return tl_err.c_str(); }
+const char* gcb_version(void) { return "gcb200 0.1 (sm_100a)"; }
+
+int gcb_set_device(int device) {
+    if (device < 0) return fail(GCB_E_ARG, "negative device index");
+    tl_device = device;
+    return GCB_OK;
+}
+int gcb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// Page-locked host memory for the slabs the Go side pools per circuit
+// (garbleScratchPool, circuit/garble.go:193-224): buffers from here are DMA'd
+// in place by the host entry points instead of being staged.
+void* gcb_host_alloc(size_t bytes) {
+    if (select_device(nullptr)) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        fail(GCB_E_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void gcb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ plans -------
+int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wires, uint32_t num_inputs,
+                    uint32_t num_outputs, gcb_plan** out) {
+    if (!out) return fail(GCB_E_ARG, "null plan output pointer");
+    *out = nullptr;
+    if (!gates && num_gates) return fail(GCB_E_ARG, "null gate array");
+    if (num_inputs > num_wires || num_outputs > num_wires) return fail(GCB_E_ARG, "more I/O wires than wires");
+    PlanSpec spec;
+    spec.gates = gates; spec.num_gates = num_gates; spec.num_wires = num_wires;
+    for (uint32_t i = 0; i < num_inputs; i++) spec.live_in.push_back(i);
+    for (uint32_t i = 0; i < num_outputs; i++) spec.live_out.push_back(num_wires - num_outputs + i);
+    auto pl = std::make_unique<gcb_plan>();
+    std::string err;
+    int rc = build_plan(spec, pl->p, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    team_geometry(pl->p.info.num_slots, &pl->p.info.teams_per_sm, &pl->p.info.team_threads);
+    if (pl->p.info.teams_per_sm == 0)
+        return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; at most %zu fit on chip",
+                    pl->p.info.num_slots, (kSmemOptin - AES_TABLE_BYTES - 128 - GC_RK_BYTES) / 16);
+    pl->p.gates.assign(gates, gates + num_gates);
+    *out = pl.release();
+    return GCB_OK;
+}
+void gcb_plan_destroy(gcb_plan* plan) { delete plan; }
+int gcb_plan_get_info(const gcb_plan* plan, gcb_plan_info* info) {
+    if (!plan || !info) return fail(GCB_E_ARG, "null argument");
+    *info = plan->p.info;
+    return GCB_OK;
+}
+int gcb_plan_row_offsets(const gcb_plan* plan, uint32_t* row_off) {
+    if (!plan || !row_off) return fail(GCB_E_ARG, "null argument");
+    memcpy(row_off, plan->p.row_off.data(), plan->p.row_off.size() * sizeof(uint32_t));
+    return GCB_OK;
+}
+
+// ----------------------------------------------------------- garble / eval ------
+int gcb_garble_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
+                   uint32_t batch, const gcb_label* r, const gcb_label* in_l0, gcb_label* tables,
+                   gcb_wire* io_wires, gcb_wire* wires_full, uint32_t flags, void* stream) {
+    (void)flags;
+    if (!plan || !keys || !r || (!in_l0 && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows))
+        return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
+    if (batch == 0) return GCB_OK;
+    DeviceInfo* di;
+    if ((rc = select_device(&di))) return rc;
+    return launch_gc(true, plan->p, di, tl_device, keys, keylen, key_stride, batch, r, in_l0, tables, io_wires,
+                     wires_full, (cudaStream_t)stream);
+}
+
+int gcb_eval_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                 const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels,
+                 gcb_label* wires_full, uint32_t flags, void* stream) {
+    (void)flags;
+    if (!plan || !keys || (!in_labels && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows) ||
+        (!out_labels && plan->p.info.num_outputs))
+        return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
+    if (batch == 0) return GCB_OK;
+    DeviceInfo* di;
+    if ((rc = select_device(&di))) return rc;
+    return launch_gc(false, plan->p, di, tl_device, keys, keylen, key_stride, batch, nullptr, in_labels,
+                     const_cast<gcb_label*>(tables), out_labels, wires_full, (cudaStream_t)stream);
+}
+
+// Host-buffer variants: the batch is cut into slices that move through pinned
+// staging on three streams' worth of overlap (H2D of slice i+1, kernel of slice
+// i, D2H of slice i-1 proceed concurrently).
+int gcb_garble(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+               const gcb_label* r, const gcb_label* in_l0, gcb_label* tables, gcb_wire* io_wires,
+               gcb_wire* wires_full, uint32_t flags) {
+    if (!plan || !keys || !r || (!in_l0 && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows))
+        return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (batch == 0) return GCB_OK;
+    DeviceInfo* di;
+    if ((rc = select_device(&di))) return rc;
+    const gcb_plan_info& in = plan->p.info;
+    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
+    HostPipe& pipe = thread_pipe(tl_device);
+    if ((rc = pipe.init())) return rc;
+    const size_t per_inst = 16 + nin * 16 + rows * 16 + (io_wires ? (nin + nout) * 32 : 0) +
+                            (wires_full ? nw * 32 : 0) + (key_stride ? key_stride : 0);
+    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm * (uint32_t)di->sm_count);
+    DevBuf dkey;
+    if (!key_stride) {
+        CK(dkey.alloc(keylen));
+        CK(cudaMemcpy(dkey.p, keys, keylen, cudaMemcpyHostToDevice));
+    }
+    for (uint32_t b0 = 0, k = 0; b0 < batch; b0 += slice, k++) {
+        const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
+        HostPipe::Slot& s = pipe.slot(k);
+        if ((rc = s.begin())) return rc;
+        const uint8_t* dk = dkey.as<uint8_t>();
+        if (key_stride) {
+            if ((rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk))) return rc;
+        }
+        const gcb_label *dr, *dl0 = nullptr;
+        if ((rc = s.in(r + b0, (size_t)nb * 16, (const void**)&dr))) return rc;
+        if (nin && (rc = s.in(in_l0 + (size_t)b0 * nin, (size_t)nb * nin * 16, (const void**)&dl0))) return rc;
+        gcb_label* dt = nullptr;
+        gcb_wire *dio = nullptr, *dwf = nullptr;
+        if ((rc = s.out(tables + (size_t)b0 * rows, (size_t)nb * rows * 16, (void**)&dt))) return rc;
+        if (io_wires && (rc = s.out(io_wires + (size_t)b0 * (nin + nout), (size_t)nb * (nin + nout) * 32, (void**)&dio)))
+            return rc;
+        if (wires_full && (rc = s.out(wires_full + (size_t)b0 * nw, (size_t)nb * nw * 32, (void**)&dwf))) return rc;
+        if ((rc = s.upload())) return rc;
+        rc = launch_gc(true, plan->p, di, tl_device, dk, keylen, key_stride, nb, dr, dl0, dt, dio, dwf, s.compute);
+        if (rc) return rc;
+        if ((rc = s.download())) return rc;
+    }
+    (void)flags;
+    return pipe.finish();
+}
+
+int gcb_eval(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+             const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels, gcb_label* wires_full,
+             uint32_t flags) {
+    if (!plan || !keys || (!in_labels && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows) ||
+        (!out_labels && plan->p.info.num_outputs))
+        return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (batch == 0) return GCB_OK;
+    DeviceInfo* di;
+    if ((rc = select_device(&di))) return rc;
+    const gcb_plan_info& in = plan->p.info;
+    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
+    HostPipe& pipe = thread_pipe(tl_device);
+    if ((rc = pipe.init())) return rc;
+    const size_t per_inst = nin * 16 + rows * 16 + nout * 16 + (wires_full ? nw * 16 : 0) + key_stride;
+    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm * (uint32_t)di->sm_count);
+    DevBuf dkey;
+    if (!key_stride) {
+        CK(dkey.alloc(keylen));
+        CK(cudaMemcpy(dkey.p, keys, keylen, cudaMemcpyHostToDevice));
+    }
+    for (uint32_t b0 = 0, k = 0; b0 < batch; b0 += slice, k++) {
+        const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
+        HostPipe::Slot& s = pipe.slot(k);
+        if ((rc = s.begin())) return rc;
+        const uint8_t* dk = dkey.as<uint8_t>();
+        if (key_stride) {
+            if ((rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk))) return rc;
+        }
+        const gcb_label *dt = nullptr, *dil = nullptr;
+        if (rows && (rc = s.in(tables + (size_t)b0 * rows, (size_t)nb * rows * 16, (const void**)&dt))) return rc;
+        if (nin && (rc = s.in(in_labels + (size_t)b0 * nin, (size_t)nb * nin * 16, (const void**)&dil))) return rc;
+        gcb_label *dol = nullptr, *dwf = nullptr;
+        if (nout && (rc = s.out(out_labels + (size_t)b0 * nout, (size_t)nb * nout * 16, (void**)&dol))) return rc;
+        if (wires_full && (rc = s.out(wires_full + (size_t)b0 * nw, (size_t)nb * nw * 16, (void**)&dwf))) return rc;
+        if ((rc = s.upload())) return rc;
+        rc = launch_gc(false, plan->p, di, tl_device, dk, keylen, key_stride, nb, nullptr, dil,
+                       const_cast<gcb_label*>(dt), dol, dwf, s.compute);
+        if (rc) return rc;
+        if ((rc = s.download())) return rc;
+    }
+    (void)flags;
+    return pipe.finish();
+}
+
+int gcb_select_labels_dev(const gcb_wire* wires, size_t wire_stride, const uint8_t* bits, gcb_label* out,
+                          uint32_t batch, uint32_t n, void* stream) {
+    if (!wires || !bits || !out) return fail(GCB_E_ARG, "null argument");
+    if (!batch || !n) return GCB_OK;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    select_labels_kernel<<<di->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(wires), wire_stride, bits, reinterpret_cast<uint4*>(out), batch, n);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+int gcb_decode_bits_dev(const gcb_wire* wires, size_t wire_stride, const gcb_label* labels, uint8_t* bits,
+                        uint32_t batch, uint32_t n, void* stream) {
+    if (!wires || !bits || !labels) return fail(GCB_E_ARG, "null argument");
+    if (!batch || !n) return GCB_OK;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    decode_bits_kernel<<<di->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(wires), wire_stride, reinterpret_cast<const uint4*>(labels), bits, batch, n);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+
+// ------------------------------------------------------------- gate hashes ------
+// key: DEVICE pointer in the _dev variant.
+int gcb_hash_half_dev(const uint8_t* key, uint32_t keylen, const gcb_label* x, uint32_t tweak0, gcb_label* out,
+                      uint64_t n, void* stream) {
+    if (!key || (n && (!x || !out))) return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (n == 0) return GCB_OK;
+    DeviceInfo* di;
+    if ((rc = select_device(&di))) return rc;
+    HashParams p{key, keylen, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), tweak0, n};
+    const uint64_t want = (n + 1023) / 1024;
+    const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
+    const size_t smem = AES_TABLE_BYTES + 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (keylen == 16) hash_half_kernel<10><<<grid, 1024, smem, s>>>(p);
+    else if (keylen == 24) hash_half_kernel<12><<<grid, 1024, smem, s>>>(p);
+    else hash_half_kernel<14><<<grid, 1024, smem, s>>>(p);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+int gcb_hash_half(const uint8_t* key, uint32_t keylen, const gcb_label* x, uint32_t tweak0, gcb_label* out,
+                  uint64_t n) {
+    if (!key || (n && (!x || !out))) return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (n == 0) return GCB_OK;
+    if ((rc = select_device(nullptr))) return rc;
+    DevBuf dk, dx, dout;
+    CK(dk.alloc(keylen)); CK(dx.alloc(n * 16)); CK(dout.alloc(n * 16));
+    CK(cudaMemcpy(dk.p, key, keylen, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dx.p, x, n * 16, cudaMemcpyHostToDevice));
+    if ((rc = gcb_hash_half_dev(dk.as<uint8_t>(), keylen, dx.as<gcb_label>(), tweak0, dout.as<gcb_label>(), n, nullptr)))
+        return rc;
+    CK(cudaMemcpy(out, dout.p, n * 16, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+// --------------------------------------------------------------- streaming ------
+int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch, const gcb_label* r,
+                      const uint32_t* input_ids, uint32_t ninputs, const gcb_label* in_l0, gcb_stream** out) {
+    if (!out) return fail(GCB_E_ARG, "null stream output pointer");
+    *out = nullptr;
+    if (!keys || !r || (ninputs && (!input_ids || !in_l0)) || batch == 0) return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
+    DeviceInfo* di;
+    if ((rc = select_device(&di))) return rc;
+    auto s = std::make_unique<gcb_stream>();
+    s->device = tl_device; s->batch = batch; s->keylen = keylen; s->key_stride = key_stride;
+    CK(cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking));
+    const size_t kb = key_stride ? (size_t)key_stride * batch : keylen;
+    CK(s->keys.alloc(kb));
+    CK(cudaMemcpyAsync(s->keys.p, keys, kb, cudaMemcpyHostToDevice, s->cs));
+    CK(s->r.alloc((size_t)batch * 16));
+    CK(cudaMemcpyAsync(s->r.p, r, (size_t)batch * 16, cudaMemcpyHostToDevice, s->cs));
+    force_s_kernel<<<(batch + 255) / 256, 256, 0, s->cs>>>(s->r.as<uint4>(), batch);
+    CK(cudaGetLastError());
+    if (ninputs) {
+        uint32_t mx = 0;
+        for (uint32_t i = 0; i < ninputs; i++) mx = input_ids[i] > mx ? input_ids[i] : mx;
+        if ((rc = ensure_wires(s.get(), mx))) return rc;
+        DevBuf dl0;
+        CK(dl0.alloc((size_t)batch * ninputs * 16));
+        if ((rc = grow(s->ids, s->ids_cap, (size_t)ninputs * 4))) return rc;
+        CK(cudaMemcpyAsync(s->ids.p, input_ids, (size_t)ninputs * 4, cudaMemcpyHostToDevice, s->cs));
+        CK(cudaMemcpyAsync(dl0.p, in_l0, (size_t)batch * ninputs * 16, cudaMemcpyHostToDevice, s->cs));
+        wf_set_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
+                                                           s->ids.as<uint32_t>(), ninputs, dl0.as<uint4>(), batch);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s->cs));
+    }
+    CK(cudaStreamSynchronize(s->cs));
+    *out = s.release();
+    return GCB_OK;
+}
+void gcb_stream_destroy(gcb_stream* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->cs) cudaStreamSynchronize(s->cs);
+    delete s;
+}
+
+int gcb_stream_get_wires(gcb_stream* s, const uint32_t* ids, uint32_t n, gcb_wire* wires) {
+    if (!s || (n && (!ids || !wires))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    tl_device = s->device;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++)
+        if (((size_t)ids[i] >> WF_PAGE_SHIFT) >= s->pages.size())
+            return fail(GCB_E_WIRE, "wire %u not allocated", ids[i]);
+    if ((rc = grow(s->ids, s->ids_cap, (size_t)n * 4))) return rc;
+    if ((rc = grow(s->wires, s->wires_cap, (size_t)s->batch * n * 32))) return rc;
+    CK(cudaMemcpyAsync(s->ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s->cs));
+    wf_get_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
+                                                       s->ids.as<uint32_t>(), n, s->r.as<uint4>(),
+                                                       s->wires.as<uint4>(), s->batch);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(wires, s->wires.p, (size_t)s->batch * n * 32, cudaMemcpyDeviceToHost, s->cs));
+    CK(cudaStreamSynchronize(s->cs));
+    return GCB_OK;
+}
+
+int gcb_stream_step_size(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
+                         uint32_t nout, size_t* bytes) {
+    if (!s || !plan || !bytes || (nin && !in) || (nout && !out)) return fail(GCB_E_ARG, "null argument");
+    StreamLayout lay;
+    std::string err;
+    int rc = build_stream_layout(plan->p.gates, plan->p.info.num_wires, in, nin, out, nout, lay, err);
+    if (rc) return fail(rc, "%s", err.c_str());
+    *bytes = lay.tmpl.size();
+    return GCB_OK;
+}
+
+int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
+                      uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written, uint64_t* ns_init,
+                      uint64_t* ns_garble) {
+    using clk = std::chrono::steady_clock;
+    const auto t_start = clk::now();
+    if (!s || !plan || (nin && !in) || (nout && !out)) return fail(GCB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    tl_device = s->device;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    const Plan& base = plan->p;
+    const uint32_t nw = base.info.num_wires;
+    if (nin > nw || nout > nw) return fail(GCB_E_ARG, "more wire ids than wires");
+    // initCircuit (stream_garble.go:102-114)
+    StreamLayout lay;
+    std::string err;
+    if ((rc = build_stream_layout(base.gates, nw, in, nin, out, nout, lay, err))) return fail(rc, "%s", err.c_str());
+    const size_t total = lay.tmpl.size();
+    if (written) *written = total;
+    if (total && (!dst || dst_stride < total)) return fail(GCB_E_BUFFER, "stream buffer too small: need %zu bytes per instance", total);
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < nin; i++) mx = in[i] > mx ? in[i] : mx;
+    for (uint32_t i = 0; i < nout; i++) mx = out[i] > mx ? out[i] : mx;
+    if ((rc = ensure_wires(s, mx))) return rc;
+
+    // The compiled plan can be used as is when the in / out id sets are disjoint,
+    // the out ids are distinct, and no gate assigns an input wire; otherwise
+    // build a plan in which aliased wires share one location, so that the result
+    // equals the reference's sequential reads and writes of the wire file.
+    bool alias = nin != base.info.num_inputs || nout != base.info.num_outputs;
+    std::unordered_map<uint32_t, uint32_t> loc_of_id;
+    if (!alias) {
+        for (uint32_t i = 0; i < nin; i++) loc_of_id.emplace(in[i], 0);
+        for (uint32_t i = 0; i < nout && !alias; i++) alias = !loc_of_id.emplace(out[i], 1).second;
+        const uint32_t first_out = nw - nout;
+        for (size_t g = 0; g < base.gates.size() && !alias; g++) {
+            const gcb_gate& gt = base.gates[g];
+            alias = gt.out < nin || (first_out < nin);
+        }
+    }
+    std::unique_ptr<Plan> aliased;
+    std::vector<uint32_t> in_eff(in, in + nin), out_eff(out, out + nout);
+    const Plan* use = &base;
+    if (alias) {
+        loc_of_id.clear();
+        std::vector<uint32_t> ids;
+        auto loc_for = [&](uint32_t id) {
+            auto it = loc_of_id.find(id);
+            if (it != loc_of_id.end()) return it->second;
+            const uint32_t l = (uint32_t)ids.size();
+            loc_of_id.emplace(id, l);
+            ids.push_back(id);
+            return l;
+        };
+        PlanSpec spec;
+        spec.gates = base.gates.data(); spec.num_gates = (uint32_t)base.gates.size(); spec.num_wires = nw;
+        spec.loc.resize(nw);
+        const uint32_t first_out = nw - nout;
+        for (uint32_t w = 0; w < nw; w++) {
+            if (w < nin) spec.loc[w] = loc_for(in[w]);
+            else if (w >= first_out) spec.loc[w] = loc_for(out[w - first_out]);
+        }
+        const uint32_t np = (uint32_t)ids.size();
+        for (uint32_t w = nin; w < first_out && w < nw; w++) spec.loc[w] = np + w;
+        spec.num_locs = np + nw;
+        for (uint32_t l = 0; l < np; l++) spec.live_in.push_back(l);
+        std::vector<uint8_t> written_loc(np, 0);
+        for (const gcb_gate& gt : base.gates) if (spec.loc[gt.out] < np) written_loc[spec.loc[gt.out]] = 1;
+        in_eff = ids;
+        out_eff.clear();
+        for (uint32_t l = 0; l < np; l++) if (written_loc[l]) { spec.live_out.push_back(l); out_eff.push_back(ids[l]); }
+        aliased = std::make_unique<Plan>();
+        if ((rc = build_plan(spec, *aliased, err))) return fail(rc, "%s", err.c_str());
+        team_geometry(aliased->info.num_slots, &aliased->info.teams_per_sm, &aliased->info.team_threads);
+        if (aliased->info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", aliased->info.num_slots);
+        use = aliased.get();
+    }
+    const size_t n_rows = use->info.num_rows;
+    const size_t stride16 = (total + 15) & ~(size_t)15;
+    const size_t nids = in_eff.size() + out_eff.size();
+    if ((rc = grow(s->ids, s->ids_cap, (nids ? nids : 1) * 4))) return rc;
+    if ((rc = grow(s->slab, s->slab_cap, (size_t)s->batch * n_rows * 16))) return rc;
+    if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
+    if ((rc = grow(s->tmpl, s->tmpl_cap, stride16 + 16))) return rc;
+    if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
+    uint32_t* d_in = s->ids.as<uint32_t>();
+    uint32_t* d_out = d_in + in_eff.size();
+    if (!in_eff.empty()) CK(cudaMemcpyAsync(d_in, in_eff.data(), in_eff.size() * 4, cudaMemcpyHostToDevice, s->cs));
+    if (!out_eff.empty()) CK(cudaMemcpyAsync(d_out, out_eff.data(), out_eff.size() * 4, cudaMemcpyHostToDevice, s->cs));
+    lay.tmpl.resize(stride16, 0);
+    if (total) CK(cudaMemcpyAsync(s->tmpl.p, lay.tmpl.data(), stride16, cudaMemcpyHostToDevice, s->cs));
+    if (n_rows) CK(cudaMemcpyAsync(s->row_pos.p, lay.row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
+    const auto t_mid = clk::now();
+
+    // the gate loop (stream_garble.go:179-190)
+    rc = launch_gc(true, *use, di, s->device, s->keys.as<uint8_t>(), s->keylen, s->key_stride, s->batch,
+                   s->r.as<gcb_label>(), nullptr, s->slab.as<gcb_label>(), nullptr, nullptr, s->cs, d_in, d_out,
+                   reinterpret_cast<uint4* const*>(s->page_table.p));
+    if (rc) return rc;
+    if (total) {
+        SerParams sp{s->tmpl.as<uint8_t>(), (uint32_t)total, s->row_pos.as<uint32_t>(), (uint32_t)n_rows,
+                     s->slab.as<uint4>(), s->ser.as<uint8_t>(), stride16};
+        const dim3 grid((unsigned)((total + SER_TILE - 1) / SER_TILE), s->batch);
+        serialize_kernel<<<grid, SER_THREADS, 0, s->cs>>>(sp);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy2DAsync(dst, dst_stride, s->ser.p, stride16, total, s->batch, cudaMemcpyDeviceToHost, s->cs));
+    }
+    CK(cudaStreamSynchronize(s->cs));
+    const auto t_end = clk::now();
+    if (ns_init) *ns_init = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_mid - t_start).count();
+    if (ns_garble) *ns_garble = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_end - t_mid).count();
+    return GCB_OK;
+}
+
+// ------------------------------------------------------------------- IKNP -------
+size_t gcb_iknp_u_size(uint64_t n) {
+    const uint64_t full = n / IKNP_CHUNK_ROWS, rem = n % IKNP_CHUNK_ROWS;
+    return (size_t)(full * 64 * 128 + ((rem + 7) / 8) * 128);
+}
+uint64_t gcb_iknp_stream_advance(uint64_t n) {
+    const uint64_t full = n / IKNP_CHUNK_ROWS, rem = n % IKNP_CHUNK_ROWS;
+    return full * 64 + (rem + 7) / 8;
+}
+
+static int launch_iknp(bool receiver, const IknpParams& p0, void* stream) {
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    IknpParams p = p0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = fresh_counter(di, s, &p.counter))) return rc;
+    const uint64_t nchunks = (p.n + IKNP_CHUNK_ROWS - 1) / IKNP_CHUNK_ROWS;
+    const uint32_t groups = receiver ? 2 : 4;
+    const uint64_t want = (nchunks + groups - 1) / groups;
+    const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
+    const size_t smem = AES_TABLE_BYTES + groups * (IKNP_STAGE_BYTES + 8192 + 128);
+    if (receiver) iknp_kernel<true><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
+    else iknp_kernel<false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+
+int gcb_iknp_receiver_expand_dev(const gcb_label* k0, const gcb_label* k1, uint64_t stream_pos,
+                                 const uint8_t* choice, uint64_t n, uint8_t* u_out, gcb_label* labels,
+                                 void* stream) {
+    if (!k0 || !k1 || (n && (!choice || !u_out || !labels))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    if (reinterpret_cast<uintptr_t>(u_out) & 15) return fail(GCB_E_ARG, "u_out must be 16-byte aligned");
+    IknpParams p{};
+    p.k0 = reinterpret_cast<const uint4*>(k0); p.k1 = reinterpret_cast<const uint4*>(k1);
+    p.stream_pos = stream_pos; p.choice = choice; p.u_out = u_out;
+    p.labels = reinterpret_cast<uint4*>(labels); p.n = n;
+    return launch_iknp(true, p, stream);
+}
+int gcb_iknp_sender_expand_dev(const gcb_label* k, const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
+                               size_t u_len, uint64_t n, gcb_label* labels, void* stream) {
+    if (!k || !delta || (n && (!u || !labels))) return fail(GCB_E_ARG, "null argument");
+    if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
+                                                 (unsigned long long)n);
+    if (n == 0) return GCB_OK;
+    if (reinterpret_cast<uintptr_t>(u) & 15) return fail(GCB_E_ARG, "u must be 16-byte aligned");
+    IknpParams p{};
+    p.k0 = reinterpret_cast<const uint4*>(k); p.delta = reinterpret_cast<const uint4*>(delta);
+    p.stream_pos = stream_pos; p.u_in = u; p.labels = reinterpret_cast<uint4*>(labels); p.n = n;
+    return launch_iknp(false, p, stream);
+}
+
+int gcb_iknp_receiver_expand(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
+                             const uint8_t* choice, uint64_t n, uint8_t* u_out, gcb_label* labels) {
+    if (!k0 || !k1 || (n && (!choice || !u_out || !labels))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    const size_t ul = gcb_iknp_u_size(n);
+    DevBuf dk, dc, du, dl;
+    CK(dk.alloc(256 * 16)); CK(dc.alloc(n)); CK(du.alloc(ul)); CK(dl.alloc(n * 16));
+    CK(cudaMemcpy(dk.p, k0, 128 * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.as<gcb_label>() + 128, k1, 128 * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, choice, n, cudaMemcpyHostToDevice));
+    rc = gcb_iknp_receiver_expand_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, dc.as<uint8_t>(), n,
+                                      du.as<uint8_t>(), dl.as<gcb_label>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(u_out, du.p, ul, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(labels, dl.p, n * 16, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+int gcb_iknp_sender_expand(const gcb_label k[128], const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
+                           size_t u_len, uint64_t n, gcb_label* labels) {
+    if (!k || !delta || (n && (!u || !labels))) return fail(GCB_E_ARG, "null argument");
+    if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
+                                                 (unsigned long long)n);
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    DevBuf dk, du, dl;
+    CK(dk.alloc(129 * 16)); CK(du.alloc(u_len)); CK(dl.alloc(n * 16));
+    CK(cudaMemcpy(dk.p, k, 128 * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.as<gcb_label>() + 128, delta, 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du.p, u, u_len, cudaMemcpyHostToDevice));
+    rc = gcb_iknp_sender_expand_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, du.as<uint8_t>(), u_len,
+                                    n, dl.as<gcb_label>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(labels, dl.p, n * 16, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+// ----------------------------------------------------------------- MiTCCRH ------
+int gcb_mitccrh_hash_dev(const gcb_label* seed_host, uint64_t gid_start, gcb_label* blks, uint64_t nkeys, uint32_t h,
+                         void* stream) {
+    if (!seed_host || (nkeys && !blks)) return fail(GCB_E_ARG, "null argument");
+    if (h == 0 || h > 64) return fail(GCB_E_ARG, "MITCCRH.Hash: invalid H %u", h);   // mitccrh.go:94-102 panics
+    if (nkeys == 0) return GCB_OK;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    MitccrhParams p{seed_host->d0, seed_host->d1, gid_start, reinterpret_cast<uint4*>(blks), nkeys, h};
+    const uint64_t want = (nkeys + 511) / 512;
+    const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
+    mitccrh_kernel<<<grid, 512, AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+int gcb_mitccrh_hash(const gcb_label* seed, uint64_t gid_start, gcb_label* blks, uint64_t nkeys, uint32_t h) {
+    if (!seed || (nkeys && !blks)) return fail(GCB_E_ARG, "null argument");
+    if (h == 0 || h > 64) return fail(GCB_E_ARG, "MITCCRH.Hash: invalid H %u", h);
+    if (nkeys == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    DevBuf db;
+    const size_t bytes = (size_t)nkeys * h * 16;
+    CK(db.alloc(bytes));
+    CK(cudaMemcpy(db.p, blks, bytes, cudaMemcpyHostToDevice));
+    if ((rc = gcb_mitccrh_hash_dev(seed, gid_start, db.as<gcb_label>(), nkeys, h, nullptr))) return rc;
+    CK(cudaMemcpy(blks, db.p, bytes, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+}  // extern "C"

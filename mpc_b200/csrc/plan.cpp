@@ -209,3 +209,50 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
 }
 
 }  // namespace gcb
+
+namespace gcb {
+
+int build_stream_layout(const std::vector<gcb_gate>& gates, uint32_t num_wires, const uint32_t* in, uint32_t nin,
+                        const uint32_t* out, uint32_t nout, StreamLayout& lay, std::string& err) {
+    if (nout > num_wires) { err = "more output ids than wires"; return GCB_E_ARG; }
+    const uint32_t first_tmp = nin, first_out = num_wires - nout;          // stream_garble.go:112-113
+    lay.tmpl.clear();
+    lay.row_pos.clear();
+    lay.tmpl.reserve(gates.size() * 10);
+    // Streaming.Get / Set index resolution (stream_garble.go:131-157)
+    auto resolve = [&](uint32_t w, uint32_t& index, bool& tmp) {
+        if (w < first_tmp) { index = in[w]; tmp = false; }
+        else if (w >= first_out) { index = out[w - first_out]; tmp = false; }
+        else { index = w; tmp = true; }
+    };
+    auto put16 = [&](uint32_t v) { lay.tmpl.push_back((uint8_t)(v >> 8)); lay.tmpl.push_back((uint8_t)v); };
+    auto put32 = [&](uint32_t v) { put16(v >> 16); put16(v & 0xffff); };
+    for (size_t i = 0; i < gates.size(); i++) {
+        const gcb_gate& g = gates[i];
+        if (g.op > OP_INV) { err = "invalid gate type"; return GCB_E_BADOP; }
+        uint32_t ai = 0, bi = 0, ci = 0;
+        bool at = false, bt = false, ct = false;
+        const bool unary = g.op == OP_INV;
+        if (!unary) resolve(g.in1, bi, bt);
+        resolve(g.in0, ai, at);
+        resolve(g.out, ci, ct);
+        uint8_t op = g.op;
+        if (at) op |= 0x80;
+        if (bt) op |= 0x40;
+        if (ct) op |= 0x20;
+        const bool shrt = ai <= 0xffff && bi <= 0xffff && ci <= 0xffff;
+        if (shrt) op |= 0x10;
+        lay.tmpl.push_back(op);
+        if (shrt) { put16(ai); if (!unary) put16(bi); put16(ci); }
+        else { put32(ai); if (!unary) put32(bi); put32(ci); }
+        const int rows = g.op == OP_AND ? 2 : g.op == OP_OR ? 3 : g.op == OP_INV ? 1 : 0;
+        for (int k = 0; k < rows; k++) {
+            if (lay.tmpl.size() > 0xfffffff0u) { err = "record stream exceeds 4 GiB"; return GCB_E_TOO_LARGE; }
+            lay.row_pos.push_back((uint32_t)lay.tmpl.size());
+            lay.tmpl.insert(lay.tmpl.end(), 16, 0);
+        }
+    }
+    return GCB_OK;
+}
+
+}  // namespace gcb

@@ -83,3 +83,15 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err);
 struct gcb_plan {
     gcb::Plan p;
 };
+
+namespace gcb {
+// Byte layout of the record stream Streaming.Garble emits for one sub-circuit
+// (circuit/stream_garble.go:391-446): the template holds every header byte
+// with the garbled rows zeroed; row_pos[r] is the stream offset of slab row r.
+struct StreamLayout {
+    std::vector<uint8_t> tmpl;
+    std::vector<uint32_t> row_pos;
+};
+int build_stream_layout(const std::vector<gcb_gate>& gates, uint32_t num_wires, const uint32_t* in, uint32_t nin,
+                        const uint32_t* out, uint32_t nout, StreamLayout& lay, std::string& err);
+}  // namespace gcb

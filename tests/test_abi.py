@@ -1,0 +1,113 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads and
+exports every symbol include/gcb200.h declares; the host-side plan compiler
+agrees with the circuit's static row / tweak layout; and the product has no CPU
+fallback (compute calls fail loudly without a device)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_circuit, millionaire_circuit, mixed_circuit
+from mpc_b200 import _lib
+from mpc_b200.circuit import GarbleEngine, hash_half
+from mpc_b200.circuit_io import AND, INV, LABEL_DTYPE, OR
+
+HEADER = os.path.join(ROOT, "include", "gcb200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"libgcb200.so does not export {n}"
+    assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
+    assert b"sm_100a" in L.gcb_version()
+
+
+def test_library_has_sm100a_code_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib._build.SO], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.parametrize("name", ["and", "not", "add64", "sub64", "mul64", "aes_128", "sha256", "sha256xor",
+                                  "chacha20block", "mixed", "millionaire"])
+def test_plan_matches_static_layout(name):
+    circ = {"mixed": lambda: mixed_circuit(3, 400, 20, 8), "millionaire": millionaire_circuit}.get(
+        name, lambda: load_circuit(name))()
+    eng = GarbleEngine(circ)
+    i = eng.info
+    ops = circ.gates["op"]
+    n_and, n_or, n_inv = (int(np.count_nonzero(ops == o)) for o in (AND, OR, INV))
+    assert (i.num_gates, i.num_wires, i.num_inputs, i.num_outputs) == (
+        circ.num_gates, circ.num_wires, circ.num_inputs, circ.num_outputs)
+    assert (i.num_and, i.num_or, i.num_inv) == (n_and, n_or, n_inv)
+    assert i.num_rows == circ.num_rows == 2 * n_and + 3 * n_or + n_inv
+    assert i.num_tweaks == 2 * n_and + n_or + n_inv
+    assert i.garble_hashes == 4 * n_and + 4 * n_or + 2 * n_inv
+    assert i.eval_hashes == 2 * n_and + n_or + n_inv
+    assert np.array_equal(eng.row_off, circ.row_offsets())
+    assert 1 <= i.teams_per_sm <= 32 and i.teams_per_sm * i.team_threads <= 1024
+    assert i.num_slots >= 1 and i.num_steps >= 1
+
+
+def test_survey_sizes_of_the_baseline_circuits():
+    a, s = GarbleEngine(load_circuit("aes_128")).info, GarbleEngine(load_circuit("sha256")).info
+    assert (a.num_gates, a.num_and, a.num_inv, a.num_rows) == (36663, 6400, 2087, 14887)
+    assert (s.num_gates, s.num_and, s.num_inv, s.num_rows) == (135073, 22573, 1856, 47002)
+    x = GarbleEngine(load_circuit("sha256xor")).info
+    assert x.num_rows == 42914                       # sha2pc/params.go:26
+
+
+def test_plan_rejects_bad_circuits():
+    circ = load_circuit("add64")
+    g = circ.gates.copy()
+    g["op"][5] = 9
+    h = C.c_void_p()
+    rc = _lib.lib().gcb_plan_create(_lib.ptr(g), len(g), circ.num_wires, circ.num_inputs, circ.num_outputs, C.byref(h))
+    assert rc == _lib.E_BADOP and b"invalid gate type" in _lib.lib().gcb_last_error()
+    g = circ.gates.copy()
+    g["in0"][0] = circ.num_wires + 7
+    rc = _lib.lib().gcb_plan_create(_lib.ptr(g), len(g), circ.num_wires, circ.num_inputs, circ.num_outputs, C.byref(h))
+    assert rc == _lib.E_WIRE
+    g = circ.gates.copy()
+    g["in0"][0] = circ.num_wires - 1                 # read before assignment
+    rc = _lib.lib().gcb_plan_create(_lib.ptr(g), len(g), circ.num_wires, circ.num_inputs, circ.num_outputs, C.byref(h))
+    assert rc == _lib.E_WIRE and b"not set" in _lib.lib().gcb_last_error()
+
+
+def test_iknp_size_helpers():
+    L = _lib.lib()
+    for n, (u, adv) in {0: (0, 0), 1: (128, 1), 129: (17 * 128, 17), 512: (8192, 64), 513: (8192 + 128, 65),
+                        1100: (2 * 8192 + 10 * 128, 138), 1 << 24: (1 << 28, 1 << 21)}.items():
+        assert L.gcb_iknp_u_size(n) == u and L.gcb_iknp_stream_advance(n) == adv
+
+
+def test_bad_key_length_is_rejected_before_the_device():
+    x = np.zeros(4, dtype=LABEL_DTYPE)
+    with pytest.raises(_lib.GcbError) as e:
+        hash_half(b"\0" * 15, x)
+    assert e.value.rc == _lib.E_KEYLEN and "invalid key size" in str(e.value)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box WITHOUT a GPU")
+def test_no_cpu_fallback_without_a_device():
+    x = np.zeros(4, dtype=LABEL_DTYPE)
+    with pytest.raises(_lib.GcbError) as e:
+        hash_half(b"\0" * 16, x)
+    assert e.value.rc == _lib.E_CUDA and "no CPU path" in str(e.value)
+    eng = GarbleEngine(load_circuit("and"))
+    with pytest.raises(_lib.GcbError) as e:
+        eng.garble(b"\1" * 48, b"\0" * 16)
+    assert e.value.rc == _lib.E_CUDA

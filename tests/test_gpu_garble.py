@@ -1,0 +1,164 @@
+"""GPU parity: batched garble / eval through the C ABI against the CPU oracle,
+bit-exact (integer / byte work), on the same seeded inputs.  Also the
+reference's single-instance API (Garble / Eval mirrors) and its error paths."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_circuit, millionaire_circuit, mixed_circuit
+from mpc_b200 import _lib
+from mpc_b200.circuit import Garbled, GarbleEngine, decode_bits_dev, select_labels_dev
+from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
+from oracle import pyoracle as O
+from util import DRBG, decode, eq, garble_inputs, rand_to_labels, select
+
+pytestmark = pytest.mark.gpu
+
+_engines = {}
+
+
+def get(name):
+    if name not in _engines:
+        circ = {"mixed1": lambda: mixed_circuit(1), "mixed2": lambda: mixed_circuit(2, 500, 30, 12),
+                "mixed3": lambda: mixed_circuit(5, 3000, 64, 32),
+                "millionaire": millionaire_circuit}.get(name, lambda: load_circuit(name))()
+        _engines[name] = (circ, GarbleEngine(circ))
+    return _engines[name]
+
+
+CASES = [("and", 70, 16), ("not", 33, 32), ("add64", 40, 16), ("sub64", 17, 24), ("mixed1", 37, 16),
+         ("mixed2", 21, 32), ("mixed3", 9, 24), ("millionaire", 12, 32), ("mul64", 5, 16), ("div64", 3, 32),
+         ("aes_128", 13, 16), ("aes_128", 7, 32), ("aes_256", 3, 24), ("sha256", 3, 16), ("sha256xor", 2, 32),
+         ("chacha20block", 2, 16), ("sha512", 2, 32)]
+
+
+@pytest.mark.parametrize("per_instance_keys", [False, True])
+@pytest.mark.parametrize("name,batch,klen", CASES)
+def test_garble_eval_batch_bit_exact(name, batch, klen, per_instance_keys):
+    circ, eng = get(name)
+    keys, rand = garble_inputs(f"gpu/{name}/{klen}", batch, circ.num_inputs, klen)
+    if not per_instance_keys:
+        keys = keys[0].tobytes()
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    o_r, o_tables, o_io = O.garble_batch(circ, keys, rand, threads=4)
+    assert eq(tables, o_tables), "garbled tables differ from the oracle"
+    assert eq(io, o_io), "input / output wires differ from the oracle"
+    # evaluate on random input bits
+    rng = np.random.default_rng(batch * 1000 + klen)
+    bits = rng.integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+    inl = select(io[:, : circ.num_inputs], bits)
+    out = eng.eval_batch(keys, tables, inl)
+    o_out = O.eval_batch(circ, keys, o_tables, inl, threads=4)
+    assert eq(out, o_out), "output labels differ from the oracle"
+    got = decode(io[:, circ.num_inputs:], out)
+    for i in range(min(batch, 3)):
+        assert np.array_equal(got[i], circ.compute_bits(bits[i].tolist()))
+
+
+@pytest.mark.parametrize("name,klen", [("and", 16), ("not", 32), ("mixed1", 24), ("add64", 32), ("sha256xor", 32)])
+def test_reference_api_single_instance(name, klen):
+    """(*Circuit).Garble(rand, key) / (*Circuit).Eval(key, wires, garbled) mirrors: every wire and row."""
+    circ, eng = get(name)
+    key = DRBG(f"key/{name}").read(klen)
+    rand = DRBG(f"rand/{name}").read(16 * (1 + circ.num_inputs))
+    g = eng.garble(rand, key)
+    o_r, o_wires, o_slab, o_off = O.garble(circ, key, rand)
+    assert g.R == o_r and int(g.R["d0"]) >> 63 == 1
+    assert eq(g.Wires, o_wires) and eq(g.slab, o_slab)
+    gates = g.Gates
+    for i, op in enumerate(circ.gates["op"].tolist()):
+        n = {0: 0, 1: 0, 2: 2, 3: 3, 4: 1}[op]
+        assert (gates[i] is None) == (n == 0) and (n == 0 or len(gates[i]) == n)
+    bits = np.random.default_rng(1).integers(0, 2, circ.num_inputs)
+    wires = np.zeros(circ.num_wires, dtype=LABEL_DTYPE)
+    wires[: circ.num_inputs] = np.where(bits.astype(bool), g.Wires["l1"][: circ.num_inputs], g.Wires["l0"][: circ.num_inputs])
+    o_w = O.eval_(circ, key, wires[: circ.num_inputs].copy(), o_slab, o_off)
+    eng.eval(key, wires, gates)
+    assert eq(wires, o_w)
+
+
+def test_eval_error_paths_match_reference():
+    circ, eng = get("mixed1")
+    key = b"k" * 16
+    g = eng.garble(DRBG("e").read(16 * (1 + circ.num_inputs)), key)
+    wires = np.zeros(circ.num_wires, dtype=LABEL_DTYPE)
+    gates = list(g.Gates)
+    and_i = int(np.nonzero(circ.gates["op"] == 2)[0][0])
+    gates[and_i] = gates[and_i][:1]
+    with pytest.raises(_lib.GcbError, match="AND row length"):
+        eng.eval(key, wires, gates)
+    gates = list(g.Gates)
+    inv_i = int(np.nonzero(circ.gates["op"] == 4)[0][0])
+    gates[inv_i] = None
+    with pytest.raises(_lib.GcbError, match="index 0 >= row len 0"):
+        eng.eval(key, wires, gates)
+    with pytest.raises(_lib.GcbError, match="invalid key size"):
+        eng.eval(b"x" * 17, wires, g)
+
+
+def test_empty_batch_and_ragged_last_wave():
+    circ, eng = get("add64")
+    t, io = eng.garble_batch(b"\0" * 16, np.zeros(0, LABEL_DTYPE), np.zeros((0, circ.num_inputs), LABEL_DTYPE))
+    assert t.shape == (0, circ.num_rows) and io.shape[0] == 0
+    # a batch that is not a multiple of the resident team count, larger than one wave
+    batch = 16 * 148 + 5
+    keys, rand = garble_inputs("ragged", batch, circ.num_inputs, 16)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    _, o_tables, o_io = O.garble_batch(circ, keys, rand, threads=8)
+    assert eq(tables, o_tables) and eq(io, o_io)
+
+
+def test_device_resident_path_with_label_plumbing():
+    """gcb_garble_dev -> gcb_select_labels_dev -> gcb_eval_dev -> gcb_decode_bits_dev on torch buffers."""
+    circ, eng = get("aes_128")
+    batch, nin, nout = 64, circ.num_inputs, circ.num_outputs
+    _, rand = garble_inputs("dev", batch, nin, 0)
+    key = b"0123456789abcdef"                       # circuit/garble_bench_test.go:34
+    r, l0 = rand_to_labels(rand, nin)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.view(np.uint8).reshape(a.shape + (-1,))).to(dev)
+    d_key, d_r, d_l0 = torch.frombuffer(bytearray(key), dtype=torch.uint8).to(dev), t(r), t(l0)
+    d_tab = torch.zeros((batch, circ.num_rows, 16), dtype=torch.uint8, device=dev)
+    d_io = torch.zeros((batch, nin + nout, 32), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    eng.garble_dev(d_key, 16, 0, batch, d_r, d_l0, d_tab, d_io, stream=s)
+    # plaintext: AES key 000102..0f, block = instance index (big-endian integer, wire i = bit i)
+    pt_key = int.from_bytes(bytes(range(16)), "big")
+    bits = np.zeros((batch, nin), dtype=np.uint8)
+    for i in range(batch):
+        bits[i, :128] = [(pt_key >> b) & 1 for b in range(128)]
+        bits[i, 128:] = [(i >> b) & 1 for b in range(128)]
+    d_bits = torch.from_numpy(bits).to(dev)
+    d_in = torch.zeros((batch, nin, 16), dtype=torch.uint8, device=dev)
+    select_labels_dev(d_io, nin + nout, d_bits, d_in, batch, nin, stream=s)
+    d_out = torch.zeros((batch, nout, 16), dtype=torch.uint8, device=dev)
+    eng.eval_dev(d_key, 16, 0, batch, d_tab, d_in, d_out, stream=s)
+    d_obits = torch.zeros((batch, nout), dtype=torch.uint8, device=dev)
+    decode_bits_dev(d_io[:, nin:].contiguous(), nout, d_out, d_obits, batch, nout, stream=s)
+    torch.cuda.synchronize()
+    ob = d_obits.cpu().numpy()
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+    enc = Cipher(algorithms.AES(bytes(range(16))), modes.ECB()).encryptor()
+    for i in range(batch):
+        want = int.from_bytes(enc.update(i.to_bytes(16, "big")), "big")
+        assert sum(int(b) << k for k, b in enumerate(ob[i])) == want
+    # and the tables equal the oracle's
+    _, o_tables, _ = O.garble_batch(circ, key, rand, threads=4)
+    assert d_tab.cpu().numpy().tobytes() == o_tables.tobytes()
+
+
+def test_fips197_kat_through_garble_eval():
+    """aes_128.circ(key=000102..0f, pt=00112233..ff) = 69c4e0d8...c55a (FIPS-197 C.1) through GPU garble+eval."""
+    circ, eng = get("aes_128")
+    key = DRBG("kat").read(32)
+    g = eng.garble(DRBG("kat/r").read(16 * 257), key)
+    k = int.from_bytes(bytes(range(16)), "big")
+    p = int.from_bytes(bytes.fromhex("00112233445566778899aabbccddeeff"), "big")
+    bits = [(k >> i) & 1 for i in range(128)] + [(p >> i) & 1 for i in range(128)]
+    wires = np.zeros(circ.num_wires, dtype=LABEL_DTYPE)
+    wires[:256] = np.where(np.array(bits, dtype=bool), g.Wires["l1"][:256], g.Wires["l0"][:256])
+    eng.eval(key, wires, g)
+    ob = decode(g.Wires[-128:], wires[-128:])
+    assert sum(int(b) << i for i, b in enumerate(ob)) == 0x69c4e0d86a7b0430d8cdb78070b4c55a
