@@ -68,44 +68,49 @@ def algorithmic_bytes(circ):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML during the timed region."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.mx = index, [], set(), None
+        self._stop = threading.Event()
+        self.t = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+        except Exception as e:               # NVML missing: say so instead of inventing a clock
+            self.reasons.add(f"nvml unavailable: {e}")
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "samples": len(self.sm), "reasons": sorted(self.reasons)}
 
 
 def cpu_arm(circ, threads: int, sample: int, reps: int):
@@ -256,42 +261,44 @@ def run_gcb(args):
     g_ms = float(np.mean([a.elapsed_time(b) for a, b in kern["garble"]]))
     e_ms = float(np.mean([a.elapsed_time(b) for a, b in kern["eval"]]))
 
-    # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region
-    L = _lib.lib()
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region
+        L = _lib.lib()
 
-    def pinned(shape, dtype):
-        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        p = L.gcb_host_alloc(max(n, 1))
-        assert p, "gcb_host_alloc failed"
-        import ctypes as C
-        arr = np.frombuffer((C.c_uint8 * n).from_address(p), dtype=dtype).reshape(shape)
-        return arr, p
+        def pinned(shape, dtype):
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            p = L.gcb_host_alloc(max(n, 1))
+            assert p, "gcb_host_alloc failed"
+            import ctypes as C
+            arr = np.frombuffer((C.c_uint8 * n).from_address(p), dtype=dtype).reshape(shape)
+            return arr, p
 
-    h_r, p1 = pinned((batch,), LABEL_DTYPE); h_r[:] = r
-    h_l0, p2 = pinned((batch, nin), LABEL_DTYPE); h_l0[:] = l0
-    h_tab, p3 = pinned((batch, rows), LABEL_DTYPE)
-    h_io, p4 = pinned((batch, nin + nout), WIRE_DTYPE)
-    h_in, p5 = pinned((batch, nin), LABEL_DTYPE)
-    h_out, p6 = pinned((batch, nout), LABEL_DTYPE)
+        h_r, p1 = pinned((batch,), LABEL_DTYPE); h_r[:] = r
+        h_l0, p2 = pinned((batch, nin), LABEL_DTYPE); h_l0[:] = l0
+        h_tab, p3 = pinned((batch, rows), LABEL_DTYPE)
+        h_io, p4 = pinned((batch, nin + nout), WIRE_DTYPE)
+        h_in, p5 = pinned((batch, nin), LABEL_DTYPE)
+        h_out, p6 = pinned((batch, nout), LABEL_DTYPE)
 
-    def e2e_step():
-        eng.garble_batch(KEY, h_r, h_l0, tables=h_tab, io_wires=h_io)
-        eng.eval_batch(KEY, h_tab, h_in, out_labels=h_out)
+        def e2e_step():
+            eng.garble_batch(KEY, h_r, h_l0, tables=h_tab, io_wires=h_io)
+            eng.eval_batch(KEY, h_tab, h_in, out_labels=h_out)
 
-    e2e_step()
-    h_in[:] = np.where(bits.astype(bool), h_io["l1"][:, :nin], h_io["l0"][:, :nin])
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    ok_e2e = h_out.tobytes() == d_out.cpu().numpy().tobytes() and h_tab.tobytes() == d_tab.cpu().numpy().tobytes()
-    assert ok_e2e, "host-pointer path and device-resident path disagree"
-    for p in (p1, p2, p3, p4, p5, p6):
-        L.gcb_host_free(p)
+        h_in[:] = np.where(bits.astype(bool), h_io["l1"][:, :nin], h_io["l0"][:, :nin])
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        ok_e2e = h_out.tobytes() == d_out.cpu().numpy().tobytes() and h_tab.tobytes() == d_tab.cpu().numpy().tobytes()
+        assert ok_e2e, "host-pointer path and device-resident path disagree"
+        for p in (p1, p2, p3, p4, p5, p6):
+            L.gcb_host_free(p)
 
     # max over ranks
     tt = torch.tensor([ms, e2e_s * 1e3, g_ms, e_ms], dtype=torch.float64, device=dev)
@@ -334,7 +341,7 @@ def run_gcb(args):
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
                          "note": "integer/LDS-bound: no AES instruction on the GPU; see DESIGN.md"},
             "cpu_baseline": cpu,
-            "e2e": {"value": total_and / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
+            "e2e": None if args.no_e2e else {"value": total_and / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": int(batch * (16 * (1 + nin) + 16 * rows + 16 * nin)),
                     "d2h_bytes_per_step": int(batch * (16 * rows + 32 * (nin + nout) + 16 * nout)),
                     "ms_per_step": e2e_ms},
@@ -349,10 +356,11 @@ def run_gcb(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gcb", choices=["gcb", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
