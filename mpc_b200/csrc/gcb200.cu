@@ -65,6 +65,45 @@ static cudaError_t opt_in(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptin);
 }
 
+// every (rounds, mode, ILP) instantiation of the gate kernels
+#define GC_FOR_ILP(M, NR, MODE) M(NR, MODE, 1, 1024) M(NR, MODE, 2, 512) M(NR, MODE, 4, 256)
+#define GC_FOR_NR(M, MODE) GC_FOR_ILP(M, 10, MODE) GC_FOR_ILP(M, 12, MODE) GC_FOR_ILP(M, 14, MODE)
+static cudaError_t opt_in_gc() {
+    cudaError_t e = cudaSuccess;
+#define GC_OPT_G(NR, MODE, ILP, MAXT) if (e == cudaSuccess) e = opt_in(garble_kernel<NR, MODE, ILP, MAXT>);
+#define GC_OPT_E(NR, MODE, ILP, MAXT) if (e == cudaSuccess) e = opt_in(eval_kernel<NR, MODE, ILP, MAXT>);
+    GC_FOR_NR(GC_OPT_G, GC_PLAIN) GC_FOR_NR(GC_OPT_G, GC_FULL) GC_FOR_NR(GC_OPT_G, GC_STREAM)
+    GC_FOR_NR(GC_OPT_E, GC_PLAIN) GC_FOR_NR(GC_OPT_E, GC_FULL)
+#undef GC_OPT_G
+#undef GC_OPT_E
+    return e;
+}
+
+template <int NR, int MODE>
+static void launch_garble(uint32_t ilp, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
+    if (ilp == 4) garble_kernel<NR, MODE, 4, 256><<<grid, block, smem, s>>>(p);
+    else if (ilp == 2) garble_kernel<NR, MODE, 2, 512><<<grid, block, smem, s>>>(p);
+    else garble_kernel<NR, MODE, 1, 1024><<<grid, block, smem, s>>>(p);
+}
+template <int NR, int MODE>
+static void launch_eval(uint32_t ilp, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
+    if (ilp == 4) eval_kernel<NR, MODE, 4, 256><<<grid, block, smem, s>>>(p);
+    else if (ilp == 2) eval_kernel<NR, MODE, 2, 512><<<grid, block, smem, s>>>(p);
+    else eval_kernel<NR, MODE, 1, 1024><<<grid, block, smem, s>>>(p);
+}
+template <int MODE>
+static void launch_garble_nr(uint32_t keylen, uint32_t ilp, dim3 g, dim3 b, size_t sm, cudaStream_t s, const GcParams& p) {
+    if (keylen == 16) launch_garble<10, MODE>(ilp, g, b, sm, s, p);
+    else if (keylen == 24) launch_garble<12, MODE>(ilp, g, b, sm, s, p);
+    else launch_garble<14, MODE>(ilp, g, b, sm, s, p);
+}
+template <int MODE>
+static void launch_eval_nr(uint32_t keylen, uint32_t ilp, dim3 g, dim3 b, size_t sm, cudaStream_t s, const GcParams& p) {
+    if (keylen == 16) launch_eval<10, MODE>(ilp, g, b, sm, s, p);
+    else if (keylen == 24) launch_eval<12, MODE>(ilp, g, b, sm, s, p);
+    else launch_eval<14, MODE>(ilp, g, b, sm, s, p);
+}
+
 int select_device(DeviceInfo** out) {
     if (tl_device < 0) {
         const char* lr = getenv("LOCAL_RANK");
@@ -91,12 +130,7 @@ int select_device(DeviceInfo** out) {
         di->sm_count = prop.multiProcessorCount;
         CK(cudaMalloc(&di->counters, kCounterRing * sizeof(uint32_t)));
         CK(cudaMemset(di->counters, 0, kCounterRing * sizeof(uint32_t)));
-        CK(opt_in(garble_kernel<10, GC_PLAIN>)); CK(opt_in(garble_kernel<10, GC_FULL>)); CK(opt_in(garble_kernel<10, GC_STREAM>));
-        CK(opt_in(garble_kernel<12, GC_PLAIN>)); CK(opt_in(garble_kernel<12, GC_FULL>)); CK(opt_in(garble_kernel<12, GC_STREAM>));
-        CK(opt_in(garble_kernel<14, GC_PLAIN>)); CK(opt_in(garble_kernel<14, GC_FULL>)); CK(opt_in(garble_kernel<14, GC_STREAM>));
-        CK(opt_in(eval_kernel<10, GC_PLAIN>)); CK(opt_in(eval_kernel<10, GC_FULL>));
-        CK(opt_in(eval_kernel<12, GC_PLAIN>)); CK(opt_in(eval_kernel<12, GC_FULL>));
-        CK(opt_in(eval_kernel<14, GC_PLAIN>)); CK(opt_in(eval_kernel<14, GC_FULL>));
+        CK(opt_in_gc());
         CK(opt_in(hash_half_kernel<10>)); CK(opt_in(hash_half_kernel<12>)); CK(opt_in(hash_half_kernel<14>));
         CK(opt_in(mitccrh_kernel));
         CK(opt_in(iknp_kernel<false>)); CK(opt_in(iknp_kernel<true>));
@@ -140,7 +174,12 @@ int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* ou
     auto dp = std::make_shared<DevicePlan>();
     dp->device = device;
     CK(upload(&dp->recs, plan.recs));
-    CK(upload(&dp->steps, plan.steps));
+    {
+        std::vector<StepRec> padded(plan.steps);
+        padded.push_back(StepRec{0, 0, 0, 0});          // the kernels read two records ahead
+        padded.push_back(StepRec{0, 0, 0, 0});
+        CK(upload(&dp->steps, padded));
+    }
     CK(upload(&dp->out_wire, plan.out_wire));
     CK(upload(&dp->live_in, plan.live_in));
     CK(upload(&dp->live_out, plan.live_out));
@@ -149,15 +188,30 @@ int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* ou
     return GCB_OK;
 }
 
-// Team geometry for a plan: how many instances one SM keeps resident.
-void team_geometry(uint32_t num_slots, uint32_t* n_teams, uint32_t* team_threads) {
+// Team geometry for a plan: how many instances one SM keeps resident, how many
+// threads work on each, and how many AES blocks a thread interleaves.  Few large
+// instances -> few threads with deep ILP; many small ones -> one warp each.
+// GCB_ILP / GCB_TEAM_THREADS override the choice (tuning experiments).
+void team_geometry(Plan& plan) {
+    gcb_plan_info& in = plan.info;
     const size_t avail = kSmemOptin - AES_TABLE_BYTES - 128;
-    const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES;
+    const size_t per_team = (size_t)in.num_slots * 16 + GC_RK_BYTES;
     size_t n = avail / per_team;
-    if (n >= 32) { *n_teams = 32; *team_threads = 32; }
-    else if (n >= 16) { *n_teams = 16; *team_threads = 64; }
-    else if (n == 0) { *n_teams = 0; *team_threads = 0; }
-    else { *n_teams = (uint32_t)n; *team_threads = 32u * (32u / (uint32_t)n); }
+    in.teams_per_sm = in.team_threads = 0;
+    plan.ilp = 1;
+    if (n == 0) return;
+    if (n >= 32) n = 32; else if (n > 16) n = 16;
+    uint32_t ilp = n <= 8 ? 4 : n <= 16 ? 2 : 1;
+    if (const char* e = getenv("GCB_ILP")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) ilp = (uint32_t)v; }
+    const uint32_t maxt = ilp == 4 ? 256 : ilp == 2 ? 512 : 1024;
+    while (n * 32 > maxt) n--;                      // at least one warp per team
+    uint32_t tt = 32u * (uint32_t)(maxt / 32 / n);
+    if (n > 16) tt = 32;                            // named barriers: at most 16 multi-warp teams
+    if (const char* e = getenv("GCB_TEAM_THREADS")) {
+        const int v = atoi(e);
+        if (v >= 32 && v % 32 == 0 && (size_t)v * n <= maxt && (v == 32 || n <= 16)) tt = (uint32_t)v;
+    }
+    in.teams_per_sm = (uint32_t)n; in.team_threads = tt; plan.ilp = ilp;
 }
 size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams) {
     return AES_TABLE_BYTES + (size_t)n_teams * GC_RK_BYTES + (size_t)n_teams * num_slots * 16 + 128;
@@ -201,25 +255,11 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const dim3 block(p.n_teams * p.team_threads);
     const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams);
     const bool full = wires_full != nullptr;
-#define GC_LAUNCH(K, NR)                                                         \
-    do {                                                                         \
-        if (full) K<NR, GC_FULL><<<grid, block, smem, stream>>>(p);              \
-        else K<NR, GC_PLAIN><<<grid, block, smem, stream>>>(p);                  \
-    } while (0)
-    if (pages) {
-        if (keylen == 16) garble_kernel<10, GC_STREAM><<<grid, block, smem, stream>>>(p);
-        else if (keylen == 24) garble_kernel<12, GC_STREAM><<<grid, block, smem, stream>>>(p);
-        else garble_kernel<14, GC_STREAM><<<grid, block, smem, stream>>>(p);
-    } else if (garble) {
-        if (keylen == 16) GC_LAUNCH(garble_kernel, 10);
-        else if (keylen == 24) GC_LAUNCH(garble_kernel, 12);
-        else GC_LAUNCH(garble_kernel, 14);
-    } else {
-        if (keylen == 16) GC_LAUNCH(eval_kernel, 10);
-        else if (keylen == 24) GC_LAUNCH(eval_kernel, 12);
-        else GC_LAUNCH(eval_kernel, 14);
-    }
-#undef GC_LAUNCH
+    if (pages) launch_garble_nr<GC_STREAM>(keylen, plan.ilp, grid, block, smem, stream, p);
+    else if (garble && full) launch_garble_nr<GC_FULL>(keylen, plan.ilp, grid, block, smem, stream, p);
+    else if (garble) launch_garble_nr<GC_PLAIN>(keylen, plan.ilp, grid, block, smem, stream, p);
+    else if (full) launch_eval_nr<GC_FULL>(keylen, plan.ilp, grid, block, smem, stream, p);
+    else launch_eval_nr<GC_PLAIN>(keylen, plan.ilp, grid, block, smem, stream, p);
     CK(cudaGetLastError());
     return GCB_OK;
 }
@@ -371,7 +411,7 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     std::string err;
     int rc = build_plan(spec, pl->p, err);
     if (rc) return fail(rc, "%s", err.c_str());
-    team_geometry(pl->p.info.num_slots, &pl->p.info.teams_per_sm, &pl->p.info.team_threads);
+    team_geometry(pl->p);
     if (pl->p.info.teams_per_sm == 0)
         return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; at most %zu fit on chip",
                     pl->p.info.num_slots, (kSmemOptin - AES_TABLE_BYTES - 128 - GC_RK_BYTES) / 16);
@@ -739,7 +779,7 @@ int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, u
         for (uint32_t l = 0; l < np; l++) if (written_loc[l]) { spec.live_out.push_back(l); out_eff.push_back(ids[l]); }
         aliased = std::make_unique<Plan>();
         if ((rc = build_plan(spec, *aliased, err))) return fail(rc, "%s", err.c_str());
-        team_geometry(aliased->info.num_slots, &aliased->info.teams_per_sm, &aliased->info.team_threads);
+        team_geometry(*aliased);
         if (aliased->info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", aliased->info.num_slots);
         use = aliased.get();
     }

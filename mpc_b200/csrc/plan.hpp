@@ -62,6 +62,7 @@ struct DevicePlan {                   // per-device copy of the tables (plan_dev
 
 struct Plan {
     gcb_plan_info info{};
+    uint32_t ilp = 1;                     // AES blocks a thread interleaves (kernel variant)
     std::vector<GateRec> recs;            // sorted by (step, class, original index)
     std::vector<uint32_t> out_wire;       // original output wire of recs[i]
     std::vector<uint32_t> orig_index;     // original gate index of recs[i]
