@@ -10,16 +10,21 @@
 // labels in its slice of shared memory (slots assigned by the plan compiler), so
 // intermediate labels never touch HBM: per instance HBM sees the input labels
 // once, the garbled rows once (written by the garbler, read by the evaluator)
-// and the output labels once.  A team walks the plan's dependency steps with a
-// team-local barrier between steps (a __syncwarp for one-warp teams).  Inside a
-// step every AES block is one task: an AND gate is a quad of tasks hashing
+// and the output labels once.
+//
+// A team walks the plan's PHASES.  A phase is (1) the run of Free-XOR gates that
+// became computable after the previous cipher level -- executed by ONE warp of
+// the team, 32 gates (a chunk) at a time with warp-level synchronisation only,
+// the gate records streaming through a register ring that is loaded several
+// chunks ahead -- and (2) one level of ciphered gates executed by the whole
+// team: every AES block is a task; an AND gate is a quad of tasks hashing
 // (a0,j0) (a1,j0) (b0,j1) (b1,j1) on four adjacent lanes and combining with warp
-// shuffles, INV a pair, OR a quad; XOR/XNOR gates are one lane and no AES
-// (Free-XOR).  A thread runs up to ILP tasks at once (their AES rounds
-// interleaved) so that a few warps per SM keep the shared-memory pipe busy, and
-// it loads the gate records of the NEXT step before it starts on the current
-// one, which takes the global-memory latency off the step-to-step chain.  All
-// teams share the 128 KiB of replicated AES T-tables (aes_core.cuh).
+// shuffles, INV a pair, OR a quad.  A thread runs up to ILP tasks at once (AES
+// rounds interleaved) and has loaded its gate records while the XOR run was in
+// progress.  Two team barriers per phase.  Teams start staggered so that the
+// shared-memory-bound cipher levels of one team overlap the latency-bound XOR
+// runs of the others.  All teams share the 128 KiB of replicated AES T-tables
+// (aes_core.cuh).
 #pragma once
 #include "aes_core.cuh"
 #include "plan.hpp"
@@ -28,14 +33,18 @@ namespace gcb {
 
 constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-barrier teams
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
+constexpr int GC_RING = 4;                // free-gate chunks in flight ahead of the XOR run
+constexpr int GC_PRE = 6;                 // cipher records per thread loaded ahead of the cipher level
 
 struct GcParams {
-    const uint4* recs;                    // GateRec[]
-    const uint4* steps;                   // StepRec[] followed by two zero records
-    const uint32_t* out_wire;
+    const uint4* phases;                  // PhaseRec[] (two uint4 each) followed by two zero records
+    const uint2* frecs;                   // FreeRec[], whole chunks, followed by GC_RING+1 zero chunks
+    const uint4* crecs;                   // GateRec[]
+    const uint32_t* fout_wire;            // original output wire of frecs[i] / crecs[i] (GC_FULL)
+    const uint32_t* cout_wire;
     const uint2* live_in;                 // SlotRef[]
     const uint2* live_out;
-    uint32_t n_steps, n_in, n_out, n_slots, n_rows, n_wires;
+    uint32_t n_phases, n_in, n_out, n_slots, n_rows, n_wires;
     const uint8_t* keys;
     uint32_t keylen, key_stride;
     uint32_t batch;
@@ -46,6 +55,7 @@ struct GcParams {
     uint4* wires_full;                    // optional
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
+    uint32_t stagger;                     // SM cycles by which consecutive teams start apart
     // streaming mode (GC_STREAM): live-in / live-out labels come from and go to
     // the permanent wire file instead of in_labels / io
     const uint32_t* in_ids;               // [n_in] permanent wire id of live-in k
@@ -140,37 +150,91 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     return c;
 }
 
-// Gate index of cipher task t of a step.  Garble: 4 tasks per AND/OR, 2 per INV;
+// Gate index of cipher task t of a phase.  Garble: 4 tasks per AND/OR, 2 per INV;
 // eval: 2 per AND/OR (OR uses one), 1 per INV.
+struct Phase {
+    uint32_t free_chunk, n_chunks, cipher_first, n_quad, n_inv;
+};
+__device__ __forceinline__ Phase load_phase(const uint4* phases, uint32_t i) {
+    const uint4 a = __ldg(phases + 2 * i), b = __ldg(phases + 2 * i + 1);
+    return Phase{a.x, a.y, a.z, a.w, b.x};
+}
 template <bool GARBLE>
-__device__ __forceinline__ uint32_t task_gate(const uint4& st, uint32_t t, uint32_t& k) {
+__device__ __forceinline__ uint32_t task_gate(const Phase& ph, uint32_t t, uint32_t& k) {
     constexpr uint32_t QS = GARBLE ? 2 : 1;           // log2 tasks per AND/OR
     constexpr uint32_t IS = GARBLE ? 1 : 0;           // log2 tasks per INV
-    const uint32_t nq = st.z << QS, cbase = st.x + st.y;
-    if (t < nq) { k = t & ((1u << QS) - 1); return cbase + (t >> QS); }
+    const uint32_t nq = ph.n_quad << QS;
+    if (t < nq) { k = t & ((1u << QS) - 1); return ph.cipher_first + (t >> QS); }
     const uint32_t u = t - nq;
     k = u & ((1u << IS) - 1);
-    return cbase + st.z + (u >> IS);
+    return ph.cipher_first + ph.n_quad + (u >> IS);
 }
 template <bool GARBLE>
-__device__ __forceinline__ uint32_t task_count(const uint4& st) {
-    return GARBLE ? 4 * st.z + 2 * st.w : 2 * st.z + st.w;
+__device__ __forceinline__ uint32_t task_count(const Phase& ph) {
+    return GARBLE ? 4 * ph.n_quad + 2 * ph.n_inv : 2 * ph.n_quad + ph.n_inv;
 }
 
-// Records of the first pass of a step, loaded one step ahead.
-template <bool GARBLE, int ILP>
-__device__ __forceinline__ void prefetch_step(const GcParams& p, const uint4& st, uint32_t ttid, uint32_t TT,
-                                              uint4& free_rec, uint4 (&cipher_rec)[ILP]) {
-    free_rec = make_uint4(0, 0, 0, 0);
-    if (ttid < st.y) free_rec = __ldg(p.recs + st.x + ttid);
-    const uint32_t ntask = task_count<GARBLE>(st);
+// Cipher records of this thread's first GC_PRE tasks (t = k*TT + ttid) of a phase.
+template <bool GARBLE>
+__device__ __forceinline__ void prefetch_cipher(const GcParams& p, const Phase& ph, uint32_t ttid, uint32_t TT,
+                                                uint4 (&pre)[GC_PRE]) {
+    const uint32_t ntask = task_count<GARBLE>(ph);
 #pragma unroll
-    for (int j = 0; j < ILP; j++) {
+    for (int j = 0; j < GC_PRE; j++) {
         uint32_t k;
         const uint32_t t = j * TT + ttid;
-        cipher_rec[j] = make_uint4(0, 0, 0, 0);
-        if (t < ntask) cipher_rec[j] = __ldg(p.recs + task_gate<GARBLE>(st, t, k));
+        pre[j] = make_uint4(0, 0, 0, 0);
+        if (t < ntask) pre[j] = __ldg(p.crecs + task_gate<GARBLE>(ph, t, k));
     }
+}
+__device__ __forceinline__ uint4 pick(const uint4 (&pre)[GC_PRE], uint32_t i) {
+    uint4 r = pre[0];
+#pragma unroll
+    for (int j = 1; j < GC_PRE; j++) if (i == (uint32_t)j) r = pre[j];
+    return r;
+}
+
+// The Free-XOR run of a phase, executed by one warp (garble.go:331-351,
+// eval.go:48-50).  ring[] holds the next GC_RING chunks of free-gate records;
+// *next_chunk is the chunk index the ring will load next.
+template <bool GARBLE, bool FULL>
+__device__ __forceinline__ void free_run(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t lane,
+                                         uint32_t n_chunks, uint2 (&ring)[GC_RING], uint32_t& next_chunk) {
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint2 g = ring[0];
+#pragma unroll
+        for (int j = 0; j + 1 < GC_RING; j++) ring[j] = ring[j + 1];
+        ring[GC_RING - 1] = __ldg(p.frecs + (size_t)next_chunk * 32 + lane);
+        const uint32_t chunk = next_chunk - GC_RING;
+        next_chunk++;
+        const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff, op = (g.y >> 16) & 0xff, wave = g.y >> 24;
+        const bool active = op != FREE_PAD;
+        const uint32_t maxw = __reduce_max_sync(0xffffffffu, active ? wave : 0u);
+        for (uint32_t w = 0; w <= maxw; w++) {
+            if (active && wave == w) {
+                Label c0 = lds_label(slots, sa) ^ lds_label(slots, sb);
+                if (GARBLE && op == OP_XNOR) c0 = c0 ^ R;      // XNOR swaps (L0, L1); plain XOR for the evaluator
+                sts_label(slots, sc, c0);
+                if (FULL) {
+                    const size_t ow = (size_t)inst * p.n_wires + __ldg(p.fout_wire + (size_t)chunk * 32 + lane);
+                    if (GARBLE) {
+                        p.wires_full[2 * ow] = label_to_mem(c0);
+                        p.wires_full[2 * ow + 1] = label_to_mem(c0 ^ R);
+                    } else {
+                        p.wires_full[ow] = label_to_mem(c0);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Start teams `stagger` cycles apart.
+__device__ __forceinline__ void stagger_start(uint32_t team, uint32_t stagger) {
+    if (stagger == 0 || team == 0) return;
+    const long long until = clock64() + (long long)team * stagger;
+    while (clock64() < until) __nanosleep(2000);
 }
 
 // ------------------------------------------------------------------ garble ----
@@ -183,27 +247,25 @@ struct GarbleEnv {
     uint32_t inst;
 };
 
-// One pass of UU cipher tasks per thread: tasks base + j*TT + ttid.
-template <int NR, int MODE, int UU, int ILP>
-__device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv& e, const uint4& st, uint32_t ntask,
-                                            uint32_t base, uint32_t ttid, uint32_t TT, const uint4 (&pre)[ILP]) {
-    static_assert(UU <= ILP, "pass wider than the prefetch");
+// One pass of UU cipher tasks per thread: tasks (k0 + j)*TT + ttid.
+template <int NR, int MODE, int UU>
+__device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv& e, const Phase& ph, uint32_t ntask,
+                                            uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&pre)[GC_PRE]) {
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
     uint4* const slots = e.slots;
     const Label R = e.R;
-    const bool first = base == 0;
     uint4 g[UU];
     Label a0[UU], K[UU], H[UU];
     uint32_t op[UU], kk[UU], pp[UU], gidx[UU];
 #pragma unroll
     for (int j = 0; j < UU; j++) {
-        const uint32_t t = base + j * TT + ttid;
+        const uint32_t t = (k0 + j) * TT + ttid;
         const bool active = t < ntask;
         uint32_t k;
-        const uint32_t gi = task_gate<true>(st, t, k);
-        g[j] = pre[j];
-        if (!first) { g[j] = make_uint4(0, 0, 0, 0); if (active) g[j] = __ldg(p.recs + gi); }
+        const uint32_t gi = task_gate<true>(ph, t, k);
+        if (k0 + j < GC_PRE) g[j] = pick(pre, k0 + j);
+        else { g[j] = make_uint4(0, 0, 0, 0); if (active) g[j] = __ldg(p.crecs + gi); }
         const uint32_t sa = g[j].x & 0xffff, sb = g[j].x >> 16;
         op[j] = active ? ((g[j].y >> 16) & 0xff) : 0xffu;
         kk[j] = k; gidx[j] = gi;
@@ -248,7 +310,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
                 e.tab[g[j].w] = label_to_mem(u ^ R);
                 sts_label(slots, sc, c0);
                 if (FULL) {
-                    uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.out_wire + gidx[j])) * 2;
+                    uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.cout_wire + gidx[j])) * 2;
                     w[0] = label_to_mem(c0);
                     w[1] = label_to_mem(c0 ^ R);
                 }
@@ -265,7 +327,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
                 if (k == 0) {
                     sts_label(slots, sc, c0);
                     if (FULL) {
-                        uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.out_wire + gidx[j])) * 2;
+                        uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.cout_wire + gidx[j])) * 2;
                         w[0] = label_to_mem(c0);
                         w[1] = label_to_mem(c1);
                     }
@@ -276,7 +338,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
         if (op[j] == OP_AND && k == 0) {                   // combine halves (garble.go:383-392)
             sts_label(slots, sc, w2);
             if (FULL) {
-                uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.out_wire + gidx[j])) * 2;
+                uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.cout_wire + gidx[j])) * 2;
                 w[0] = label_to_mem(w2);
                 w[1] = label_to_mem(w2 ^ R);
             }
@@ -293,12 +355,14 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     aes_tables_to_smem(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
-    const uint32_t TT = p.team_threads, ttid = tc.ttid;
+    const uint32_t TT = p.team_threads, ttid = tc.ttid, lane_id = threadIdx.x & 31u;
+    const bool xor_warp = ttid < 32;                           // the team's first warp runs the XOR runs
     if (p.key_stride == 0) {
         if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
     uint4* const slots = tc.slots;
+    stagger_start(tc.team, p.stagger);
 
     for (;;) {
         if (ttid == 0) *tc.claim = atomicAdd(p.counter, 1u);
@@ -309,10 +373,14 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Label R = label_from_mem(__ldg(p.r + inst));
         R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
-        // the records of steps 0 and 1 load while the inputs do
-        uint4 st = __ldg(p.steps), st_n = __ldg(p.steps + 1);
-        uint4 cf, cc[ILP];
-        prefetch_step<true, ILP>(p, st, ttid, TT, cf, cc);
+        // plan records of the first phases load while the inputs do
+        Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
+        uint2 ring[GC_RING];
+        uint32_t next_chunk = GC_RING;
+        if (xor_warp) {
+#pragma unroll
+            for (int j = 0; j < GC_RING; j++) ring[j] = __ldg(p.frecs + j * 32 + lane_id);
+        }
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
@@ -334,40 +402,28 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         team_barrier(tc.team, TT);
         const GarbleEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, R, inst};
 
-        for (uint32_t s = 0; s < p.n_steps; s++) {
-            // ---- records of the next step, in flight while this one computes
-            const uint4 st_nn = __ldg(p.steps + s + 2);
-            uint4 nf, nc[ILP];
-            prefetch_step<true, ILP>(p, st_n, ttid, TT, nf, nc);
-            // ---- Free-XOR gates (garble.go:331-351): one lane each, no AES
-            for (uint32_t j = ttid; j < st.y; j += TT) {
-                uint4 g = cf;
-                if (j != ttid) g = __ldg(p.recs + st.x + j);
-                const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff, op = (g.y >> 16) & 0xff;
-                Label c0 = lds_label(slots, sa) ^ lds_label(slots, sb);
-                if (op == OP_XNOR) c0 = c0 ^ R;                // XNOR swaps (L0, L1)
-                sts_label(slots, sc, c0);
-                if (FULL) {
-                    uint4* w = p.wires_full + ((size_t)inst * p.n_wires + __ldg(p.out_wire + st.x + j)) * 2;
-                    w[0] = label_to_mem(c0);
-                    w[1] = label_to_mem(c0 ^ R);
-                }
+        for (uint32_t pi = 0; pi < p.n_phases; pi++) {
+            const Phase ph_nn = load_phase(p.phases, pi + 2);  // two zero records of padding
+            uint4 pre[GC_PRE];
+            prefetch_cipher<true>(p, ph, ttid, TT, pre);
+            // ---- Free-XOR run: one warp, warp-level synchronisation only
+            if (ph.n_chunks) {
+                if (xor_warp) free_run<true, FULL>(p, slots, R, inst, lane_id, ph.n_chunks, ring, next_chunk);
+                team_barrier(tc.team, TT);
             }
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
-            const uint32_t ntask = task_count<true>(st);
-            for (uint32_t base = 0; base < ntask; base += TT * ILP) {
-                const uint32_t left = ntask - base;
-                if (ILP >= 4 && left > 2 * TT)
-                    garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP>(lane, env, st, ntask, base, ttid, TT, cc);
-                else if (ILP >= 2 && left > TT)
-                    garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP>(lane, env, st, ntask, base, ttid, TT, cc);
-                else if (base + (ttid & ~31u) < ntask)
-                    garble_pass<NR, MODE, 1, ILP>(lane, env, st, ntask, base, ttid, TT, cc);
+            const uint32_t ntask = task_count<true>(ph);
+            if (ntask) {
+                const uint32_t per_thread = (ntask + TT - 1) / TT;        // tasks k = 0 .. per_thread-1
+                for (uint32_t k0 = 0; k0 < per_thread;) {
+                    const uint32_t left = per_thread - k0;
+                    if (ILP >= 4 && left >= 3) { garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 4; }
+                    else if (ILP >= 2 && left >= 2) { garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 2; }
+                    else { if (k0 * TT + (ttid & ~31u) < ntask) garble_pass<NR, MODE, 1>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 1; }
+                }
+                team_barrier(tc.team, TT);
             }
-            team_barrier(tc.team, TT);
-            st = st_n; st_n = st_nn; cf = nf;
-#pragma unroll
-            for (int j = 0; j < ILP; j++) cc[j] = nc[j];
+            ph = ph_n; ph_n = ph_nn;
         }
         // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
@@ -397,26 +453,24 @@ struct EvalEnv {
     uint32_t inst;
 };
 
-template <int NR, int MODE, int UU, int ILP>
-__device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e, const uint4& st, uint32_t ntask,
-                                          uint32_t base, uint32_t ttid, uint32_t TT, const uint4 (&pre)[ILP]) {
-    static_assert(UU <= ILP, "pass wider than the prefetch");
+template <int NR, int MODE, int UU>
+__device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e, const Phase& ph, uint32_t ntask,
+                                          uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&pre)[GC_PRE]) {
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
     uint4* const slots = e.slots;
-    const bool first = base == 0;
     uint4 g[UU];
     Label K[UU], H[UU], row[UU];
     uint32_t op[UU], kk[UU], gidx[UU];
     bool act[UU];
 #pragma unroll
     for (int j = 0; j < UU; j++) {
-        const uint32_t t = base + j * TT + ttid;
+        const uint32_t t = (k0 + j) * TT + ttid;
         act[j] = t < ntask;
         uint32_t k;
-        const uint32_t gi = task_gate<false>(st, t, k);
-        g[j] = pre[j];
-        if (!first) { g[j] = make_uint4(0, 0, 0, 0); if (act[j]) g[j] = __ldg(p.recs + gi); }
+        const uint32_t gi = task_gate<false>(ph, t, k);
+        if (k0 + j < GC_PRE) g[j] = pick(pre, k0 + j);
+        else { g[j] = make_uint4(0, 0, 0, 0); if (act[j]) g[j] = __ldg(p.crecs + gi); }
         const uint32_t sa = g[j].x & 0xffff, sb = g[j].x >> 16;
         op[j] = act[j] ? ((g[j].y >> 16) & 0xff) : 0xffu;
         kk[j] = k; gidx[j] = gi;
@@ -451,7 +505,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
         if (act[j] && (kk[j] == 0)) {
             const Label res = (op[j] == OP_AND) ? o : v;
             sts_label(slots, g[j].y & 0xffff, res);
-            if (FULL) p.wires_full[(size_t)e.inst * p.n_wires + __ldg(p.out_wire + gidx[j])] = label_to_mem(res);
+            if (FULL) p.wires_full[(size_t)e.inst * p.n_wires + __ldg(p.cout_wire + gidx[j])] = label_to_mem(res);
         }
     }
 }
@@ -464,12 +518,14 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     aes_tables_to_smem(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
-    const uint32_t TT = p.team_threads, ttid = tc.ttid;
+    const uint32_t TT = p.team_threads, ttid = tc.ttid, lane_id = threadIdx.x & 31u;
+    const bool xor_warp = ttid < 32;
     if (p.key_stride == 0) {
         if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
     uint4* const slots = tc.slots;
+    stagger_start(tc.team, p.stagger);
 
     for (;;) {
         if (ttid == 0) *tc.claim = atomicAdd(p.counter, 1u);
@@ -478,9 +534,13 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         if (inst >= p.batch) break;
         if (p.key_stride != 0 && ttid == 0)
             aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
-        uint4 st = __ldg(p.steps), st_n = __ldg(p.steps + 1);
-        uint4 cf, cc[ILP];
-        prefetch_step<false, ILP>(p, st, ttid, TT, cf, cc);
+        Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
+        uint2 ring[GC_RING];
+        uint32_t next_chunk = GC_RING;
+        if (xor_warp) {
+#pragma unroll
+            for (int j = 0; j < GC_RING; j++) ring[j] = __ldg(p.frecs + j * 32 + lane_id);
+        }
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
             const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
@@ -490,35 +550,28 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         team_barrier(tc.team, TT);
         const EvalEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, inst};
 
-        for (uint32_t s = 0; s < p.n_steps; s++) {
-            const uint4 st_nn = __ldg(p.steps + s + 2);
-            uint4 nf, nc[ILP];
-            prefetch_step<false, ILP>(p, st_n, ttid, TT, nf, nc);
-            // XOR and XNOR are both a plain XOR on the evaluator side (eval.go:48-50)
-            for (uint32_t j = ttid; j < st.y; j += TT) {
-                uint4 g = cf;
-                if (j != ttid) g = __ldg(p.recs + st.x + j);
-                const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff;
-                const Label c = lds_label(slots, sa) ^ lds_label(slots, sb);
-                sts_label(slots, sc, c);
-                if (FULL) p.wires_full[(size_t)inst * p.n_wires + __ldg(p.out_wire + st.x + j)] = label_to_mem(c);
+        for (uint32_t pi = 0; pi < p.n_phases; pi++) {
+            const Phase ph_nn = load_phase(p.phases, pi + 2);
+            uint4 pre[GC_PRE];
+            prefetch_cipher<false>(p, ph, ttid, TT, pre);
+            if (ph.n_chunks) {
+                if (xor_warp) free_run<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, lane_id, ph.n_chunks, ring, next_chunk);
+                team_barrier(tc.team, TT);
             }
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
-            const uint32_t ntask = task_count<false>(st);
-            for (uint32_t base = 0; base < ntask; base += TT * ILP) {
-                const uint32_t left = ntask - base;
-                if (ILP >= 4 && left > 2 * TT)
-                    eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP>(lane, env, st, ntask, base, ttid, TT, cc);
-                else if (ILP >= 2 && left > TT)
-                    eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP>(lane, env, st, ntask, base, ttid, TT, cc);
-                else if (base + (ttid & ~31u) < ntask)
-                    eval_pass<NR, MODE, 1, ILP>(lane, env, st, ntask, base, ttid, TT, cc);
+            const uint32_t ntask = task_count<false>(ph);
+            if (ntask) {
+                const uint32_t per_thread = (ntask + TT - 1) / TT;
+                for (uint32_t k0 = 0; k0 < per_thread;) {
+                    const uint32_t left = per_thread - k0;
+                    if (ILP >= 4 && left >= 3) { eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 4; }
+                    else if (ILP >= 2 && left >= 2) { eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 2; }
+                    else { if (k0 * TT + (ttid & ~31u) < ntask) eval_pass<NR, MODE, 1>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 1; }
+                }
+                team_barrier(tc.team, TT);
             }
-            team_barrier(tc.team, TT);
-            st = st_n; st_n = st_nn; cf = nf;
-#pragma unroll
-            for (int j = 0; j < ILP; j++) cc[j] = nc[j];
+            ph = ph_n; ph_n = ph_nn;
         }
         for (uint32_t k = ttid; k < p.n_out; k += TT) {
             const uint2 ref = __ldg(p.live_out + k);

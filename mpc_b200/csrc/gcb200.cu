@@ -151,9 +151,11 @@ static int fresh_counter(DeviceInfo* di, cudaStream_t stream, uint32_t** out) {
 // ------------------------------------------------------------- plan upload ----
 DevicePlan::~DevicePlan() {
     // best effort: the context may already be gone at process exit
-    if (recs) cudaFree(recs);
-    if (steps) cudaFree(steps);
-    if (out_wire) cudaFree(out_wire);
+    if (phases) cudaFree(phases);
+    if (frecs) cudaFree(frecs);
+    if (crecs) cudaFree(crecs);
+    if (fout_wire) cudaFree(fout_wire);
+    if (cout_wire) cudaFree(cout_wire);
     if (live_in) cudaFree(live_in);
     if (live_out) cudaFree(live_out);
 }
@@ -173,14 +175,18 @@ int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* ou
     if (it != plan.dev.end()) { *out = it->second; return GCB_OK; }
     auto dp = std::make_shared<DevicePlan>();
     dp->device = device;
-    CK(upload(&dp->recs, plan.recs));
     {
-        std::vector<StepRec> padded(plan.steps);
-        padded.push_back(StepRec{0, 0, 0, 0});          // the kernels read two records ahead
-        padded.push_back(StepRec{0, 0, 0, 0});
-        CK(upload(&dp->steps, padded));
+        std::vector<PhaseRec> ph(plan.phases);
+        ph.push_back(PhaseRec{});                       // the kernels read two records ahead
+        ph.push_back(PhaseRec{});
+        CK(upload(&dp->phases, ph));
+        std::vector<FreeRec> fr(plan.frecs);
+        fr.resize(fr.size() + (GC_RING + 1) * 32, FreeRec{0, 0, 0, FREE_PAD, 0});   // the chunk ring runs ahead
+        CK(upload(&dp->frecs, fr));
     }
-    CK(upload(&dp->out_wire, plan.out_wire));
+    CK(upload(&dp->crecs, plan.crecs));
+    CK(upload(&dp->fout_wire, plan.fout_wire));
+    CK(upload(&dp->cout_wire, plan.cout_wire));
     CK(upload(&dp->live_in, plan.live_in));
     CK(upload(&dp->live_out, plan.live_out));
     plan.dev[device] = dp;
@@ -212,6 +218,8 @@ void team_geometry(Plan& plan) {
         if (v >= 32 && v % 32 == 0 && (size_t)v * n <= maxt && (v == 32 || n <= 16)) tt = (uint32_t)v;
     }
     in.teams_per_sm = (uint32_t)n; in.team_threads = tt; plan.ilp = ilp;
+    plan.stagger = 0;
+    if (const char* e = getenv("GCB_STAGGER")) plan.stagger = (uint32_t)atoi(e);
 }
 size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams) {
     return AES_TABLE_BYTES + (size_t)n_teams * GC_RK_BYTES + (size_t)n_teams * num_slots * 16 + 128;
@@ -233,12 +241,14 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     if (rc) return rc;
     const gcb_plan_info& in = plan.info;
     GcParams p{};
-    p.recs = reinterpret_cast<const uint4*>(dp->recs);
-    p.steps = reinterpret_cast<const uint4*>(dp->steps);
-    p.out_wire = dp->out_wire;
+    p.phases = reinterpret_cast<const uint4*>(dp->phases);
+    p.frecs = reinterpret_cast<const uint2*>(dp->frecs);
+    p.crecs = reinterpret_cast<const uint4*>(dp->crecs);
+    p.fout_wire = dp->fout_wire;
+    p.cout_wire = dp->cout_wire;
     p.live_in = reinterpret_cast<const uint2*>(dp->live_in);
     p.live_out = reinterpret_cast<const uint2*>(dp->live_out);
-    p.n_steps = in.num_steps; p.n_in = in.num_inputs; p.n_out = in.num_outputs;
+    p.n_phases = (uint32_t)plan.phases.size(); p.n_in = in.num_inputs; p.n_out = in.num_outputs;
     p.n_slots = in.num_slots; p.n_rows = in.num_rows; p.n_wires = in.num_wires;
     p.keys = keys; p.keylen = keylen; p.key_stride = key_stride; p.batch = batch;
     p.r = reinterpret_cast<const uint4*>(r);
@@ -248,6 +258,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     p.wires_full = reinterpret_cast<uint4*>(wires_full);
     p.team_threads = in.team_threads; p.n_teams = in.teams_per_sm;
     p.in_ids = in_ids; p.out_ids = out_ids; p.pages = pages;
+    p.stagger = plan.stagger;
     rc = fresh_counter(di, stream, &p.counter);
     if (rc) return rc;
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;

@@ -173,23 +173,61 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
     for (size_t k = 0; k < spec.live_out.size(); k++)
         plan.live_out.push_back(SlotRef{slot[(size_t)cur_def[spec.live_out[k]]], (uint32_t)k});
 
-    // ---- gate records in schedule order
-    plan.recs.resize(ng);
-    plan.out_wire.resize(ng);
-    plan.orig_index.resize(ng);
-    for (uint32_t pos = 0; pos < ng; pos++) {
-        const uint32_t i = order[pos];
-        GateRec r;
-        r.a = (uint16_t)slot[(size_t)def_a[i]];
-        r.b = (uint16_t)slot[(size_t)def_b[i]];
-        r.c = (uint16_t)slot[ninit + i];
-        r.op = spec.gates[i].op;
-        r.pad = 0;
-        r.tweak = tweak_of[i];
-        r.row = plan.row_off[i];
-        plan.recs[pos] = r;
-        plan.out_wire[pos] = spec.gates[i].out;
-        plan.orig_index[pos] = i;
+    // ---- gate records in schedule order, grouped into phases
+    plan.phases.clear(); plan.frecs.clear(); plan.crecs.clear();
+    plan.fout_wire.clear(); plan.cout_wire.clear();
+    {
+        PhaseRec ph{};
+        bool open = false;
+        uint32_t run_start = 0;                       // index in frecs of the phase's first free gate
+        std::vector<uint32_t> rank_of;                // sub-level rank of every free gate of the open phase
+        auto close_phase = [&]() {
+            // waves: rank of the gate's sub-level minus the rank of its chunk's first gate
+            for (uint32_t i = 0; i < ph.n_free; i++) {
+                const uint32_t chunk_first = i & ~31u;
+                plan.frecs[run_start + i].wave = (uint8_t)(rank_of[i] - rank_of[chunk_first]);
+            }
+            while (plan.frecs.size() % 32) {          // whole chunks
+                plan.frecs.push_back(FreeRec{0, 0, 0, FREE_PAD, 0});
+                plan.fout_wire.push_back(0);
+            }
+            ph.n_chunks = (ph.n_free + 31) / 32;
+            plan.phases.push_back(ph);
+            ph = PhaseRec{};
+            rank_of.clear();
+            open = false;
+        };
+        uint32_t rank = 0;
+        for (size_t si = 0; si < plan.steps.size(); si++) {
+            const StepRec& st = plan.steps[si];
+            if (!open) {
+                run_start = (uint32_t)plan.frecs.size();
+                ph.free_chunk = run_start / 32;
+                ph.cipher_first = (uint32_t)plan.crecs.size();
+                rank = 0;
+                open = true;
+            }
+            const uint32_t n = st.n_free + st.n_quad + st.n_inv;
+            for (uint32_t j = 0; j < n; j++) {
+                const uint32_t i = order[st.first + j];
+                const gcb_gate& g = spec.gates[i];
+                const uint16_t sa = (uint16_t)slot[(size_t)def_a[i]], sb = (uint16_t)slot[(size_t)def_b[i]];
+                const uint16_t sc = (uint16_t)slot[ninit + i];
+                if (g.op <= OP_XNOR) {
+                    plan.frecs.push_back(FreeRec{sa, sb, sc, g.op, 0});
+                    plan.fout_wire.push_back(g.out);
+                    rank_of.push_back(rank);
+                    ph.n_free++;
+                } else {
+                    plan.crecs.push_back(GateRec{sa, sb, sc, g.op, 0, tweak_of[i], plan.row_off[i]});
+                    plan.cout_wire.push_back(g.out);
+                    (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
+                }
+            }
+            if (st.n_free) rank++;
+            if (st.n_quad + st.n_inv) { ph.cipher_first = (uint32_t)plan.crecs.size() - st.n_quad - st.n_inv; close_phase(); }
+        }
+        if (open) close_phase();
     }
 
     gcb_plan_info& in = plan.info;

@@ -36,14 +36,18 @@ def main():
     d_out = torch.zeros((batch, nout, 16), dtype=torch.uint8, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     ref = None
-    configs = [(None, None)] + [(i, t) for i in (1, 2, 4) for t in (32, 64, 96, 128, 160, 256)]
+    configs = [(None, None, 0)] + [(i, t, sg) for i in (1, 2, 4) for t in (32, 64, 96, 128, 160, 256)
+                                   for sg in (0, 100000)]
+    if len(sys.argv) > 4:
+        configs = [tuple(int(x) for x in c.split(",")) for c in sys.argv[4:]]
     print(f"{name} batch={batch} keylen={klen}: slots/rows see plan; times in ms")
-    for ilp, tt in configs:
-        for k in ("GCB_ILP", "GCB_TEAM_THREADS"):
+    for ilp, tt, sg in configs:
+        for k in ("GCB_ILP", "GCB_TEAM_THREADS", "GCB_STAGGER"):
             os.environ.pop(k, None)
         if ilp:
             os.environ["GCB_ILP"] = str(ilp)
             os.environ["GCB_TEAM_THREADS"] = str(tt)
+            os.environ["GCB_STAGGER"] = str(sg)
         eng = GarbleEngine(circ)
         info = eng.info
         if ilp and info.team_threads != tt:
@@ -67,7 +71,7 @@ def main():
             ref = sig
         ok = "same" if sig == ref else "DIFFERENT"
         n_and = circ.count(2)
-        print(f"ilp={ilp} tt={tt}: teams={info.teams_per_sm} x {info.team_threads} slots={info.num_slots} "
+        print(f"ilp={ilp} tt={tt} stagger={sg}: teams={info.teams_per_sm} x {info.team_threads} slots={info.num_slots} "
               f"garble={best_g:.3f} eval={best_e:.3f} total={best_g + best_e:.3f} "
               f"-> {n_and * batch / (best_g + best_e) / 1e3:.1f} M AND/s  [{ok}]", flush=True)
 
