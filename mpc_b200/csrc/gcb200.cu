@@ -207,18 +207,21 @@ void team_geometry(Plan& plan) {
     plan.ilp = 1;
     if (n == 0) return;
     if (n >= 32) n = 32; else if (n > 16) n = 16;
-    uint32_t ilp = n <= 8 ? 4 : n <= 16 ? 2 : 1;
+    // measured on B200 (tools/tune_geometry.py, aes_128.circ): two interleaved AES
+    // blocks per thread and two-warp teams beat both deeper ILP and wider teams
+    uint32_t ilp = n <= 16 ? 2 : 1;
     if (const char* e = getenv("GCB_ILP")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) ilp = (uint32_t)v; }
     const uint32_t maxt = ilp == 4 ? 256 : ilp == 2 ? 512 : 1024;
     while (n * 32 > maxt) n--;                      // at least one warp per team
     uint32_t tt = 32u * (uint32_t)(maxt / 32 / n);
+    if (tt > 64) tt = 64;
     if (n > 16) tt = 32;                            // named barriers: at most 16 multi-warp teams
     if (const char* e = getenv("GCB_TEAM_THREADS")) {
         const int v = atoi(e);
         if (v >= 32 && v % 32 == 0 && (size_t)v * n <= maxt && (v == 32 || n <= 16)) tt = (uint32_t)v;
     }
     in.teams_per_sm = (uint32_t)n; in.team_threads = tt; plan.ilp = ilp;
-    plan.stagger = 0;
+    plan.stagger = n > 1 ? 100000 : 0;              // teams start ~50 us apart
     if (const char* e = getenv("GCB_STAGGER")) plan.stagger = (uint32_t)atoi(e);
 }
 size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams) {
