@@ -12,19 +12,19 @@
 // once, the garbled rows once (written by the garbler, read by the evaluator)
 // and the output labels once.
 //
-// A team walks the plan's PHASES.  A phase is (1) the run of Free-XOR gates that
-// became computable after the previous cipher level -- executed by ONE warp of
-// the team, 32 gates (a chunk) at a time with warp-level synchronisation only,
-// the gate records streaming through a register ring that is loaded several
-// chunks ahead -- and (2) one level of ciphered gates executed by the whole
-// team: every AES block is a task; an AND gate is a quad of tasks hashing
+// A team walks the plan's PHASES.  A phase is (1) the free wires (XOR / XNOR
+// results) that became computable after the previous cipher level and that
+// something reads: the plan compiler has flattened the Free-XOR gates into
+// NODES, each the XOR of up to 14 already existing labels, grouped into waves of
+// mutually independent nodes (almost always one wave) -- one thread per node,
+// one team barrier per wave; and (2) one level of ciphered gates executed by the
+// whole team: every AES block is a task; an AND gate is a quad of tasks hashing
 // (a0,j0) (a1,j0) (b0,j1) (b1,j1) on four adjacent lanes and combining with warp
 // shuffles, INV a pair, OR a quad.  A thread runs up to ILP tasks at once (AES
-// rounds interleaved) and has loaded its gate records while the XOR run was in
-// progress.  Two team barriers per phase.  Teams start staggered so that the
-// shared-memory-bound cipher levels of one team overlap the latency-bound XOR
-// runs of the others.  All teams share the 128 KiB of replicated AES T-tables
-// (aes_core.cuh).
+// rounds interleaved).  Node and gate records are loaded one phase ahead, so no
+// global-memory latency sits on the phase-to-phase chain.  Teams start staggered
+// so that their shared-memory-bound cipher levels and latency-bound node waves
+// interleave.  All teams share the replicated AES T-tables (aes_core.cuh).
 #pragma once
 #include "aes_core.cuh"
 #include "plan.hpp"
@@ -33,14 +33,14 @@ namespace gcb {
 
 constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-barrier teams
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
-constexpr int GC_RING = 4;                // free-gate chunks in flight ahead of the XOR run
 constexpr int GC_PRE = 6;                 // cipher records per thread loaded ahead of the cipher level
 
 struct GcParams {
     const uint4* phases;                  // PhaseRec[] (two uint4 each) followed by two zero records
-    const uint2* frecs;                   // FreeRec[], whole chunks, followed by GC_RING+1 zero chunks
+    const uint2* waves;                   // WaveRec[]
+    const uint4* nodes;                   // NodeRec[] (two uint4 each)
     const uint4* crecs;                   // GateRec[]
-    const uint32_t* fout_wire;            // original output wire of frecs[i] / crecs[i] (GC_FULL)
+    const uint32_t* nout_wire;            // original output wire of nodes[i] / crecs[i] (GC_FULL)
     const uint32_t* cout_wire;
     const uint2* live_in;                 // SlotRef[]
     const uint2* live_out;
@@ -56,6 +56,7 @@ struct GcParams {
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
     uint32_t stagger;                     // SM cycles by which consecutive teams start apart
+    long long* trace;                     // optional: phase timestamps of block 0 / team 0 (tools/trace_phases.py)
     // streaming mode (GC_STREAM): live-in / live-out labels come from and go to
     // the permanent wire file instead of in_labels / io
     const uint32_t* in_ids;               // [n_in] permanent wire id of live-in k
@@ -153,11 +154,11 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
 // Gate index of cipher task t of a phase.  Garble: 4 tasks per AND/OR, 2 per INV;
 // eval: 2 per AND/OR (OR uses one), 1 per INV.
 struct Phase {
-    uint32_t free_chunk, n_chunks, cipher_first, n_quad, n_inv;
+    uint32_t wave_first, n_waves, cipher_first, n_quad, n_inv, w0_first, w0_count;
 };
 __device__ __forceinline__ Phase load_phase(const uint4* phases, uint32_t i) {
     const uint4 a = __ldg(phases + 2 * i), b = __ldg(phases + 2 * i + 1);
-    return Phase{a.x, a.y, a.z, a.w, b.x};
+    return Phase{a.x, a.y, a.z, a.w, b.x, b.y, b.z};
 }
 template <bool GARBLE>
 __device__ __forceinline__ uint32_t task_gate(const Phase& ph, uint32_t t, uint32_t& k) {
@@ -194,39 +195,57 @@ __device__ __forceinline__ uint4 pick(const uint4 (&pre)[GC_PRE], uint32_t i) {
     return r;
 }
 
-// The Free-XOR run of a phase, executed by one warp (garble.go:331-351,
-// eval.go:48-50).  ring[] holds the next GC_RING chunks of free-gate records;
-// *next_chunk is the chunk index the ring will load next.
+// One node: dst = XOR of its leaves (^ R for an odd number of XNORs on the way,
+// garbler only: garble.go:342-351 swaps the labels of an XNOR, eval.go:48-50 does not).
+struct NodeRegs { uint4 lo, hi; };
+__device__ __forceinline__ NodeRegs load_node(const uint4* nodes, uint32_t i) {
+    return NodeRegs{__ldg(nodes + 2 * (size_t)i), __ldg(nodes + 2 * (size_t)i + 1)};
+}
 template <bool GARBLE, bool FULL>
-__device__ __forceinline__ void free_run(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t lane,
-                                         uint32_t n_chunks, uint2 (&ring)[GC_RING], uint32_t& next_chunk) {
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint2 g = ring[0];
+__device__ __forceinline__ void run_node(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t node_index,
+                                         const NodeRegs& n, bool active) {
+    // words: lo.x = dst | k<<16 | parity<<24; then 14 leaf slots, two per word
+    const uint32_t w[7] = {n.lo.y, n.lo.z, n.lo.w, n.hi.x, n.hi.y, n.hi.z, n.hi.w};
+    const uint32_t k = active ? (n.lo.x >> 16) & 0xff : 0u;
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);
+    Label acc = Label{0, 0, 0, 0};
+    if (GARBLE) acc = label_and_mask(R, mask_of(n.lo.x >> 24));
 #pragma unroll
-        for (int j = 0; j + 1 < GC_RING; j++) ring[j] = ring[j + 1];
-        ring[GC_RING - 1] = __ldg(p.frecs + (size_t)next_chunk * 32 + lane);
-        const uint32_t chunk = next_chunk - GC_RING;
-        next_chunk++;
-        const uint32_t sa = g.x & 0xffff, sb = g.x >> 16, sc = g.y & 0xffff, op = (g.y >> 16) & 0xff, wave = g.y >> 24;
-        const bool active = op != FREE_PAD;
-        const uint32_t maxw = __reduce_max_sync(0xffffffffu, active ? wave : 0u);
-        for (uint32_t w = 0; w <= maxw; w++) {
-            if (active && wave == w) {
-                Label c0 = lds_label(slots, sa) ^ lds_label(slots, sb);
-                if (GARBLE && op == OP_XNOR) c0 = c0 ^ R;      // XNOR swaps (L0, L1); plain XOR for the evaluator
-                sts_label(slots, sc, c0);
-                if (FULL) {
-                    const size_t ow = (size_t)inst * p.n_wires + __ldg(p.fout_wire + (size_t)chunk * 32 + lane);
-                    if (GARBLE) {
-                        p.wires_full[2 * ow] = label_to_mem(c0);
-                        p.wires_full[2 * ow + 1] = label_to_mem(c0 ^ R);
-                    } else {
-                        p.wires_full[ow] = label_to_mem(c0);
-                    }
-                }
+    for (int j = 0; j < NODE_MAX_FANIN; j++) {
+        if ((uint32_t)j >= kmax) break;                        // warp-uniform
+        const uint32_t s = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffff);
+        if ((uint32_t)j < k) acc = acc ^ lds_label(slots, s);
+    }
+    if (active) {
+        sts_label(slots, n.lo.x & 0xffff, acc);
+        if (FULL) {
+            const size_t ow = (size_t)inst * p.n_wires + __ldg(p.nout_wire + node_index);
+            if (GARBLE) {
+                p.wires_full[2 * ow] = label_to_mem(acc);
+                p.wires_full[2 * ow + 1] = label_to_mem(acc ^ R);
+            } else {
+                p.wires_full[ow] = label_to_mem(acc);
             }
-            __syncwarp();
         }
+    }
+}
+
+// All node waves of a phase.  `pre` is this thread's node of wave 0 (index
+// w0_first + ttid), loaded during the previous phase.
+template <bool GARBLE, bool FULL>
+__device__ __forceinline__ void run_waves(const GcParams& p, uint4* slots, const Label R, uint32_t inst, const Phase& ph,
+                                          uint32_t team, uint32_t ttid, uint32_t TT, const NodeRegs& pre) {
+    for (uint32_t w = 0; w < ph.n_waves; w++) {
+        uint32_t first = ph.w0_first, count = ph.w0_count;
+        if (w) { const uint2 wr = __ldg(p.waves + ph.wave_first + w); first = wr.x; count = wr.y; }
+        const uint32_t rounded = (count + 31u) & ~31u;
+        for (uint32_t j = ttid; j < rounded; j += TT) {
+            const bool active = j < count;
+            NodeRegs n = pre;
+            if (w || j != ttid) { n = NodeRegs{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}; if (active) n = load_node(p.nodes, first + j); }
+            run_node<GARBLE, FULL>(p, slots, R, inst, first + j, n, active);
+        }
+        team_barrier(team, TT);
     }
 }
 
@@ -355,8 +374,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     aes_tables_to_smem(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
-    const uint32_t TT = p.team_threads, ttid = tc.ttid, lane_id = threadIdx.x & 31u;
-    const bool xor_warp = ttid < 32;                           // the team's first warp runs the XOR runs
+    const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
         if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
@@ -375,12 +393,8 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
         // plan records of the first phases load while the inputs do
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
-        uint2 ring[GC_RING];
-        uint32_t next_chunk = GC_RING;
-        if (xor_warp) {
-#pragma unroll
-            for (int j = 0; j < GC_RING; j++) ring[j] = __ldg(p.frecs + j * 32 + lane_id);
-        }
+        NodeRegs npre{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (ttid < ph.w0_count) npre = load_node(p.nodes, ph.w0_first + ttid);
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
@@ -406,11 +420,13 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);  // two zero records of padding
             uint4 pre[GC_PRE];
             prefetch_cipher<true>(p, ph, ttid, TT, pre);
-            // ---- Free-XOR run: one warp, warp-level synchronisation only
-            if (ph.n_chunks) {
-                if (xor_warp) free_run<true, FULL>(p, slots, R, inst, lane_id, ph.n_chunks, ring, next_chunk);
-                team_barrier(tc.team, TT);
-            }
+            NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (ttid < ph_n.w0_count) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
+            const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
+            if (tracing) p.trace[4 * pi] = clock64();
+            // ---- free wires: waves of independent XOR nodes, one thread per node
+            run_waves<true, FULL>(p, slots, R, inst, ph, tc.team, ttid, TT, npre);
+            if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
             const uint32_t ntask = task_count<true>(ph);
             if (ntask) {
@@ -421,9 +437,10 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                     else if (ILP >= 2 && left >= 2) { garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 2; }
                     else { if (k0 * TT + (ttid & ~31u) < ntask) garble_pass<NR, MODE, 1>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 1; }
                 }
+                if (tracing) p.trace[4 * pi + 3] = clock64();
                 team_barrier(tc.team, TT);
             }
-            ph = ph_n; ph_n = ph_nn;
+            ph = ph_n; ph_n = ph_nn; npre = npre_n;
         }
         // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
@@ -518,8 +535,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     aes_tables_to_smem(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
-    const uint32_t TT = p.team_threads, ttid = tc.ttid, lane_id = threadIdx.x & 31u;
-    const bool xor_warp = ttid < 32;
+    const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
         if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
@@ -535,12 +551,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         if (p.key_stride != 0 && ttid == 0)
             aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
-        uint2 ring[GC_RING];
-        uint32_t next_chunk = GC_RING;
-        if (xor_warp) {
-#pragma unroll
-            for (int j = 0; j < GC_RING; j++) ring[j] = __ldg(p.frecs + j * 32 + lane_id);
-        }
+        NodeRegs npre{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (ttid < ph.w0_count) npre = load_node(p.nodes, ph.w0_first + ttid);
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
             const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
@@ -554,10 +566,9 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);
             uint4 pre[GC_PRE];
             prefetch_cipher<false>(p, ph, ttid, TT, pre);
-            if (ph.n_chunks) {
-                if (xor_warp) free_run<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, lane_id, ph.n_chunks, ring, next_chunk);
-                team_barrier(tc.team, TT);
-            }
+            NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (ttid < ph_n.w0_count) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
+            run_waves<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);
@@ -571,7 +582,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                 }
                 team_barrier(tc.team, TT);
             }
-            ph = ph_n; ph_n = ph_nn;
+            ph = ph_n; ph_n = ph_nn; npre = npre_n;
         }
         for (uint32_t k = ttid; k < p.n_out; k += TT) {
             const uint2 ref = __ldg(p.live_out + k);

@@ -148,13 +148,19 @@ static int fresh_counter(DeviceInfo* di, cudaStream_t stream, uint32_t** out) {
     return GCB_OK;
 }
 
+// Developer hook (not in the public header): device buffer of 4 timestamps per phase
+// written by block 0 / team 0 of the next garble launches; nullptr switches it off.
+static long long* g_trace = nullptr;
+extern "C" void gcb_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+
 // ------------------------------------------------------------- plan upload ----
 DevicePlan::~DevicePlan() {
     // best effort: the context may already be gone at process exit
     if (phases) cudaFree(phases);
-    if (frecs) cudaFree(frecs);
+    if (waves) cudaFree(waves);
+    if (nodes) cudaFree(nodes);
     if (crecs) cudaFree(crecs);
-    if (fout_wire) cudaFree(fout_wire);
+    if (nout_wire) cudaFree(nout_wire);
     if (cout_wire) cudaFree(cout_wire);
     if (live_in) cudaFree(live_in);
     if (live_out) cudaFree(live_out);
@@ -180,12 +186,11 @@ int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* ou
         ph.push_back(PhaseRec{});                       // the kernels read two records ahead
         ph.push_back(PhaseRec{});
         CK(upload(&dp->phases, ph));
-        std::vector<FreeRec> fr(plan.frecs);
-        fr.resize(fr.size() + (GC_RING + 1) * 32, FreeRec{0, 0, 0, FREE_PAD, 0});   // the chunk ring runs ahead
-        CK(upload(&dp->frecs, fr));
     }
+    CK(upload(&dp->waves, plan.waves));
+    CK(upload(&dp->nodes, plan.nodes));
     CK(upload(&dp->crecs, plan.crecs));
-    CK(upload(&dp->fout_wire, plan.fout_wire));
+    CK(upload(&dp->nout_wire, plan.nout_wire));
     CK(upload(&dp->cout_wire, plan.cout_wire));
     CK(upload(&dp->live_in, plan.live_in));
     CK(upload(&dp->live_out, plan.live_out));
@@ -228,6 +233,30 @@ size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams) {
     return AES_TABLE_BYTES + (size_t)n_teams * GC_RK_BYTES + (size_t)n_teams * num_slots * 16 + 128;
 }
 
+// The plan a call runs on: the flattened one, or -- when the caller wants every wire
+// label (Garbled.Wires / Eval's in-place wires) -- one that keeps every XOR gate.
+static int plan_for(const gcb_plan* plan, bool full, const Plan** out) {
+    if (!full) { *out = &plan->p; return GCB_OK; }
+    std::lock_guard<std::mutex> lk(plan->full_mu);
+    if (!plan->full) {
+        const Plan& base = plan->p;
+        PlanSpec spec;
+        spec.gates = base.gates.data(); spec.num_gates = (uint32_t)base.gates.size(); spec.num_wires = base.info.num_wires;
+        for (uint32_t i = 0; i < base.info.num_inputs; i++) spec.live_in.push_back(i);
+        for (uint32_t i = 0; i < base.info.num_outputs; i++) spec.live_out.push_back(base.info.num_wires - base.info.num_outputs + i);
+        auto fp = std::make_unique<Plan>();
+        std::string err;
+        int rc = build_plan(spec, *fp, err, 2);
+        if (rc) return fail(rc, "%s", err.c_str());
+        team_geometry(*fp);
+        if (fp->info.teams_per_sm == 0)
+            return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live with every wire materialised", fp->info.num_slots);
+        plan->full = std::move(fp);
+    }
+    *out = plan->full.get();
+    return GCB_OK;
+}
+
 static int check_keylen(uint32_t keylen) {
     if (keylen != 16 && keylen != 24 && keylen != 32)
         return fail(GCB_E_KEYLEN, "crypto/aes: invalid key size %u", keylen);
@@ -245,9 +274,10 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const gcb_plan_info& in = plan.info;
     GcParams p{};
     p.phases = reinterpret_cast<const uint4*>(dp->phases);
-    p.frecs = reinterpret_cast<const uint2*>(dp->frecs);
+    p.waves = reinterpret_cast<const uint2*>(dp->waves);
+    p.nodes = reinterpret_cast<const uint4*>(dp->nodes);
     p.crecs = reinterpret_cast<const uint4*>(dp->crecs);
-    p.fout_wire = dp->fout_wire;
+    p.nout_wire = dp->nout_wire;
     p.cout_wire = dp->cout_wire;
     p.live_in = reinterpret_cast<const uint2*>(dp->live_in);
     p.live_out = reinterpret_cast<const uint2*>(dp->live_out);
@@ -262,6 +292,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     p.team_threads = in.team_threads; p.n_teams = in.teams_per_sm;
     p.in_ids = in_ids; p.out_ids = out_ids; p.pages = pages;
     p.stagger = plan.stagger;
+    p.trace = g_trace;
     rc = fresh_counter(di, stream, &p.counter);
     if (rc) return rc;
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;
@@ -458,7 +489,9 @@ int gcb_garble_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, u
     if (batch == 0) return GCB_OK;
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
-    return launch_gc(true, plan->p, di, tl_device, keys, keylen, key_stride, batch, r, in_l0, tables, io_wires,
+    const Plan* use;
+    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
+    return launch_gc(true, *use, di, tl_device, keys, keylen, key_stride, batch, r, in_l0, tables, io_wires,
                      wires_full, (cudaStream_t)stream);
 }
 
@@ -475,7 +508,9 @@ int gcb_eval_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uin
     if (batch == 0) return GCB_OK;
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
-    return launch_gc(false, plan->p, di, tl_device, keys, keylen, key_stride, batch, nullptr, in_labels,
+    const Plan* use;
+    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
+    return launch_gc(false, *use, di, tl_device, keys, keylen, key_stride, batch, nullptr, in_labels,
                      const_cast<gcb_label*>(tables), out_labels, wires_full, (cudaStream_t)stream);
 }
 
@@ -492,7 +527,9 @@ int gcb_garble(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint3
     if (batch == 0) return GCB_OK;
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
-    const gcb_plan_info& in = plan->p.info;
+    const Plan* use;
+    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
+    const gcb_plan_info& in = use->info;
     const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
     HostPipe& pipe = thread_pipe(tl_device);
     if ((rc = pipe.init())) return rc;
@@ -522,7 +559,7 @@ int gcb_garble(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint3
             return rc;
         if (wires_full && (rc = s.out(wires_full + (size_t)b0 * nw, (size_t)nb * nw * 32, (void**)&dwf))) return rc;
         if ((rc = s.upload())) return rc;
-        rc = launch_gc(true, plan->p, di, tl_device, dk, keylen, key_stride, nb, dr, dl0, dt, dio, dwf, s.compute);
+        rc = launch_gc(true, *use, di, tl_device, dk, keylen, key_stride, nb, dr, dl0, dt, dio, dwf, s.compute);
         if (rc) return rc;
         if ((rc = s.download())) return rc;
     }
@@ -541,7 +578,9 @@ int gcb_eval(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_
     if (batch == 0) return GCB_OK;
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
-    const gcb_plan_info& in = plan->p.info;
+    const Plan* use;
+    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
+    const gcb_plan_info& in = use->info;
     const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
     HostPipe& pipe = thread_pipe(tl_device);
     if ((rc = pipe.init())) return rc;
@@ -567,7 +606,7 @@ int gcb_eval(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_
         if (nout && (rc = s.out(out_labels + (size_t)b0 * nout, (size_t)nb * nout * 16, (void**)&dol))) return rc;
         if (wires_full && (rc = s.out(wires_full + (size_t)b0 * nw, (size_t)nb * nw * 16, (void**)&dwf))) return rc;
         if ((rc = s.upload())) return rc;
-        rc = launch_gc(false, plan->p, di, tl_device, dk, keylen, key_stride, nb, nullptr, dil,
+        rc = launch_gc(false, *use, di, tl_device, dk, keylen, key_stride, nb, nullptr, dil,
                        const_cast<gcb_label*>(dt), dol, dwf, s.compute);
         if (rc) return rc;
         if ((rc = s.download())) return rc;

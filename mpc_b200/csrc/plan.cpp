@@ -4,24 +4,27 @@
 #include <algorithm>
 #include <cstdio>
 #include <functional>
+#include <iterator>
 #include <limits>
 #include <queue>
 
 namespace gcb {
 
 namespace {
-constexpr uint32_t kCipherSub = 0xffffffffu;   // sub-level of the cipher gates of a level
 constexpr int64_t kForever = std::numeric_limits<int64_t>::max();
 
 inline int op_class(uint8_t op) { return op <= OP_XNOR ? 0 : (op == OP_INV ? 2 : 1); }
 }  // namespace
 
-int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin) {
     char msg[160];
     const uint32_t ng = spec.num_gates, nw = spec.num_wires;
     const bool identity = spec.loc.empty();
     const uint32_t nloc = identity ? nw : spec.num_locs;
     if (!identity && spec.loc.size() != nw) { err = "location map size mismatch"; return GCB_E_ARG; }
+    if (max_fanin < 2 || max_fanin > NODE_MAX_FANIN) { err = "bad fan-in limit"; return GCB_E_ARG; }
+    const bool keep_all = max_fanin == 2;
+    const size_t K = (size_t)max_fanin;
     auto loc_of = [&](uint32_t w) { return identity ? w : spec.loc[w]; };
 
     const size_t ninit = spec.live_in.size();
@@ -31,8 +34,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
     // file formats, and the norm for aliased streaming wires) get a new
     // definition each time, which makes every hazard a plain RAW dependency.
     std::vector<int64_t> cur_def(nloc, -1);
-    std::vector<uint32_t> cd(ndefs, 0), xd(ndefs, 0);       // cipher depth, free sub-depth
-    std::vector<int64_t> born(ndefs, -1), last(ndefs, -1);
+    std::vector<uint32_t> cd(ndefs, 0);                     // cipher depth of a definition
     for (size_t k = 0; k < ninit; k++) {
         const uint32_t l = spec.live_in[k];
         if (l >= nloc) { err = "live-in location out of range"; return GCB_E_WIRE; }
@@ -40,9 +42,10 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
         cur_def[l] = (int64_t)k;
     }
 
-    std::vector<uint64_t> key(ng);
+    // ---- pass 1: definitions, phases, static tweak ids and slab rows (original order)
     std::vector<int64_t> def_a(ng), def_b(ng);
-    uint32_t n_and = 0, n_or = 0, n_inv = 0, n_free = 0;
+    std::vector<uint32_t> phase_of(ng);
+    uint32_t n_and = 0, n_or = 0, n_inv = 0, n_free = 0, n_phases = 0;
     plan.row_off.assign(ng + 1, 0);
     plan.ops.resize(ng);
     std::vector<uint32_t> tweak_of(ng);
@@ -67,20 +70,12 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
             err = msg;
             return GCB_E_WIRE;
         }
-        uint32_t d, x;
-        if (cd[da] > cd[db]) { d = cd[da]; x = xd[da]; }
-        else if (cd[db] > cd[da]) { d = cd[db]; x = xd[db]; }
-        else { d = cd[da]; x = std::max(xd[da], xd[db]); }
-        const size_t dout = ninit + i;
-        if (g.op >= OP_AND) {
-            key[i] = ((uint64_t)d << 32) | kCipherSub;
-            cd[dout] = d + 1; xd[dout] = 0;
-        } else {
-            key[i] = ((uint64_t)d << 32) | x;
-            cd[dout] = d; xd[dout] = x + 1;
-        }
+        const uint32_t d = std::max(cd[da], cd[db]);
+        phase_of[i] = d;
+        n_phases = std::max(n_phases, d + 1);
+        cd[ninit + i] = g.op >= OP_AND ? d + 1 : d;
         def_a[i] = da; def_b[i] = db;
-        cur_def[loc_of(g.out)] = (int64_t)dout;
+        cur_def[loc_of(g.out)] = (int64_t)(ninit + i);
         plan.ops[i] = g.op;
         plan.row_off[i] = row;
         tweak_of[i] = tweak;
@@ -92,40 +87,17 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
         }
     }
     plan.row_off[ng] = row;
+    auto is_free_def = [&](int64_t d) { return d >= (int64_t)ninit && spec.gates[(size_t)d - ninit].op <= OP_XNOR; };
 
-    // ---- steps: sort gates by (level key, class, original index)
-    std::vector<uint32_t> order(ng);
-    for (uint32_t i = 0; i < ng; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t p, uint32_t q) {
-        if (key[p] != key[q]) return key[p] < key[q];
-        const int cp = op_class(spec.gates[p].op), cq = op_class(spec.gates[q].op);
-        if (cp != cq) return cp < cq;
-        return p < q;
-    });
-    std::vector<int64_t> step_of(ng);
-    plan.steps.clear();
-    for (uint32_t pos = 0; pos < ng;) {
-        uint32_t end = pos;
-        StepRec st{pos, 0, 0, 0};
-        while (end < ng && key[order[end]] == key[order[pos]]) {
-            const int c = op_class(spec.gates[order[end]].op);
-            (c == 0 ? st.n_free : c == 1 ? st.n_quad : st.n_inv)++;
-            step_of[order[end]] = (int64_t)plan.steps.size();
-            end++;
-        }
-        plan.steps.push_back(st);
-        pos = end;
-    }
-    const int64_t nsteps = (int64_t)plan.steps.size();
-
-    // ---- liveness
+    // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
+    // free gate of a later phase, or by the caller afterwards
+    std::vector<uint8_t> required(ng, keep_all ? 1 : 0);
     for (uint32_t i = 0; i < ng; i++) {
-        const int64_t s = step_of[i];
-        born[ninit + i] = s;
-        last[def_a[i]] = std::max(last[def_a[i]], s);
-        last[def_b[i]] = std::max(last[def_b[i]], s);
+        const bool cipher = spec.gates[i].op >= OP_AND;
+        for (const int64_t d : {def_a[i], def_b[i]})
+            if (is_free_def(d) && (cipher || phase_of[(size_t)d - ninit] != phase_of[i])) required[(size_t)d - ninit] = 1;
     }
-    plan.live_out.clear();
+    std::vector<int64_t> out_def(spec.live_out.size());
     for (size_t k = 0; k < spec.live_out.size(); k++) {
         const uint32_t l = spec.live_out[k];
         if (l >= nloc || cur_def[l] < 0) {
@@ -133,13 +105,92 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
             err = msg;
             return GCB_E_WIRE;
         }
-        last[cur_def[l]] = kForever;
+        out_def[k] = cur_def[l];
+        if (is_free_def(cur_def[l])) required[(size_t)cur_def[l] - ninit] = 1;
     }
+
+    // ---- pass 3: flatten the free gates of each phase into nodes of bounded fan-in.
+    // flat[i] = the leaves whose XOR is gate i's output: definitions that exist when the
+    // phase starts, or nodes of the same phase that had to be cut off to respect the fan-in
+    // limit (a "forced" node).  Same-phase free inputs are otherwise inlined, which keeps
+    // the dependency depth (waves) low.
+    struct Node { uint32_t gate; uint32_t wave; uint8_t parity; std::vector<uint32_t> leaves; };
+    std::vector<std::vector<uint32_t>> flat(ng);
+    std::vector<uint8_t> parity(ng, 0), forced(ng, 0), emitted(ng, 0);
+    std::vector<uint32_t> wave_of(ng, 0);
+    std::vector<std::vector<Node>> phase_nodes(n_phases);
+    auto sym_diff = [](const std::vector<uint32_t>& x, const std::vector<uint32_t>& y, std::vector<uint32_t>& o) {
+        o.clear();
+        std::set_symmetric_difference(x.begin(), x.end(), y.begin(), y.end(), std::back_inserter(o));
+    };
+    auto emit_node = [&](uint32_t i) {
+        if (emitted[i]) return;
+        emitted[i] = 1;
+        uint32_t w = 0;
+        for (uint32_t l : flat[i])
+            if (is_free_def(l) && phase_of[l - ninit] == phase_of[i]) w = std::max(w, wave_of[l - ninit] + 1);
+        wave_of[i] = w;
+        phase_nodes[phase_of[i]].push_back(Node{i, w, parity[i], flat[i]});
+    };
+    std::vector<uint32_t> la, lb, tmp;
+    for (uint32_t i = 0; i < ng; i++) {
+        const gcb_gate& g = spec.gates[i];
+        if (g.op > OP_XNOR) continue;
+        for (int attempt = 0;; attempt++) {
+            uint8_t par = g.op == OP_XNOR;
+            auto leafset = [&](int64_t d, std::vector<uint32_t>& o) {
+                if (is_free_def(d) && phase_of[(size_t)d - ninit] == phase_of[i] && !forced[(size_t)d - ninit] && !keep_all) {
+                    o = flat[(size_t)d - ninit];
+                    par ^= parity[(size_t)d - ninit];
+                } else {
+                    o.assign(1, (uint32_t)d);
+                }
+            };
+            leafset(def_a[i], la);
+            leafset(def_b[i], lb);
+            sym_diff(la, lb, tmp);
+            if (tmp.size() <= K || attempt == 2) { flat[i] = tmp; parity[i] = par; break; }
+            // too wide: cut off the wider inlined input as a node of its own and refer to it
+            const int64_t cand = (la.size() >= lb.size() && la.size() > 1) ? def_a[i] : (lb.size() > 1 ? def_b[i] : def_a[i]);
+            const uint32_t cg = (uint32_t)((size_t)cand - ninit);
+            emit_node(cg);
+            forced[cg] = 1;
+        }
+        if (required[i]) emit_node(i);
+    }
+
+    // ---- pass 4: the time axis (one step per wave, one per cipher level), liveness
+    std::vector<std::vector<uint32_t>> phase_cipher(n_phases);
+    for (uint32_t i = 0; i < ng; i++)
+        if (spec.gates[i].op >= OP_AND) phase_cipher[phase_of[i]].push_back(i);
+    std::vector<int64_t> born(ndefs, -1), last(ndefs, -1);
+    std::vector<uint32_t> wave_step0(n_phases, 0), cipher_step(n_phases, 0), n_waves(n_phases, 0);
+    int64_t nsteps = 0;
+    for (uint32_t p = 0; p < n_phases; p++) {
+        for (const Node& nd : phase_nodes[p]) n_waves[p] = std::max(n_waves[p], nd.wave + 1);
+        wave_step0[p] = (uint32_t)nsteps;
+        nsteps += n_waves[p];
+        cipher_step[p] = (uint32_t)nsteps;
+        if (!phase_cipher[p].empty()) nsteps++;
+    }
+    for (uint32_t p = 0; p < n_phases; p++) {
+        for (const Node& nd : phase_nodes[p]) {
+            const int64_t s = wave_step0[p] + nd.wave;
+            born[ninit + nd.gate] = s;
+            for (uint32_t l : nd.leaves) last[l] = std::max(last[l], s);
+        }
+        for (uint32_t i : phase_cipher[p]) {
+            const int64_t s = cipher_step[p];
+            born[ninit + i] = s;
+            last[def_a[i]] = std::max(last[def_a[i]], s);
+            last[def_b[i]] = std::max(last[def_b[i]], s);
+        }
+    }
+    for (const int64_t d : out_def) last[(size_t)d] = kForever;
     for (size_t d = 0; d < ndefs; d++) last[d] = std::max(last[d], born[d]);
 
-    // ---- slots: lowest free index first; a slot whose value was last read in
-    // step s may be rewritten from step s+1 on (reads and writes of one step are
-    // unordered).
+    // ---- slots: lowest free index first; a slot whose value was last read in step s may
+    // be rewritten from step s+1 on (reads and writes of one step are unordered).
     std::vector<std::vector<size_t>> expire((size_t)nsteps + 1);
     std::vector<uint32_t> slot(ndefs, 0);
     std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_slots;
@@ -151,18 +202,36 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
         if (last[k] < 0) free_slots.push(slot[k]);                 // never read, not live-out
         else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
     }
-    for (int64_t s = 0; s < nsteps; s++) {
-        if (s > 0) {
-            for (size_t d : expire[(size_t)s - 1]) free_slots.push(slot[d]);
-            expire[(size_t)s - 1].clear();
-        }
-        const StepRec& st = plan.steps[(size_t)s];
-        const uint32_t n = st.n_free + st.n_quad + st.n_inv;
-        for (uint32_t j = 0; j < n; j++) {
-            const size_t d = ninit + order[st.first + j];
-            if (free_slots.empty()) slot[d] = next_slot++;
-            else { slot[d] = free_slots.top(); free_slots.pop(); }
-            if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+    auto take_slot = [&](size_t d) {
+        if (free_slots.empty()) slot[d] = next_slot++;
+        else { slot[d] = free_slots.top(); free_slots.pop(); }
+        if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+    };
+    {
+        int64_t s = 0;
+        auto advance = [&]() {
+            if (s > 0) {
+                for (size_t d : expire[(size_t)s - 1]) free_slots.push(slot[d]);
+                expire[(size_t)s - 1].clear();
+            }
+        };
+        for (uint32_t p = 0; p < n_phases; p++) {
+            // nodes sorted by (wave, fan-in descending) so that the lanes of a warp do similar work
+            std::stable_sort(phase_nodes[p].begin(), phase_nodes[p].end(), [](const Node& x, const Node& y) {
+                if (x.wave != y.wave) return x.wave < y.wave;
+                return x.leaves.size() > y.leaves.size();
+            });
+            size_t pos = 0;
+            for (uint32_t w = 0; w < n_waves[p]; w++, s++) {
+                advance();
+                for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++)
+                    take_slot(ninit + phase_nodes[p][pos].gate);
+            }
+            if (!phase_cipher[p].empty()) {
+                advance();
+                for (uint32_t i : phase_cipher[p]) take_slot(ninit + i);
+                s++;
+            }
         }
     }
     if (next_slot > 65535) {
@@ -170,64 +239,49 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err) {
         err = msg;
         return GCB_E_TOO_LARGE;
     }
+    plan.live_out.clear();
     for (size_t k = 0; k < spec.live_out.size(); k++)
-        plan.live_out.push_back(SlotRef{slot[(size_t)cur_def[spec.live_out[k]]], (uint32_t)k});
+        plan.live_out.push_back(SlotRef{slot[(size_t)out_def[k]], (uint32_t)k});
 
-    // ---- gate records in schedule order, grouped into phases
-    plan.phases.clear(); plan.frecs.clear(); plan.crecs.clear();
-    plan.fout_wire.clear(); plan.cout_wire.clear();
-    {
+    // ---- records in schedule order
+    plan.phases.clear(); plan.waves.clear(); plan.nodes.clear(); plan.crecs.clear();
+    plan.nout_wire.clear(); plan.cout_wire.clear();
+    plan.node_loads = 0;
+    for (uint32_t p = 0; p < n_phases; p++) {
         PhaseRec ph{};
-        bool open = false;
-        uint32_t run_start = 0;                       // index in frecs of the phase's first free gate
-        std::vector<uint32_t> rank_of;                // sub-level rank of every free gate of the open phase
-        auto close_phase = [&]() {
-            // waves: rank of the gate's sub-level minus the rank of its chunk's first gate
-            for (uint32_t i = 0; i < ph.n_free; i++) {
-                const uint32_t chunk_first = i & ~31u;
-                plan.frecs[run_start + i].wave = (uint8_t)(rank_of[i] - rank_of[chunk_first]);
+        ph.wave_first = (uint32_t)plan.waves.size();
+        ph.n_waves = n_waves[p];
+        size_t pos = 0;
+        for (uint32_t w = 0; w < n_waves[p]; w++) {
+            WaveRec wr{(uint32_t)plan.nodes.size(), 0};
+            for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++) {
+                const Node& nd = phase_nodes[p][pos];
+                NodeRec r{};
+                r.dst = (uint16_t)slot[ninit + nd.gate];
+                r.k = (uint8_t)nd.leaves.size();
+                r.parity = nd.parity;
+                for (size_t j = 0; j < nd.leaves.size(); j++) r.leaf[j] = (uint16_t)slot[nd.leaves[j]];
+                plan.nodes.push_back(r);
+                plan.nout_wire.push_back(spec.gates[nd.gate].out);
+                plan.node_loads += r.k;
+                wr.count++;
             }
-            while (plan.frecs.size() % 32) {          // whole chunks
-                plan.frecs.push_back(FreeRec{0, 0, 0, FREE_PAD, 0});
-                plan.fout_wire.push_back(0);
-            }
-            ph.n_chunks = (ph.n_free + 31) / 32;
-            plan.phases.push_back(ph);
-            ph = PhaseRec{};
-            rank_of.clear();
-            open = false;
-        };
-        uint32_t rank = 0;
-        for (size_t si = 0; si < plan.steps.size(); si++) {
-            const StepRec& st = plan.steps[si];
-            if (!open) {
-                run_start = (uint32_t)plan.frecs.size();
-                ph.free_chunk = run_start / 32;
-                ph.cipher_first = (uint32_t)plan.crecs.size();
-                rank = 0;
-                open = true;
-            }
-            const uint32_t n = st.n_free + st.n_quad + st.n_inv;
-            for (uint32_t j = 0; j < n; j++) {
-                const uint32_t i = order[st.first + j];
-                const gcb_gate& g = spec.gates[i];
-                const uint16_t sa = (uint16_t)slot[(size_t)def_a[i]], sb = (uint16_t)slot[(size_t)def_b[i]];
-                const uint16_t sc = (uint16_t)slot[ninit + i];
-                if (g.op <= OP_XNOR) {
-                    plan.frecs.push_back(FreeRec{sa, sb, sc, g.op, 0});
-                    plan.fout_wire.push_back(g.out);
-                    rank_of.push_back(rank);
-                    ph.n_free++;
-                } else {
-                    plan.crecs.push_back(GateRec{sa, sb, sc, g.op, 0, tweak_of[i], plan.row_off[i]});
-                    plan.cout_wire.push_back(g.out);
-                    (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
-                }
-            }
-            if (st.n_free) rank++;
-            if (st.n_quad + st.n_inv) { ph.cipher_first = (uint32_t)plan.crecs.size() - st.n_quad - st.n_inv; close_phase(); }
+            plan.waves.push_back(wr);
+            if (w == 0) { ph.w0_first = wr.first; ph.w0_count = wr.count; }
         }
-        if (open) close_phase();
+        // ciphered gates: AND/OR first, then INV (the kernels give 4 / 2 tasks to each)
+        std::stable_sort(phase_cipher[p].begin(), phase_cipher[p].end(), [&](uint32_t x, uint32_t y) {
+            return op_class(spec.gates[x].op) < op_class(spec.gates[y].op);
+        });
+        ph.cipher_first = (uint32_t)plan.crecs.size();
+        for (uint32_t i : phase_cipher[p]) {
+            const gcb_gate& g = spec.gates[i];
+            plan.crecs.push_back(GateRec{(uint16_t)slot[(size_t)def_a[i]], (uint16_t)slot[(size_t)def_b[i]],
+                                         (uint16_t)slot[ninit + i], g.op, 0, tweak_of[i], plan.row_off[i]});
+            plan.cout_wire.push_back(g.out);
+            (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
+        }
+        plan.phases.push_back(ph);
     }
 
     gcb_plan_info& in = plan.info;

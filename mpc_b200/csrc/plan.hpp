@@ -29,34 +29,38 @@ struct GateRec {
 };
 static_assert(sizeof(GateRec) == 16, "GateRec must be 16 bytes");
 
-// One free gate (XOR / XNOR): 8 bytes.  `wave` orders the gates of one 32-gate
-// chunk: a gate of wave w may read what gates of waves < w of its chunk wrote.
-struct FreeRec {
-    uint16_t a, b, c;
-    uint8_t op;
-    uint8_t wave;
+// One materialised free wire.  The plan compiler flattens the XOR / XNOR gates of a
+// phase: a wire that a ciphered gate, a later phase or the caller reads becomes a
+// NODE = the XOR of up to NODE_MAX_FANIN leaves (wires that exist when the phase
+// starts, or nodes of an earlier wave of the same phase), plus R when an odd
+// number of XNORs lie on the way (garbler only; the evaluator's XNOR is a plain
+// XOR, eval.go:48-50).  Intermediate XOR wires that nothing else reads are never
+// computed or stored.  32 bytes, two 128-bit loads.
+constexpr int NODE_MAX_FANIN = 14;
+struct NodeRec {
+    uint16_t dst;         // wire slot of the result
+    uint8_t k;            // number of leaves
+    uint8_t parity;       // 1: XOR R in (garbler)
+    uint16_t leaf[NODE_MAX_FANIN];
 };
-static_assert(sizeof(FreeRec) == 8, "FreeRec must be 8 bytes");
+static_assert(sizeof(NodeRec) == 32, "NodeRec must be 32 bytes");
 
-// One phase = every free gate that becomes computable after the previous cipher
-// level (sorted by dependency sub-level, executed by ONE warp of the team with
-// warp-level synchronisation only), followed by one level of ciphered gates
-// (executed by the whole team): AND/OR first, then INV.
+// Nodes of one wave are independent of each other; wave w+1 may read wave w.
+struct WaveRec {
+    uint32_t first, count;            // range in the NodeRec array
+};
+
+// One phase = the waves of free-wire nodes that become computable after the
+// previous cipher level, followed by one level of ciphered gates: AND/OR first,
+// then INV.
 struct PhaseRec {
-    uint32_t free_chunk, n_chunks;    // 32-record chunks of the FreeRec array (runs are padded with
-                                      // op = FREE_PAD records to whole chunks)
+    uint32_t wave_first, n_waves;     // range in the WaveRec array
     uint32_t cipher_first, n_quad;    // range in the GateRec array: n_quad AND/OR gates ...
     uint32_t n_inv;                   // ... then n_inv INV gates
-    uint32_t n_free;                  // free gates of the phase (without padding)
-    uint32_t pad[2];
+    uint32_t w0_first, w0_count;      // copy of the first wave (saves a dependent load)
+    uint32_t pad;
 };
-constexpr uint8_t FREE_PAD = 0xff;
 static_assert(sizeof(PhaseRec) == 32, "PhaseRec must be 32 bytes");
-
-// One dependency step of the schedule (host-side bookkeeping: liveness, stats).
-struct StepRec {
-    uint32_t first, n_free, n_quad, n_inv;
-};
 
 struct SlotRef {
     uint32_t slot;
@@ -77,9 +81,10 @@ struct PlanSpec {
 struct DevicePlan {                   // per-device copy of the tables
     int device = -1;
     PhaseRec* phases = nullptr;       // + two zero records of padding
-    FreeRec* frecs = nullptr;         // + 256 zero records of padding (chunk prefetch runs ahead)
+    WaveRec* waves = nullptr;
+    NodeRec* nodes = nullptr;
     GateRec* crecs = nullptr;
-    uint32_t* fout_wire = nullptr;    // original output wire of each free / ciphered gate
+    uint32_t* nout_wire = nullptr;    // original output wire of each node / ciphered gate
     uint32_t* cout_wire = nullptr;
     SlotRef* live_in = nullptr;
     SlotRef* live_out = nullptr;
@@ -91,10 +96,11 @@ struct Plan {
     uint32_t ilp = 1;                     // AES blocks a thread interleaves (kernel variant)
     uint32_t stagger = 0;                 // SM cycles between the starts of consecutive teams
     std::vector<PhaseRec> phases;
-    std::vector<FreeRec> frecs;           // free gates in schedule order
+    std::vector<WaveRec> waves;
+    std::vector<NodeRec> nodes;           // free-wire nodes in schedule order
     std::vector<GateRec> crecs;           // ciphered gates in schedule order
-    std::vector<uint32_t> fout_wire, cout_wire;   // original output wire of frecs[i] / crecs[i]
-    std::vector<StepRec> steps;
+    std::vector<uint32_t> nout_wire, cout_wire;   // original output wire of nodes[i] / crecs[i]
+    uint32_t node_loads = 0;              // sum of node fan-ins (label loads of the free part)
     std::vector<SlotRef> live_in, live_out;
     std::vector<uint32_t> row_off;        // num_gates+1, original order
     std::vector<uint8_t> ops;             // original order
@@ -104,13 +110,17 @@ struct Plan {
     mutable std::map<int, std::shared_ptr<DevicePlan>> dev;
 };
 
-// Returns GCB_OK or a negative status; message in err.
-int build_plan(const PlanSpec& spec, Plan& plan, std::string& err);
+// Returns GCB_OK or a negative status; message in err.  max_fanin = NODE_MAX_FANIN
+// for the normal plan; 2 keeps every XOR / XNOR gate as its own node (the
+// wires_full variant, where every wire label has to be produced).
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN);
 
 }  // namespace gcb
 
 struct gcb_plan {
-    gcb::Plan p;
+    gcb::Plan p;                              // flattened free wires (the fast plan)
+    mutable std::mutex full_mu;
+    mutable std::unique_ptr<gcb::Plan> full;  // every wire materialised (wires_full requests), built on demand
 };
 
 namespace gcb {
