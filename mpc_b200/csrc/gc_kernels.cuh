@@ -56,6 +56,7 @@ struct GcParams {
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
     uint32_t stagger;                     // SM cycles by which consecutive teams start apart
+    uint32_t debug_skip;                  // developer switch: 1 = skip node waves, 2 = skip cipher levels (timing experiments)
     long long* trace;                     // optional: phase timestamps of block 0 / team 0 (tools/trace_phases.py)
     // streaming mode (GC_STREAM): live-in / live-out labels come from and go to
     // the permanent wire file instead of in_labels / io
@@ -201,49 +202,83 @@ struct NodeRegs { uint4 lo, hi; };
 __device__ __forceinline__ NodeRegs load_node(const uint4* nodes, uint32_t i) {
     return NodeRegs{__ldg(nodes + 2 * (size_t)i), __ldg(nodes + 2 * (size_t)i + 1)};
 }
-template <bool GARBLE, bool FULL>
-__device__ __forceinline__ void run_node(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t node_index,
-                                         const NodeRegs& n, bool active) {
+
+// NU nodes at once: dst = XOR of the leaves (^ R for an odd number of XNORs on the way).
+template <bool GARBLE, bool FULL, int NU>
+__device__ __forceinline__ void run_nodes(const GcParams& p, uint4* slots, const Label R, uint32_t inst,
+                                          const uint32_t (&index)[NU], const NodeRegs (&n)[NU], const bool (&active)[NU]) {
     // words: lo.x = dst | k<<16 | parity<<24; then 14 leaf slots, two per word
-    const uint32_t w[7] = {n.lo.y, n.lo.z, n.lo.w, n.hi.x, n.hi.y, n.hi.z, n.hi.w};
-    const uint32_t k = active ? (n.lo.x >> 16) & 0xff : 0u;
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);
-    Label acc = Label{0, 0, 0, 0};
-    if (GARBLE) acc = label_and_mask(R, mask_of(n.lo.x >> 24));
+    uint32_t k[NU], kall = 0;
+    Label acc[NU];
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+        k[u] = active[u] ? (n[u].lo.x >> 16) & 0xff : 0u;
+        kall = max(kall, k[u]);
+        acc[u] = Label{0, 0, 0, 0};
+        if (GARBLE) acc[u] = label_and_mask(R, mask_of(n[u].lo.x >> 24));
+    }
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, kall);
 #pragma unroll
     for (int j = 0; j < NODE_MAX_FANIN; j++) {
         if ((uint32_t)j >= kmax) break;                        // warp-uniform
-        const uint32_t s = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffff);
-        if ((uint32_t)j < k) acc = acc ^ lds_label(slots, s);
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+            const uint32_t w = j < 2 ? n[u].lo.y : j < 4 ? n[u].lo.z : j < 6 ? n[u].lo.w : j < 8 ? n[u].hi.x
+                             : j < 10 ? n[u].hi.y : j < 12 ? n[u].hi.z : n[u].hi.w;
+            const uint32_t s = (j & 1) ? (w >> 16) : (w & 0xffff);
+            if ((uint32_t)j < k[u]) acc[u] = acc[u] ^ lds_label(slots, s);
+        }
     }
-    if (active) {
-        sts_label(slots, n.lo.x & 0xffff, acc);
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+        if (!active[u]) continue;
+        sts_label(slots, n[u].lo.x & 0xffff, acc[u]);
         if (FULL) {
-            const size_t ow = (size_t)inst * p.n_wires + __ldg(p.nout_wire + node_index);
+            const size_t ow = (size_t)inst * p.n_wires + __ldg(p.nout_wire + index[u]);
             if (GARBLE) {
-                p.wires_full[2 * ow] = label_to_mem(acc);
-                p.wires_full[2 * ow + 1] = label_to_mem(acc ^ R);
+                p.wires_full[2 * ow] = label_to_mem(acc[u]);
+                p.wires_full[2 * ow + 1] = label_to_mem(acc[u] ^ R);
             } else {
-                p.wires_full[ow] = label_to_mem(acc);
+                p.wires_full[ow] = label_to_mem(acc[u]);
             }
         }
     }
 }
 
-// All node waves of a phase.  `pre` is this thread's node of wave 0 (index
+template <bool GARBLE, bool FULL, int NU>
+__device__ __forceinline__ void wave_group(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t first,
+                                           uint32_t count, uint32_t w, uint32_t j, uint32_t ttid, uint32_t TT,
+                                           const NodeRegs& pre) {
+    uint32_t index[NU];
+    NodeRegs n[NU];
+    bool active[NU];
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+        const uint32_t ju = j + u * TT;
+        index[u] = first + ju;
+        active[u] = ju < count;
+        n[u] = NodeRegs{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (active[u]) n[u] = (w == 0 && ju == ttid) ? pre : load_node(p.nodes, first + ju);
+    }
+    run_nodes<GARBLE, FULL, NU>(p, slots, R, inst, index, n, active);
+}
+
+// All node waves of a phase.  `pre` is this thread's first node of wave 0 (index
 // w0_first + ttid), loaded during the previous phase.
-template <bool GARBLE, bool FULL>
+template <bool GARBLE, bool FULL, int NILP>
 __device__ __forceinline__ void run_waves(const GcParams& p, uint4* slots, const Label R, uint32_t inst, const Phase& ph,
                                           uint32_t team, uint32_t ttid, uint32_t TT, const NodeRegs& pre) {
     for (uint32_t w = 0; w < ph.n_waves; w++) {
         uint32_t first = ph.w0_first, count = ph.w0_count;
         if (w) { const uint2 wr = __ldg(p.waves + ph.wave_first + w); first = wr.x; count = wr.y; }
-        const uint32_t rounded = (count + 31u) & ~31u;
-        for (uint32_t j = ttid; j < rounded; j += TT) {
-            const bool active = j < count;
-            NodeRegs n = pre;
-            if (w || j != ttid) { n = NodeRegs{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}; if (active) n = load_node(p.nodes, first + j); }
-            run_node<GARBLE, FULL>(p, slots, R, inst, first + j, n, active);
+        // this warp's nodes: j = ttid + i*TT, i < n_i (warp-uniform)
+        const uint32_t wbase = ttid & ~31u;
+        const uint32_t n_i = count > wbase ? (count - wbase + TT - 1) / TT : 0u;
+        for (uint32_t i = 0; i < n_i;) {
+            const uint32_t left = n_i - i, j = ttid + i * TT;
+            if (NILP >= 4 && left >= 3) { wave_group<GARBLE, FULL, (NILP >= 4 ? 4 : 1)>(p, slots, R, inst, first, count, w, j, ttid, TT, pre); i += 4; }
+            else if (NILP >= 2 && left >= 2) { wave_group<GARBLE, FULL, (NILP >= 2 ? 2 : 1)>(p, slots, R, inst, first, count, w, j, ttid, TT, pre); i += 2; }
+            else { wave_group<GARBLE, FULL, 1>(p, slots, R, inst, first, count, w, j, ttid, TT, pre); i += 1; }
         }
         team_barrier(team, TT);
     }
@@ -368,6 +403,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
 template <int NR, int MODE, int ILP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     constexpr bool FULL = MODE == GC_FULL;
+    constexpr int NILP = 1;   // nodes a thread works on at once (measured: wider groups issue too many predicated-off loads)
     constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
@@ -425,10 +461,10 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
-            run_waves<true, FULL>(p, slots, R, inst, ph, tc.team, ttid, TT, npre);
+            if (!(p.debug_skip & 1)) run_waves<true, FULL, NILP>(p, slots, R, inst, ph, tc.team, ttid, TT, npre);
             if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
-            const uint32_t ntask = task_count<true>(ph);
+            const uint32_t ntask = (p.debug_skip & 2) ? 0u : task_count<true>(ph);
             if (ntask) {
                 const uint32_t per_thread = (ntask + TT - 1) / TT;        // tasks k = 0 .. per_thread-1
                 for (uint32_t k0 = 0; k0 < per_thread;) {
@@ -530,6 +566,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
 template <int NR, int MODE, int ILP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     constexpr bool FULL = MODE == GC_FULL;
+    constexpr int NILP = 1;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
     aes_tables_to_smem(tc.tables);
@@ -568,7 +605,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             prefetch_cipher<false>(p, ph, ttid, TT, pre);
             NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
             if (ttid < ph_n.w0_count) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
-            run_waves<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
+            run_waves<false, FULL, NILP>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);

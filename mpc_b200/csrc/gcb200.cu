@@ -66,7 +66,7 @@ static cudaError_t opt_in(K kernel) {
 }
 
 // every (rounds, mode, ILP) instantiation of the gate kernels
-#define GC_FOR_ILP(M, NR, MODE) M(NR, MODE, 1, 1024) M(NR, MODE, 2, 512) M(NR, MODE, 4, 256)
+#define GC_FOR_ILP(M, NR, MODE) M(NR, MODE, 1, 1024) M(NR, MODE, 2, 512) M(NR, MODE, 2, 768) M(NR, MODE, 4, 256)
 #define GC_FOR_NR(M, MODE) GC_FOR_ILP(M, 10, MODE) GC_FOR_ILP(M, 12, MODE) GC_FOR_ILP(M, 14, MODE)
 static cudaError_t opt_in_gc() {
     cudaError_t e = cudaSuccess;
@@ -82,12 +82,14 @@ static cudaError_t opt_in_gc() {
 template <int NR, int MODE>
 static void launch_garble(uint32_t ilp, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
     if (ilp == 4) garble_kernel<NR, MODE, 4, 256><<<grid, block, smem, s>>>(p);
+    else if (ilp == 2 && block.x > 512) garble_kernel<NR, MODE, 2, 768><<<grid, block, smem, s>>>(p);
     else if (ilp == 2) garble_kernel<NR, MODE, 2, 512><<<grid, block, smem, s>>>(p);
     else garble_kernel<NR, MODE, 1, 1024><<<grid, block, smem, s>>>(p);
 }
 template <int NR, int MODE>
 static void launch_eval(uint32_t ilp, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
     if (ilp == 4) eval_kernel<NR, MODE, 4, 256><<<grid, block, smem, s>>>(p);
+    else if (ilp == 2 && block.x > 512) eval_kernel<NR, MODE, 2, 768><<<grid, block, smem, s>>>(p);
     else if (ilp == 2) eval_kernel<NR, MODE, 2, 512><<<grid, block, smem, s>>>(p);
     else eval_kernel<NR, MODE, 1, 1024><<<grid, block, smem, s>>>(p);
 }
@@ -216,14 +218,15 @@ void team_geometry(Plan& plan) {
     // blocks per thread and two-warp teams beat both deeper ILP and wider teams
     uint32_t ilp = n <= 16 ? 2 : 1;
     if (const char* e = getenv("GCB_ILP")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) ilp = (uint32_t)v; }
+    // threads per CTA: the 512-thread ILP-2 variant has 128 registers per thread and no spills
     const uint32_t maxt = ilp == 4 ? 256 : ilp == 2 ? 512 : 1024;
     while (n * 32 > maxt) n--;                      // at least one warp per team
     uint32_t tt = 32u * (uint32_t)(maxt / 32 / n);
-    if (tt > 64) tt = 64;
+    if (tt > 96) tt = 96;
     if (n > 16) tt = 32;                            // named barriers: at most 16 multi-warp teams
     if (const char* e = getenv("GCB_TEAM_THREADS")) {
         const int v = atoi(e);
-        if (v >= 32 && v % 32 == 0 && (size_t)v * n <= maxt && (v == 32 || n <= 16)) tt = (uint32_t)v;
+        if (v >= 32 && v % 32 == 0 && (size_t)v * n <= (ilp == 2 ? 768u : maxt) && (v == 32 || n <= 16)) tt = (uint32_t)v;
     }
     in.teams_per_sm = (uint32_t)n; in.team_threads = tt; plan.ilp = ilp;
     plan.stagger = n > 1 ? 100000 : 0;              // teams start ~50 us apart
@@ -293,6 +296,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     p.in_ids = in_ids; p.out_ids = out_ids; p.pages = pages;
     p.stagger = plan.stagger;
     p.trace = g_trace;
+    if (const char* e = getenv("GCB_DEBUG_SKIP")) p.debug_skip = (uint32_t)atoi(e);
     rc = fresh_counter(di, stream, &p.counter);
     if (rc) return rc;
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;

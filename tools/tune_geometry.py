@@ -66,6 +66,18 @@ def main():
             torch.cuda.synchronize()
             if it:
                 best_g, best_e = min(best_g, e0.elapsed_time(e1)), min(best_e, e2.elapsed_time(e3))
+        for skip in (1, 2, 3):
+            os.environ["GCB_DEBUG_SKIP"] = str(skip)
+            ts = []
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); eng.garble_dev(d_key, klen, 0, batch, d_r, d_l0, d_tab, d_io, stream=s); e1.record()
+                torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+            print(f"    garble with skip={skip} (1=no nodes, 2=no cipher, 3=neither): {min(ts):.3f} ms")
+        os.environ.pop("GCB_DEBUG_SKIP", None)
+        eng.garble_dev(d_key, klen, 0, batch, d_r, d_l0, d_tab, d_io, stream=s)
+        eng.eval_dev(d_key, klen, 0, batch, d_tab, d_in, d_out, stream=s)
+        torch.cuda.synchronize()
         sig = (hash(d_tab.cpu().numpy().tobytes()), hash(d_out.cpu().numpy().tobytes()))
         if ref is None:
             ref = sig
