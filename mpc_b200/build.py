@@ -35,7 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", SO] + srcs
+    extra = os.environ.get("GCB_NVCC_EXTRA", "").split()      # e.g. -DGCB_AES_TABLES=2 for experiments
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

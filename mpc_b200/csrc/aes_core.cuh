@@ -79,7 +79,13 @@ __device__ const Te0Array g_te0 = make_te0();
 // Entry x of table t for lane l lives at byte offset
 //     (t >> 1) * 65536 + x * 256 + (t & 1) * 128 + l * 4
 // (two tables interleaved per 64 KiB region with a 256-byte entry stride).
-constexpr int AES_TABLE_BYTES = 4 * 256 * 32 * 4;   // 131072
+// GCB_AES_TABLES = 4: T0..T3 resident (128 KiB).  GCB_AES_TABLES = 2: only T0/T1 resident
+// (64 KiB); T2 = rot16(T0) and T3 = rot16(T1) cost one more PRMT per lookup of those
+// tables (8 per round) and free 64 KiB of shared memory for wire labels.
+#ifndef GCB_AES_TABLES
+#define GCB_AES_TABLES 4
+#endif
+constexpr int AES_TABLE_BYTES = GCB_AES_TABLES * 256 * 32 * 4;   // 131072 or 65536
 constexpr int AES_MAX_RK_WORDS = 60;                 // AES-256: 15 round keys
 
 __device__ __forceinline__ uint32_t ror8(uint32_t x) { return __funnelshift_r(x, x, 8); }
@@ -94,8 +100,10 @@ __device__ __forceinline__ void aes_tables_to_smem(uint8_t* smem_tables) {
         uint8_t* e = smem_tables + x * 256 + l * 4;
         *reinterpret_cast<uint32_t*>(e) = t0;
         *reinterpret_cast<uint32_t*>(e + 128) = t1;
-        *reinterpret_cast<uint32_t*>(e + 65536) = t2;
-        *reinterpret_cast<uint32_t*>(e + 65536 + 128) = t3;
+        if (GCB_AES_TABLES == 4) {
+            *reinterpret_cast<uint32_t*>(e + 65536) = t2;
+            *reinterpret_cast<uint32_t*>(e + 65536 + 128) = t3;
+        }
     }
 }
 
@@ -121,10 +129,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // Table T lookup of byte K (0 = LSB) of s.
 template <int T, int K>
 __device__ __forceinline__ uint32_t te(const AesLane& a, uint32_t s) {
-    constexpr int OFF = (T >> 1) * 65536 + (T & 1) * 128;
     // PRMT: byte0 = lane4, byte1 = byte K of s, bytes 2,3 = 0
     const uint32_t e = __byte_perm(s, a.lane4, 0x5504 | (K << 4));
-    return lds_u32(a.tb + OFF + e);
+    if (GCB_AES_TABLES == 4) {
+        constexpr int OFF = (T >> 1) * 65536 + (T & 1) * 128;
+        return lds_u32(a.tb + OFF + e);
+    }
+    const uint32_t v = lds_u32(a.tb + (T & 1) * 128 + e);
+    return (T & 2) ? __byte_perm(v, 0, 0x1032) : v;
 }
 
 // One full round on (s0..s3) with round-key words k.

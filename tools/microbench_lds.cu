@@ -75,6 +75,48 @@ __global__ void k_aes(uint4* out, int iters, long long* cycles) {
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// C2: AES-128 rounds with only T0/T1 resident (64 KiB); T2 = rot16(T0), T3 = rot16(T1) by PRMT
+template <int T, int K> __device__ __forceinline__ uint32_t te2(const AesLane& a, uint32_t s) {
+    const uint32_t e = __byte_perm(s, a.lane4, 0x5504 | (K << 4));
+    const uint32_t v = lds_u32(a.tb + (T & 1) * 128 + e);
+    return (T & 2) ? __byte_perm(v, 0, 0x1032) : v;
+}
+__device__ __forceinline__ void aes_round2(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3, const uint4 k) {
+    const uint32_t t0 = te2<0, 3>(a, s0) ^ te2<1, 2>(a, s1) ^ te2<2, 1>(a, s2) ^ te2<3, 0>(a, s3) ^ k.x;
+    const uint32_t t1 = te2<0, 3>(a, s1) ^ te2<1, 2>(a, s2) ^ te2<2, 1>(a, s3) ^ te2<3, 0>(a, s0) ^ k.y;
+    const uint32_t t2 = te2<0, 3>(a, s2) ^ te2<1, 2>(a, s3) ^ te2<2, 1>(a, s0) ^ te2<3, 0>(a, s1) ^ k.z;
+    const uint32_t t3 = te2<0, 3>(a, s3) ^ te2<1, 2>(a, s0) ^ te2<2, 1>(a, s1) ^ te2<3, 0>(a, s2) ^ k.w;
+    s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+}
+template <int U>
+__global__ void k_aes2(uint4* out, int iters, long long* cycles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    aes_tables_to_smem(smem);
+    uint32_t* rk = (uint32_t*)(smem + AES_TABLE_BYTES);
+    if (threadIdx.x < 44) rk[threadIdx.x] = threadIdx.x * 0x9e3779b9u;
+    __syncthreads();
+    const AesLane a = aes_lane(smem);
+    uint32_t s[U][4];
+#pragma unroll
+    for (int j = 0; j < U; j++) { s[j][0] = threadIdx.x + j; s[j][1] = blockIdx.x; s[j][2] = j * 17; s[j][3] = 99; }
+    const uint4* k4 = (const uint4*)rk;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+#pragma unroll 1
+        for (int r = 1; r <= 10; r++) {
+            const uint4 k = k4[r];
+#pragma unroll
+            for (int j = 0; j < U; j++) aes_round2(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
+        }
+    }
+    long long t1 = clock64();
+    uint4 o = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < U; j++) { o.x ^= s[j][0]; o.y ^= s[j][1]; o.z ^= s[j][2]; o.w ^= s[j][3]; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = o;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 // D: ALU only (LOP3 / PRMT chains)
 __global__ void k_alu(uint32_t* out, int iters, long long* cycles) {
     uint32_t a = threadIdx.x, b = blockIdx.x + 1, c = 0x12345, d = 77;
@@ -120,6 +162,15 @@ int main() {
         if (warps * 32 <= 512) { k_aes<4><<<sms, warps * 32, smem>>>(out, it, cyc); r[u++] = (double)warps * 32 * it * 4 / avg(); } else r[u++] = 0;
         printf("AES-128 warps=%2d: blocks/clk/SM  U=1 %.4f  U=2 %.4f  U=4 %.4f   (x148 SMs x1.9GHz: %.1f / %.1f / %.1f G blocks/s)\n", warps,
                r[0], r[1], r[2], r[0] * 148 * 1.9, r[1] * 148 * 1.9, r[2] * 148 * 1.9);
+    }
+    CK(cudaFuncSetAttribute(k_aes2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_aes2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int warps : {8, 12, 16, 24, 32}) {
+        const int it = 200;
+        k_aes2<1><<<sms, warps * 32, smem>>>(out, it, cyc); const double r1 = (double)warps * 32 * it / avg();
+        double r2 = 0;
+        if (warps <= 16) { k_aes2<2><<<sms, warps * 32, smem>>>(out, it, cyc); r2 = (double)warps * 32 * it * 2 / avg(); }
+        printf("AES-128 with 2 resident tables (64 KiB) warps=%2d: blocks/clk/SM U=1 %.4f U=2 %.4f\n", warps, r1, r2);
     }
     for (int warps : {4, 8, 16, 32}) {
         const int it = 2000;
