@@ -6,9 +6,9 @@
 // four T-tables held in shared memory.  Each table is replicated 32x so that
 // lane l of a warp only ever touches bank l: a warp-wide lookup is exactly one
 // conflict-free shared-memory wavefront whatever the 32 indices are.  One
-// lookup costs one PRMT (address = byte k of the state word in bits 8..15, the
-// lane's bank offset in bits 0..7) and one LDS [R + UR + imm]; one round is
-// 16 PRMT + 16 LDS + 8 LOP3.  The kernels built on this core are bound by the
+// lookup costs one PRMT (the complete address: 64 KiB-aligned table base in bits
+// 16.., byte k of the state word in bits 8..15, the lane's bank offset in bits
+// 0..7) and one LDS [R + imm]; one round is 16 PRMT + 16 LDS + 8 LOP3.  The kernels built on this core are bound by the
 // shared-memory wavefront rate (16 per round per 32 blocks), not by HBM; see
 // DESIGN.md.
 //
@@ -107,35 +107,40 @@ __device__ __forceinline__ void aes_tables_to_smem(uint8_t* smem_tables) {
     }
 }
 
-// Per-thread lookup context.
-struct AesLane {
-    uint32_t tb;        // shared-window address of the tables (warp-uniform)
-    uint32_t lane4;     // (lane id) * 4: this lane's bank
-};
+// The tables start at a shared-window address that is a multiple of 64 KiB, so that the
+// whole lookup address -- table base, entry x * 256 and the lane's bank offset -- comes
+// out of ONE PRMT of the state word with a per-lane constant (no add, no uniform-register
+// operand), and the table selection is the immediate offset of the LDS.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint8_t* aes_align_tables(uint8_t* smem) {
+    const uint32_t a = smem_addr(smem);
+    return smem + (((a + 0xffffu) & ~0xffffu) - a);
+}
 
-__device__ __forceinline__ AesLane aes_lane(const uint8_t* smem_tables) {
+// Per-thread lookup context: (table base | lane * 4); bits 8..15 are zero.
+struct AesLane {
+    uint32_t lb;
+};
+__device__ __forceinline__ AesLane aes_lane(const uint8_t* aligned_tables) {
     AesLane a;
-    a.tb = static_cast<uint32_t>(__cvta_generic_to_shared(smem_tables));
-    a.lane4 = (threadIdx.x & 31u) * 4u;
+    a.lb = smem_addr(aligned_tables) | ((threadIdx.x & 31u) * 4u);
     return a;
 }
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32_off(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     return v;
 }
 
 // Table T lookup of byte K (0 = LSB) of s.
 template <int T, int K>
 __device__ __forceinline__ uint32_t te(const AesLane& a, uint32_t s) {
-    // PRMT: byte0 = lane4, byte1 = byte K of s, bytes 2,3 = 0
-    const uint32_t e = __byte_perm(s, a.lane4, 0x5504 | (K << 4));
-    if (GCB_AES_TABLES == 4) {
-        constexpr int OFF = (T >> 1) * 65536 + (T & 1) * 128;
-        return lds_u32(a.tb + OFF + e);
-    }
-    const uint32_t v = lds_u32(a.tb + (T & 1) * 128 + e);
+    // PRMT: byte1 = byte K of s, bytes 0, 2, 3 = those of the lane constant
+    const uint32_t e = __byte_perm(s, a.lb, 0x7604 | (K << 4));
+    if (GCB_AES_TABLES == 4) return lds_u32_off<(T >> 1) * 65536 + (T & 1) * 128>(e);
+    const uint32_t v = lds_u32_off<(T & 1) * 128>(e);
     return (T & 2) ? __byte_perm(v, 0, 0x1032) : v;
 }
 

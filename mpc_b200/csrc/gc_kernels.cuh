@@ -138,17 +138,21 @@ struct TeamCtx {
     uint32_t team, ttid;
 };
 
+// Shared-memory map of the gate kernels: [region A | 64 KiB-aligned tables | region B].
+// Region A is the pad below the tables; teams are packed into A first, then B.  A team's
+// block is: round keys (GC_RK_BYTES), claim word (16 B), wire labels (n_slots * 16).
+__device__ __forceinline__ uint32_t team_block_bytes(uint32_t n_slots) { return GC_RK_BYTES + 16 + n_slots * 16; }
 __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     TeamCtx c;
-    c.tables = smem;
+    c.tables = aes_align_tables(smem);
     c.team = threadIdx.x / p.team_threads;
     c.ttid = threadIdx.x - c.team * p.team_threads;
-    uint8_t* q = smem + AES_TABLE_BYTES;
-    c.rk = reinterpret_cast<uint32_t*>(q + c.team * GC_RK_BYTES);
-    q += p.n_teams * GC_RK_BYTES;
-    c.slots = reinterpret_cast<uint4*>(q + (size_t)c.team * p.n_slots * 16);
-    q += (size_t)p.n_teams * p.n_slots * 16;
-    c.claim = reinterpret_cast<volatile uint32_t*>(q) + c.team;
+    const uint32_t tb = team_block_bytes(p.n_slots);
+    const uint32_t in_a = (uint32_t)(c.tables - smem) / tb;               // teams that fit below the tables
+    uint8_t* q = c.team < in_a ? smem + c.team * tb : c.tables + AES_TABLE_BYTES + (c.team - in_a) * tb;
+    c.rk = reinterpret_cast<uint32_t*>(q);
+    c.claim = reinterpret_cast<volatile uint32_t*>(q + GC_RK_BYTES);
+    c.slots = reinterpret_cast<uint4*>(q + GC_RK_BYTES + 16);
     return c;
 }
 

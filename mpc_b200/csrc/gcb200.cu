@@ -54,6 +54,7 @@ constexpr uint32_t kCounterRing = 1024;
 
 struct DeviceInfo {
     int sm_count = 0;
+    uint32_t smem_base = 1024;                  // shared-window address at which dynamic shared memory starts
     uint32_t* counters = nullptr;               // ring of work-claim counters
     std::atomic<uint32_t> next{0};
 };
@@ -106,6 +107,15 @@ static void launch_eval_nr(uint32_t keylen, uint32_t ilp, dim3 g, dim3 b, size_t
     else launch_eval<14, MODE>(ilp, g, b, sm, s, p);
 }
 
+// Where dynamic shared memory starts in the shared window (the AES tables are placed at
+// the next multiple of 64 KiB, see aes_core.cuh).
+__global__ void smem_base_probe(uint32_t* out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    if (threadIdx.x == 0) *out = smem_addr(smem);
+}
+constexpr uint32_t kAssumedSmemBase = 1024;
+static uint32_t table_pad(uint32_t smem_base) { return ((smem_base + 0xffffu) & ~0xffffu) - smem_base; }
+
 int select_device(DeviceInfo** out) {
     if (tl_device < 0) {
         const char* lr = getenv("LOCAL_RANK");
@@ -132,6 +142,9 @@ int select_device(DeviceInfo** out) {
         di->sm_count = prop.multiProcessorCount;
         CK(cudaMalloc(&di->counters, kCounterRing * sizeof(uint32_t)));
         CK(cudaMemset(di->counters, 0, kCounterRing * sizeof(uint32_t)));
+        smem_base_probe<<<1, 32, 1024>>>(di->counters);
+        CK(cudaMemcpy(&di->smem_base, di->counters, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemset(di->counters, 0, sizeof(uint32_t)));
         CK(opt_in_gc());
         CK(opt_in(hash_half_kernel<10>)); CK(opt_in(hash_half_kernel<12>)); CK(opt_in(hash_half_kernel<14>));
         CK(opt_in(mitccrh_kernel));
@@ -202,20 +215,19 @@ int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* ou
 }
 
 // Team geometry for a plan: how many instances one SM keeps resident, how many
-// threads work on each, and how many AES blocks a thread interleaves.  Few large
-// instances -> few threads with deep ILP; many small ones -> one warp each.
-// GCB_ILP / GCB_TEAM_THREADS override the choice (tuning experiments).
-void team_geometry(Plan& plan) {
-    gcb_plan_info& in = plan.info;
-    const size_t avail = kSmemOptin - AES_TABLE_BYTES - 128;
-    const size_t per_team = (size_t)in.num_slots * 16 + GC_RK_BYTES;
-    size_t n = avail / per_team;
-    in.teams_per_sm = in.team_threads = 0;
-    plan.ilp = 1;
-    if (n == 0) return;
+// threads work on each, and how many AES blocks a thread interleaves.
+// GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
+struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, stagger = 0; };
+static Geometry compute_geometry(uint32_t num_slots, uint32_t smem_base) {
+    Geometry g;
+    // teams are packed below the 64 KiB-aligned tables first, then above them
+    const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
+    const size_t pad = table_pad(smem_base);
+    size_t n = pad / per_team + (kSmemOptin - pad - AES_TABLE_BYTES) / per_team;
+    if (n == 0) return g;
     if (n >= 32) n = 32; else if (n > 16) n = 16;
-    // measured on B200 (tools/tune_geometry.py, aes_128.circ): two interleaved AES
-    // blocks per thread and two-warp teams beat both deeper ILP and wider teams
+    // measured on B200 (tools/tune_geometry.py, aes_128.circ): two interleaved AES blocks
+    // per thread and three-warp teams beat both deeper ILP and wider teams
     uint32_t ilp = n <= 16 ? 2 : 1;
     if (const char* e = getenv("GCB_ILP")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) ilp = (uint32_t)v; }
     // threads per CTA: the 512-thread ILP-2 variant has 128 registers per thread and no spills
@@ -228,12 +240,20 @@ void team_geometry(Plan& plan) {
         const int v = atoi(e);
         if (v >= 32 && v % 32 == 0 && (size_t)v * n <= (ilp == 2 ? 768u : maxt) && (v == 32 || n <= 16)) tt = (uint32_t)v;
     }
-    in.teams_per_sm = (uint32_t)n; in.team_threads = tt; plan.ilp = ilp;
-    plan.stagger = n > 1 ? 100000 : 0;              // teams start ~50 us apart
-    if (const char* e = getenv("GCB_STAGGER")) plan.stagger = (uint32_t)atoi(e);
+    g.n_teams = (uint32_t)n; g.team_threads = tt; g.ilp = ilp;
+    g.stagger = n > 1 ? 100000 : 0;                 // teams start ~50 us apart
+    if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
+    return g;
 }
-size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams) {
-    return AES_TABLE_BYTES + (size_t)n_teams * GC_RK_BYTES + (size_t)n_teams * num_slots * 16 + 128;
+void team_geometry(Plan& plan) {                    // what gcb_plan_get_info reports (typical device)
+    const Geometry g = compute_geometry(plan.info.num_slots, kAssumedSmemBase);
+    plan.info.teams_per_sm = g.n_teams; plan.info.team_threads = g.team_threads;
+    plan.ilp = g.ilp; plan.stagger = g.stagger;
+}
+size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams, uint32_t smem_base) {
+    const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
+    const size_t pad = table_pad(smem_base), in_a = pad / per_team;
+    return pad + AES_TABLE_BYTES + (n_teams > in_a ? (n_teams - in_a) * per_team : 0);
 }
 
 // The plan a call runs on: the flattened one, or -- when the caller wants every wire
@@ -292,9 +312,11 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     p.tables = reinterpret_cast<uint4*>(tables);
     p.io = reinterpret_cast<uint4*>(io);
     p.wires_full = reinterpret_cast<uint4*>(wires_full);
-    p.team_threads = in.team_threads; p.n_teams = in.teams_per_sm;
+    const Geometry geo = compute_geometry(in.num_slots, di->smem_base);
+    if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
+    p.team_threads = geo.team_threads; p.n_teams = geo.n_teams;
     p.in_ids = in_ids; p.out_ids = out_ids; p.pages = pages;
-    p.stagger = plan.stagger;
+    p.stagger = geo.stagger;
     p.trace = g_trace;
     if (const char* e = getenv("GCB_DEBUG_SKIP")) p.debug_skip = (uint32_t)atoi(e);
     rc = fresh_counter(di, stream, &p.counter);
@@ -302,13 +324,13 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;
     const dim3 grid(want < (uint32_t)di->sm_count ? want : (uint32_t)di->sm_count);
     const dim3 block(p.n_teams * p.team_threads);
-    const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams);
+    const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams, di->smem_base);
     const bool full = wires_full != nullptr;
-    if (pages) launch_garble_nr<GC_STREAM>(keylen, plan.ilp, grid, block, smem, stream, p);
-    else if (garble && full) launch_garble_nr<GC_FULL>(keylen, plan.ilp, grid, block, smem, stream, p);
-    else if (garble) launch_garble_nr<GC_PLAIN>(keylen, plan.ilp, grid, block, smem, stream, p);
-    else if (full) launch_eval_nr<GC_FULL>(keylen, plan.ilp, grid, block, smem, stream, p);
-    else launch_eval_nr<GC_PLAIN>(keylen, plan.ilp, grid, block, smem, stream, p);
+    if (pages) launch_garble_nr<GC_STREAM>(keylen, geo.ilp, grid, block, smem, stream, p);
+    else if (garble && full) launch_garble_nr<GC_FULL>(keylen, geo.ilp, grid, block, smem, stream, p);
+    else if (garble) launch_garble_nr<GC_PLAIN>(keylen, geo.ilp, grid, block, smem, stream, p);
+    else if (full) launch_eval_nr<GC_FULL>(keylen, geo.ilp, grid, block, smem, stream, p);
+    else launch_eval_nr<GC_PLAIN>(keylen, geo.ilp, grid, block, smem, stream, p);
     CK(cudaGetLastError());
     return GCB_OK;
 }
@@ -463,7 +485,7 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     team_geometry(pl->p);
     if (pl->p.info.teams_per_sm == 0)
         return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; at most %zu fit on chip",
-                    pl->p.info.num_slots, (kSmemOptin - AES_TABLE_BYTES - 128 - GC_RK_BYTES) / 16);
+                    pl->p.info.num_slots, (kSmemOptin - table_pad(kAssumedSmemBase) - AES_TABLE_BYTES - GC_RK_BYTES - 16) / 16);
     pl->p.gates.assign(gates, gates + num_gates);
     *out = pl.release();
     return GCB_OK;
@@ -657,7 +679,7 @@ int gcb_hash_half_dev(const uint8_t* key, uint32_t keylen, const gcb_label* x, u
     HashParams p{key, keylen, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out), tweak0, n};
     const uint64_t want = (n + 1023) / 1024;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
-    const size_t smem = AES_TABLE_BYTES + 256;
+    const size_t smem = table_pad(di->smem_base) + AES_TABLE_BYTES + 256;
     cudaStream_t s = (cudaStream_t)stream;
     if (keylen == 16) hash_half_kernel<10><<<grid, 1024, smem, s>>>(p);
     else if (keylen == 24) hash_half_kernel<12><<<grid, 1024, smem, s>>>(p);
@@ -898,7 +920,7 @@ static int launch_iknp(bool receiver, const IknpParams& p0, void* stream) {
     const uint32_t groups = receiver ? 2 : 4;
     const uint64_t want = (nchunks + groups - 1) / groups;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
-    const size_t smem = AES_TABLE_BYTES + groups * (IKNP_STAGE_BYTES + 8192 + 128);
+    const size_t smem = table_pad(di->smem_base) + AES_TABLE_BYTES + groups * (IKNP_STAGE_BYTES + (receiver ? 8192 : 0) + 128);
     if (receiver) iknp_kernel<true><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
     else iknp_kernel<false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
     CK(cudaGetLastError());
@@ -981,7 +1003,7 @@ int gcb_mitccrh_hash_dev(const gcb_label* seed_host, uint64_t gid_start, gcb_lab
     MitccrhParams p{seed_host->d0, seed_host->d1, gid_start, reinterpret_cast<uint4*>(blks), nkeys, h};
     const uint64_t want = (nkeys + 511) / 512;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
-    mitccrh_kernel<<<grid, 512, AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
+    mitccrh_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
     return GCB_OK;
 }

@@ -35,7 +35,8 @@ struct HashParams {
 
 template <int NR>
 __global__ void __launch_bounds__(1024, 1) hash_half_kernel(const HashParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
     uint32_t* rk = reinterpret_cast<uint32_t*>(smem + AES_TABLE_BYTES);
     aes_tables_to_smem(smem);
     __syncthreads();
@@ -61,7 +62,8 @@ struct MitccrhParams {
 };
 
 __global__ void __launch_bounds__(512, 1) mitccrh_kernel(const MitccrhParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
     aes_tables_to_smem(smem);
     __syncthreads();
     const AesLane lane = aes_lane(smem);
@@ -134,17 +136,19 @@ __device__ __forceinline__ void ks_extract(const uint32_t (&W)[20], uint32_t sh,
 template <bool RECEIVER>
 __global__ void __launch_bounds__(IKNP_CTA_THREADS, 1) iknp_kernel(const IknpParams p) {
     constexpr int GT = RECEIVER ? 256 : 128;              // threads per group
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
     aes_tables_to_smem(smem);
     __syncthreads();
     const AesLane al = aes_lane(smem);
     const uint32_t group = threadIdx.x / GT, gt = threadIdx.x % GT;
     const uint32_t col = gt & 127u, lane = threadIdx.x & 31u, wcol = (gt >> 5) & 3u;
     const bool second = RECEIVER && gt >= 128;
-    uint8_t* gs = smem + AES_TABLE_BYTES + group * (IKNP_STAGE_BYTES + 8192 + 128);
+    constexpr int XCHG = RECEIVER ? 8192 : 0;                             // [16][128] T1 words (receiver only)
+    uint8_t* gs = smem + AES_TABLE_BYTES + group * (IKNP_STAGE_BYTES + XCHG + 128);
     uint32_t* stage = reinterpret_cast<uint32_t*>(gs);                    // [512][4] swizzled
-    uint32_t* xchg = reinterpret_cast<uint32_t*>(gs + IKNP_STAGE_BYTES);  // [16][128] T1 words
-    uint32_t* bbuf = reinterpret_cast<uint32_t*>(gs + IKNP_STAGE_BYTES + 8192);   // [16] + claim
+    uint32_t* xchg = reinterpret_cast<uint32_t*>(gs + IKNP_STAGE_BYTES);
+    uint32_t* bbuf = reinterpret_cast<uint32_t*>(gs + IKNP_STAGE_BYTES + XCHG);   // [16] + claim
     volatile uint32_t* claim = bbuf + 16;
     const uint32_t bar_id = group + 1;
 

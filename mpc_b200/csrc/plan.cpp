@@ -89,15 +89,11 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
     plan.row_off[ng] = row;
     auto is_free_def = [&](int64_t d) { return d >= (int64_t)ninit && spec.gates[(size_t)d - ninit].op <= OP_XNOR; };
 
-    // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
-    // free gate of a later phase, or by the caller afterwards
-    std::vector<uint8_t> required(ng, keep_all ? 1 : 0);
-    for (uint32_t i = 0; i < ng; i++) {
-        const bool cipher = spec.gates[i].op >= OP_AND;
-        for (const int64_t d : {def_a[i], def_b[i]})
-            if (is_free_def(d) && (cipher || phase_of[(size_t)d - ninit] != phase_of[i])) required[(size_t)d - ninit] = 1;
-    }
-    std::vector<int64_t> out_def(spec.live_out.size());
+    // ---- the latest phase at which each gate may run without lengthening the schedule
+    // (ALAP): a ciphered gate must run one level before its earliest consumer, a free gate
+    // no later than it.  Gates whose output nothing reads stay where ASAP put them.
+    const std::vector<uint32_t> asap(phase_of);
+    std::vector<uint8_t> is_out_def(ndefs, 0);
     for (size_t k = 0; k < spec.live_out.size(); k++) {
         const uint32_t l = spec.live_out[k];
         if (l >= nloc || cur_def[l] < 0) {
@@ -105,198 +101,270 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             err = msg;
             return GCB_E_WIRE;
         }
-        out_def[k] = cur_def[l];
-        if (is_free_def(cur_def[l])) required[(size_t)cur_def[l] - ninit] = 1;
+        is_out_def[(size_t)cur_def[l]] = 1;
     }
+    auto alap_levels = [&](bool cipher_asap) {
+        constexpr uint32_t kNone = 0xffffffffu;
+        std::vector<uint32_t> need(ndefs, kNone);          // latest phase in which the definition may appear
+        const uint32_t last_phase = n_phases ? n_phases - 1 : 0;
+        for (size_t d = 0; d < ndefs; d++) if (is_out_def[d]) need[d] = last_phase;
+        std::vector<uint32_t> lv(ng);
+        for (uint32_t i = ng; i-- > 0;) {
+            const bool cipher = spec.gates[i].op >= OP_AND;
+            uint32_t l = need[ninit + i];
+            if (cipher) l = (l == kNone || cipher_asap) ? asap[i] : (l == 0 ? 0 : l - 1);
+            else if (l == kNone) l = asap[i];
+            if (l < asap[i]) l = asap[i];
+            lv[i] = l;
+            // what this gate demands of its inputs: available in phase lv (free producers) --
+            // the kernel runs a phase's free wires before its cipher level
+            for (const int64_t d : {def_a[i], def_b[i]}) need[(size_t)d] = std::min(need[(size_t)d], lv[i]);
+        }
+        return lv;
+    };
 
-    // ---- pass 3: flatten the free gates of each phase into nodes of bounded fan-in.
-    // flat[i] = the leaves whose XOR is gate i's output: definitions that exist when the
-    // phase starts, or nodes of the same phase that had to be cut off to respect the fan-in
-    // limit (a "forced" node).  Same-phase free inputs are otherwise inlined, which keeps
-    // the dependency depth (waves) low.
-    struct Node { uint32_t gate; uint32_t wave; uint8_t parity; std::vector<uint32_t> leaves; };
-    std::vector<std::vector<uint32_t>> flat(ng);
-    std::vector<uint8_t> parity(ng, 0), forced(ng, 0), emitted(ng, 0);
-    std::vector<uint32_t> wave_of(ng, 0);
-    std::vector<std::vector<Node>> phase_nodes(n_phases);
-    auto sym_diff = [](const std::vector<uint32_t>& x, const std::vector<uint32_t>& y, std::vector<uint32_t>& o) {
-        o.clear();
-        std::set_symmetric_difference(x.begin(), x.end(), y.begin(), y.end(), std::back_inserter(o));
-    };
-    auto emit_node = [&](uint32_t i) {
-        if (emitted[i]) return;
-        emitted[i] = 1;
-        uint32_t w = 0;
-        for (uint32_t l : flat[i])
-            if (is_free_def(l) && phase_of[l - ninit] == phase_of[i]) w = std::max(w, wave_of[l - ninit] + 1);
-        wave_of[i] = w;
-        phase_nodes[phase_of[i]].push_back(Node{i, w, parity[i], flat[i]});
-    };
-    std::vector<uint32_t> la, lb, tmp;
-    for (uint32_t i = 0; i < ng; i++) {
-        const gcb_gate& g = spec.gates[i];
-        if (g.op > OP_XNOR) continue;
-        for (int attempt = 0;; attempt++) {
-            uint8_t par = g.op == OP_XNOR;
-            auto leafset = [&](int64_t d, std::vector<uint32_t>& o) {
-                if (is_free_def(d) && phase_of[(size_t)d - ninit] == phase_of[i] && !forced[(size_t)d - ninit] && !keep_all) {
-                    o = flat[(size_t)d - ninit];
-                    par ^= parity[(size_t)d - ninit];
-                } else {
-                    o.assign(1, (uint32_t)d);
+    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out) -> int {
+        // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
+        // free gate of a later phase, or by the caller afterwards
+        std::vector<uint8_t> required(ng, keep_all ? 1 : 0);
+        for (uint32_t i = 0; i < ng; i++) {
+            const bool cipher = spec.gates[i].op >= OP_AND;
+            for (const int64_t d : {def_a[i], def_b[i]})
+                if (is_free_def(d) && (cipher || phase_of[(size_t)d - ninit] != phase_of[i])) required[(size_t)d - ninit] = 1;
+        }
+        std::vector<int64_t> out_def(spec.live_out.size());
+        for (size_t k = 0; k < spec.live_out.size(); k++) {
+            const uint32_t l = spec.live_out[k];
+            if (l >= nloc || cur_def[l] < 0) {
+                snprintf(msg, sizeof msg, "wire %u not assigned", l);
+                err = msg;
+                return GCB_E_WIRE;
+            }
+            out_def[k] = cur_def[l];
+            if (is_free_def(cur_def[l])) required[(size_t)cur_def[l] - ninit] = 1;
+        }
+
+        // ---- pass 3: flatten the free gates of each phase into nodes of bounded fan-in.
+        // flat[i] = the leaves whose XOR is gate i's output: definitions that exist when the
+        // phase starts, or nodes of the same phase that had to be cut off to respect the fan-in
+        // limit (a "forced" node).  Same-phase free inputs are otherwise inlined, which keeps
+        // the dependency depth (waves) low.
+        struct Node { uint32_t gate; uint32_t wave; uint8_t parity; std::vector<uint32_t> leaves; };
+        std::vector<std::vector<uint32_t>> flat(ng);
+        std::vector<uint8_t> parity(ng, 0), forced(ng, 0), emitted(ng, 0);
+        std::vector<uint32_t> wave_of(ng, 0);
+        std::vector<std::vector<Node>> phase_nodes(n_phases);
+        auto sym_diff = [](const std::vector<uint32_t>& x, const std::vector<uint32_t>& y, std::vector<uint32_t>& o) {
+            o.clear();
+            std::set_symmetric_difference(x.begin(), x.end(), y.begin(), y.end(), std::back_inserter(o));
+        };
+        auto emit_node = [&](uint32_t i) {
+            if (emitted[i]) return;
+            emitted[i] = 1;
+            uint32_t w = 0;
+            for (uint32_t l : flat[i])
+                if (is_free_def(l) && phase_of[l - ninit] == phase_of[i]) w = std::max(w, wave_of[l - ninit] + 1);
+            wave_of[i] = w;
+            phase_nodes[phase_of[i]].push_back(Node{i, w, parity[i], flat[i]});
+        };
+        std::vector<uint32_t> la, lb, tmp;
+        for (uint32_t i = 0; i < ng; i++) {
+            const gcb_gate& g = spec.gates[i];
+            if (g.op > OP_XNOR) continue;
+            for (int attempt = 0;; attempt++) {
+                uint8_t par = g.op == OP_XNOR;
+                auto leafset = [&](int64_t d, std::vector<uint32_t>& o) {
+                    if (is_free_def(d) && phase_of[(size_t)d - ninit] == phase_of[i] && !forced[(size_t)d - ninit] && !keep_all) {
+                        o = flat[(size_t)d - ninit];
+                        par ^= parity[(size_t)d - ninit];
+                    } else {
+                        o.assign(1, (uint32_t)d);
+                    }
+                };
+                leafset(def_a[i], la);
+                leafset(def_b[i], lb);
+                sym_diff(la, lb, tmp);
+                if (tmp.size() <= K || attempt == 2) { flat[i] = tmp; parity[i] = par; break; }
+                // too wide: cut off the wider inlined input as a node of its own and refer to it
+                const int64_t cand = (la.size() >= lb.size() && la.size() > 1) ? def_a[i] : (lb.size() > 1 ? def_b[i] : def_a[i]);
+                const uint32_t cg = (uint32_t)((size_t)cand - ninit);
+                emit_node(cg);
+                forced[cg] = 1;
+            }
+            if (required[i]) emit_node(i);
+        }
+
+        // ---- pass 4: the time axis (one step per wave, one per cipher level), liveness
+        std::vector<std::vector<uint32_t>> phase_cipher(n_phases);
+        for (uint32_t i = 0; i < ng; i++)
+            if (spec.gates[i].op >= OP_AND) phase_cipher[phase_of[i]].push_back(i);
+        std::vector<int64_t> born(ndefs, -1), last(ndefs, -1);
+        std::vector<uint32_t> wave_step0(n_phases, 0), cipher_step(n_phases, 0), n_waves(n_phases, 0);
+        int64_t nsteps = 0;
+        for (uint32_t p = 0; p < n_phases; p++) {
+            for (const Node& nd : phase_nodes[p]) n_waves[p] = std::max(n_waves[p], nd.wave + 1);
+            wave_step0[p] = (uint32_t)nsteps;
+            nsteps += n_waves[p];
+            cipher_step[p] = (uint32_t)nsteps;
+            if (!phase_cipher[p].empty()) nsteps++;
+        }
+        for (uint32_t p = 0; p < n_phases; p++) {
+            for (const Node& nd : phase_nodes[p]) {
+                const int64_t s = wave_step0[p] + nd.wave;
+                born[ninit + nd.gate] = s;
+                for (uint32_t l : nd.leaves) last[l] = std::max(last[l], s);
+            }
+            for (uint32_t i : phase_cipher[p]) {
+                const int64_t s = cipher_step[p];
+                born[ninit + i] = s;
+                last[def_a[i]] = std::max(last[def_a[i]], s);
+                last[def_b[i]] = std::max(last[def_b[i]], s);
+            }
+        }
+        for (const int64_t d : out_def) last[(size_t)d] = kForever;
+        for (size_t d = 0; d < ndefs; d++) last[d] = std::max(last[d], born[d]);
+
+        // ---- slots: lowest free index first; a slot whose value was last read in step s may
+        // be rewritten from step s+1 on (reads and writes of one step are unordered).
+        std::vector<std::vector<size_t>> expire((size_t)nsteps + 1);
+        std::vector<uint32_t> slot(ndefs, 0);
+        std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_slots;
+        uint32_t next_slot = 0;
+        out.live_in.clear();
+        for (size_t k = 0; k < ninit; k++) {
+            slot[k] = next_slot++;
+            out.live_in.push_back(SlotRef{slot[k], (uint32_t)k});
+            if (last[k] < 0) free_slots.push(slot[k]);                 // never read, not live-out
+            else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
+        }
+        auto take_slot = [&](size_t d) {
+            if (free_slots.empty()) slot[d] = next_slot++;
+            else { slot[d] = free_slots.top(); free_slots.pop(); }
+            if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+        };
+        {
+            int64_t s = 0;
+            auto advance = [&]() {
+                if (s > 0) {
+                    for (size_t d : expire[(size_t)s - 1]) free_slots.push(slot[d]);
+                    expire[(size_t)s - 1].clear();
                 }
             };
-            leafset(def_a[i], la);
-            leafset(def_b[i], lb);
-            sym_diff(la, lb, tmp);
-            if (tmp.size() <= K || attempt == 2) { flat[i] = tmp; parity[i] = par; break; }
-            // too wide: cut off the wider inlined input as a node of its own and refer to it
-            const int64_t cand = (la.size() >= lb.size() && la.size() > 1) ? def_a[i] : (lb.size() > 1 ? def_b[i] : def_a[i]);
-            const uint32_t cg = (uint32_t)((size_t)cand - ninit);
-            emit_node(cg);
-            forced[cg] = 1;
-        }
-        if (required[i]) emit_node(i);
-    }
-
-    // ---- pass 4: the time axis (one step per wave, one per cipher level), liveness
-    std::vector<std::vector<uint32_t>> phase_cipher(n_phases);
-    for (uint32_t i = 0; i < ng; i++)
-        if (spec.gates[i].op >= OP_AND) phase_cipher[phase_of[i]].push_back(i);
-    std::vector<int64_t> born(ndefs, -1), last(ndefs, -1);
-    std::vector<uint32_t> wave_step0(n_phases, 0), cipher_step(n_phases, 0), n_waves(n_phases, 0);
-    int64_t nsteps = 0;
-    for (uint32_t p = 0; p < n_phases; p++) {
-        for (const Node& nd : phase_nodes[p]) n_waves[p] = std::max(n_waves[p], nd.wave + 1);
-        wave_step0[p] = (uint32_t)nsteps;
-        nsteps += n_waves[p];
-        cipher_step[p] = (uint32_t)nsteps;
-        if (!phase_cipher[p].empty()) nsteps++;
-    }
-    for (uint32_t p = 0; p < n_phases; p++) {
-        for (const Node& nd : phase_nodes[p]) {
-            const int64_t s = wave_step0[p] + nd.wave;
-            born[ninit + nd.gate] = s;
-            for (uint32_t l : nd.leaves) last[l] = std::max(last[l], s);
-        }
-        for (uint32_t i : phase_cipher[p]) {
-            const int64_t s = cipher_step[p];
-            born[ninit + i] = s;
-            last[def_a[i]] = std::max(last[def_a[i]], s);
-            last[def_b[i]] = std::max(last[def_b[i]], s);
-        }
-    }
-    for (const int64_t d : out_def) last[(size_t)d] = kForever;
-    for (size_t d = 0; d < ndefs; d++) last[d] = std::max(last[d], born[d]);
-
-    // ---- slots: lowest free index first; a slot whose value was last read in step s may
-    // be rewritten from step s+1 on (reads and writes of one step are unordered).
-    std::vector<std::vector<size_t>> expire((size_t)nsteps + 1);
-    std::vector<uint32_t> slot(ndefs, 0);
-    std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_slots;
-    uint32_t next_slot = 0;
-    plan.live_in.clear();
-    for (size_t k = 0; k < ninit; k++) {
-        slot[k] = next_slot++;
-        plan.live_in.push_back(SlotRef{slot[k], (uint32_t)k});
-        if (last[k] < 0) free_slots.push(slot[k]);                 // never read, not live-out
-        else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
-    }
-    auto take_slot = [&](size_t d) {
-        if (free_slots.empty()) slot[d] = next_slot++;
-        else { slot[d] = free_slots.top(); free_slots.pop(); }
-        if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
-    };
-    {
-        int64_t s = 0;
-        auto advance = [&]() {
-            if (s > 0) {
-                for (size_t d : expire[(size_t)s - 1]) free_slots.push(slot[d]);
-                expire[(size_t)s - 1].clear();
+            for (uint32_t p = 0; p < n_phases; p++) {
+                // nodes sorted by (wave, fan-in descending) so that the lanes of a warp do similar work
+                std::stable_sort(phase_nodes[p].begin(), phase_nodes[p].end(), [](const Node& x, const Node& y) {
+                    if (x.wave != y.wave) return x.wave < y.wave;
+                    return x.leaves.size() > y.leaves.size();
+                });
+                size_t pos = 0;
+                for (uint32_t w = 0; w < n_waves[p]; w++, s++) {
+                    advance();
+                    for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++)
+                        take_slot(ninit + phase_nodes[p][pos].gate);
+                }
+                if (!phase_cipher[p].empty()) {
+                    advance();
+                    for (uint32_t i : phase_cipher[p]) take_slot(ninit + i);
+                    s++;
+                }
             }
-        };
+        }
+        if (next_slot > 65535) {
+            snprintf(msg, sizeof msg, "circuit needs %u live wire slots (limit 65535)", next_slot);
+            err = msg;
+            return GCB_E_TOO_LARGE;
+        }
+        out.live_out.clear();
+        for (size_t k = 0; k < spec.live_out.size(); k++)
+            out.live_out.push_back(SlotRef{slot[(size_t)out_def[k]], (uint32_t)k});
+
+        // ---- records in schedule order
+        out.phases.clear(); out.waves.clear(); out.nodes.clear(); out.crecs.clear();
+        out.nout_wire.clear(); out.cout_wire.clear();
+        out.node_loads = 0;
         for (uint32_t p = 0; p < n_phases; p++) {
-            // nodes sorted by (wave, fan-in descending) so that the lanes of a warp do similar work
-            std::stable_sort(phase_nodes[p].begin(), phase_nodes[p].end(), [](const Node& x, const Node& y) {
-                if (x.wave != y.wave) return x.wave < y.wave;
-                return x.leaves.size() > y.leaves.size();
-            });
+            PhaseRec ph{};
+            ph.wave_first = (uint32_t)out.waves.size();
+            ph.n_waves = n_waves[p];
             size_t pos = 0;
-            for (uint32_t w = 0; w < n_waves[p]; w++, s++) {
-                advance();
-                for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++)
-                    take_slot(ninit + phase_nodes[p][pos].gate);
+            for (uint32_t w = 0; w < n_waves[p]; w++) {
+                WaveRec wr{(uint32_t)out.nodes.size(), 0};
+                for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++) {
+                    const Node& nd = phase_nodes[p][pos];
+                    NodeRec r{};
+                    r.dst = (uint16_t)slot[ninit + nd.gate];
+                    r.k = (uint8_t)nd.leaves.size();
+                    r.parity = nd.parity;
+                    for (size_t j = 0; j < nd.leaves.size(); j++) r.leaf[j] = (uint16_t)slot[nd.leaves[j]];
+                    out.nodes.push_back(r);
+                    out.nout_wire.push_back(spec.gates[nd.gate].out);
+                    out.node_loads += r.k;
+                    wr.count++;
+                }
+                out.waves.push_back(wr);
+                if (w == 0) { ph.w0_first = wr.first; ph.w0_count = wr.count; }
             }
-            if (!phase_cipher[p].empty()) {
-                advance();
-                for (uint32_t i : phase_cipher[p]) take_slot(ninit + i);
-                s++;
+            // ciphered gates: AND/OR first, then INV (the kernels give 4 / 2 tasks to each)
+            std::stable_sort(phase_cipher[p].begin(), phase_cipher[p].end(), [&](uint32_t x, uint32_t y) {
+                return op_class(spec.gates[x].op) < op_class(spec.gates[y].op);
+            });
+            ph.cipher_first = (uint32_t)out.crecs.size();
+            for (uint32_t i : phase_cipher[p]) {
+                const gcb_gate& g = spec.gates[i];
+                out.crecs.push_back(GateRec{(uint16_t)slot[(size_t)def_a[i]], (uint16_t)slot[(size_t)def_b[i]],
+                                             (uint16_t)slot[ninit + i], g.op, 0, tweak_of[i], plan.row_off[i]});
+                out.cout_wire.push_back(g.out);
+                (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
             }
+            out.phases.push_back(ph);
         }
-    }
-    if (next_slot > 65535) {
-        snprintf(msg, sizeof msg, "circuit needs %u live wire slots (limit 65535)", next_slot);
-        err = msg;
-        return GCB_E_TOO_LARGE;
-    }
-    plan.live_out.clear();
-    for (size_t k = 0; k < spec.live_out.size(); k++)
-        plan.live_out.push_back(SlotRef{slot[(size_t)out_def[k]], (uint32_t)k});
 
-    // ---- records in schedule order
-    plan.phases.clear(); plan.waves.clear(); plan.nodes.clear(); plan.crecs.clear();
-    plan.nout_wire.clear(); plan.cout_wire.clear();
-    plan.node_loads = 0;
-    for (uint32_t p = 0; p < n_phases; p++) {
-        PhaseRec ph{};
-        ph.wave_first = (uint32_t)plan.waves.size();
-        ph.n_waves = n_waves[p];
-        size_t pos = 0;
-        for (uint32_t w = 0; w < n_waves[p]; w++) {
-            WaveRec wr{(uint32_t)plan.nodes.size(), 0};
-            for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++) {
-                const Node& nd = phase_nodes[p][pos];
-                NodeRec r{};
-                r.dst = (uint16_t)slot[ninit + nd.gate];
-                r.k = (uint8_t)nd.leaves.size();
-                r.parity = nd.parity;
-                for (size_t j = 0; j < nd.leaves.size(); j++) r.leaf[j] = (uint16_t)slot[nd.leaves[j]];
-                plan.nodes.push_back(r);
-                plan.nout_wire.push_back(spec.gates[nd.gate].out);
-                plan.node_loads += r.k;
-                wr.count++;
-            }
-            plan.waves.push_back(wr);
-            if (w == 0) { ph.w0_first = wr.first; ph.w0_count = wr.count; }
-        }
-        // ciphered gates: AND/OR first, then INV (the kernels give 4 / 2 tasks to each)
-        std::stable_sort(phase_cipher[p].begin(), phase_cipher[p].end(), [&](uint32_t x, uint32_t y) {
-            return op_class(spec.gates[x].op) < op_class(spec.gates[y].op);
-        });
-        ph.cipher_first = (uint32_t)plan.crecs.size();
-        for (uint32_t i : phase_cipher[p]) {
-            const gcb_gate& g = spec.gates[i];
-            plan.crecs.push_back(GateRec{(uint16_t)slot[(size_t)def_a[i]], (uint16_t)slot[(size_t)def_b[i]],
-                                         (uint16_t)slot[ninit + i], g.op, 0, tweak_of[i], plan.row_off[i]});
-            plan.cout_wire.push_back(g.out);
-            (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
-        }
-        plan.phases.push_back(ph);
-    }
+        gcb_plan_info& in = out.info;
+        in = gcb_plan_info{};
+        in.num_gates = ng;
+        in.num_wires = nw;
+        in.num_inputs = (uint32_t)ninit;
+        in.num_outputs = (uint32_t)spec.live_out.size();
+        in.num_rows = row;
+        in.num_tweaks = tweak;
+        in.num_steps = (uint32_t)nsteps;
+        in.num_slots = next_slot;
+        in.num_and = n_and; in.num_or = n_or; in.num_inv = n_inv; in.num_free = n_free;
+        in.garble_hashes = 4 * n_and + 4 * n_or + 2 * n_inv;
+        in.eval_hashes = 2 * n_and + n_or + n_inv;
+        return GCB_OK;
+    };
 
-    gcb_plan_info& in = plan.info;
-    in = gcb_plan_info{};
-    in.num_gates = ng;
-    in.num_wires = nw;
-    in.num_inputs = (uint32_t)ninit;
-    in.num_outputs = (uint32_t)spec.live_out.size();
-    in.num_rows = row;
-    in.num_tweaks = tweak;
-    in.num_steps = (uint32_t)nsteps;
-    in.num_slots = next_slot;
-    in.num_and = n_and; in.num_or = n_or; in.num_inv = n_inv; in.num_free = n_free;
-    in.garble_hashes = 4 * n_and + 4 * n_or + 2 * n_inv;
-    in.eval_hashes = 2 * n_and + n_or + n_inv;
+    // ---- try the schedules and keep the one that needs the fewest wire slots
+    int best_rc = GCB_OK;
+    {
+        Plan best;
+        bool have = false;
+        std::string first_err;
+        for (int policy = 0; policy < 3; policy++) {
+            std::vector<uint32_t> ph = policy == 0 ? asap : alap_levels(policy == 2);
+            Plan cand;
+            cand.row_off = plan.row_off; cand.ops = plan.ops;
+            const int rc = schedule(ph, cand);
+            if (rc != GCB_OK) { if (!have && first_err.empty()) { first_err = err; best_rc = rc; } continue; }
+            if (!have || cand.info.num_slots < best.info.num_slots ||
+                (cand.info.num_slots == best.info.num_slots && cand.info.num_steps < best.info.num_steps)) {
+                best.info = cand.info; best.ilp = cand.ilp; best.stagger = cand.stagger;
+                best.phases.swap(cand.phases); best.waves.swap(cand.waves); best.nodes.swap(cand.nodes);
+                best.crecs.swap(cand.crecs); best.nout_wire.swap(cand.nout_wire); best.cout_wire.swap(cand.cout_wire);
+                best.live_in.swap(cand.live_in); best.live_out.swap(cand.live_out);
+                best.node_loads = cand.node_loads;
+                have = true;
+            }
+            if (keep_all) break;                     // the full-wire plan keeps the simple schedule
+        }
+        if (!have) { err = first_err; return best_rc; }
+        plan.info = best.info;
+        plan.phases.swap(best.phases); plan.waves.swap(best.waves); plan.nodes.swap(best.nodes);
+        plan.crecs.swap(best.crecs); plan.nout_wire.swap(best.nout_wire); plan.cout_wire.swap(best.cout_wire);
+        plan.live_in.swap(best.live_in); plan.live_out.swap(best.live_out);
+        plan.node_loads = best.node_loads;
+    }
     return GCB_OK;
 }
 

@@ -46,7 +46,8 @@ __global__ void k_lds(uint32_t* out, int iters, long long* cycles) {
 // C: real AES-128 rounds, U interleaved blocks per thread, round keys in smem
 template <int U>
 __global__ void k_aes(uint4* out, int iters, long long* cycles) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
     aes_tables_to_smem(smem);
     uint32_t* rk = (uint32_t*)(smem + AES_TABLE_BYTES);
     if (threadIdx.x < 44) rk[threadIdx.x] = threadIdx.x * 0x9e3779b9u;
@@ -77,8 +78,8 @@ __global__ void k_aes(uint4* out, int iters, long long* cycles) {
 
 // C2: AES-128 rounds with only T0/T1 resident (64 KiB); T2 = rot16(T0), T3 = rot16(T1) by PRMT
 template <int T, int K> __device__ __forceinline__ uint32_t te2(const AesLane& a, uint32_t s) {
-    const uint32_t e = __byte_perm(s, a.lane4, 0x5504 | (K << 4));
-    const uint32_t v = lds_u32(a.tb + (T & 1) * 128 + e);
+    const uint32_t e = __byte_perm(s, a.lb, 0x7604 | (K << 4));
+    const uint32_t v = lds_u32_off<(T & 1) * 128>(e);
     return (T & 2) ? __byte_perm(v, 0, 0x1032) : v;
 }
 __device__ __forceinline__ void aes_round2(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3, const uint4 k) {
@@ -90,7 +91,8 @@ __device__ __forceinline__ void aes_round2(const AesLane& a, uint32_t& s0, uint3
 }
 template <int U>
 __global__ void k_aes2(uint4* out, int iters, long long* cycles) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
     aes_tables_to_smem(smem);
     uint32_t* rk = (uint32_t*)(smem + AES_TABLE_BYTES);
     if (threadIdx.x < 44) rk[threadIdx.x] = threadIdx.x * 0x9e3779b9u;
@@ -136,7 +138,7 @@ int main() {
     int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     uint4* out; long long* cyc; CK(cudaMalloc(&out, 148 * 1024 * 16)); CK(cudaMalloc(&cyc, 148 * 8));
     long long h[148];
-    const int smem = AES_TABLE_BYTES + 1024;
+    const int smem = 65536 + AES_TABLE_BYTES + 1024;
     CK(cudaFuncSetAttribute(k_lds<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_lds<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_lds<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
