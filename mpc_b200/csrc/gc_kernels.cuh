@@ -159,11 +159,18 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
 // Gate index of cipher task t of a phase.  Garble: 4 tasks per AND/OR, 2 per INV;
 // eval: 2 per AND/OR (OR uses one), 1 per INV.
 struct Phase {
-    uint32_t wave_first, n_waves, cipher_first, n_quad, n_inv, w0_first, w0_count;
+    uint32_t wave_first, n_waves, cipher_first, n_quad, n_inv, w0_first, wc01, wc23;
 };
 __device__ __forceinline__ Phase load_phase(const uint4* phases, uint32_t i) {
     const uint4 a = __ldg(phases + 2 * i), b = __ldg(phases + 2 * i + 1);
-    return Phase{a.x, a.y, a.z, a.w, b.x, b.y, b.z};
+    return Phase{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+}
+// Node count of wave w of a phase: waves 0..3 are inline in the PhaseRec.
+__device__ __forceinline__ uint32_t wave_count(const GcParams& p, const Phase& ph, uint32_t w) {
+    uint32_t c = 0xffffu;
+    if (w < 4) { const uint32_t pair = w < 2 ? ph.wc01 : ph.wc23; c = (w & 1) ? pair >> 16 : pair & 0xffffu; }
+    if (c == 0xffffu) c = __ldg(p.waves + ph.wave_first + w).y;
+    return c;
 }
 template <bool GARBLE>
 __device__ __forceinline__ uint32_t task_gate(const Phase& ph, uint32_t t, uint32_t& k) {
@@ -249,42 +256,37 @@ __device__ __forceinline__ void run_nodes(const GcParams& p, uint4* slots, const
     }
 }
 
-template <bool GARBLE, bool FULL, int NU>
-__device__ __forceinline__ void wave_group(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t first,
-                                           uint32_t count, uint32_t w, uint32_t j, uint32_t ttid, uint32_t TT,
-                                           const NodeRegs& pre) {
-    uint32_t index[NU];
-    NodeRegs n[NU];
-    bool active[NU];
-#pragma unroll
-    for (int u = 0; u < NU; u++) {
-        const uint32_t ju = j + u * TT;
-        index[u] = first + ju;
-        active[u] = ju < count;
-        n[u] = NodeRegs{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (active[u]) n[u] = (w == 0 && ju == ttid) ? pre : load_node(p.nodes, first + ju);
-    }
-    run_nodes<GARBLE, FULL, NU>(p, slots, R, inst, index, n, active);
-}
-
-// All node waves of a phase.  `pre` is this thread's first node of wave 0 (index
-// w0_first + ttid), loaded during the previous phase.
-template <bool GARBLE, bool FULL, int NILP>
+// All node waves of a phase, one node per thread at a time.  `pre` is this thread's first
+// node of wave 0 (index w0_first + ttid), loaded during the previous phase; the first node
+// of wave w+1 is loaded while wave w runs.
+template <bool GARBLE, bool FULL>
 __device__ __forceinline__ void run_waves(const GcParams& p, uint4* slots, const Label R, uint32_t inst, const Phase& ph,
                                           uint32_t team, uint32_t ttid, uint32_t TT, const NodeRegs& pre) {
+    const NodeRegs zero{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    uint32_t first = ph.w0_first;
+    uint32_t count = ph.n_waves ? wave_count(p, ph, 0) : 0u;
+    NodeRegs cur = pre;
     for (uint32_t w = 0; w < ph.n_waves; w++) {
-        uint32_t first = ph.w0_first, count = ph.w0_count;
-        if (w) { const uint2 wr = __ldg(p.waves + ph.wave_first + w); first = wr.x; count = wr.y; }
+        const uint32_t next_first = first + count;
+        uint32_t next_count = 0;
+        NodeRegs nxt = zero;
+        if (w + 1 < ph.n_waves) {
+            next_count = wave_count(p, ph, w + 1);
+            if (ttid < next_count) nxt = load_node(p.nodes, next_first + ttid);
+        }
         // this warp's nodes: j = ttid + i*TT, i < n_i (warp-uniform)
         const uint32_t wbase = ttid & ~31u;
         const uint32_t n_i = count > wbase ? (count - wbase + TT - 1) / TT : 0u;
-        for (uint32_t i = 0; i < n_i;) {
-            const uint32_t left = n_i - i, j = ttid + i * TT;
-            if (NILP >= 4 && left >= 3) { wave_group<GARBLE, FULL, (NILP >= 4 ? 4 : 1)>(p, slots, R, inst, first, count, w, j, ttid, TT, pre); i += 4; }
-            else if (NILP >= 2 && left >= 2) { wave_group<GARBLE, FULL, (NILP >= 2 ? 2 : 1)>(p, slots, R, inst, first, count, w, j, ttid, TT, pre); i += 2; }
-            else { wave_group<GARBLE, FULL, 1>(p, slots, R, inst, first, count, w, j, ttid, TT, pre); i += 1; }
+        for (uint32_t i = 0; i < n_i; i++) {
+            const uint32_t j = ttid + i * TT;
+            const uint32_t index[1] = {first + j};
+            const bool active[1] = {j < count};
+            NodeRegs n[1] = {cur};
+            if (i) { n[0] = zero; if (active[0]) n[0] = load_node(p.nodes, first + j); }
+            run_nodes<GARBLE, FULL, 1>(p, slots, R, inst, index, n, active);
         }
         team_barrier(team, TT);
+        first = next_first; count = next_count; cur = nxt;
     }
 }
 
@@ -407,7 +409,6 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
 template <int NR, int MODE, int ILP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     constexpr bool FULL = MODE == GC_FULL;
-    constexpr int NILP = 1;   // nodes a thread works on at once (measured: wider groups issue too many predicated-off loads)
     constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         // plan records of the first phases load while the inputs do
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
         NodeRegs npre{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ttid < ph.w0_count) npre = load_node(p.nodes, ph.w0_first + ttid);
+        if (ph.n_waves && ttid < wave_count(p, ph, 0)) npre = load_node(p.nodes, ph.w0_first + ttid);
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
@@ -461,11 +462,11 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             uint4 pre[GC_PRE];
             prefetch_cipher<true>(p, ph, ttid, TT, pre);
             NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (ttid < ph_n.w0_count) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
+            if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
-            if (!(p.debug_skip & 1)) run_waves<true, FULL, NILP>(p, slots, R, inst, ph, tc.team, ttid, TT, npre);
+            if (!(p.debug_skip & 1)) run_waves<true, FULL>(p, slots, R, inst, ph, tc.team, ttid, TT, npre);
             if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
             const uint32_t ntask = (p.debug_skip & 2) ? 0u : task_count<true>(ph);
@@ -570,7 +571,6 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
 template <int NR, int MODE, int ILP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     constexpr bool FULL = MODE == GC_FULL;
-    constexpr int NILP = 1;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
     aes_tables_to_smem(tc.tables);
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
         NodeRegs npre{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ttid < ph.w0_count) npre = load_node(p.nodes, ph.w0_first + ttid);
+        if (ph.n_waves && ttid < wave_count(p, ph, 0)) npre = load_node(p.nodes, ph.w0_first + ttid);
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
             const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
@@ -608,8 +608,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             uint4 pre[GC_PRE];
             prefetch_cipher<false>(p, ph, ttid, TT, pre);
             NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (ttid < ph_n.w0_count) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
-            run_waves<false, FULL, NILP>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
+            if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
+            run_waves<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);

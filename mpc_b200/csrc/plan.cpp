@@ -302,7 +302,8 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                     wr.count++;
                 }
                 out.waves.push_back(wr);
-                if (w == 0) { ph.w0_first = wr.first; ph.w0_count = wr.count; }
+                if (w == 0) ph.w0_first = wr.first;
+                if (w < 4) ph.wave_count[w] = (uint16_t)(wr.count < 0xffffu ? wr.count : 0xffffu);
             }
             // ciphered gates: AND/OR first, then INV (the kernels give 4 / 2 tasks to each)
             std::stable_sort(phase_cipher[p].begin(), phase_cipher[p].end(), [&](uint32_t x, uint32_t y) {

@@ -57,8 +57,8 @@ struct PhaseRec {
     uint32_t wave_first, n_waves;     // range in the WaveRec array
     uint32_t cipher_first, n_quad;    // range in the GateRec array: n_quad AND/OR gates ...
     uint32_t n_inv;                   // ... then n_inv INV gates
-    uint32_t w0_first, w0_count;      // copy of the first wave (saves a dependent load)
-    uint32_t pad;
+    uint32_t w0_first;                // first node of the phase; its waves are contiguous in the NodeRec array
+    uint16_t wave_count[4];           // node counts of waves 0..3 (saves dependent loads); 0xffff = see WaveRec
 };
 static_assert(sizeof(PhaseRec) == 32, "PhaseRec must be 32 bytes");
 
