@@ -423,13 +423,27 @@ static int ensure_wires(gcb_stream* s, uint32_t max_id) {
     return GCB_OK;
 }
 
-// One staging pipe per (host thread, device), kept across calls so that repeated
-// Garble / Eval calls do not re-allocate their arenas.
-static HostPipe& thread_pipe(int device) {
-    static thread_local std::map<int, std::unique_ptr<HostPipe>> pipes;
-    auto& p = pipes[device];
-    if (!p) p = std::make_unique<HostPipe>();
-    return *p;
+// Staging pipes are pooled per device and checked out for the duration of one host-pointer
+// call, so that repeated Garble / Eval calls -- from any host thread -- reuse warm arenas
+// and streams instead of re-allocating them.
+struct PipeLease {
+    int device;
+    std::unique_ptr<HostPipe> pipe;
+    PipeLease(int dev);
+    ~PipeLease();
+    HostPipe& operator*() { return *pipe; }
+};
+static std::mutex g_pipe_mu;
+static std::map<int, std::vector<std::unique_ptr<HostPipe>>> g_pipe_pool;
+PipeLease::PipeLease(int dev) : device(dev) {
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    auto& v = g_pipe_pool[dev];
+    if (!v.empty()) { pipe = std::move(v.back()); v.pop_back(); }
+    else pipe = std::make_unique<HostPipe>();
+}
+PipeLease::~PipeLease() {
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    g_pipe_pool[device].push_back(std::move(pipe));
 }
 
 }  // namespace gcb
@@ -459,7 +473,7 @@ int gcb_device_count(void) {
 void* gcb_host_alloc(size_t bytes) {
     if (select_device(nullptr)) return nullptr;
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         fail(GCB_E_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -557,24 +571,22 @@ int gcb_garble(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint3
     if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
     const gcb_plan_info& in = use->info;
     const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
-    HostPipe& pipe = thread_pipe(tl_device);
+    PipeLease lease(tl_device);
+    HostPipe& pipe = *lease;
     if ((rc = pipe.init())) return rc;
     const size_t per_inst = 16 + nin * 16 + rows * 16 + (io_wires ? (nin + nout) * 32 : 0) +
                             (wires_full ? nw * 32 : 0) + (key_stride ? key_stride : 0);
-    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm * (uint32_t)di->sm_count);
-    DevBuf dkey;
-    if (!key_stride) {
-        CK(dkey.alloc(keylen));
-        CK(cudaMemcpy(dkey.p, keys, keylen, cudaMemcpyHostToDevice));
-    }
+    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm ? in.teams_per_sm : 1);
     for (uint32_t b0 = 0, k = 0; b0 < batch; b0 += slice, k++) {
         const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
         HostPipe::Slot& s = pipe.slot(k);
         if ((rc = s.begin())) return rc;
-        const uint8_t* dk = dkey.as<uint8_t>();
-        if (key_stride) {
-            if ((rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk))) return rc;
-        }
+        // the key(s) travel with every slice: no per-call device allocation (cudaFree would
+        // synchronise the whole device and serialise concurrent callers)
+        const uint8_t* dk = nullptr;
+        if (key_stride) rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk);
+        else rc = s.in(keys, keylen, (const void**)&dk);
+        if (rc) return rc;
         const gcb_label *dr, *dl0 = nullptr;
         if ((rc = s.in(r + b0, (size_t)nb * 16, (const void**)&dr))) return rc;
         if (nin && (rc = s.in(in_l0 + (size_t)b0 * nin, (size_t)nb * nin * 16, (const void**)&dl0))) return rc;
@@ -608,23 +620,21 @@ int gcb_eval(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_
     if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
     const gcb_plan_info& in = use->info;
     const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
-    HostPipe& pipe = thread_pipe(tl_device);
+    PipeLease lease(tl_device);
+    HostPipe& pipe = *lease;
     if ((rc = pipe.init())) return rc;
     const size_t per_inst = nin * 16 + rows * 16 + nout * 16 + (wires_full ? nw * 16 : 0) + key_stride;
-    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm * (uint32_t)di->sm_count);
-    DevBuf dkey;
-    if (!key_stride) {
-        CK(dkey.alloc(keylen));
-        CK(cudaMemcpy(dkey.p, keys, keylen, cudaMemcpyHostToDevice));
-    }
+    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm ? in.teams_per_sm : 1);
     for (uint32_t b0 = 0, k = 0; b0 < batch; b0 += slice, k++) {
         const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
         HostPipe::Slot& s = pipe.slot(k);
         if ((rc = s.begin())) return rc;
-        const uint8_t* dk = dkey.as<uint8_t>();
-        if (key_stride) {
-            if ((rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk))) return rc;
-        }
+        // the key(s) travel with every slice: no per-call device allocation (cudaFree would
+        // synchronise the whole device and serialise concurrent callers)
+        const uint8_t* dk = nullptr;
+        if (key_stride) rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk);
+        else rc = s.in(keys, keylen, (const void**)&dk);
+        if (rc) return rc;
         const gcb_label *dt = nullptr, *dil = nullptr;
         if (rows && (rc = s.in(tables + (size_t)b0 * rows, (size_t)nb * rows * 16, (const void**)&dt))) return rc;
         if (nin && (rc = s.in(in_labels + (size_t)b0 * nin, (size_t)nb * nin * 16, (const void**)&dil))) return rc;

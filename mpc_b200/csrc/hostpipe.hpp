@@ -1,7 +1,7 @@
 // hostpipe.hpp -- staging of HOST buffers through the device for the host-pointer
 // entry points of the C ABI.
 //
-// A call is cut into slices; slice k uses slot k % 3.  Each slot owns a CUDA
+// A call is cut into slices; slice k uses slot k % kSlots.  Each slot owns a CUDA
 // stream and a device arena, so the host->device copy of one slice, the kernel
 // of the previous one and the device->host copy of the one before overlap.
 // User memory that is already page-locked (allocated with gcb_host_alloc, or
@@ -33,7 +33,7 @@ struct Arena {
         if (bytes <= cap) return cudaSuccess;
         release();
         bytes = (bytes + (1u << 20)) & ~((size_t)(1u << 20) - 1);
-        cudaError_t e = pinned_host ? cudaHostAlloc((void**)&base, bytes, cudaHostAllocDefault)
+        cudaError_t e = pinned_host ? cudaHostAlloc((void**)&base, bytes, cudaHostAllocMapped | cudaHostAllocPortable)
                                     : cudaMalloc((void**)&base, bytes);
         if (e == cudaSuccess) cap = bytes;
         return e;
@@ -52,10 +52,15 @@ inline bool is_pinned(const void* p) {
 }
 
 struct HostPipe {
-    static constexpr int kSlots = 3;
-    static constexpr size_t kSliceBytes = 160u << 20;
+    static constexpr int kSlots = 4;
+    static constexpr size_t kSliceBytes = 48u << 20;   // ~1 ms of PCIe per slice: copies of one slice hide the kernel of the next
 
-    struct Region { const void* src; void* dst; size_t bytes, dev_off, pin_off; bool pinned; };
+    // Regions up to this size are not copied at all: the kernel reads / writes the page-locked
+    // host memory directly (UVA).  Besides saving a copy this keeps small transfers out of the
+    // copy-engine queues, where they would wait behind other callers' bulk table copies.
+    static constexpr size_t kZeroCopyBytes = 4u << 20;
+
+    struct Region { const void* src; void* dst; size_t bytes, dev_off, pin_off; bool pinned; bool zero_copy; };
 
     struct Slot {
         cudaStream_t compute = nullptr;
@@ -86,32 +91,50 @@ struct HostPipe {
         }
         // Declare an input / output region; *dptr receives its device address
         // (valid once upload() has run, which may re-allocate the arenas).
-        std::vector<void**> fixups;
+        struct Fixup { void** where; bool from_pin; bool direct; void* direct_ptr; };
+        std::vector<Fixup> fixups;
+        static void* mapped_ptr(const void* host) {       // device view of page-locked host memory, or null
+            void* d = nullptr;
+            if (cudaHostGetDevicePointer(&d, const_cast<void*>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return d;
+        }
         int in(const void* src, size_t bytes, const void** dptr) {
-            Region r{src, nullptr, bytes, dev.take(bytes), 0, is_pinned(src)};
+            Region r{src, nullptr, bytes, 0, 0, is_pinned(src), bytes <= kZeroCopyBytes};
+            void* direct = (r.pinned && r.zero_copy) ? mapped_ptr(src) : nullptr;
+            if (r.pinned && r.zero_copy && !direct) r.zero_copy = false;
             if (!r.pinned) r.pin_off = pin.take(bytes);
+            if (!r.zero_copy) r.dev_off = dev.take(bytes);
             ins.push_back(r);
-            fixups.push_back(const_cast<void**>(reinterpret_cast<const void**>(dptr)));
-            *dptr = reinterpret_cast<const void*>(r.dev_off);
+            fixups.push_back(Fixup{const_cast<void**>(reinterpret_cast<const void**>(dptr)), r.zero_copy && !r.pinned, direct != nullptr, direct});
+            *dptr = reinterpret_cast<const void*>(r.zero_copy ? r.pin_off : r.dev_off);
             return GCB_OK;
         }
         int out(void* dst, size_t bytes, void** dptr) {
-            Region r{nullptr, dst, bytes, dev.take(bytes), 0, is_pinned(dst)};
+            Region r{nullptr, dst, bytes, 0, 0, is_pinned(dst), bytes <= kZeroCopyBytes};
+            void* direct = (r.pinned && r.zero_copy) ? mapped_ptr(dst) : nullptr;
+            if (r.pinned && r.zero_copy && !direct) r.zero_copy = false;
             if (!r.pinned) r.pin_off = pin.take(bytes);
+            if (!r.zero_copy) r.dev_off = dev.take(bytes);
             outs.push_back(r);
-            fixups.push_back(dptr);
-            *dptr = reinterpret_cast<void*>(r.dev_off);
+            fixups.push_back(Fixup{dptr, r.zero_copy && !r.pinned, direct != nullptr, direct});
+            *dptr = reinterpret_cast<void*>(r.zero_copy ? r.pin_off : r.dev_off);
             return GCB_OK;
         }
         int upload() {
             int rc = check(dev.reserve(dev.used), "device staging allocation");
             if (rc) return rc;
             if (pin.used && (rc = check(pin.reserve(pin.used), "pinned staging allocation"))) return rc;
-            for (void** f : fixups) *f = dev.base + reinterpret_cast<size_t>(*f);
+            uint8_t* pin_dev = pin.base ? static_cast<uint8_t*>(mapped_ptr(pin.base)) : nullptr;
+            for (const Fixup& f : fixups) {
+                if (f.direct) *f.where = f.direct_ptr;
+                else if (f.from_pin) *f.where = pin_dev + reinterpret_cast<size_t>(*f.where);
+                else *f.where = dev.base + reinterpret_cast<size_t>(*f.where);
+            }
             fixups.clear();
             for (const Region& r : ins) {
                 const void* h = r.src;
                 if (!r.pinned) { memcpy(pin.base + r.pin_off, r.src, r.bytes); h = pin.base + r.pin_off; }
+                if (r.zero_copy) continue;                 // the kernel reads it in place
                 rc = check(cudaMemcpyAsync(dev.base + r.dev_off, h, r.bytes, cudaMemcpyHostToDevice, compute), "H2D copy");
                 if (rc) return rc;
             }
@@ -120,6 +143,7 @@ struct HostPipe {
         }
         int download() {
             for (const Region& r : outs) {
+                if (r.zero_copy) continue;                 // the kernel wrote it in place
                 void* h = r.pinned ? r.dst : (void*)(pin.base + r.pin_off);
                 int rc = check(cudaMemcpyAsync(h, dev.base + r.dev_off, r.bytes, cudaMemcpyDeviceToHost, compute), "D2H copy");
                 if (rc) return rc;
@@ -142,14 +166,13 @@ struct HostPipe {
         return GCB_OK;
     }
     Slot& slot(uint32_t k) { return slots[k % kSlots]; }
-    // Instances per slice: whole waves of `resident` instances, about kSliceBytes.
-    uint32_t slice_for(size_t per_inst, uint32_t batch, uint32_t resident) const {
-        if (resident == 0) resident = 1;
-        const size_t wave_bytes = per_inst * resident;
-        size_t waves = kSliceBytes / (wave_bytes ? wave_bytes : 1);
-        if (waves == 0) waves = 1;
-        const size_t s = waves * resident;
-        return s >= batch ? batch : (uint32_t)s;
+    // Instances per slice: about kSliceBytes, a multiple of `granule` (instances one SM holds).
+    uint32_t slice_for(size_t per_inst, uint32_t batch, uint32_t granule) const {
+        if (granule == 0) granule = 1;
+        size_t n = kSliceBytes / (per_inst ? per_inst : 1);
+        n = n / granule * granule;
+        if (n < granule) n = granule;
+        return n >= batch ? batch : (uint32_t)n;
     }
     int finish() {
         int rc = GCB_OK;
