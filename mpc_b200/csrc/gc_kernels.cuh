@@ -33,7 +33,6 @@ namespace gcb {
 
 constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-barrier teams
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
-constexpr int GC_PRE = 6;                 // cipher records per thread loaded ahead of the cipher level
 
 struct GcParams {
     const uint4* phases;                  // PhaseRec[] (two uint4 each) followed by two zero records
@@ -160,10 +159,11 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
 // eval: 2 per AND/OR (OR uses one), 1 per INV.
 struct Phase {
     uint32_t wave_first, n_waves, cipher_first, n_quad, n_inv, w0_first, wc01, wc23;
+    bool has_or;
 };
 __device__ __forceinline__ Phase load_phase(const uint4* phases, uint32_t i) {
     const uint4 a = __ldg(phases + 2 * i), b = __ldg(phases + 2 * i + 1);
-    return Phase{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    return Phase{a.x, a.y & 0x7fffffffu, a.z, a.w, b.x, b.y, b.z, b.w, (a.y >> 31) != 0};
 }
 // Node count of wave w of a phase: waves 0..3 are inline in the PhaseRec.
 __device__ __forceinline__ uint32_t wave_count(const GcParams& p, const Phase& ph, uint32_t w) {
@@ -187,24 +187,18 @@ __device__ __forceinline__ uint32_t task_count(const Phase& ph) {
     return GARBLE ? 4 * ph.n_quad + 2 * ph.n_inv : 2 * ph.n_quad + ph.n_inv;
 }
 
-// Cipher records of this thread's first GC_PRE tasks (t = k*TT + ttid) of a phase.
-template <bool GARBLE>
-__device__ __forceinline__ void prefetch_cipher(const GcParams& p, const Phase& ph, uint32_t ttid, uint32_t TT,
-                                                uint4 (&pre)[GC_PRE]) {
+// Cipher records of this thread's tasks (k0 + j)*TT + ttid, j < N, of a phase.
+template <bool GARBLE, int N>
+__device__ __forceinline__ void prefetch_cipher(const GcParams& p, const Phase& ph, uint32_t k0, uint32_t ttid, uint32_t TT,
+                                                uint4 (&rec)[N]) {
     const uint32_t ntask = task_count<GARBLE>(ph);
 #pragma unroll
-    for (int j = 0; j < GC_PRE; j++) {
+    for (int j = 0; j < N; j++) {
         uint32_t k;
-        const uint32_t t = j * TT + ttid;
-        pre[j] = make_uint4(0, 0, 0, 0);
-        if (t < ntask) pre[j] = __ldg(p.crecs + task_gate<GARBLE>(ph, t, k));
+        const uint32_t t = (k0 + j) * TT + ttid;
+        rec[j] = make_uint4(0, 0, 0, 0);
+        if (t < ntask) rec[j] = __ldg(p.crecs + task_gate<GARBLE>(ph, t, k));
     }
-}
-__device__ __forceinline__ uint4 pick(const uint4 (&pre)[GC_PRE], uint32_t i) {
-    uint4 r = pre[0];
-#pragma unroll
-    for (int j = 1; j < GC_PRE; j++) if (i == (uint32_t)j) r = pre[j];
-    return r;
 }
 
 // One node: dst = XOR of its leaves (^ R for an odd number of XNORs on the way,
@@ -308,13 +302,61 @@ struct GarbleEnv {
 };
 
 // One pass of UU cipher tasks per thread: tasks (k0 + j)*TT + ttid.
-template <int NR, int MODE, int UU>
+template <int NR, int MODE, int UU, int ILP, bool AND_ONLY>
 __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv& e, const Phase& ph, uint32_t ntask,
-                                            uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&pre)[GC_PRE]) {
+                                            uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP]) {
+    static_assert(UU <= ILP, "pass wider than the record buffer");
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
     uint4* const slots = e.slots;
     const Label R = e.R;
+    if constexpr (AND_ONLY) {
+        // every task of the pass belongs to an AND gate: (a0,j0) (a1,j0) (b0,j1) (b1,j1) on four
+        // adjacent lanes (garble.go:353-395; the reference hashes a0 and b0 twice)
+        const uint32_t k = ttid & 3u;
+        Label keep[UU], K[UU], H[UU];
+        uint32_t pab[UU];
+#pragma unroll
+        for (int j = 0; j < UU; j++) {
+            const uint4 g = rec[j];
+            const Label a0 = lds_label(slots, g.x & 0xffff), b0 = lds_label(slots, g.x >> 16);
+            pab[j] = 2 * label_s(a0) + label_s(b0);
+            keep[j] = a0;
+            Label x = (k & 2) ? b0 : a0;
+            x = x ^ label_and_mask(R, mask_of(k));
+            K[j] = label_shl(x, 1);
+            K[j].w3 ^= g.z + (k >> 1);
+        }
+        aes_hash_multi<NR, UU>(lane, e.rk, K, H);
+#pragma unroll
+        for (int j = 0; j < UU; j++) {
+            const uint4 g = rec[j];
+            const Label h = H[j];
+            const uint32_t pa = pab[j] >> 1, pb = pab[j] & 1;
+            const Label u = h ^ shfl_xor_label(h, 1);
+            Label v = Label{0, 0, 0, 0};
+            if (k == 0) {                                      // generator half (garble.go:361-369)
+                const Label tg = u ^ label_and_mask(R, mask_of(pb));
+                v = h ^ label_and_mask(tg, mask_of(pa));
+                e.tab[g.w] = label_to_mem(tg);
+            } else if (k == 2) {                               // evaluator half (garble.go:372-380)
+                v = h ^ label_and_mask(u, mask_of(pb));
+                e.tab[g.w + 1] = label_to_mem(u ^ keep[j]);
+            }
+            const Label w2 = v ^ shfl_xor_label(v, 2);
+            if (k == 0) {                                      // combine halves (garble.go:383-392)
+                sts_label(slots, g.y & 0xffff, w2);
+                if (FULL) {
+                    uint32_t kk;
+                    const uint32_t gi = task_gate<true>(ph, (k0 + j) * TT + ttid, kk);
+                    uint4* w = p.wires_full + ((size_t)e.inst * p.n_wires + __ldg(p.cout_wire + gi)) * 2;
+                    w[0] = label_to_mem(w2);
+                    w[1] = label_to_mem(w2 ^ R);
+                }
+            }
+        }
+        return;
+    }
     uint4 g[UU];
     Label a0[UU], K[UU], H[UU];
     uint32_t op[UU], kk[UU], pp[UU], gidx[UU];
@@ -324,8 +366,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
         const bool active = t < ntask;
         uint32_t k;
         const uint32_t gi = task_gate<true>(ph, t, k);
-        if (k0 + j < GC_PRE) g[j] = pick(pre, k0 + j);
-        else { g[j] = make_uint4(0, 0, 0, 0); if (active) g[j] = __ldg(p.crecs + gi); }
+        g[j] = rec[j];
         const uint32_t sa = g[j].x & 0xffff, sb = g[j].x >> 16;
         op[j] = active ? ((g[j].y >> 16) & 0xff) : 0xffu;
         kk[j] = k; gidx[j] = gi;
@@ -459,8 +500,8 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
 
         for (uint32_t pi = 0; pi < p.n_phases; pi++) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);  // two zero records of padding
-            uint4 pre[GC_PRE];
-            prefetch_cipher<true>(p, ph, ttid, TT, pre);
+            uint4 cur[ILP];
+            prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
             NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
             if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
@@ -472,11 +513,26 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             const uint32_t ntask = (p.debug_skip & 2) ? 0u : task_count<true>(ph);
             if (ntask) {
                 const uint32_t per_thread = (ntask + TT - 1) / TT;        // tasks k = 0 .. per_thread-1
+                const uint32_t and_tasks = ph.has_or ? 0u : 4 * ph.n_quad;  // leading tasks that are all AND
                 for (uint32_t k0 = 0; k0 < per_thread;) {
                     const uint32_t left = per_thread - k0;
-                    if (ILP >= 4 && left >= 3) { garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 4; }
-                    else if (ILP >= 2 && left >= 2) { garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 2; }
-                    else { if (k0 * TT + (ttid & ~31u) < ntask) garble_pass<NR, MODE, 1>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 1; }
+                    const uint32_t uu = (ILP >= 4 && left >= 3) ? 4u : (ILP >= 2 && left >= 2) ? 2u : 1u;
+                    uint4 nxt[ILP];                                        // records of the next pass, in flight during this one
+                    prefetch_cipher<true, ILP>(p, ph, k0 + uu, ttid, TT, nxt);
+                    const bool and_only = (k0 + uu) * TT <= and_tasks;
+                    if (ILP >= 4 && uu == 4) {
+                        if (and_only) garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                    } else if (ILP >= 2 && uu == 2) {
+                        if (and_only) garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                    } else if (k0 * TT + (ttid & ~31u) < ntask) {
+                        if (and_only) garble_pass<NR, MODE, 1, ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else garble_pass<NR, MODE, 1, ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                    }
+                    k0 += uu;
+#pragma unroll
+                    for (int j = 0; j < ILP; j++) cur[j] = nxt[j];
                 }
                 if (tracing) p.trace[4 * pi + 3] = clock64();
                 team_barrier(tc.team, TT);
@@ -511,12 +567,45 @@ struct EvalEnv {
     uint32_t inst;
 };
 
-template <int NR, int MODE, int UU>
+template <int NR, int MODE, int UU, int ILP, bool AND_ONLY>
 __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e, const Phase& ph, uint32_t ntask,
-                                          uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&pre)[GC_PRE]) {
+                                          uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP]) {
+    static_assert(UU <= ILP, "pass wider than the record buffer");
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
     uint4* const slots = e.slots;
+    if constexpr (AND_ONLY) {
+        // every task of the pass belongs to an AND gate: lane pair (a, j0) (b, j1), eval.go:52-78
+        const uint32_t k = ttid & 1u;
+        Label K[UU], H[UU], row[UU];
+#pragma unroll
+        for (int j = 0; j < UU; j++) {
+            const uint4 g = rec[j];
+            const Label a = lds_label(slots, g.x & 0xffff), b = lds_label(slots, g.x >> 16);
+            const Label x = k ? b : a;
+            row[j] = Label{0, 0, 0, 0};
+            if (label_s(x)) row[j] = label_from_mem(__ldg(e.tab + g.w + k));   // tg when S(a), te when S(b)
+            if (k) row[j] = row[j] ^ label_and_mask(a, mask_of(label_s(b)));   // we ^= a when S(b)
+            K[j] = label_shl(x, 1);
+            K[j].w3 ^= g.z + k;
+        }
+        aes_hash_multi<NR, UU>(lane, e.rk, K, H);
+#pragma unroll
+        for (int j = 0; j < UU; j++) {
+            const uint4 g = rec[j];
+            const Label v = H[j] ^ row[j];
+            const Label o = v ^ shfl_xor_label(v, 1);
+            if (k == 0) {
+                sts_label(slots, g.y & 0xffff, o);
+                if (FULL) {
+                    uint32_t kk;
+                    const uint32_t gi = task_gate<false>(ph, (k0 + j) * TT + ttid, kk);
+                    p.wires_full[(size_t)e.inst * p.n_wires + __ldg(p.cout_wire + gi)] = label_to_mem(o);
+                }
+            }
+        }
+        return;
+    }
     uint4 g[UU];
     Label K[UU], H[UU], row[UU];
     uint32_t op[UU], kk[UU], gidx[UU];
@@ -527,8 +616,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
         act[j] = t < ntask;
         uint32_t k;
         const uint32_t gi = task_gate<false>(ph, t, k);
-        if (k0 + j < GC_PRE) g[j] = pick(pre, k0 + j);
-        else { g[j] = make_uint4(0, 0, 0, 0); if (act[j]) g[j] = __ldg(p.crecs + gi); }
+        g[j] = rec[j];
         const uint32_t sa = g[j].x & 0xffff, sb = g[j].x >> 16;
         op[j] = act[j] ? ((g[j].y >> 16) & 0xff) : 0xffu;
         kk[j] = k; gidx[j] = gi;
@@ -605,8 +693,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
 
         for (uint32_t pi = 0; pi < p.n_phases; pi++) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);
-            uint4 pre[GC_PRE];
-            prefetch_cipher<false>(p, ph, ttid, TT, pre);
+            uint4 cur[ILP];
+            prefetch_cipher<false, ILP>(p, ph, 0, ttid, TT, cur);
             NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
             if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
             run_waves<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
@@ -615,11 +703,26 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             const uint32_t ntask = task_count<false>(ph);
             if (ntask) {
                 const uint32_t per_thread = (ntask + TT - 1) / TT;
+                const uint32_t and_tasks = ph.has_or ? 0u : 2 * ph.n_quad;  // leading tasks that are all AND
                 for (uint32_t k0 = 0; k0 < per_thread;) {
                     const uint32_t left = per_thread - k0;
-                    if (ILP >= 4 && left >= 3) { eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 4; }
-                    else if (ILP >= 2 && left >= 2) { eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1)>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 2; }
-                    else { if (k0 * TT + (ttid & ~31u) < ntask) eval_pass<NR, MODE, 1>(lane, env, ph, ntask, k0, ttid, TT, pre); k0 += 1; }
+                    const uint32_t uu = (ILP >= 4 && left >= 3) ? 4u : (ILP >= 2 && left >= 2) ? 2u : 1u;
+                    uint4 nxt[ILP];                                        // records of the next pass, in flight during this one
+                    prefetch_cipher<false, ILP>(p, ph, k0 + uu, ttid, TT, nxt);
+                    const bool and_only = (k0 + uu) * TT <= and_tasks;
+                    if (ILP >= 4 && uu == 4) {
+                        if (and_only) eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                    } else if (ILP >= 2 && uu == 2) {
+                        if (and_only) eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                    } else if (k0 * TT + (ttid & ~31u) < ntask) {
+                        if (and_only) eval_pass<NR, MODE, 1, ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else eval_pass<NR, MODE, 1, ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                    }
+                    k0 += uu;
+#pragma unroll
+                    for (int j = 0; j < ILP; j++) cur[j] = nxt[j];
                 }
                 team_barrier(tc.team, TT);
             }

@@ -316,6 +316,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                                              (uint16_t)slot[ninit + i], g.op, 0, tweak_of[i], plan.row_off[i]});
                 out.cout_wire.push_back(g.out);
                 (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
+                if (g.op == OP_OR) ph.n_waves |= 0x80000000u;       // flag: the level has OR gates (no AND-only fast path)
             }
             out.phases.push_back(ph);
         }

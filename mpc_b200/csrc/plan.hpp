@@ -54,7 +54,7 @@ struct WaveRec {
 // previous cipher level, followed by one level of ciphered gates: AND/OR first,
 // then INV.
 struct PhaseRec {
-    uint32_t wave_first, n_waves;     // range in the WaveRec array
+    uint32_t wave_first, n_waves;     // range in the WaveRec array; bit 31 of n_waves: the level has OR gates
     uint32_t cipher_first, n_quad;    // range in the GateRec array: n_quad AND/OR gates ...
     uint32_t n_inv;                   // ... then n_inv INV gates
     uint32_t w0_first;                // first node of the phase; its waves are contiguous in the NodeRec array
