@@ -212,6 +212,23 @@ int gcb_iknp_sender_expand_dev(const gcb_label *k, const gcb_label *delta, uint6
                                const uint8_t *u, size_t u_len, uint64_t n, gcb_label *labels,
                                void *stream);
 
+/* Bit-COT variants.  Replace IKNPReceiver.ReceiveBits (ot/iknp.go:554-620) and
+ * IKNPSender.SendBits (ot/iknp.go:259-310), used by gmw/triples.go:335-422: the
+ * same U exchange, the output is Bit(0) of every label packed LSB-first into
+ * uint64 words ((n+63)/64 words, overwritten).  choices: the packed []uint64 of
+ * the Go API; as in the reference they are XORed into U in whole 64-bit words
+ * (words = byteRows / 8 per chunk), and the _dev variant reads choice words up to
+ * the end of the last 512-row chunk. */
+int gcb_iknp_receiver_expand_bits(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
+                                  const uint64_t *choices, uint64_t n, uint8_t *u_out, uint64_t *result);
+int gcb_iknp_sender_expand_bits(const gcb_label k[128], const gcb_label *delta, uint64_t stream_pos,
+                                const uint8_t *u, size_t u_len, uint64_t n, uint64_t *result);
+int gcb_iknp_receiver_expand_bits_dev(const gcb_label *k0, const gcb_label *k1, uint64_t stream_pos,
+                                      const uint64_t *choices, uint64_t n, uint8_t *u_out, uint64_t *result,
+                                      void *stream);
+int gcb_iknp_sender_expand_bits_dev(const gcb_label *k, const gcb_label *delta, uint64_t stream_pos,
+                                    const uint8_t *u, size_t u_len, uint64_t n, uint64_t *result, void *stream);
+
 /* ----------------------------------------------------------------- MiTCCRH --- */
 /* Replaces MITCCRH.Hash (ot/mitccrh.go:93-128) over many keys at once: key
  * number g (renewKeys :70-89) is BE64(seed.D0 ^ g) || BE64(seed.D1); key

@@ -68,6 +68,10 @@ SYMBOLS = {
     "gcb_iknp_sender_expand": (_int, [_vp, _vp, _u64, _vp, _sz, _u64, _vp]),
     "gcb_iknp_receiver_expand_dev": (_int, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "gcb_iknp_sender_expand_dev": (_int, [_vp, _vp, _u64, _vp, _sz, _u64, _vp, _vp]),
+    "gcb_iknp_receiver_expand_bits": (_int, [_vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "gcb_iknp_sender_expand_bits": (_int, [_vp, _vp, _u64, _vp, _sz, _u64, _vp]),
+    "gcb_iknp_receiver_expand_bits_dev": (_int, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "gcb_iknp_sender_expand_bits_dev": (_int, [_vp, _vp, _u64, _vp, _sz, _u64, _vp, _vp]),
     "gcb_mitccrh_hash": (_int, [C.POINTER(Label), _u64, _vp, _u64, _u32]),
     "gcb_mitccrh_hash_dev": (_int, [C.POINTER(Label), _u64, _vp, _u64, _u32, _vp]),
 }

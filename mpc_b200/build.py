@@ -18,7 +18,7 @@ HEADERS = ["aes_core.cuh", "gc_kernels.cuh", "ot_kernels.cuh", "stream_kernels.c
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "--use_fast_math",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", "-diag-suppress", "128",
 ]
 
 

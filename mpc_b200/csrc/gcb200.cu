@@ -148,7 +148,8 @@ int select_device(DeviceInfo** out) {
         CK(opt_in_gc());
         CK(opt_in(hash_half_kernel<10>)); CK(opt_in(hash_half_kernel<12>)); CK(opt_in(hash_half_kernel<14>));
         CK(opt_in(mitccrh_kernel));
-        CK(opt_in(iknp_kernel<false>)); CK(opt_in(iknp_kernel<true>));
+        CK(opt_in(iknp_kernel<false, false>)); CK(opt_in(iknp_kernel<true, false>));
+        CK(opt_in(iknp_kernel<false, true>)); CK(opt_in(iknp_kernel<true, true>));
         slot = std::move(di);
     }
     if (out) *out = slot.get();
@@ -919,7 +920,7 @@ uint64_t gcb_iknp_stream_advance(uint64_t n) {
     return full * 64 + (rem + 7) / 8;
 }
 
-static int launch_iknp(bool receiver, const IknpParams& p0, void* stream) {
+static int launch_iknp(bool receiver, bool bits, const IknpParams& p0, void* stream) {
     DeviceInfo* di;
     int rc = select_device(&di);
     if (rc) return rc;
@@ -931,8 +932,10 @@ static int launch_iknp(bool receiver, const IknpParams& p0, void* stream) {
     const uint64_t want = (nchunks + groups - 1) / groups;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
     const size_t smem = table_pad(di->smem_base) + AES_TABLE_BYTES + groups * (IKNP_STAGE_BYTES + (receiver ? 8192 : 0) + 128);
-    if (receiver) iknp_kernel<true><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
-    else iknp_kernel<false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
+    if (receiver && bits) iknp_kernel<true, true><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
+    else if (receiver) iknp_kernel<true, false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
+    else if (bits) iknp_kernel<false, true><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
+    else iknp_kernel<false, false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
     CK(cudaGetLastError());
     return GCB_OK;
 }
@@ -947,7 +950,7 @@ int gcb_iknp_receiver_expand_dev(const gcb_label* k0, const gcb_label* k1, uint6
     p.k0 = reinterpret_cast<const uint4*>(k0); p.k1 = reinterpret_cast<const uint4*>(k1);
     p.stream_pos = stream_pos; p.choice = choice; p.u_out = u_out;
     p.labels = reinterpret_cast<uint4*>(labels); p.n = n;
-    return launch_iknp(true, p, stream);
+    return launch_iknp(true, false, p, stream);
 }
 int gcb_iknp_sender_expand_dev(const gcb_label* k, const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
                                size_t u_len, uint64_t n, gcb_label* labels, void* stream) {
@@ -959,7 +962,7 @@ int gcb_iknp_sender_expand_dev(const gcb_label* k, const gcb_label* delta, uint6
     IknpParams p{};
     p.k0 = reinterpret_cast<const uint4*>(k); p.delta = reinterpret_cast<const uint4*>(delta);
     p.stream_pos = stream_pos; p.u_in = u; p.labels = reinterpret_cast<uint4*>(labels); p.n = n;
-    return launch_iknp(false, p, stream);
+    return launch_iknp(false, false, p, stream);
 }
 
 int gcb_iknp_receiver_expand(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
@@ -998,6 +1001,77 @@ int gcb_iknp_sender_expand(const gcb_label k[128], const gcb_label* delta, uint6
                                     n, dl.as<gcb_label>(), nullptr);
     if (rc) return rc;
     CK(cudaMemcpy(labels, dl.p, n * 16, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+// Bit-COT variants: ReceiveBits / SendBits (ot/iknp.go:554-620, 259-310).  choices / result are
+// the packed LSB-first []uint64 of the Go API ((n+63)/64 words; result is overwritten).
+int gcb_iknp_receiver_expand_bits_dev(const gcb_label* k0, const gcb_label* k1, uint64_t stream_pos,
+                                      const uint64_t* choices, uint64_t n, uint8_t* u_out, uint64_t* result,
+                                      void* stream) {
+    if (!k0 || !k1 || (n && (!choices || !u_out || !result))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    if (reinterpret_cast<uintptr_t>(u_out) & 15) return fail(GCB_E_ARG, "u_out must be 16-byte aligned");
+    CK(cudaMemsetAsync(result, 0, ((n + 63) / 64) * 8, (cudaStream_t)stream));
+    IknpParams p{};
+    p.k0 = reinterpret_cast<const uint4*>(k0); p.k1 = reinterpret_cast<const uint4*>(k1);
+    p.stream_pos = stream_pos; p.choice_bits = reinterpret_cast<const uint32_t*>(choices); p.u_out = u_out;
+    p.result_bits = reinterpret_cast<uint32_t*>(result); p.n = n;
+    return launch_iknp(true, true, p, stream);
+}
+int gcb_iknp_sender_expand_bits_dev(const gcb_label* k, const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
+                                    size_t u_len, uint64_t n, uint64_t* result, void* stream) {
+    if (!k || !delta || (n && (!u || !result))) return fail(GCB_E_ARG, "null argument");
+    if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
+                                                 (unsigned long long)n);
+    if (n == 0) return GCB_OK;
+    if (reinterpret_cast<uintptr_t>(u) & 15) return fail(GCB_E_ARG, "u must be 16-byte aligned");
+    CK(cudaMemsetAsync(result, 0, ((n + 63) / 64) * 8, (cudaStream_t)stream));
+    IknpParams p{};
+    p.k0 = reinterpret_cast<const uint4*>(k); p.delta = reinterpret_cast<const uint4*>(delta);
+    p.stream_pos = stream_pos; p.u_in = u; p.result_bits = reinterpret_cast<uint32_t*>(result); p.n = n;
+    return launch_iknp(false, true, p, stream);
+}
+int gcb_iknp_receiver_expand_bits(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
+                                  const uint64_t* choices, uint64_t n, uint8_t* u_out, uint64_t* result) {
+    if (!k0 || !k1 || (n && (!choices || !u_out || !result))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    const size_t ul = gcb_iknp_u_size(n), words = (n + 63) / 64;
+    // the reference reads whole 64-bit choice words per full 8-byte row group: round the copy up to the chunk
+    const size_t cwords = ((n + 511) / 512) * 8;
+    DevBuf dk, dc, du, dr;
+    CK(dk.alloc(256 * 16)); CK(dc.alloc(cwords * 8)); CK(du.alloc(ul)); CK(dr.alloc(words * 8));
+    CK(cudaMemset(dc.p, 0, cwords * 8));
+    CK(cudaMemcpy(dk.p, k0, 128 * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.as<gcb_label>() + 128, k1, 128 * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dc.p, choices, words * 8, cudaMemcpyHostToDevice));
+    rc = gcb_iknp_receiver_expand_bits_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, dc.as<uint64_t>(), n,
+                                           du.as<uint8_t>(), dr.as<uint64_t>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(u_out, du.p, ul, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(result, dr.p, words * 8, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+int gcb_iknp_sender_expand_bits(const gcb_label k[128], const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
+                                size_t u_len, uint64_t n, uint64_t* result) {
+    if (!k || !delta || (n && (!u || !result))) return fail(GCB_E_ARG, "null argument");
+    if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
+                                                 (unsigned long long)n);
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    const size_t words = (n + 63) / 64;
+    DevBuf dk, du, dr;
+    CK(dk.alloc(129 * 16)); CK(du.alloc(u_len)); CK(dr.alloc(words * 8));
+    CK(cudaMemcpy(dk.p, k, 128 * 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dk.as<gcb_label>() + 128, delta, 16, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du.p, u, u_len, cudaMemcpyHostToDevice));
+    rc = gcb_iknp_sender_expand_bits_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, du.as<uint8_t>(), u_len, n,
+                                         dr.as<uint64_t>(), nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(result, dr.p, words * 8, cudaMemcpyDeviceToHost));
     return GCB_OK;
 }
 

@@ -94,7 +94,9 @@ struct IknpParams {
     const uint4* k1;          // [128] receiver only: the L1 seeds
     const uint4* delta;       // sender only
     uint64_t stream_pos;      // keystream bytes already consumed by every column PRG
-    const uint8_t* choice;    // receiver: n bytes of 0/1
+    const uint8_t* choice;    // receiver: n bytes of 0/1 (label variant)
+    const uint32_t* choice_bits;   // receiver, bit variant: packed LSB-first words (the []uint64 of ReceiveBits)
+    uint32_t* result_bits;    // bit variants: packed LSB-first output bits (column 0 of the matrix)
     const uint8_t* u_in;      // sender: received U, chunked layout
     uint8_t* u_out;           // receiver: U to send
     uint4* labels;            // [n] out
@@ -133,7 +135,10 @@ __device__ __forceinline__ void ks_extract(const uint32_t (&W)[20], uint32_t sh,
 // RECEIVER = false: group of 128 threads, thread c = column c.
 // RECEIVER = true : group of 256 threads, thread c < 128 -> T0 of column c,
 //                   thread c >= 128 -> T1 of column c - 128.
-template <bool RECEIVER>
+// BITS: the bit-COT variants SendBits / ReceiveBits (ot/iknp.go:259-310, 554-620): same U
+// exchange, but the output is only Bit(0) of every label, i.e. column 0 of the matrix, packed
+// LSB-first; no transpose is needed.
+template <bool RECEIVER, bool BITS>
 __global__ void __launch_bounds__(IKNP_CTA_THREADS, 1) iknp_kernel(const IknpParams p) {
     constexpr int GT = RECEIVER ? 256 : 128;              // threads per group
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -207,11 +212,17 @@ __global__ void __launch_bounds__(IKNP_CTA_THREADS, 1) iknp_kernel(const IknpPar
         }
 
         if (RECEIVER) {
-            // choice bits of the chunk packed LSB-first, iknp.go:472-477
-            for (uint32_t r = gt; r < IKNP_CHUNK_ROWS; r += GT) {
-                const bool bit = (r < rows) && (__ldg(p.choice + row0 + r) != 0);
-                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) bbuf[r >> 5] = bal;
+            if (BITS) {
+                // ReceiveBits XORs the packed choice words in whole 64-bit units: words = byteRows / 8
+                // (iknp.go:583-593), so the tail bytes of a short last chunk get no choice bits
+                if (gt < 16) bbuf[gt] = (gt >> 1) < (w >> 3) ? __ldg(p.choice_bits + (row0 >> 5) + gt) : 0u;
+            } else {
+                // choice bits of the chunk packed LSB-first, iknp.go:472-477
+                for (uint32_t r = gt; r < IKNP_CHUNK_ROWS; r += GT) {
+                    const bool bit = (r < rows) && (__ldg(p.choice + row0 + r) != 0);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0) bbuf[r >> 5] = bal;
+                }
             }
             if (second) {
 #pragma unroll
@@ -256,6 +267,17 @@ __global__ void __launch_bounds__(IKNP_CTA_THREADS, 1) iknp_kernel(const IknpPar
             }
         }
 
+        if (BITS) {
+            // Bit(0) of label r = bit r of column 0 (T0 for the receiver, q for the sender)
+            if (!second && col == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const uint32_t lo = 32u * q;
+                    if (lo < rows) p.result_bits[(row0 >> 5) + q] = (lo + 32 <= rows) ? T[q] : (T[q] & (0xffffffffu >> (lo + 32 - rows)));
+                }
+            }
+            continue;                                      // the claim barrier orders the shared buffers
+        }
         // ---- createLabels, iknp.go:647-683: label r = row r of the bit matrix
         if (!second) {
 #pragma unroll

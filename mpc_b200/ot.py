@@ -50,6 +50,19 @@ class IKNPReceiver:
         return u[: u_size(n)], labels[:n]
 
 
+    def receive_bits(self, choices: np.ndarray, n: int):
+        """IKNPReceiver.ReceiveBits (ot/iknp.go:554-620).  choices: packed uint64 words.
+        Returns (u, result words)."""
+        ch = np.ascontiguousarray(choices, dtype=np.uint64)
+        if (n + 63) // 64 > len(ch):
+            raise ValueError(f"choices buffer len={len(ch)} too short for n={n}")
+        u = np.zeros(max(u_size(n), 16), dtype=np.uint8)
+        res = np.zeros(max((n + 63) // 64, 1), dtype=np.uint64)
+        check(_lib.lib().gcb_iknp_receiver_expand_bits(ptr(self.k0), ptr(self.k1), self.pos, ptr(ch), n, ptr(u), ptr(res)))
+        self.pos += stream_advance(n)
+        return u[: u_size(n)], res[: (n + 63) // 64]
+
+
 class IKNPSender:
     """ot.IKNPSender after setup (ot/iknp.go:80-125): k are the 128 seeds
     received by base OT with choice bits Delta."""
@@ -68,6 +81,16 @@ class IKNPSender:
                                                 len(u), n, ptr(labels)))
         self.pos += stream_advance(n)
         return labels[:n]
+
+
+    def send_bits(self, u: np.ndarray, n: int) -> np.ndarray:
+        """IKNPSender.SendBits (ot/iknp.go:259-310): packed result words."""
+        u = np.ascontiguousarray(u, dtype=np.uint8)
+        res = np.zeros(max((n + 63) // 64, 1), dtype=np.uint64)
+        check(_lib.lib().gcb_iknp_sender_expand_bits(ptr(self.k), ptr(self.delta), self.pos, ptr(u) if len(u) else None,
+                                                     len(u), n, ptr(res)))
+        self.pos += stream_advance(n)
+        return res[: (n + 63) // 64]
 
 
 class MITCCRH:

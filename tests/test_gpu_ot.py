@@ -96,3 +96,22 @@ def test_iknp_rejects_bad_chunk_size():
     with pytest.raises(_lib.GcbError, match="invalid chunk size") as e:
         snd.send(np.zeros(100, np.uint8), 512)
     assert e.value.rc == _lib.E_CHUNK
+
+
+@pytest.mark.parametrize("n", [1, 64, 100, 511, 512, 1000, 4096 + 77, 1 << 16])
+def test_iknp_bit_cot_bit_exact(n):
+    """ReceiveBits / SendBits (gmw/triples.go's bit-COT): U bytes and packed result words vs the oracle,
+    including the reference's whole-word choice XOR on short last chunks."""
+    k0, k1, delta, ks = _keys("bits")
+    rcv, snd = IKNPReceiver(k0, k1), IKNPSender(ks, delta)
+    rcv.pos = snd.pos = 5
+    words = (n + 63) // 64
+    choices = np.frombuffer(DRBG(f"bits/c/{n}").read(8 * words), dtype=np.uint64).copy()
+    u, r = rcv.receive_bits(choices, n)
+    o_u, o_r, o_pos = O.iknp_receive_bits(k0, k1, 5, choices, n)
+    assert eq(u, o_u), "U differs"
+    assert np.array_equal(r, o_r), "receiver bits differ"
+    s = snd.send_bits(u, n)
+    o_s, _ = O.iknp_send_bits(ks, delta[0], 5, o_u, n)
+    assert np.array_equal(s, o_s), "sender bits differ"
+    assert rcv.pos == snd.pos == o_pos
