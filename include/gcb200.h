@@ -187,6 +187,25 @@ int gcb_stream_garble(gcb_stream *s, const gcb_plan *plan, const uint32_t *in, u
                       const uint32_t *out, uint32_t nout, uint8_t *dst, size_t dst_stride,
                       size_t *written, uint64_t *ns_init, uint64_t *ns_garble);
 
+/* ------------------------------------------------------ streaming evaluator --- */
+/* Replaces circuit.StreamEval (circuit/stream_evaluator.go:29-96: NewStreamEval,
+ * Get, Set, SetInputs, InitCircuit) and the gate loop of StreamEvaluator for one
+ * OpCircuit body (:270-432), for `batch` program instances in lock step. */
+typedef struct gcb_seval gcb_seval;
+int gcb_seval_create(const uint8_t *keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                     gcb_seval **out);
+void gcb_seval_destroy(gcb_seval *s);
+/* labels: [batch][n] */
+int gcb_seval_set_wires(gcb_seval *s, const uint32_t *ids, uint32_t n, const gcb_label *labels);
+int gcb_seval_get_wires(gcb_seval *s, const uint32_t *ids, uint32_t n, gcb_label *labels);
+/* src: [batch][src_stride] bytes received after the OpCircuit header (step,
+ * numGates, numTmpWires, numWires: compiler/ssa/streamer.go:679-693): `ngates`
+ * gate records; *consumed = bytes of one instance's records.  All instances
+ * must carry the same gate headers (same circuit and wire ids).  Malformed
+ * records give GCB_E_BUFFER / GCB_E_BADOP / GCB_E_CORRUPT. */
+int gcb_seval_circuit(gcb_seval *s, const uint8_t *src, size_t src_stride, size_t len, uint32_t ngates,
+                      uint32_t ntmp, uint32_t nwires, size_t *consumed);
+
 /* ------------------------------------------------------------------- IKNP --- */
 /* Replaces the inner loops of IKNPReceiver.receive (ot/iknp.go:468-511) and
  * IKNPSender.send (ot/iknp.go:197-226): AES-128-CTR column expansion

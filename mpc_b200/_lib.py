@@ -62,6 +62,11 @@ SYMBOLS = {
     "gcb_stream_step_size": (_int, [_vp, _vp, _vp, _u32, _vp, _u32, C.POINTER(_sz)]),
     "gcb_stream_garble": (_int, [_vp, _vp, _vp, _u32, _vp, _u32, _vp, _sz, C.POINTER(_sz),
                                  C.POINTER(_u64), C.POINTER(_u64)]),
+    "gcb_seval_create": (_int, [_vp, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "gcb_seval_destroy": (None, [_vp]),
+    "gcb_seval_set_wires": (_int, [_vp, _vp, _u32, _vp]),
+    "gcb_seval_get_wires": (_int, [_vp, _vp, _u32, _vp]),
+    "gcb_seval_circuit": (_int, [_vp, _vp, _sz, _sz, _u32, _u32, _u32, C.POINTER(_sz)]),
     "gcb_iknp_u_size": (_sz, [_u64]),
     "gcb_iknp_stream_advance": (_u64, [_u64]),
     "gcb_iknp_receiver_expand": (_int, [_vp, _vp, _u64, _vp, _u64, _vp, _vp]),

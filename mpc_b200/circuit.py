@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import GcbError, PlanInfo, check, ptr
 from .circuit_io import AND, INV, LABEL_DTYPE, OR, WIRE_DTYPE, Circuit
 
-__all__ = ["Garbled", "GarbleEngine", "GcbError"]
+__all__ = ["Garbled", "GarbleEngine", "Streaming", "StreamEval", "GcbError"]
 
 
 def _read(rand, n: int) -> bytes:
@@ -287,3 +287,45 @@ class Streaming:
                                            ptr(o) if len(o) else None, len(o), ptr(buf), buf.shape[1],
                                            C.byref(w), C.byref(t0), C.byref(t1)))
         return buf[:, : int(w.value)], int(t0.value), int(t1.value)
+
+
+class StreamEval:
+    """circuit.StreamEval + the OpCircuit gate loop of StreamEvaluator
+    (circuit/stream_evaluator.go:29-96, 270-432) for ``batch`` instances."""
+
+    def __init__(self, keys, batch: int = 1):
+        ka, kl, ks = _key_args(keys, batch)
+        self.batch = batch
+        h = C.c_void_p()
+        check(_lib.lib().gcb_seval_create(ptr(ka), kl, ks, batch, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().gcb_seval_destroy(h)
+            except Exception:
+                pass
+
+    def set(self, ids, labels: np.ndarray) -> None:
+        """Set / SetInputs: labels LABEL[batch, n]."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        labels = np.ascontiguousarray(labels, dtype=LABEL_DTYPE).reshape(self.batch, len(ids))
+        check(_lib.lib().gcb_seval_set_wires(self._h, ptr(ids) if len(ids) else None, len(ids),
+                                             ptr(labels) if len(ids) else None))
+
+    def get(self, ids) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.zeros((self.batch, len(ids)), dtype=LABEL_DTYPE)
+        check(_lib.lib().gcb_seval_get_wires(self._h, ptr(ids) if len(ids) else None, len(ids),
+                                             ptr(out) if len(ids) else None))
+        return out
+
+    def circuit(self, stream: np.ndarray, ngates: int, ntmp: int, nwires: int) -> int:
+        """Evaluate one OpCircuit body.  stream: uint8[batch, n] record bytes; returns bytes consumed."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8).reshape(self.batch, -1)
+        used = C.c_size_t()
+        check(_lib.lib().gcb_seval_circuit(self._h, ptr(stream), stream.shape[1], stream.shape[1], ngates, ntmp,
+                                           nwires, C.byref(used)))
+        return int(used.value)

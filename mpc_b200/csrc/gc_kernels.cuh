@@ -659,6 +659,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
 template <int NR, int MODE, int ILP, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     constexpr bool FULL = MODE == GC_FULL;
+    constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
     const TeamCtx tc = team_ctx(smem, p);
     aes_tables_to_smem(tc.tables);
@@ -684,7 +685,9 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         if (ph.n_waves && ttid < wave_count(p, ph, 0)) npre = load_node(p.nodes, ph.w0_first + ttid);
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
-            const uint4 m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
+            uint4 m;
+            if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + ref.y), inst);    // StreamEval.Get, stream_evaluator.go:57-66
+            else m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
             slots[ref.x] = m;
             if (FULL) p.wires_full[(size_t)inst * p.n_wires + ref.y] = m;
         }
@@ -730,7 +733,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         }
         for (uint32_t k = ttid; k < p.n_out; k += TT) {
             const uint2 ref = __ldg(p.live_out + k);
-            p.io[(size_t)inst * p.n_out + ref.y] = slots[ref.x];
+            if (STREAM) *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots[ref.x];   // StreamEval.Set
+            else p.io[(size_t)inst * p.n_out + ref.y] = slots[ref.x];
         }
         team_barrier(tc.team, TT);
     }

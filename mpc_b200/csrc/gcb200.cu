@@ -2,6 +2,7 @@
 // selection, plan upload, kernel launches and the host-buffer staging paths.
 // There is no CPU fallback in this file: without a CUDA device every compute
 // entry point fails with GCB_E_CUDA.
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -74,7 +75,7 @@ static cudaError_t opt_in_gc() {
 #define GC_OPT_G(NR, MODE, ILP, MAXT) if (e == cudaSuccess) e = opt_in(garble_kernel<NR, MODE, ILP, MAXT>);
 #define GC_OPT_E(NR, MODE, ILP, MAXT) if (e == cudaSuccess) e = opt_in(eval_kernel<NR, MODE, ILP, MAXT>);
     GC_FOR_NR(GC_OPT_G, GC_PLAIN) GC_FOR_NR(GC_OPT_G, GC_FULL) GC_FOR_NR(GC_OPT_G, GC_STREAM)
-    GC_FOR_NR(GC_OPT_E, GC_PLAIN) GC_FOR_NR(GC_OPT_E, GC_FULL)
+    GC_FOR_NR(GC_OPT_E, GC_PLAIN) GC_FOR_NR(GC_OPT_E, GC_FULL) GC_FOR_NR(GC_OPT_E, GC_STREAM)
 #undef GC_OPT_G
 #undef GC_OPT_E
     return e;
@@ -327,7 +328,8 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const dim3 block(p.n_teams * p.team_threads);
     const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams, di->smem_base);
     const bool full = wires_full != nullptr;
-    if (pages) launch_garble_nr<GC_STREAM>(keylen, geo.ilp, grid, block, smem, stream, p);
+    if (pages && garble) launch_garble_nr<GC_STREAM>(keylen, geo.ilp, grid, block, smem, stream, p);
+    else if (pages) launch_eval_nr<GC_STREAM>(keylen, geo.ilp, grid, block, smem, stream, p);
     else if (garble && full) launch_garble_nr<GC_FULL>(keylen, geo.ilp, grid, block, smem, stream, p);
     else if (garble) launch_garble_nr<GC_PLAIN>(keylen, geo.ilp, grid, block, smem, stream, p);
     else if (full) launch_eval_nr<GC_FULL>(keylen, geo.ilp, grid, block, smem, stream, p);
@@ -385,6 +387,9 @@ struct gcb_stream {
     gcb::DevBuf slab, ser, ids, tmpl, row_pos, wires;
     size_t slab_cap = 0, ser_cap = 0, ids_cap = 0, tmpl_cap = 0, row_pos_cap = 0, wires_cap = 0;
     std::mutex mu;
+    // evaluator side: plans recovered from record streams, keyed by a hash of the gate headers
+    struct EvalPlan { gcb::Plan plan; std::vector<uint32_t> in_ids, out_ids; };
+    std::unordered_map<uint64_t, std::shared_ptr<EvalPlan>> eval_plans;
     ~gcb_stream() {
         for (uint4* p : pages) if (p) cudaFree(p);
         if (cs) cudaStreamDestroy(cs);
@@ -907,6 +912,180 @@ int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, u
     const auto t_end = clk::now();
     if (ns_init) *ns_init = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_mid - t_start).count();
     if (ns_garble) *ns_garble = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_end - t_mid).count();
+    return GCB_OK;
+}
+
+// ------------------------------------------------------- streaming evaluator ----
+}  // extern "C"  (helpers below are C++)
+
+struct gcb_seval : gcb_stream {};
+
+extern "C" {
+
+int gcb_seval_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch, gcb_seval** out) {
+    if (!out) return fail(GCB_E_ARG, "null output pointer");
+    *out = nullptr;
+    if (!keys || batch == 0) return fail(GCB_E_ARG, "null argument");
+    int rc = check_keylen(keylen);
+    if (rc) return rc;
+    if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
+    if ((rc = select_device(nullptr))) return rc;
+    auto s = std::make_unique<gcb_seval>();
+    s->device = tl_device; s->batch = batch; s->keylen = keylen; s->key_stride = key_stride;
+    CK(cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking));
+    const size_t kb = key_stride ? (size_t)key_stride * batch : keylen;
+    CK(s->keys.alloc(kb));
+    CK(cudaMemcpyAsync(s->keys.p, keys, kb, cudaMemcpyHostToDevice, s->cs));
+    CK(cudaStreamSynchronize(s->cs));
+    *out = s.release();
+    return GCB_OK;
+}
+void gcb_seval_destroy(gcb_seval* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->cs) cudaStreamSynchronize(s->cs);
+    delete s;
+}
+
+// StreamEval.Set / SetInputs (stream_evaluator.go:68-96): labels [batch][n].
+int gcb_seval_set_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, const gcb_label* labels) {
+    if (!s || (n && (!ids || !labels))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    tl_device = s->device;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    uint32_t mx = 0;
+    for (uint32_t i = 0; i < n; i++) mx = ids[i] > mx ? ids[i] : mx;
+    if ((rc = ensure_wires(s, mx))) return rc;
+    if ((rc = grow(s->ids, s->ids_cap, (size_t)n * 4))) return rc;
+    if ((rc = grow(s->wires, s->wires_cap, (size_t)s->batch * n * 16))) return rc;
+    CK(cudaMemcpyAsync(s->ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s->cs));
+    CK(cudaMemcpyAsync(s->wires.p, labels, (size_t)s->batch * n * 16, cudaMemcpyHostToDevice, s->cs));
+    wf_set_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
+                                                       s->ids.as<uint32_t>(), n, s->wires.as<uint4>(), s->batch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s->cs));
+    return GCB_OK;
+}
+// StreamEval.Get (stream_evaluator.go:57-66): labels [batch][n].
+int gcb_seval_get_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, gcb_label* labels) {
+    if (!s || (n && (!ids || !labels))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    tl_device = s->device;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++)
+        if (((size_t)ids[i] >> WF_PAGE_SHIFT) >= s->pages.size()) return fail(GCB_E_WIRE, "wire %u not allocated", ids[i]);
+    if ((rc = grow(s->ids, s->ids_cap, (size_t)n * 4))) return rc;
+    if ((rc = grow(s->wires, s->wires_cap, (size_t)s->batch * n * 16))) return rc;
+    CK(cudaMemcpyAsync(s->ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s->cs));
+    wf_get_labels_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
+                                                              s->ids.as<uint32_t>(), n, s->wires.as<uint4>(), s->batch);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(labels, s->wires.p, (size_t)s->batch * n * 16, cudaMemcpyDeviceToHost, s->cs));
+    CK(cudaStreamSynchronize(s->cs));
+    return GCB_OK;
+}
+
+// The gate loop of StreamEvaluator for one OpCircuit body (stream_evaluator.go:270-432).
+// src: [batch][src_stride] host bytes, each instance's record stream for this circuit (all
+// instances carry the same gate headers: same circuit, same wire ids; only the rows differ).
+int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_t len, uint32_t ngates,
+                      uint32_t ntmp, uint32_t nwires, size_t* consumed) {
+    if (!s || (ngates && !src)) return fail(GCB_E_ARG, "null argument");
+    if (src_stride < len && s->batch > 1) return fail(GCB_E_ARG, "src_stride smaller than len");
+    std::lock_guard<std::mutex> lk(s->mu);
+    tl_device = s->device;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    // parse instance 0's headers
+    std::vector<StreamGate> sg;
+    std::vector<uint32_t> row_pos;
+    std::string err;
+    size_t used = 0;
+    if ((rc = parse_stream(src, len, ngates, sg, row_pos, &used, err))) return fail(rc, "%s", err.c_str());
+    if (consumed) *consumed = used;
+    if (ngates == 0) return GCB_OK;
+    // InitCircuit (stream_evaluator.go:86-96): wires up to nwires exist
+    if (nwires) { if ((rc = ensure_wires(s, nwires - 1))) return rc; }
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix(ntmp);
+    for (const StreamGate& g : sg) { mix(g.op | (g.a_tmp << 8) | (g.b_tmp << 9) | (g.c_tmp << 10)); mix(g.a); mix(g.b); mix(g.c); }
+    std::shared_ptr<gcb_stream::EvalPlan> ep;
+    auto it = s->eval_plans.find(h);
+    if (it != s->eval_plans.end()) ep = it->second;
+    else {
+        // wire space of the recovered circuit: [permanent ids in order of first use | tmp wires]
+        std::unordered_map<uint32_t, uint32_t> perm;
+        std::vector<uint32_t> perm_ids;
+        std::vector<uint8_t> first_is_read, written;
+        auto perm_loc = [&](uint32_t id, bool is_read) {
+            auto f = perm.find(id);
+            if (f != perm.end()) { if (!is_read) written[f->second] = 1; return f->second; }
+            const uint32_t l = (uint32_t)perm_ids.size();
+            perm.emplace(id, l); perm_ids.push_back(id);
+            first_is_read.push_back(is_read); written.push_back(!is_read);
+            return l;
+        };
+        struct Ref { uint32_t loc; bool tmp; };
+        std::vector<gcb_gate> gates(sg.size());
+        std::vector<std::array<Ref, 3>> refs(sg.size());
+        for (size_t i = 0; i < sg.size(); i++) {
+            const StreamGate& g = sg[i];
+            for (const auto& t : {std::pair<uint32_t, bool>{g.a, g.a_tmp}, {g.b, g.b_tmp}, {g.c, g.c_tmp}})
+                if (t.second && t.first >= ntmp) return fail(GCB_E_WIRE, "tmp wire %u out of range (gate %zu)", t.first, i);
+            if (!g.a_tmp && g.a >= nwires) return fail(GCB_E_WIRE, "wire %u out of range (gate %zu)", g.a, i);
+            refs[i][0] = Ref{g.a_tmp ? g.a : perm_loc(g.a, true), (bool)g.a_tmp};
+            refs[i][1] = g.op == OP_INV ? refs[i][0] : Ref{g.b_tmp ? g.b : perm_loc(g.b, true), (bool)g.b_tmp};
+            refs[i][2] = Ref{g.c_tmp ? g.c : perm_loc(g.c, false), (bool)g.c_tmp};
+        }
+        const uint32_t np = (uint32_t)perm_ids.size();
+        for (size_t i = 0; i < sg.size(); i++) {
+            auto w = [&](const Ref& r) { return r.tmp ? np + r.loc : r.loc; };
+            gates[i] = gcb_gate{w(refs[i][0]), w(refs[i][1]), w(refs[i][2]), sg[i].op, {0, 0, 0}, 0};
+        }
+        ep = std::make_shared<gcb_stream::EvalPlan>();
+        PlanSpec spec;
+        spec.gates = gates.data(); spec.num_gates = (uint32_t)gates.size(); spec.num_wires = np + ntmp;
+        for (uint32_t l = 0; l < np; l++) {
+            if (first_is_read[l]) { spec.live_in.push_back(l); ep->in_ids.push_back(perm_ids[l]); }
+            if (written[l]) { spec.live_out.push_back(l); ep->out_ids.push_back(perm_ids[l]); }
+        }
+        if ((rc = build_plan(spec, ep->plan, err))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
+        team_geometry(ep->plan);
+        if (ep->plan.info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ep->plan.info.num_slots);
+        if (s->eval_plans.size() > 64) s->eval_plans.clear();
+        s->eval_plans.emplace(h, ep);
+    }
+    const size_t n_rows = row_pos.size();
+    const size_t stride16 = ((len + 15) & ~(size_t)15) + 16;
+    const size_t nids = ep->in_ids.size() + ep->out_ids.size();
+    if ((rc = grow(s->ids, s->ids_cap, (nids ? nids : 1) * 4))) return rc;
+    if ((rc = grow(s->slab, s->slab_cap, (size_t)s->batch * (n_rows ? n_rows : 1) * 16))) return rc;
+    if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
+    if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
+    uint32_t* d_in = s->ids.as<uint32_t>();
+    uint32_t* d_out = d_in + ep->in_ids.size();
+    if (!ep->in_ids.empty()) CK(cudaMemcpyAsync(d_in, ep->in_ids.data(), ep->in_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
+    if (!ep->out_ids.empty()) CK(cudaMemcpyAsync(d_out, ep->out_ids.data(), ep->out_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
+    if (n_rows) {
+        CK(cudaMemcpyAsync(s->row_pos.p, row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
+        CK(cudaMemcpy2DAsync(s->ser.p, stride16, src, s->batch > 1 ? src_stride : len, len, s->batch, cudaMemcpyHostToDevice, s->cs));
+        DeserParams dp{s->ser.as<uint8_t>(), stride16, s->row_pos.as<uint32_t>(), (uint32_t)n_rows, s->slab.as<uint4>(), s->batch};
+        deserialize_kernel<<<di->sm_count * 8, 256, 0, s->cs>>>(dp);
+        CK(cudaGetLastError());
+    }
+    rc = launch_gc(false, ep->plan, di, s->device, s->keys.as<uint8_t>(), s->keylen, s->key_stride, s->batch, nullptr,
+                   nullptr, s->slab.as<gcb_label>(), nullptr, nullptr, s->cs, d_in, d_out,
+                   reinterpret_cast<uint4* const*>(s->page_table.p));
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
 }
 

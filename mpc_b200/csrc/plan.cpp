@@ -374,6 +374,45 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 
 namespace gcb {
 
+int parse_stream(const uint8_t* buf, size_t len, uint32_t ngates, std::vector<StreamGate>& gates,
+                 std::vector<uint32_t>& row_pos, size_t* consumed, std::string& err) {
+    gates.clear(); row_pos.clear();
+    gates.reserve(ngates);
+    size_t pos = 0;
+    auto need = [&](size_t n) { return pos + n <= len; };
+    for (uint32_t i = 0; i < ngates; i++) {
+        if (!need(1)) { err = "record stream truncated"; return GCB_E_BUFFER; }
+        uint8_t gop = buf[pos++];
+        StreamGate g{};
+        g.a_tmp = (gop & 0x80) != 0; g.b_tmp = (gop & 0x40) != 0; g.c_tmp = (gop & 0x20) != 0;
+        const bool shrt = (gop & 0x10) != 0;
+        gop &= 0x0f;
+        if (gop > OP_INV) { err = "invalid operation in record stream"; return GCB_E_BADOP; }
+        g.op = gop;
+        const int nidx = gop == OP_INV ? 2 : 3;
+        const size_t w = shrt ? 2 : 4;
+        if (!need(nidx * w)) { err = "record stream truncated"; return GCB_E_BUFFER; }
+        uint32_t idx[3] = {0, 0, 0};
+        for (int k = 0; k < nidx; k++) {
+            uint32_t v = 0;
+            for (size_t q = 0; q < w; q++) v = (v << 8) | buf[pos++];
+            idx[k] = v;
+        }
+        g.a = idx[0];
+        if (nidx == 3) { g.b = idx[1]; g.c = idx[2]; } else { g.b = 0; g.c = idx[1]; g.b_tmp = 0; }
+        const int rows = gop == OP_AND ? 2 : gop == OP_OR ? 3 : gop == OP_INV ? 1 : 0;
+        if (!need((size_t)rows * 16)) { err = "record stream truncated"; return GCB_E_BUFFER; }
+        for (int k = 0; k < rows; k++) {
+            if (pos > 0xfffffff0u) { err = "record stream exceeds 4 GiB"; return GCB_E_TOO_LARGE; }
+            row_pos.push_back((uint32_t)pos);
+            pos += 16;
+        }
+        gates.push_back(g);
+    }
+    if (consumed) *consumed = pos;
+    return GCB_OK;
+}
+
 int build_stream_layout(const std::vector<gcb_gate>& gates, uint32_t num_wires, const uint32_t* in, uint32_t nin,
                         const uint32_t* out, uint32_t nout, StreamLayout& lay, std::string& err) {
     if (nout > num_wires) { err = "more output ids than wires"; return GCB_E_ARG; }

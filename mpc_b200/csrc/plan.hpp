@@ -131,6 +131,11 @@ struct StreamLayout {
     std::vector<uint8_t> tmpl;
     std::vector<uint32_t> row_pos;
 };
+// One gate record parsed back from a record stream (the evaluator's view): wire indices with
+// their tmp flags (stream_evaluator.go:272-343).
+struct StreamGate { uint32_t a, b, c; uint8_t op, a_tmp, b_tmp, c_tmp; };
+int parse_stream(const uint8_t* buf, size_t len, uint32_t ngates, std::vector<StreamGate>& gates,
+                 std::vector<uint32_t>& row_pos, size_t* consumed, std::string& err);
 int build_stream_layout(const std::vector<gcb_gate>& gates, uint32_t num_wires, const uint32_t* in, uint32_t nin,
                         const uint32_t* out, uint32_t nout, StreamLayout& lay, std::string& err);
 }  // namespace gcb

@@ -29,6 +29,15 @@ __global__ void wf_get_kernel(uint4* const* pages, const uint32_t* ids, uint32_t
     }
 }
 
+// StreamEval.Get for a list of ids: labels [batch][n].
+__global__ void wf_get_labels_kernel(uint4* const* pages, const uint32_t* ids, uint32_t n, uint4* labels, uint32_t batch) {
+    const size_t total = (size_t)batch * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t inst = (uint32_t)(i / n), k = (uint32_t)(i % n);
+        labels[i] = *wf_slot(pages, __ldg(ids + k), inst);
+    }
+}
+
 // R with the S bit forced (stream_garble.go:44-50), once at NewStreaming.
 __global__ void force_s_kernel(uint4* r, uint32_t batch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,6 +95,40 @@ __global__ void __launch_bounds__(SER_THREADS) serialize_kernel(const SerParams 
     __syncthreads();
     uint4* out = reinterpret_cast<uint4*>(p.dst + (size_t)inst * p.dst_stride + t0);
     for (uint32_t i = threadIdx.x; i < len16; i += SER_THREADS) out[i] = reinterpret_cast<const uint4*>(tile)[i];
+}
+
+// The inverse of serialize_kernel for the streaming evaluator: gathers the garbled rows
+// (16 big-endian bytes each, at arbitrary byte offsets of each instance's record stream)
+// into the dense slab the eval kernel reads.  src rows are padded by 16 bytes.
+struct DeserParams {
+    const uint8_t* src;         // [batch][src_stride], src_stride % 16 == 0
+    size_t src_stride;
+    const uint32_t* row_pos;    // [n_rows]
+    uint32_t n_rows;
+    uint4* slab;                // [batch][n_rows]
+    uint32_t batch;
+};
+__global__ void deserialize_kernel(const DeserParams p) {
+    const size_t total = (size_t)p.batch * p.n_rows;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t inst = (uint32_t)(i / p.n_rows), r = (uint32_t)(i % p.n_rows);
+        const uint32_t pos = __ldg(p.row_pos + r), off = pos & 15u;
+        const uint4* a = reinterpret_cast<const uint4*>(p.src + (size_t)inst * p.src_stride + (pos - off));
+        const uint4 lo = __ldg(a), hi = __ldg(a + 1);
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const uint32_t wo = off >> 2, sh = (off & 3u) * 8u;
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t x0 = w[q], x1 = w[q + 1];
+            if (wo == 1) { x0 = w[q + 1]; x1 = w[q + 2]; }
+            else if (wo == 2) { x0 = w[q + 2]; x1 = w[q + 3]; }
+            else if (wo == 3) { x0 = w[q + 3]; x1 = w[q + 4]; }
+            v[q] = __byte_perm(__funnelshift_r(x0, x1, sh), 0, 0x0123);   // bytes of the stream, then big-endian -> word
+        }
+        // Label.SetData: D0 = BE64(bytes 0..7), D1 = BE64(bytes 8..15); memory words lo(D0) hi(D0) lo(D1) hi(D1)
+        p.slab[i] = make_uint4(v[1], v[0], v[3], v[2]);
+    }
 }
 
 }  // namespace gcb

@@ -87,3 +87,106 @@ def test_streaming_batch_matches_single_instances():
     for b in range(batch):
         ost = O.Streaming(keys[b].tobytes(), rands[b], ids)
         assert buf[b].tobytes() == ost.garble(circ, ids, list(range(1000, 1064))), f"instance {b}"
+
+
+# ------------------------------------------------------------------ streaming evaluator
+from mpc_b200.circuit import StreamEval  # noqa: E402
+
+
+def _lab_tuple(l):
+    return (int(l["d0"]), int(l["d1"]))
+
+
+def _eval_step(sev, osev, buf, circ, ins, outs, nwires):
+    """Feed one sub-circuit's record stream to the device evaluator and to the oracle's."""
+    used = sev.circuit(buf, circ.num_gates, circ.num_wires, nwires)
+    assert used == buf.shape[1]
+    o_used = osev.circuit(buf[0].tobytes(), circ.num_gates, circ.num_wires, nwires)
+    assert o_used == used
+    ids = list(dict.fromkeys(list(ins) + list(outs)))
+    got = sev.get(ids)[0]
+    for k, wid in enumerate(ids):
+        assert _lab_tuple(got[k]) == osev.get(wid), f"evaluator wire {wid} differs from the oracle"
+
+
+@pytest.mark.parametrize("name,klen", [("sha256", 16), ("aes_128", 32), ("mul64", 24)])
+def test_stream_eval_one_step_bit_exact(name, klen):
+    circ = load_circuit(name)
+    key = DRBG(f"se/{name}").read(klen)
+    nin, nout = circ.num_inputs, circ.num_outputs
+    ins, outs = list(range(nin)), list(range(nin + 5, nin + 5 + nout))
+    rand = DRBG(f"se/r/{name}").read(16 * (1 + nin))
+    st, eng = Streaming.new(rand, key, ins), GarbleEngine(circ)
+    buf, _, _ = st.garble(eng, ins, outs)
+    wires = st.get_inputs(ins)[0]
+    bits = np.random.default_rng(3).integers(0, 2, nin).astype(bool)
+    labels = np.where(bits, wires["l1"], wires["l0"]).astype(LABEL_DTYPE)
+    sev, osev = StreamEval(key), O.StreamEval(key)
+    sev.set(ins, labels.reshape(1, -1))
+    for i, wid in enumerate(ins):
+        osev.set(wid, _lab_tuple(labels[i]))
+    _eval_step(sev, osev, buf, circ, ins, outs, nin + 5 + nout)
+    # and the evaluated labels decode to the plaintext circuit
+    ow = st.get_inputs(outs)[0]
+    got = sev.get(outs)[0]
+    dec = np.where(got == ow["l1"], 1, np.where(got == ow["l0"], 0, 2))
+    assert np.array_equal(dec, circ.compute_bits(bits.astype(int).tolist()))
+
+
+def test_stream_eval_chained_aliased_steps_and_long_indices():
+    circ = load_circuit("add64")
+    key = DRBG("sechain").read(16)
+    ins = list(range(70000, 70128))                   # 32-bit record form
+    rand = DRBG("sechain/r").read(16 * 129)
+    st, eng = Streaming.new(rand, key, ins), GarbleEngine(circ)
+    wires = st.get_inputs(ins)[0]
+    bits = np.random.default_rng(5).integers(0, 2, 128).astype(bool)
+    labels = np.where(bits, wires["l1"], wires["l0"]).astype(LABEL_DTYPE)
+    sev, osev = StreamEval(key), O.StreamEval(key)
+    sev.set(ins, labels.reshape(1, -1))
+    for i, wid in enumerate(ins):
+        osev.set(wid, _lab_tuple(labels[i]))
+    steps = [
+        (ins, list(range(300, 364))),
+        (list(range(300, 364)) + ins[:64], list(range(400, 464))),
+        (list(range(400, 464)) + list(range(400, 464)), list(range(400, 464))),           # in place
+        (list(range(400, 464)) + ins[64:], [500] * 32 + list(range(501, 533))),            # repeated out id
+    ]
+    for i, o in steps:
+        buf, _, _ = st.garble(eng, i, o)
+        _eval_step(sev, osev, buf, circ, i, o, 70200)
+
+
+def test_stream_eval_batch_and_malformed_stream():
+    circ = load_circuit("sub64")
+    batch, ids = 4, list(range(128))
+    keys = np.stack([DRBG(f"seb/key/{b}").array(32) for b in range(batch)])
+    rands = [DRBG(f"seb/{b}").read(16 * 129) for b in range(batch)]
+    lab = np.stack([np.frombuffer(r, dtype=">u8").astype("<u8").view(LABEL_DTYPE) for r in rands])
+    st = Streaming(keys, np.ascontiguousarray(lab[:, 0]), ids, np.ascontiguousarray(lab[:, 1:]))
+    eng = GarbleEngine(circ)
+    outs = list(range(200, 264))
+    buf, _, _ = st.garble(eng, ids, outs)
+    wires = st.get_inputs(ids)
+    bits = np.random.default_rng(9).integers(0, 2, (batch, 128)).astype(bool)
+    labels = np.where(bits, wires["l1"], wires["l0"]).astype(LABEL_DTYPE)
+    sev = StreamEval(keys, batch)
+    sev.set(ids, labels)
+    assert sev.circuit(buf, circ.num_gates, circ.num_wires, 264) == buf.shape[1]
+    got = sev.get(outs)
+    for b in range(batch):
+        osev = O.StreamEval(keys[b].tobytes())
+        for i, wid in enumerate(ids):
+            osev.set(wid, _lab_tuple(labels[b, i]))
+        osev.circuit(buf[b].tobytes(), circ.num_gates, circ.num_wires, 264)
+        for k, wid in enumerate(outs):
+            assert _lab_tuple(got[b, k]) == osev.get(wid)
+    from mpc_b200 import _lib
+    with pytest.raises(_lib.GcbError) as e:
+        sev.circuit(buf[:, : buf.shape[1] // 2], circ.num_gates, circ.num_wires, 264)
+    assert e.value.rc == _lib.E_BUFFER
+    bad = buf.copy()
+    bad[:, 0] = 0x0f
+    with pytest.raises(_lib.GcbError) as e:
+        sev.circuit(bad, circ.num_gates, circ.num_wires, 264)
+    assert e.value.rc == _lib.E_BADOP
