@@ -340,6 +340,11 @@ def run_gcb(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = gb * batch / (g_ms * 1e-3) / 1e9
+        traffic = None                              # DRAM bytes per launch from the committed ncu capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["garble_kernel"]["dram_bytes"]
+        except Exception:
+            pass
         total_and = n_and * batch * world
         value = total_and * args.steps / (ms * 1e-3) / 1e6
         cores = os.cpu_count() or 1
@@ -362,9 +367,11 @@ def run_gcb(args):
                        "l2": "tables are 976 MB per step, larger than L2; no flush needed",
                        "kernel_ms": {"garble": g_ms, "eval": e_ms}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "garble_kernel<10,PLAIN>",
+                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": gb * batch,
+                         "kernel": "garble_kernel<10,PLAIN,ILP2>",
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
-                         "note": "integer/LDS-bound: no AES instruction on the GPU; see DESIGN.md"},
+                         "note": "bound by the shared-memory pipe (AES T-table lookups, 82% busy in the ncu capture), "
+                                 "not HBM: there is no AES instruction on the GPU; see DESIGN.md and profiles/"},
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {"value": total_and / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": int(world * batch * (16 * (1 + nin) + 16 * rows + 16 * nin)),
