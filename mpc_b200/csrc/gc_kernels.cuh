@@ -569,7 +569,8 @@ struct EvalEnv {
 
 template <int NR, int MODE, int UU, int ILP, bool AND_ONLY>
 __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e, const Phase& ph, uint32_t ntask,
-                                          uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP]) {
+                                          uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP],
+                                          const uint4 (&rowpre)[ILP], bool have_rows) {
     static_assert(UU <= ILP, "pass wider than the record buffer");
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
@@ -583,8 +584,10 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
             const uint4 g = rec[j];
             const Label a = lds_label(slots, g.x & 0xffff), b = lds_label(slots, g.x >> 16);
             const Label x = k ? b : a;
-            row[j] = Label{0, 0, 0, 0};
-            if (label_s(x)) row[j] = label_from_mem(__ldg(e.tab + g.w + k));   // tg when S(a), te when S(b)
+            // tg when S(a), te when S(b); the row was requested a phase ago when this is the first pass
+            uint4 rm = rowpre[j];
+            if (!have_rows) rm = __ldg(e.tab + g.w + k);
+            row[j] = label_and_mask(label_from_mem(rm), mask_of(label_s(x)));
             if (k) row[j] = row[j] ^ label_and_mask(a, mask_of(label_s(b)));   // we ^= a when S(b)
             K[j] = label_shl(x, 1);
             K[j].w3 ^= g.z + k;
@@ -631,7 +634,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
         else if (op[j] == OP_INV) { need = sA; }
         else if (op[j] == OP_OR) { const uint32_t ix = 2 * sA + sB; need = (ix > 0) && (k == 0); ridx += ix - 1; }
         row[j] = Label{0, 0, 0, 0};
-        if (need) row[j] = label_from_mem(__ldg(e.tab + ridx));
+        if (need) row[j] = label_from_mem((have_rows && op[j] != OP_OR) ? rowpre[j] : __ldg(e.tab + ridx));
         uint32_t tw = g[j].z;
         if (op[j] == OP_OR) {
             K[j] = label_shl(a, 1) ^ label_shl(b, 2);         // makeK, garble.go:75-83
@@ -693,11 +696,25 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         }
         team_barrier(tc.team, TT);
         const EvalEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, inst};
+        uint4 cur[ILP];
+        prefetch_cipher<false, ILP>(p, ph, 0, ttid, TT, cur);
 
         for (uint32_t pi = 0; pi < p.n_phases; pi++) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);
-            uint4 cur[ILP];
-            prefetch_cipher<false, ILP>(p, ph, 0, ttid, TT, cur);
+            // the first-pass records were loaded a phase ago; request their garbled rows now, so the
+            // HBM latency hides behind the node waves (AND: row k of the pair; INV: its one row)
+            uint4 rows[ILP];
+            {
+                const uint32_t nt = task_count<false>(ph);
+#pragma unroll
+                for (int j = 0; j < ILP; j++) {
+                    const uint32_t t = j * TT + ttid;
+                    rows[j] = make_uint4(0, 0, 0, 0);
+                    if (t < nt) rows[j] = __ldg(env.tab + cur[j].w + ((t < 2 * ph.n_quad) ? (t & 1u) : 0u));
+                }
+            }
+            uint4 cur_n[ILP];
+            prefetch_cipher<false, ILP>(p, ph_n, 0, ttid, TT, cur_n);
             NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
             if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
             run_waves<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
@@ -714,14 +731,14 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                     prefetch_cipher<false, ILP>(p, ph, k0 + uu, ttid, TT, nxt);
                     const bool and_only = (k0 + uu) * TT <= and_tasks;
                     if (ILP >= 4 && uu == 4) {
-                        if (and_only) eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                        else eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        if (and_only) eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        else eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     } else if (ILP >= 2 && uu == 2) {
-                        if (and_only) eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                        else eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        if (and_only) eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        else eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     } else if (k0 * TT + (ttid & ~31u) < ntask) {
-                        if (and_only) eval_pass<NR, MODE, 1, ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                        else eval_pass<NR, MODE, 1, ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        if (and_only) eval_pass<NR, MODE, 1, ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        else eval_pass<NR, MODE, 1, ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     }
                     k0 += uu;
 #pragma unroll
@@ -730,6 +747,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                 team_barrier(tc.team, TT);
             }
             ph = ph_n; ph_n = ph_nn; npre = npre_n;
+#pragma unroll
+            for (int j = 0; j < ILP; j++) cur[j] = cur_n[j];
         }
         for (uint32_t k = ttid; k < p.n_out; k += TT) {
             const uint2 ref = __ldg(p.live_out + k);
