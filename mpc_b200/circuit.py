@@ -255,8 +255,25 @@ class Streaming:
         if h:
             try:
                 _lib.lib().gcb_stream_destroy(h)
+                if getattr(self, "_buf_ptr", None):
+                    _lib.lib().gcb_host_free(self._buf_ptr)
+                    self._buf_ptr = None
             except Exception:
                 pass
+
+    def _stream_buffer(self, n: int) -> np.ndarray:
+        """Page-locked [batch, n] byte buffer, kept across steps (the Go side's conn.WriteBuf role).
+        The returned array is overwritten by the next garble() call."""
+        need = self.batch * n
+        if getattr(self, "_buf_cap", 0) < need:
+            if getattr(self, "_buf_ptr", None):
+                _lib.lib().gcb_host_free(self._buf_ptr)
+            self._buf_cap = need + need // 4
+            self._buf_ptr = _lib.lib().gcb_host_alloc(self._buf_cap)
+            if not self._buf_ptr:
+                raise GcbError(_lib.E_CUDA, _lib.lib().gcb_last_error().decode())
+        raw = (C.c_uint8 * need).from_address(self._buf_ptr)
+        return np.frombuffer(raw, dtype=np.uint8).reshape(self.batch, n)
 
     def get_inputs(self, ids) -> np.ndarray:
         """GetInput / GetInputs (:117-128): WIRE[batch, n]."""
@@ -281,7 +298,7 @@ class Streaming:
         i = np.ascontiguousarray(in_ids, dtype=np.uint32)
         o = np.ascontiguousarray(out_ids, dtype=np.uint32)
         n = self.step_size(eng, i, o)
-        buf = np.zeros((self.batch, max(n, 1)), dtype=np.uint8)
+        buf = self._stream_buffer(max(n, 1))
         w, t0, t1 = C.c_size_t(), C.c_uint64(), C.c_uint64()
         check(_lib.lib().gcb_stream_garble(self._h, eng.handle, ptr(i) if len(i) else None, len(i),
                                            ptr(o) if len(o) else None, len(o), ptr(buf), buf.shape[1],

@@ -1013,39 +1013,42 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     if (ngates == 0) return GCB_OK;
     // InitCircuit (stream_evaluator.go:86-96): wires up to nwires exist
     if (nwires) { if ((rc = ensure_wires(s, nwires - 1))) return rc; }
+    // wire space of the recovered circuit: [permanent ids in order of first use | tmp wires].  The
+    // plan depends only on this canonical form, not on the actual ids, so the steps of a program
+    // that reuse a sub-circuit with fresh ids share one cached plan.
+    std::unordered_map<uint32_t, uint32_t> perm;
+    std::vector<uint32_t> perm_ids;
+    std::vector<uint8_t> first_is_read, written;
+    auto perm_loc = [&](uint32_t id, bool is_read) {
+        auto f = perm.find(id);
+        if (f != perm.end()) { if (!is_read) written[f->second] = 1; return f->second; }
+        const uint32_t l = (uint32_t)perm_ids.size();
+        perm.emplace(id, l); perm_ids.push_back(id);
+        first_is_read.push_back(is_read); written.push_back(!is_read);
+        return l;
+    };
+    struct Ref { uint32_t loc; bool tmp; };
+    std::vector<std::array<Ref, 3>> refs(sg.size());
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
     mix(ntmp);
-    for (const StreamGate& g : sg) { mix(g.op | (g.a_tmp << 8) | (g.b_tmp << 9) | (g.c_tmp << 10)); mix(g.a); mix(g.b); mix(g.c); }
+    for (size_t i = 0; i < sg.size(); i++) {
+        const StreamGate& g = sg[i];
+        for (const auto& t : {std::pair<uint32_t, bool>{g.a, g.a_tmp}, {g.b, g.b_tmp}, {g.c, g.c_tmp}})
+            if (t.second && t.first >= ntmp) return fail(GCB_E_WIRE, "tmp wire %u out of range (gate %zu)", t.first, i);
+        if (!g.a_tmp && g.a >= nwires) return fail(GCB_E_WIRE, "wire %u out of range (gate %zu)", g.a, i);
+        refs[i][0] = Ref{g.a_tmp ? g.a : perm_loc(g.a, true), (bool)g.a_tmp};
+        refs[i][1] = g.op == OP_INV ? refs[i][0] : Ref{g.b_tmp ? g.b : perm_loc(g.b, true), (bool)g.b_tmp};
+        refs[i][2] = Ref{g.c_tmp ? g.c : perm_loc(g.c, false), (bool)g.c_tmp};
+        mix(g.op | (g.a_tmp << 8) | (g.b_tmp << 9) | (g.c_tmp << 10));
+        mix(refs[i][0].loc); mix(refs[i][1].loc); mix(refs[i][2].loc);
+    }
+    const uint32_t np = (uint32_t)perm_ids.size();
     std::shared_ptr<gcb_stream::EvalPlan> ep;
     auto it = s->eval_plans.find(h);
     if (it != s->eval_plans.end()) ep = it->second;
     else {
-        // wire space of the recovered circuit: [permanent ids in order of first use | tmp wires]
-        std::unordered_map<uint32_t, uint32_t> perm;
-        std::vector<uint32_t> perm_ids;
-        std::vector<uint8_t> first_is_read, written;
-        auto perm_loc = [&](uint32_t id, bool is_read) {
-            auto f = perm.find(id);
-            if (f != perm.end()) { if (!is_read) written[f->second] = 1; return f->second; }
-            const uint32_t l = (uint32_t)perm_ids.size();
-            perm.emplace(id, l); perm_ids.push_back(id);
-            first_is_read.push_back(is_read); written.push_back(!is_read);
-            return l;
-        };
-        struct Ref { uint32_t loc; bool tmp; };
         std::vector<gcb_gate> gates(sg.size());
-        std::vector<std::array<Ref, 3>> refs(sg.size());
-        for (size_t i = 0; i < sg.size(); i++) {
-            const StreamGate& g = sg[i];
-            for (const auto& t : {std::pair<uint32_t, bool>{g.a, g.a_tmp}, {g.b, g.b_tmp}, {g.c, g.c_tmp}})
-                if (t.second && t.first >= ntmp) return fail(GCB_E_WIRE, "tmp wire %u out of range (gate %zu)", t.first, i);
-            if (!g.a_tmp && g.a >= nwires) return fail(GCB_E_WIRE, "wire %u out of range (gate %zu)", g.a, i);
-            refs[i][0] = Ref{g.a_tmp ? g.a : perm_loc(g.a, true), (bool)g.a_tmp};
-            refs[i][1] = g.op == OP_INV ? refs[i][0] : Ref{g.b_tmp ? g.b : perm_loc(g.b, true), (bool)g.b_tmp};
-            refs[i][2] = Ref{g.c_tmp ? g.c : perm_loc(g.c, false), (bool)g.c_tmp};
-        }
-        const uint32_t np = (uint32_t)perm_ids.size();
         for (size_t i = 0; i < sg.size(); i++) {
             auto w = [&](const Ref& r) { return r.tmp ? np + r.loc : r.loc; };
             gates[i] = gcb_gate{w(refs[i][0]), w(refs[i][1]), w(refs[i][2]), sg[i].op, {0, 0, 0}, 0};
@@ -1054,8 +1057,8 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
         PlanSpec spec;
         spec.gates = gates.data(); spec.num_gates = (uint32_t)gates.size(); spec.num_wires = np + ntmp;
         for (uint32_t l = 0; l < np; l++) {
-            if (first_is_read[l]) { spec.live_in.push_back(l); ep->in_ids.push_back(perm_ids[l]); }
-            if (written[l]) { spec.live_out.push_back(l); ep->out_ids.push_back(perm_ids[l]); }
+            if (first_is_read[l]) { spec.live_in.push_back(l); ep->in_ids.push_back(l); }     // canonical locations;
+            if (written[l]) { spec.live_out.push_back(l); ep->out_ids.push_back(l); }         // mapped to ids per call
         }
         if ((rc = build_plan(spec, ep->plan, err))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
         team_geometry(ep->plan);
@@ -1063,17 +1066,20 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
         if (s->eval_plans.size() > 64) s->eval_plans.clear();
         s->eval_plans.emplace(h, ep);
     }
+    std::vector<uint32_t> in_ids(ep->in_ids.size()), out_ids(ep->out_ids.size());
+    for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = perm_ids[ep->in_ids[k]];
+    for (size_t k = 0; k < out_ids.size(); k++) out_ids[k] = perm_ids[ep->out_ids[k]];
     const size_t n_rows = row_pos.size();
     const size_t stride16 = ((len + 15) & ~(size_t)15) + 16;
-    const size_t nids = ep->in_ids.size() + ep->out_ids.size();
+    const size_t nids = in_ids.size() + out_ids.size();
     if ((rc = grow(s->ids, s->ids_cap, (nids ? nids : 1) * 4))) return rc;
     if ((rc = grow(s->slab, s->slab_cap, (size_t)s->batch * (n_rows ? n_rows : 1) * 16))) return rc;
     if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
     if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
     uint32_t* d_in = s->ids.as<uint32_t>();
-    uint32_t* d_out = d_in + ep->in_ids.size();
-    if (!ep->in_ids.empty()) CK(cudaMemcpyAsync(d_in, ep->in_ids.data(), ep->in_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
-    if (!ep->out_ids.empty()) CK(cudaMemcpyAsync(d_out, ep->out_ids.data(), ep->out_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
+    uint32_t* d_out = d_in + in_ids.size();
+    if (!in_ids.empty()) CK(cudaMemcpyAsync(d_in, in_ids.data(), in_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
+    if (!out_ids.empty()) CK(cudaMemcpyAsync(d_out, out_ids.data(), out_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
     if (n_rows) {
         CK(cudaMemcpyAsync(s->row_pos.p, row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
         CK(cudaMemcpy2DAsync(s->ser.p, stride16, src, s->batch > 1 ? src_stride : len, len, s->batch, cudaMemcpyHostToDevice, s->cs));
