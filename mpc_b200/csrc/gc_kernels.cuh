@@ -17,7 +17,10 @@
 // something reads: the plan compiler has flattened the Free-XOR gates into
 // NODES, each the XOR of up to 14 already existing labels, grouped into waves of
 // mutually independent nodes (almost always one wave) -- one thread per node,
-// one team barrier per wave; and (2) one level of ciphered gates executed by the
+// one team barrier per wave.  The node records reach the kernel as ROWS of one
+// record per team thread (plan.hpp); a thread streams its records GC_NODE_PIPE
+// rows ahead of the one it runs, across wave and phase boundaries, so the L2
+// latency of the plan never sits on the dependency chain; and (2) one level of ciphered gates executed by the
 // whole team: every AES block is a task; an AND gate is a quad of tasks hashing
 // (a0,j0) (a1,j0) (b0,j1) (b1,j1) on four adjacent lanes and combining with warp
 // shuffles, INV a pair, OR a quad.  A thread runs up to ILP tasks at once (AES
@@ -35,9 +38,8 @@ constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-b
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
 
 struct GcParams {
-    const uint4* phases;                  // PhaseRec[] (two uint4 each) followed by two zero records
-    const uint2* waves;                   // WaveRec[]
-    const uint4* nodes;                   // NodeRec[] (two uint4 each)
+    const uint4* phases;                  // DevPhaseRec[] (two uint4 each) followed by two zero records
+    const uint4* nodes;                   // NodeRec rows (two uint4 per record, team_threads records per row)
     const uint4* crecs;                   // GateRec[]
     const uint32_t* nout_wire;            // original output wire of nodes[i] / crecs[i] (GC_FULL)
     const uint32_t* cout_wire;
@@ -55,7 +57,6 @@ struct GcParams {
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
     uint32_t stagger;                     // SM cycles by which consecutive teams start apart
-    uint32_t debug_skip;                  // developer switch: 1 = skip node waves, 2 = skip cipher levels (timing experiments)
     long long* trace;                     // optional: phase timestamps of block 0 / team 0 (tools/trace_phases.py)
     // streaming mode (GC_STREAM): live-in / live-out labels come from and go to
     // the permanent wire file instead of in_labels / io
@@ -158,19 +159,12 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
 // Gate index of cipher task t of a phase.  Garble: 4 tasks per AND/OR, 2 per INV;
 // eval: 2 per AND/OR (OR uses one), 1 per INV.
 struct Phase {
-    uint32_t wave_first, n_waves, cipher_first, n_quad, n_inv, w0_first, wc01, wc23;
+    uint32_t n_rows, cipher_first, n_quad, n_inv;
     bool has_or;
 };
 __device__ __forceinline__ Phase load_phase(const uint4* phases, uint32_t i) {
-    const uint4 a = __ldg(phases + 2 * i), b = __ldg(phases + 2 * i + 1);
-    return Phase{a.x, a.y & 0x7fffffffu, a.z, a.w, b.x, b.y, b.z, b.w, (a.y >> 31) != 0};
-}
-// Node count of wave w of a phase: waves 0..3 are inline in the PhaseRec.
-__device__ __forceinline__ uint32_t wave_count(const GcParams& p, const Phase& ph, uint32_t w) {
-    uint32_t c = 0xffffu;
-    if (w < 4) { const uint32_t pair = w < 2 ? ph.wc01 : ph.wc23; c = (w & 1) ? pair >> 16 : pair & 0xffffu; }
-    if (c == 0xffffu) c = __ldg(p.waves + ph.wave_first + w).y;
-    return c;
+    const uint4 a = __ldg(phases + 2 * i);
+    return Phase{a.x & 0x7fffffffu, a.y, a.z, a.w, (a.x >> 31) != 0};
 }
 template <bool GARBLE>
 __device__ __forceinline__ uint32_t task_gate(const Phase& ph, uint32_t t, uint32_t& k) {
@@ -208,79 +202,58 @@ __device__ __forceinline__ NodeRegs load_node(const uint4* nodes, uint32_t i) {
     return NodeRegs{__ldg(nodes + 2 * (size_t)i), __ldg(nodes + 2 * (size_t)i + 1)};
 }
 
-// NU nodes at once: dst = XOR of the leaves (^ R for an odd number of XNORs on the way).
-template <bool GARBLE, bool FULL, int NU>
-__device__ __forceinline__ void run_nodes(const GcParams& p, uint4* slots, const Label R, uint32_t inst,
-                                          const uint32_t (&index)[NU], const NodeRegs (&n)[NU], const bool (&active)[NU]) {
-    // words: lo.x = dst | k<<16 | parity<<24; then 14 leaf slots, two per word
-    uint32_t k[NU], kall = 0;
-    Label acc[NU];
-#pragma unroll
-    for (int u = 0; u < NU; u++) {
-        k[u] = active[u] ? (n[u].lo.x >> 16) & 0xff : 0u;
-        kall = max(kall, k[u]);
-        acc[u] = Label{0, 0, 0, 0};
-        if (GARBLE) acc[u] = label_and_mask(R, mask_of(n[u].lo.x >> 24));
-    }
-    const uint32_t kmax = __reduce_max_sync(0xffffffffu, kall);
+// One node per thread: dst = XOR of the leaves (^ R for an odd number of XNORs on the way).
+// words: lo.x = dst | k<<16 | flags<<24 (NODE_PARITY / NODE_WAVE_END / NODE_ACTIVE); then 14 leaf
+// slots, two per word.
+template <bool GARBLE, bool FULL>
+__device__ __forceinline__ void run_node(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t index,
+                                         const NodeRegs& n) {
+    const bool active = (n.lo.x >> 24) & NODE_ACTIVE;
+    const uint32_t k = active ? (n.lo.x >> 16) & 0xff : 0u;
+    Label acc = Label{0, 0, 0, 0};
+    if (GARBLE) acc = label_and_mask(R, mask_of(n.lo.x >> 24));
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);
 #pragma unroll
     for (int j = 0; j < NODE_MAX_FANIN; j++) {
         if ((uint32_t)j >= kmax) break;                        // warp-uniform
-#pragma unroll
-        for (int u = 0; u < NU; u++) {
-            const uint32_t w = j < 2 ? n[u].lo.y : j < 4 ? n[u].lo.z : j < 6 ? n[u].lo.w : j < 8 ? n[u].hi.x
-                             : j < 10 ? n[u].hi.y : j < 12 ? n[u].hi.z : n[u].hi.w;
-            const uint32_t s = (j & 1) ? (w >> 16) : (w & 0xffff);
-            if ((uint32_t)j < k[u]) acc[u] = acc[u] ^ lds_label(slots, s);
-        }
+        const uint32_t w = j < 2 ? n.lo.y : j < 4 ? n.lo.z : j < 6 ? n.lo.w : j < 8 ? n.hi.x
+                         : j < 10 ? n.hi.y : j < 12 ? n.hi.z : n.hi.w;
+        const uint32_t s = (j & 1) ? (w >> 16) : (w & 0xffff);
+        if ((uint32_t)j < k) acc = acc ^ lds_label(slots, s);
     }
-#pragma unroll
-    for (int u = 0; u < NU; u++) {
-        if (!active[u]) continue;
-        sts_label(slots, n[u].lo.x & 0xffff, acc[u]);
-        if (FULL) {
-            const size_t ow = (size_t)inst * p.n_wires + __ldg(p.nout_wire + index[u]);
-            if (GARBLE) {
-                p.wires_full[2 * ow] = label_to_mem(acc[u]);
-                p.wires_full[2 * ow + 1] = label_to_mem(acc[u] ^ R);
-            } else {
-                p.wires_full[ow] = label_to_mem(acc[u]);
-            }
+    if (!active) return;
+    sts_label(slots, n.lo.x & 0xffff, acc);
+    if (FULL) {
+        const size_t ow = (size_t)inst * p.n_wires + __ldg(p.nout_wire + index);
+        if (GARBLE) {
+            p.wires_full[2 * ow] = label_to_mem(acc);
+            p.wires_full[2 * ow + 1] = label_to_mem(acc ^ R);
+        } else {
+            p.wires_full[ow] = label_to_mem(acc);
         }
     }
 }
 
-// All node waves of a phase, one node per thread at a time.  `pre` is this thread's first
-// node of wave 0 (index w0_first + ttid), loaded during the previous phase; the first node
-// of wave w+1 is loaded while wave w runs.
+// This thread's record of node row `row`.
+__device__ __forceinline__ NodeRegs load_row(const GcParams& p, uint32_t row, uint32_t ttid) {
+    return load_node(p.nodes, row * p.team_threads + ttid);
+}
+
+// The node rows of a phase.  pipe[] holds this thread's records of rows `row` .. `row` +
+// GC_NODE_PIPE - 1; each step retires one and requests the record GC_NODE_PIPE rows ahead (the
+// row array ends with that many empty rows).  A team barrier follows the last row of a wave.
 template <bool GARBLE, bool FULL>
-__device__ __forceinline__ void run_waves(const GcParams& p, uint4* slots, const Label R, uint32_t inst, const Phase& ph,
-                                          uint32_t team, uint32_t ttid, uint32_t TT, const NodeRegs& pre) {
-    const NodeRegs zero{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    uint32_t first = ph.w0_first;
-    uint32_t count = ph.n_waves ? wave_count(p, ph, 0) : 0u;
-    NodeRegs cur = pre;
-    for (uint32_t w = 0; w < ph.n_waves; w++) {
-        const uint32_t next_first = first + count;
-        uint32_t next_count = 0;
-        NodeRegs nxt = zero;
-        if (w + 1 < ph.n_waves) {
-            next_count = wave_count(p, ph, w + 1);
-            if (ttid < next_count) nxt = load_node(p.nodes, next_first + ttid);
-        }
-        // this warp's nodes: j = ttid + i*TT, i < n_i (warp-uniform)
-        const uint32_t wbase = ttid & ~31u;
-        const uint32_t n_i = count > wbase ? (count - wbase + TT - 1) / TT : 0u;
-        for (uint32_t i = 0; i < n_i; i++) {
-            const uint32_t j = ttid + i * TT;
-            const uint32_t index[1] = {first + j};
-            const bool active[1] = {j < count};
-            NodeRegs n[1] = {cur};
-            if (i) { n[0] = zero; if (active[0]) n[0] = load_node(p.nodes, first + j); }
-            run_nodes<GARBLE, FULL, 1>(p, slots, R, inst, index, n, active);
-        }
-        team_barrier(team, TT);
-        first = next_first; count = next_count; cur = nxt;
+__device__ __forceinline__ void run_rows(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t n_rows,
+                                         uint32_t team, uint32_t ttid, uint32_t TT, NodeRegs (&pipe)[GC_NODE_PIPE],
+                                         uint32_t& row) {
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const NodeRegs cur = pipe[0];
+#pragma unroll
+        for (uint32_t d = 0; d + 1 < GC_NODE_PIPE; d++) pipe[d] = pipe[d + 1];
+        pipe[GC_NODE_PIPE - 1] = load_row(p, row + GC_NODE_PIPE, ttid);
+        run_node<GARBLE, FULL>(p, slots, R, inst, row * TT + ttid, cur);
+        row++;
+        if ((cur.lo.x >> 24) & NODE_WAVE_END) team_barrier(team, TT);
     }
 }
 
@@ -475,8 +448,10 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
         // plan records of the first phases load while the inputs do
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
-        NodeRegs npre{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ph.n_waves && ttid < wave_count(p, ph, 0)) npre = load_node(p.nodes, ph.w0_first + ttid);
+        NodeRegs pipe[GC_NODE_PIPE];
+        uint32_t row = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < GC_NODE_PIPE; d++) pipe[d] = load_row(p, d, ttid);
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
@@ -502,15 +477,13 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);  // two zero records of padding
             uint4 cur[ILP];
             prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
-            NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
-            if (!(p.debug_skip & 1)) run_waves<true, FULL>(p, slots, R, inst, ph, tc.team, ttid, TT, npre);
+            run_rows<true, FULL>(p, slots, R, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
             if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
-            const uint32_t ntask = (p.debug_skip & 2) ? 0u : task_count<true>(ph);
+            const uint32_t ntask = task_count<true>(ph);
             if (ntask) {
                 const uint32_t per_thread = (ntask + TT - 1) / TT;        // tasks k = 0 .. per_thread-1
                 const uint32_t and_tasks = ph.has_or ? 0u : 4 * ph.n_quad;  // leading tasks that are all AND
@@ -537,7 +510,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                 if (tracing) p.trace[4 * pi + 3] = clock64();
                 team_barrier(tc.team, TT);
             }
-            ph = ph_n; ph_n = ph_nn; npre = npre_n;
+            ph = ph_n; ph_n = ph_nn;
         }
         // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
@@ -684,8 +657,10 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         if (p.key_stride != 0 && ttid == 0)
             aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
-        NodeRegs npre{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (ph.n_waves && ttid < wave_count(p, ph, 0)) npre = load_node(p.nodes, ph.w0_first + ttid);
+        NodeRegs pipe[GC_NODE_PIPE];
+        uint32_t row = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < GC_NODE_PIPE; d++) pipe[d] = load_row(p, d, ttid);
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
             uint4 m;
@@ -715,9 +690,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             }
             uint4 cur_n[ILP];
             prefetch_cipher<false, ILP>(p, ph_n, 0, ttid, TT, cur_n);
-            NodeRegs npre_n{make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (ph_n.n_waves && ttid < wave_count(p, ph_n, 0)) npre_n = load_node(p.nodes, ph_n.w0_first + ttid);
-            run_waves<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph, tc.team, ttid, TT, npre);
+            run_rows<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);
@@ -746,7 +719,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                 }
                 team_barrier(tc.team, TT);
             }
-            ph = ph_n; ph_n = ph_nn; npre = npre_n;
+            ph = ph_n; ph_n = ph_nn;
 #pragma unroll
             for (int j = 0; j < ILP; j++) cur[j] = cur_n[j];
         }

@@ -174,7 +174,6 @@ extern "C" void gcb_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 DevicePlan::~DevicePlan() {
     // best effort: the context may already be gone at process exit
     if (phases) cudaFree(phases);
-    if (waves) cudaFree(waves);
     if (nodes) cudaFree(nodes);
     if (crecs) cudaFree(crecs);
     if (nout_wire) cudaFree(nout_wire);
@@ -192,26 +191,60 @@ static cudaError_t upload(T** dst, const std::vector<T>& v) {
     return cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
-int plan_on_device(const Plan& plan, int device, std::shared_ptr<DevicePlan>* out) {
+int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::shared_ptr<DevicePlan>* out) {
     std::lock_guard<std::mutex> lk(plan.mu);
-    auto it = plan.dev.find(device);
+    const auto key = std::make_pair(device, team_threads);
+    auto it = plan.dev.find(key);
     if (it != plan.dev.end()) { *out = it->second; return GCB_OK; }
     auto dp = std::make_shared<DevicePlan>();
     dp->device = device;
-    {
-        std::vector<PhaseRec> ph(plan.phases);
-        ph.push_back(PhaseRec{});                       // the kernels read two records ahead
-        ph.push_back(PhaseRec{});
-        CK(upload(&dp->phases, ph));
+    dp->team_threads = team_threads;
+    // node rows: every wave padded to whole rows of team_threads records (plan.hpp)
+    const uint32_t TT = team_threads;
+    std::vector<DevPhaseRec> ph;
+    std::vector<NodeRec> rows;
+    std::vector<uint32_t> row_wire;
+    ph.reserve(plan.phases.size() + 2);
+    for (const PhaseRec& src : plan.phases) {
+        DevPhaseRec d{};
+        d.cipher_first = src.cipher_first; d.n_quad = src.n_quad; d.n_inv = src.n_inv;
+        d.row_first = (uint32_t)(rows.size() / TT);
+        const uint32_t nw = src.n_waves & 0x7fffffffu;
+        for (uint32_t w = 0; w < nw; w++) {
+            const WaveRec& wr = plan.waves[src.wave_first + w];
+            const uint32_t nrow = (wr.count + TT - 1) / TT;
+            for (uint32_t r = 0; r < nrow; r++) {
+                const uint8_t end = r + 1 == nrow ? NODE_WAVE_END : 0;
+                for (uint32_t t = 0; t < TT; t++) {
+                    const uint32_t j = r * TT + t;
+                    NodeRec rec{};
+                    uint32_t wire = 0;
+                    if (j < wr.count) {
+                        rec = plan.nodes[wr.first + j];
+                        rec.parity = (uint8_t)((rec.parity & NODE_PARITY) | NODE_ACTIVE);
+                        wire = plan.nout_wire[wr.first + j];
+                    }
+                    rec.parity |= end;
+                    rows.push_back(rec);
+                    row_wire.push_back(wire);
+                }
+            }
+        }
+        d.n_rows = (uint32_t)(rows.size() / TT) - d.row_first;
+        if (src.n_waves & 0x80000000u) d.n_rows |= 0x80000000u;
+        ph.push_back(d);
     }
-    CK(upload(&dp->waves, plan.waves));
-    CK(upload(&dp->nodes, plan.nodes));
+    ph.push_back(DevPhaseRec{});                        // the kernels read two records ahead
+    ph.push_back(DevPhaseRec{});
+    rows.resize(rows.size() + (size_t)GC_NODE_PIPE * TT, NodeRec{});   // and GC_NODE_PIPE rows ahead
+    CK(upload(&dp->phases, ph));
+    CK(upload(&dp->nodes, rows));
     CK(upload(&dp->crecs, plan.crecs));
-    CK(upload(&dp->nout_wire, plan.nout_wire));
+    CK(upload(&dp->nout_wire, row_wire));
     CK(upload(&dp->cout_wire, plan.cout_wire));
     CK(upload(&dp->live_in, plan.live_in));
     CK(upload(&dp->live_out, plan.live_out));
-    plan.dev[device] = dp;
+    plan.dev[key] = dp;
     *out = dp;
     return GCB_OK;
 }
@@ -293,13 +326,14 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
                      const gcb_label* in_labels, gcb_label* tables, void* io, void* wires_full,
                      cudaStream_t stream, const uint32_t* in_ids = nullptr, const uint32_t* out_ids = nullptr,
                      uint4* const* pages = nullptr) {
-    std::shared_ptr<DevicePlan> dp;
-    int rc = plan_on_device(plan, device, &dp);
-    if (rc) return rc;
     const gcb_plan_info& in = plan.info;
+    const Geometry geo = compute_geometry(in.num_slots, di->smem_base);
+    if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
+    std::shared_ptr<DevicePlan> dp;
+    int rc = plan_on_device(plan, device, geo.team_threads, &dp);
+    if (rc) return rc;
     GcParams p{};
     p.phases = reinterpret_cast<const uint4*>(dp->phases);
-    p.waves = reinterpret_cast<const uint2*>(dp->waves);
     p.nodes = reinterpret_cast<const uint4*>(dp->nodes);
     p.crecs = reinterpret_cast<const uint4*>(dp->crecs);
     p.nout_wire = dp->nout_wire;
@@ -314,13 +348,10 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     p.tables = reinterpret_cast<uint4*>(tables);
     p.io = reinterpret_cast<uint4*>(io);
     p.wires_full = reinterpret_cast<uint4*>(wires_full);
-    const Geometry geo = compute_geometry(in.num_slots, di->smem_base);
-    if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
     p.team_threads = geo.team_threads; p.n_teams = geo.n_teams;
     p.in_ids = in_ids; p.out_ids = out_ids; p.pages = pages;
     p.stagger = geo.stagger;
     p.trace = g_trace;
-    if (const char* e = getenv("GCB_DEBUG_SKIP")) p.debug_skip = (uint32_t)atoi(e);
     rc = fresh_counter(di, stream, &p.counter);
     if (rc) return rc;
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;

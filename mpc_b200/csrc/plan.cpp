@@ -7,6 +7,7 @@
 #include <iterator>
 #include <limits>
 #include <queue>
+#include <set>
 
 namespace gcb {
 
@@ -228,25 +229,81 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         // be rewritten from step s+1 on (reads and writes of one step are unordered).
         std::vector<std::vector<size_t>> expire((size_t)nsteps + 1);
         std::vector<uint32_t> slot(ndefs, 0);
-        std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<uint32_t>> free_slots;
+        // Free slots by bank group (slot & 7: a 16-byte label covers four of the 32 banks).  A
+        // 128-bit shared-memory access is served one quarter warp at a time, and the eight lanes of
+        // a quarter warp are conflict-free when their labels sit in eight different bank groups:
+        // the value written by lane position `pos` of a step prefers bank group pos & 7.  Taking a
+        // free slot of the wanted group instead of the lowest one never grows the slot count (a new
+        // slot is opened only when no slot is free).
+        std::set<uint32_t> free_slots[8];
         uint32_t next_slot = 0;
+        auto release = [&](uint32_t s) { free_slots[s & 7].insert(s); };
         out.live_in.clear();
         for (size_t k = 0; k < ninit; k++) {
             slot[k] = next_slot++;
             out.live_in.push_back(SlotRef{slot[k], (uint32_t)k});
-            if (last[k] < 0) free_slots.push(slot[k]);                 // never read, not live-out
+            if (last[k] < 0) release(slot[k]);                         // never read, not live-out
             else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
         }
-        auto take_slot = [&](size_t d) {
-            if (free_slots.empty()) slot[d] = next_slot++;
-            else { slot[d] = free_slots.top(); free_slots.pop(); }
+        auto take_slot = [&](size_t d, uint32_t want) {
+            want &= 7;
+            int from = -1;
+            if (!free_slots[want].empty()) from = (int)want;
+            else {
+                uint32_t lowest = 0xffffffffu;
+                for (int b = 0; b < 8; b++)
+                    if (!free_slots[b].empty() && *free_slots[b].begin() < lowest) { lowest = *free_slots[b].begin(); from = b; }
+            }
+            if (from < 0) slot[d] = next_slot++;
+            else { slot[d] = *free_slots[from].begin(); free_slots[from].erase(free_slots[from].begin()); }
             if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+        };
+        // Order of the ciphered gates of a level: AND/OR first, then INV (the kernels give 4 / 2
+        // tasks to each); inside a class, gates are grouped so that the lanes of a quarter warp
+        // (four AND gates in eval, two in garble; eight / four INV gates) read their first inputs
+        // from different bank groups, and their second inputs too.
+        auto group_gates = [&](std::vector<uint32_t>& gates_of_level) {
+            std::stable_sort(gates_of_level.begin(), gates_of_level.end(), [&](uint32_t x, uint32_t y) {
+                return op_class(spec.gates[x].op) < op_class(spec.gates[y].op);
+            });
+            size_t lo = 0;
+            while (lo < gates_of_level.size()) {
+                size_t hi = lo;
+                const int cls = op_class(spec.gates[gates_of_level[lo]].op);
+                while (hi < gates_of_level.size() && op_class(spec.gates[gates_of_level[hi]].op) == cls) hi++;
+                const size_t group = cls == 2 ? 8 : 4;
+                std::vector<uint32_t> rest(gates_of_level.begin() + lo, gates_of_level.begin() + hi), done;
+                done.reserve(rest.size());
+                while (!rest.empty()) {
+                    uint32_t sa[8], sb[8];
+                    size_t n = 0;
+                    while (n < group && !rest.empty()) {
+                        size_t pick = 0;
+                        int best = 1 << 30;
+                        for (size_t c = 0; c < rest.size() && best > 0; c++) {
+                            const uint32_t a = slot[(size_t)def_a[rest[c]]], b = slot[(size_t)def_b[rest[c]]];
+                            int cost = 0;
+                            for (size_t q = 0; q < n; q++) {
+                                cost += (sa[q] != a && (sa[q] & 7) == (a & 7));
+                                cost += (sb[q] != b && (sb[q] & 7) == (b & 7));
+                            }
+                            if (cost < best) { best = cost; pick = c; }
+                        }
+                        sa[n] = slot[(size_t)def_a[rest[pick]]]; sb[n] = slot[(size_t)def_b[rest[pick]]];
+                        n++;
+                        done.push_back(rest[pick]);
+                        rest.erase(rest.begin() + (long)pick);
+                    }
+                }
+                std::copy(done.begin(), done.end(), gates_of_level.begin() + lo);
+                lo = hi;
+            }
         };
         {
             int64_t s = 0;
             auto advance = [&]() {
                 if (s > 0) {
-                    for (size_t d : expire[(size_t)s - 1]) free_slots.push(slot[d]);
+                    for (size_t d : expire[(size_t)s - 1]) release(slot[d]);
                     expire[(size_t)s - 1].clear();
                 }
             };
@@ -259,12 +316,14 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                 size_t pos = 0;
                 for (uint32_t w = 0; w < n_waves[p]; w++, s++) {
                     advance();
-                    for (; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++)
-                        take_slot(ninit + phase_nodes[p][pos].gate);
+                    for (uint32_t lane = 0; pos < phase_nodes[p].size() && phase_nodes[p][pos].wave == w; pos++, lane++)
+                        take_slot(ninit + phase_nodes[p][pos].gate, lane);
                 }
                 if (!phase_cipher[p].empty()) {
                     advance();
-                    for (uint32_t i : phase_cipher[p]) take_slot(ninit + i);
+                    group_gates(phase_cipher[p]);
+                    uint32_t lane = 0;
+                    for (uint32_t i : phase_cipher[p]) take_slot(ninit + i, lane++);
                     s++;
                 }
             }
@@ -277,6 +336,71 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         out.live_out.clear();
         for (size_t k = 0; k < spec.live_out.size(); k++)
             out.live_out.push_back(SlotRef{slot[(size_t)out_def[k]], (uint32_t)k});
+
+        // ---- leaf order.  The eight nodes of a quarter warp read leaf j in the same instruction; XOR
+        // commutes, so each node's leaves are permuted to put labels of different bank groups side by
+        // side (equal slots are a broadcast and cost nothing).  Greedy per leaf position, a few seeded
+        // restarts, the cheapest kept.
+        auto order_leaves = [&](NodeRec* q, size_t n) {
+            auto cost_of = [&](const NodeRec* r) {
+                int total = 0;
+                for (int j = 0; j < NODE_MAX_FANIN; j++) {
+                    uint32_t seen[8]; int ns = 0, cnt[8] = {0}, worst = 0;
+                    for (size_t i = 0; i < n; i++) {
+                        if (j >= r[i].k) continue;
+                        bool dup = false;
+                        for (int x = 0; x < ns; x++) dup |= seen[x] == r[i].leaf[j];
+                        if (dup) continue;
+                        seen[ns++] = r[i].leaf[j];
+                        worst = std::max(worst, ++cnt[r[i].leaf[j] & 7]);
+                    }
+                    total += worst;
+                }
+                return total;
+            };
+            NodeRec best[8], cand[8];
+            std::copy(q, q + n, best);
+            int best_cost = cost_of(best);
+            uint32_t rng = 0x9e3779b9u;
+            for (int trial = 0; trial < 12; trial++) {
+                std::copy(q, q + n, cand);
+                uint16_t pool[8][NODE_MAX_FANIN];
+                int left[8];
+                for (size_t i = 0; i < n; i++) {
+                    left[i] = cand[i].k;
+                    std::copy(cand[i].leaf, cand[i].leaf + cand[i].k, pool[i]);
+                    if (trial) for (int x = left[i] - 1; x > 0; x--) {       // seeded shuffle
+                        rng = rng * 1664525u + 1013904223u;
+                        std::swap(pool[i][x], pool[i][(rng >> 8) % (uint32_t)(x + 1)]);
+                    }
+                }
+                for (int j = 0; j < NODE_MAX_FANIN; j++) {
+                    uint32_t seen[8]; int ns = 0, cnt[8] = {0};
+                    // most constrained first: nodes with the fewest leaves left choose first
+                    size_t ord[8];
+                    for (size_t i = 0; i < n; i++) ord[i] = i;
+                    std::stable_sort(ord, ord + n, [&](size_t x, size_t y) { return left[x] < left[y]; });
+                    for (size_t oi = 0; oi < n; oi++) {
+                        const size_t i = ord[oi];
+                        if (left[i] == 0) continue;
+                        int pick = 0, pick_cost = 1 << 30;
+                        for (int x = 0; x < left[i]; x++) {
+                            bool dup = false;
+                            for (int y = 0; y < ns; y++) dup |= seen[y] == pool[i][x];
+                            const int c = dup ? -1 : cnt[pool[i][x] & 7];
+                            if (c < pick_cost) { pick_cost = c; pick = x; }
+                        }
+                        const uint16_t leaf = pool[i][pick];
+                        pool[i][pick] = pool[i][--left[i]];
+                        cand[i].leaf[j] = leaf;
+                        if (pick_cost >= 0) { seen[ns++] = leaf; cnt[leaf & 7]++; }
+                    }
+                }
+                const int c = cost_of(cand);
+                if (c < best_cost) { best_cost = c; std::copy(cand, cand + n, best); }
+            }
+            std::copy(best, best + n, q);
+        };
 
         // ---- records in schedule order
         out.phases.clear(); out.waves.clear(); out.nodes.clear(); out.crecs.clear();
@@ -297,18 +421,17 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                     r.parity = nd.parity;
                     for (size_t j = 0; j < nd.leaves.size(); j++) r.leaf[j] = (uint16_t)slot[nd.leaves[j]];
                     out.nodes.push_back(r);
+                    if ((wr.count & 7) == 7) order_leaves(out.nodes.data() + out.nodes.size() - 8, 8);
                     out.nout_wire.push_back(spec.gates[nd.gate].out);
                     out.node_loads += r.k;
                     wr.count++;
                 }
+                if (wr.count & 7) order_leaves(out.nodes.data() + out.nodes.size() - (wr.count & 7), wr.count & 7);
                 out.waves.push_back(wr);
                 if (w == 0) ph.w0_first = wr.first;
                 if (w < 4) ph.wave_count[w] = (uint16_t)(wr.count < 0xffffu ? wr.count : 0xffffu);
             }
-            // ciphered gates: AND/OR first, then INV (the kernels give 4 / 2 tasks to each)
-            std::stable_sort(phase_cipher[p].begin(), phase_cipher[p].end(), [&](uint32_t x, uint32_t y) {
-                return op_class(spec.gates[x].op) < op_class(spec.gates[y].op);
-            });
+            // ciphered gates, in the order group_gates chose: AND/OR first, then INV
             ph.cipher_first = (uint32_t)out.crecs.size();
             for (uint32_t i : phase_cipher[p]) {
                 const gcb_gate& g = spec.gates[i];

@@ -67,6 +67,22 @@ struct SlotRef {
     uint32_t index;       // index into the caller's live-in / live-out array
 };
 
+// ---- what the kernels read (built per device and team width by plan_on_device) ----
+// The nodes are laid out as ROWS of team_threads records: lane t of the team runs record t of
+// each row.  A wave occupies whole rows (padded with inactive records), rows follow each other
+// in schedule order across waves and phases, so every thread streams its records with a fixed
+// prefetch distance no matter where wave and phase boundaries fall.  Flags in NodeRec::parity:
+enum : uint8_t { NODE_PARITY = 1, NODE_WAVE_END = 2, NODE_ACTIVE = 4 };   // WAVE_END: team barrier after the row
+struct DevPhaseRec {
+    uint32_t n_rows;                  // node rows of the phase; bit 31: the cipher level has OR gates
+    uint32_t cipher_first, n_quad;    // range in the GateRec array: n_quad AND/OR gates ...
+    uint32_t n_inv;                   // ... then n_inv INV gates
+    uint32_t row_first;               // first node row of the phase
+    uint32_t pad[3];
+};
+static_assert(sizeof(DevPhaseRec) == 32, "DevPhaseRec must be 32 bytes");
+constexpr uint32_t GC_NODE_PIPE = 2;  // rows a thread keeps in flight ahead of the one it runs
+
 struct PlanSpec {
     const gcb_gate* gates = nullptr;
     uint32_t num_gates = 0, num_wires = 0;
@@ -78,13 +94,13 @@ struct PlanSpec {
     std::vector<uint32_t> live_out;   // locations read back after the last gate; k-th entry stores dest k
 };
 
-struct DevicePlan {                   // per-device copy of the tables
+struct DevicePlan {                   // per (device, team width) copy of the tables
     int device = -1;
-    PhaseRec* phases = nullptr;       // + two zero records of padding
-    WaveRec* waves = nullptr;
-    NodeRec* nodes = nullptr;
+    uint32_t team_threads = 0;
+    DevPhaseRec* phases = nullptr;    // + two zero records of padding
+    NodeRec* nodes = nullptr;         // rows of team_threads records + GC_NODE_PIPE empty rows
     GateRec* crecs = nullptr;
-    uint32_t* nout_wire = nullptr;    // original output wire of each node / ciphered gate
+    uint32_t* nout_wire = nullptr;    // original output wire of each node record / ciphered gate
     uint32_t* cout_wire = nullptr;
     SlotRef* live_in = nullptr;
     SlotRef* live_out = nullptr;
@@ -107,7 +123,7 @@ struct Plan {
     std::vector<gcb_gate> gates;          // kept for streaming (header templates)
 
     mutable std::mutex mu;
-    mutable std::map<int, std::shared_ptr<DevicePlan>> dev;
+    mutable std::map<std::pair<int, uint32_t>, std::shared_ptr<DevicePlan>> dev;   // (device, team width)
 };
 
 // Returns GCB_OK or a negative status; message in err.  max_fanin = NODE_MAX_FANIN

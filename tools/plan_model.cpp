@@ -1,0 +1,139 @@
+// plan_model.cpp -- host-only model of the shared-memory traffic of a plan.
+//
+// Builds the plan of a circuit (tools/_build/<name>.gates, written by tools/plan_model.py)
+// with the product's plan compiler and counts, for a given team width, the shared-memory
+// wavefronts the gate kernels spend on wire labels: a 128-bit access is served one quarter
+// warp at a time, and a quarter warp takes as many wavefronts as the largest number of
+// distinct 16-byte words that fall into the same group of four banks (word index mod 8).
+//
+//   g++ -O2 -std=c++17 -I include -o tools/_build/plan_model tools/plan_model.cpp mpc_b200/csrc/plan.cpp
+//   tools/_build/plan_model tools/_build/aes_128.gates 96
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../mpc_b200/csrc/plan.hpp"
+
+using namespace gcb;
+
+struct Acc {
+    uint64_t instr = 0, wavefronts = 0, ideal8 = 0;   // ideal8: distinct words (8 per wavefront at best)
+    void add(const std::vector<int>& lane_slot) {     // -1 = inactive lane; 32 entries
+        bool any = false;
+        for (int q = 0; q < 4; q++) {
+            int cnt[8] = {0};
+            int seen[8], ns = 0;
+            for (int l = 0; l < 8; l++) {
+                const int s = lane_slot[q * 8 + l];
+                if (s < 0) continue;
+                bool dup = false;
+                for (int i = 0; i < ns; i++) dup |= seen[i] == s;
+                if (dup) continue;
+                seen[ns++] = s;
+                cnt[s & 7]++;
+            }
+            int m = 0;
+            for (int b = 0; b < 8; b++) m = cnt[b] > m ? cnt[b] : m;
+            wavefronts += m;
+            ideal8 += ns;
+            any |= ns > 0;
+        }
+        instr += any;
+    }
+};
+
+int main(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: plan_model file.gates team_threads\n"); return 2; }
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { perror(argv[1]); return 1; }
+    uint32_t hdr[4];
+    if (fread(hdr, 4, 4, f) != 4) return 1;
+    std::vector<gcb_gate> gates(hdr[0]);
+    if (fread(gates.data(), sizeof(gcb_gate), hdr[0], f) != hdr[0]) return 1;
+    fclose(f);
+    const uint32_t TT = (uint32_t)atoi(argv[2]);
+    PlanSpec spec;
+    spec.gates = gates.data(); spec.num_gates = hdr[0]; spec.num_wires = hdr[1];
+    for (uint32_t i = 0; i < hdr[2]; i++) spec.live_in.push_back(i);
+    for (uint32_t i = 0; i < hdr[3]; i++) spec.live_out.push_back(hdr[1] - hdr[3] + i);
+    Plan plan;
+    std::string err;
+    if (int rc = build_plan(spec, plan, err)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
+    const gcb_plan_info& in = plan.info;
+    printf("gates %u  and %u inv %u or %u free %u  slots %u  steps %u  phases %zu  waves %zu  nodes %zu  node_loads %u\n",
+           in.num_gates, in.num_and, in.num_inv, in.num_or, in.num_free, in.num_slots, in.num_steps, plan.phases.size(),
+           plan.waves.size(), plan.nodes.size(), plan.node_loads);
+
+    Acc node_ld, node_st, g_ld, g_st, e_ld, e_st;
+    uint64_t barriers = 0, garble_passes = 0, eval_passes = 0, node_iters = 0;
+    std::vector<int> ls(32);
+    for (const PhaseRec& ph : plan.phases) {
+        const uint32_t nw = ph.n_waves & 0x7fffffffu;
+        for (uint32_t w = 0; w < nw; w++) {
+            const WaveRec& wr = plan.waves[ph.wave_first + w];
+            barriers++;
+            for (uint32_t base = 0; base < wr.count; base += TT) {
+                for (uint32_t wb = 0; wb < TT && base + wb < wr.count; wb += 32) {
+                    node_iters++;
+                    uint32_t kmax = 0;
+                    for (int l = 0; l < 32; l++) {
+                        const uint32_t j = base + wb + l;
+                        if (j < wr.count) kmax = std::max<uint32_t>(kmax, plan.nodes[wr.first + j].k);
+                    }
+                    for (uint32_t k = 0; k < kmax; k++) {
+                        for (int l = 0; l < 32; l++) {
+                            const uint32_t j = base + wb + l;
+                            ls[l] = -1;
+                            if (j < wr.count && k < plan.nodes[wr.first + j].k) ls[l] = plan.nodes[wr.first + j].leaf[k];
+                        }
+                        node_ld.add(ls);
+                    }
+                    for (int l = 0; l < 32; l++) {
+                        const uint32_t j = base + wb + l;
+                        ls[l] = j < wr.count ? (int)plan.nodes[wr.first + j].dst : -1;
+                    }
+                    node_st.add(ls);
+                }
+            }
+        }
+        const uint32_t ngate = ph.n_quad + ph.n_inv;
+        if (ngate) barriers++;
+        for (int garble = 0; garble < 2; garble++) {
+            const uint32_t qs = garble ? 4 : 2, is = garble ? 2 : 1;
+            const uint32_t ntask = qs * ph.n_quad + is * ph.n_inv;
+            Acc& ld = garble ? g_ld : e_ld;
+            Acc& st = garble ? g_st : e_st;
+            for (uint32_t t0 = 0; t0 < ntask; t0 += 32) {
+                (garble ? garble_passes : eval_passes)++;
+                std::vector<int> la(32, -1), lb(32, -1), lc(32, -1);
+                for (int l = 0; l < 32; l++) {
+                    const uint32_t t = t0 + l;
+                    if (t >= ntask) continue;
+                    uint32_t gi, k;
+                    if (t < qs * ph.n_quad) { gi = t / qs; k = t % qs; }
+                    else { gi = ph.n_quad + (t - qs * ph.n_quad) / is; k = (t - qs * ph.n_quad) % is; }
+                    const GateRec& g = plan.crecs[ph.cipher_first + gi];
+                    la[l] = g.a; lb[l] = g.b;
+                    if (k == 0) lc[l] = g.c;
+                }
+                ld.add(la); ld.add(lb); st.add(lc);
+            }
+        }
+    }
+    auto pr = [](const char* n, const Acc& a) {
+        printf("%-14s instr %8llu  wavefronts %8llu  ideal %8.0f  (x%.2f)\n", n, (unsigned long long)a.instr,
+               (unsigned long long)a.wavefronts, a.ideal8 / 8.0, a.wavefronts / (a.ideal8 / 8.0 + 1e-9));
+    };
+    pr("node loads", node_ld); pr("node stores", node_st);
+    pr("garble loads", g_ld); pr("garble stores", g_st);
+    pr("eval loads", e_ld); pr("eval stores", e_st);
+    printf("barriers %llu  node warp-iterations %llu  cipher warp-passes garble %llu eval %llu\n",
+           (unsigned long long)barriers, (unsigned long long)node_iters, (unsigned long long)garble_passes,
+           (unsigned long long)eval_passes);
+    const uint64_t aes_g = (uint64_t)in.garble_hashes * 160 / 32, aes_e = (uint64_t)in.eval_hashes * 160 / 32;
+    printf("per instance wavefronts: garble AES %llu + labels %llu ; eval AES %llu + labels %llu\n",
+           (unsigned long long)aes_g, (unsigned long long)(node_ld.wavefronts + node_st.wavefronts + g_ld.wavefronts + g_st.wavefronts),
+           (unsigned long long)aes_e, (unsigned long long)(node_ld.wavefronts + node_st.wavefronts + e_ld.wavefronts + e_st.wavefronts));
+    return 0;
+}
