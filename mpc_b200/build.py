@@ -12,14 +12,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libgcb200.so")
-SOURCES = ["gcb200.cu", "stream.cu", "plan.cpp"]
+SOURCES = ["gcb200.cu", "gc_garble.cu", "gc_eval.cu", "plan.cpp"]
 HEADERS = ["aes_core.cuh", "gc_kernels.cuh", "ot_kernels.cuh", "stream_kernels.cuh", "plan.hpp", "hostpipe.hpp",
-           "common.hpp", "../../include/gcb200.h"]
+           "gc_launch.hpp", "../../include/gcb200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "--use_fast_math",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--use_fast_math",
     "-Xptxas", "-v", "-diag-suppress", "128",
 ]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def needs_build() -> bool:
@@ -31,20 +32,35 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit to an object (in parallel: the gate kernels are two
+    units of 36 instantiations each), then link the shared library."""
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
-    extra = os.environ.get("GCB_NVCC_EXTRA", "").split()      # e.g. -DGCB_AES_TABLES=2 for experiments
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    extra = os.environ.get("GCB_NVCC_EXTRA", "").split()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs = []
+    for f in SOURCES:
+        obj = os.path.join(OBJ_DIR, os.path.splitext(f)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, f)]
+        jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    out, failed = [], False
+    for cmd, obj, proc in jobs:
+        text, _ = proc.communicate()
+        out.append(" ".join(cmd) + "\n" + text)
+        failed |= proc.returncode != 0
+    if not failed:
+        cmd = [nvcc, "-shared", "-o", SO] + [obj for _, obj, _ in jobs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        out.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        failed = r.returncode != 0
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:
-        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose or r.returncode:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode:
-        raise RuntimeError(f"nvcc failed ({r.returncode}); see {log}")
+        f.write("\n".join(out))
+    if verbose or failed:
+        sys.stderr.write("\n".join(out))
+    if failed:
+        raise RuntimeError(f"nvcc failed; see {log}")
     return SO
 
 

@@ -79,19 +79,20 @@ __device__ const Te0Array g_te0 = make_te0();
 // Entry x of table t for lane l lives at byte offset
 //     (t >> 1) * 65536 + x * 256 + (t & 1) * 128 + l * 4
 // (two tables interleaved per 64 KiB region with a 256-byte entry stride).
-// GCB_AES_TABLES = 4: T0..T3 resident (128 KiB).  GCB_AES_TABLES = 2: only T0/T1 resident
-// (64 KiB); T2 = rot16(T0) and T3 = rot16(T1) cost one more PRMT per lookup of those
-// tables (8 per round) and free 64 KiB of shared memory for wire labels.
-#ifndef GCB_AES_TABLES
-#define GCB_AES_TABLES 4
-#endif
-constexpr int AES_TABLE_BYTES = GCB_AES_TABLES * 256 * 32 * 4;   // 131072 or 65536
+// Template parameter NT of everything below: NT = 4 keeps T0..T3 resident (128 KiB).  NT = 2
+// keeps only T0/T1 (64 KiB); T2 = rot16(T0) and T3 = rot16(T1) cost one more PRMT per lookup
+// of those tables (8 per round) and free 64 KiB of shared memory for wire labels -- the gate
+// kernels use it for deep, narrow circuits, which are bound by latency (resident instances),
+// not by lookup throughput.
+__host__ __device__ constexpr int aes_table_bytes(int nt) { return nt * 256 * 32 * 4; }   // 131072 or 65536
+constexpr int AES_TABLE_BYTES = aes_table_bytes(4);
 constexpr int AES_MAX_RK_WORDS = 60;                 // AES-256: 15 round keys
 
 __device__ __forceinline__ uint32_t ror8(uint32_t x) { return __funnelshift_r(x, x, 8); }
 
 // Cooperative fill of the replicated tables; all threads of the CTA call it,
 // then __syncthreads().
+template <int NT = 4>
 __device__ __forceinline__ void aes_tables_to_smem(uint8_t* smem_tables) {
     for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
         const int x = i >> 5, l = i & 31;
@@ -100,7 +101,7 @@ __device__ __forceinline__ void aes_tables_to_smem(uint8_t* smem_tables) {
         uint8_t* e = smem_tables + x * 256 + l * 4;
         *reinterpret_cast<uint32_t*>(e) = t0;
         *reinterpret_cast<uint32_t*>(e + 128) = t1;
-        if (GCB_AES_TABLES == 4) {
+        if (NT == 4) {
             *reinterpret_cast<uint32_t*>(e + 65536) = t2;
             *reinterpret_cast<uint32_t*>(e + 65536 + 128) = t3;
         }
@@ -135,73 +136,78 @@ __device__ __forceinline__ uint32_t lds_u32_off(uint32_t addr) {
 }
 
 // Table T lookup of byte K (0 = LSB) of s.
-template <int T, int K>
+template <int T, int K, int NT = 4>
 __device__ __forceinline__ uint32_t te(const AesLane& a, uint32_t s) {
     // PRMT: byte1 = byte K of s, bytes 0, 2, 3 = those of the lane constant
     const uint32_t e = __byte_perm(s, a.lb, 0x7604 | (K << 4));
-    if (GCB_AES_TABLES == 4) return lds_u32_off<(T >> 1) * 65536 + (T & 1) * 128>(e);
+    if (NT == 4) return lds_u32_off<(T >> 1) * 65536 + (T & 1) * 128>(e);
     const uint32_t v = lds_u32_off<(T & 1) * 128>(e);
     return (T & 2) ? __byte_perm(v, 0, 0x1032) : v;
 }
 
 // One full round on (s0..s3) with round-key words k.
+template <int NT = 4>
 __device__ __forceinline__ void aes_round(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2,
                                           uint32_t& s3, const uint4 k) {
-    const uint32_t t0 = te<0, 3>(a, s0) ^ te<1, 2>(a, s1) ^ te<2, 1>(a, s2) ^ te<3, 0>(a, s3) ^ k.x;
-    const uint32_t t1 = te<0, 3>(a, s1) ^ te<1, 2>(a, s2) ^ te<2, 1>(a, s3) ^ te<3, 0>(a, s0) ^ k.y;
-    const uint32_t t2 = te<0, 3>(a, s2) ^ te<1, 2>(a, s3) ^ te<2, 1>(a, s0) ^ te<3, 0>(a, s1) ^ k.z;
-    const uint32_t t3 = te<0, 3>(a, s3) ^ te<1, 2>(a, s0) ^ te<2, 1>(a, s1) ^ te<3, 0>(a, s2) ^ k.w;
+    const uint32_t t0 = te<0, 3, NT>(a, s0) ^ te<1, 2, NT>(a, s1) ^ te<2, 1, NT>(a, s2) ^ te<3, 0, NT>(a, s3) ^ k.x;
+    const uint32_t t1 = te<0, 3, NT>(a, s1) ^ te<1, 2, NT>(a, s2) ^ te<2, 1, NT>(a, s3) ^ te<3, 0, NT>(a, s0) ^ k.y;
+    const uint32_t t2 = te<0, 3, NT>(a, s2) ^ te<1, 2, NT>(a, s3) ^ te<2, 1, NT>(a, s0) ^ te<3, 0, NT>(a, s1) ^ k.z;
+    const uint32_t t3 = te<0, 3, NT>(a, s3) ^ te<1, 2, NT>(a, s0) ^ te<2, 1, NT>(a, s1) ^ te<3, 0, NT>(a, s2) ^ k.w;
     s0 = t0; s1 = t1; s2 = t2; s3 = t3;
 }
 
 // Final round (SubBytes + ShiftRows + AddRoundKey).  S[x] sits in two byte lanes
 // of every T-table entry; T2 = (S,3S,2S,S) and T3 = (S,S,3S,2S) have it in the
 // top and bottom bytes, so two PRMTs gather the four S-box bytes of a column.
+template <int NT = 4>
 __device__ __forceinline__ uint32_t last_col(const AesLane& a, uint32_t x3, uint32_t x2, uint32_t x1,
                                              uint32_t x0, uint32_t k) {
-    const uint32_t b3 = te<2, 3>(a, x3);        // S in byte 3 (and byte 0)
-    const uint32_t b2 = te<3, 2>(a, x2);        // S in bytes 3, 2
-    const uint32_t b1 = te<0, 1>(a, x1);        // (2S,S,S,3S): S in bytes 2, 1
-    const uint32_t b0 = te<1, 0>(a, x0);        // (3S,2S,S,S): S in bytes 1, 0
+    const uint32_t b3 = te<2, 3, NT>(a, x3);        // S in byte 3 (and byte 0)
+    const uint32_t b2 = te<3, 2, NT>(a, x2);        // S in bytes 3, 2
+    const uint32_t b1 = te<0, 1, NT>(a, x1);        // (2S,S,S,3S): S in bytes 2, 1
+    const uint32_t b0 = te<1, 0, NT>(a, x0);        // (3S,2S,S,S): S in bytes 1, 0
     const uint32_t hi = __byte_perm(b3, b2, 0x3600);   // byte3 = b3.3, byte2 = b2.2
     const uint32_t lo = __byte_perm(b1, b0, 0x0014);   // byte1 = b1.1, byte0 = b0.0
     return __byte_perm(hi, lo, 0x3254) ^ k;            // (hi.3, hi.2, lo.1, lo.0)
 }
+template <int NT = 4>
 __device__ __forceinline__ void aes_last_round(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2,
                                                uint32_t& s3, const uint4 k) {
-    const uint32_t t0 = last_col(a, s0, s1, s2, s3, k.x);
-    const uint32_t t1 = last_col(a, s1, s2, s3, s0, k.y);
-    const uint32_t t2 = last_col(a, s2, s3, s0, s1, k.z);
-    const uint32_t t3 = last_col(a, s3, s0, s1, s2, k.w);
+    const uint32_t t0 = last_col<NT>(a, s0, s1, s2, s3, k.x);
+    const uint32_t t1 = last_col<NT>(a, s1, s2, s3, s0, k.y);
+    const uint32_t t2 = last_col<NT>(a, s2, s3, s0, s1, k.z);
+    const uint32_t t3 = last_col<NT>(a, s3, s0, s1, s2, k.w);
     s0 = t0; s1 = t1; s2 = t2; s3 = t3;
 }
 
 // Encrypt one block in place with round keys in shared memory (warp-uniform
 // address -> one broadcast LDS.128 per round).  NR = 10/12/14.
-template <int NR>
+template <int NR, int NT = 4>
 __device__ __forceinline__ void aes_encrypt_smem(const AesLane& a, const uint32_t* __restrict__ rk,
                                                  uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
     const uint4* k4 = reinterpret_cast<const uint4*>(rk);
     uint4 k = k4[0];
     s0 ^= k.x; s1 ^= k.y; s2 ^= k.z; s3 ^= k.w;
 #pragma unroll
-    for (int r = 1; r < NR; r++) aes_round(a, s0, s1, s2, s3, k4[r]);
-    aes_last_round(a, s0, s1, s2, s3, k4[NR]);
+    for (int r = 1; r < NR; r++) aes_round<NT>(a, s0, s1, s2, s3, k4[r]);
+    aes_last_round<NT>(a, s0, s1, s2, s3, k4[NR]);
 }
 
 // Same with AES-128 round keys held in registers (IKNP: one key per thread).
+template <int NT = 4>
 __device__ __forceinline__ void aes128_encrypt_regs(const AesLane& a, const uint32_t (&rk)[44],
                                                     uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
     s0 ^= rk[0]; s1 ^= rk[1]; s2 ^= rk[2]; s3 ^= rk[3];
 #pragma unroll
     for (int r = 1; r < 10; r++)
-        aes_round(a, s0, s1, s2, s3, make_uint4(rk[4 * r], rk[4 * r + 1], rk[4 * r + 2], rk[4 * r + 3]));
-    aes_last_round(a, s0, s1, s2, s3, make_uint4(rk[40], rk[41], rk[42], rk[43]));
+        aes_round<NT>(a, s0, s1, s2, s3, make_uint4(rk[4 * r], rk[4 * r + 1], rk[4 * r + 2], rk[4 * r + 3]));
+    aes_last_round<NT>(a, s0, s1, s2, s3, make_uint4(rk[40], rk[41], rk[42], rk[43]));
 }
 
 // SubWord through this lane's table column (Te0 = (2s, s, s, 3s): bits 8..15).
+template <int NT = 4>
 __device__ __forceinline__ uint32_t sub_word(const AesLane& a, uint32_t w) {
-    const uint32_t b3 = te<2, 3>(a, w), b2 = te<3, 2>(a, w), b1 = te<0, 1>(a, w), b0 = te<1, 0>(a, w);
+    const uint32_t b3 = te<2, 3, NT>(a, w), b2 = te<3, 2, NT>(a, w), b1 = te<0, 1, NT>(a, w), b0 = te<1, 0, NT>(a, w);
     const uint32_t hi = __byte_perm(b3, b2, 0x3600);
     const uint32_t lo = __byte_perm(b1, b0, 0x0014);
     return __byte_perm(hi, lo, 0x3254);
@@ -209,6 +215,7 @@ __device__ __forceinline__ uint32_t sub_word(const AesLane& a, uint32_t w) {
 
 // FIPS-197 key expansion into big-endian words.  key: raw key bytes, keylen
 // 16/24/32.  One thread; 4*(nr+1) words written to rk (shared or local).
+template <int NT = 4>
 __device__ __forceinline__ void aes_expand_key(const AesLane& a, const uint8_t* key, int keylen, uint32_t* rk) {
     const int nk = keylen >> 2, nr = nk + 6;
     for (int i = 0; i < nk; i++)
@@ -218,16 +225,17 @@ __device__ __forceinline__ void aes_expand_key(const AesLane& a, const uint8_t* 
     for (int i = nk; i < 4 * (nr + 1); i++) {
         uint32_t t = rk[i - 1];
         if (i % nk == 0) {
-            t = sub_word(a, (t << 8) | (t >> 24)) ^ rcon;
+            t = sub_word<NT>(a, (t << 8) | (t >> 24)) ^ rcon;
             rcon = (rcon << 1) ^ ((rcon & 0x80000000u) ? 0x1b000000u : 0u);
         } else if (nk > 6 && i % nk == 4) {
-            t = sub_word(a, t);
+            t = sub_word<NT>(a, t);
         }
         rk[i] = rk[i - nk] ^ t;
     }
 }
 
 // AES-128 key expansion from four big-endian key words into registers.
+template <int NT = 4>
 __device__ __forceinline__ void aes128_expand_regs(const AesLane& a, uint32_t k0, uint32_t k1, uint32_t k2,
                                                    uint32_t k3, uint32_t (&rk)[44]) {
     rk[0] = k0; rk[1] = k1; rk[2] = k2; rk[3] = k3;
@@ -235,7 +243,7 @@ __device__ __forceinline__ void aes128_expand_regs(const AesLane& a, uint32_t k0
 #pragma unroll
     for (int r = 1; r <= 10; r++) {
         const uint32_t t = rk[4 * r - 1];
-        rk[4 * r] = rk[4 * r - 4] ^ sub_word(a, (t << 8) | (t >> 24)) ^ rcon;
+        rk[4 * r] = rk[4 * r - 4] ^ sub_word<NT>(a, (t << 8) | (t >> 24)) ^ rcon;
         rk[4 * r + 1] = rk[4 * r - 3] ^ rk[4 * r];
         rk[4 * r + 2] = rk[4 * r - 2] ^ rk[4 * r + 1];
         rk[4 * r + 3] = rk[4 * r - 1] ^ rk[4 * r + 2];
@@ -266,10 +274,10 @@ __device__ __forceinline__ Label label_shl(Label a, int n) {
 
 // H(K) = AES(K) ^ K  -- the tail shared by encryptHalf (circuit/garble.go:104-136)
 // and encrypt/decrypt (circuit/garble.go:40-73).
-template <int NR>
+template <int NR, int NT = 4>
 __device__ __forceinline__ Label aes_hash_k(const AesLane& a, const uint32_t* rk, Label k) {
     uint32_t s0 = k.w0, s1 = k.w1, s2 = k.w2, s3 = k.w3;
-    aes_encrypt_smem<NR>(a, rk, s0, s1, s2, s3);
+    aes_encrypt_smem<NR, NT>(a, rk, s0, s1, s2, s3);
     return Label{s0 ^ k.w0, s1 ^ k.w1, s2 ^ k.w2, s3 ^ k.w3};
 }
 

@@ -18,7 +18,7 @@
 // NODES, each the XOR of up to 14 already existing labels, grouped into waves of
 // mutually independent nodes (almost always one wave) -- one thread per node,
 // one team barrier per wave.  The node records reach the kernel as ROWS of one
-// record per team thread (plan.hpp); a thread streams its records GC_NODE_PIPE
+// record per team thread (plan.hpp); a thread streams its records a few
 // rows ahead of the one it runs, across wave and phase boundaries, so the L2
 // latency of the plan never sits on the dependency chain; and (2) one level of ciphered gates executed by the
 // whole team: every AES block is a task; an AND gate is a quad of tasks hashing
@@ -36,6 +36,10 @@ namespace gcb {
 
 constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-barrier teams
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
+// Node rows a thread keeps in flight ahead of the one it runs: the single-block 512-thread variant
+// (deep, narrow circuits: short rows, nothing else to hide the L2 latency behind) has the registers
+// for four, the others for two.
+__host__ __device__ constexpr uint32_t node_pipe(int ilp, int maxt) { return (ilp == 1 && maxt == 512) ? 4u : 2u; }
 
 struct GcParams {
     const uint4* phases;                  // DevPhaseRec[] (two uint4 each) followed by two zero records
@@ -96,7 +100,7 @@ __device__ __forceinline__ Label shfl_label(Label h, int src) {
 __device__ __forceinline__ uint32_t mask_of(uint32_t bit) { return 0u - (bit & 1u); }
 
 // H(K) = AES(K) ^ K for UU independent blocks, rounds interleaved.
-template <int NR, int UU>
+template <int NR, int UU, int NT>
 __device__ __forceinline__ void aes_hash_multi(const AesLane& a, const uint32_t* __restrict__ rk, const Label (&K)[UU],
                                                Label (&H)[UU]) {
     const uint4* k4 = reinterpret_cast<const uint4*>(rk);
@@ -110,20 +114,20 @@ __device__ __forceinline__ void aes_hash_multi(const AesLane& a, const uint32_t*
     }
     if (UU == 1) {
 #pragma unroll
-        for (int r = 1; r < NR; r++) aes_round(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
+        for (int r = 1; r < NR; r++) aes_round<NT>(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
     } else {
 #pragma unroll 1
         for (int r = 1; r < NR; r++) {
             const uint4 k = k4[r];
 #pragma unroll
-            for (int j = 0; j < UU; j++) aes_round(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
+            for (int j = 0; j < UU; j++) aes_round<NT>(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
         }
     }
     {
         const uint4 k = k4[NR];
 #pragma unroll
         for (int j = 0; j < UU; j++) {
-            aes_last_round(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
+            aes_last_round<NT>(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
             H[j] = Label{s[j][0] ^ K[j].w0, s[j][1] ^ K[j].w1, s[j][2] ^ K[j].w2, s[j][3] ^ K[j].w3};
         }
     }
@@ -142,6 +146,7 @@ struct TeamCtx {
 // Region A is the pad below the tables; teams are packed into A first, then B.  A team's
 // block is: round keys (GC_RK_BYTES), claim word (16 B), wire labels (n_slots * 16).
 __device__ __forceinline__ uint32_t team_block_bytes(uint32_t n_slots) { return GC_RK_BYTES + 16 + n_slots * 16; }
+template <int NT>
 __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     TeamCtx c;
     c.tables = aes_align_tables(smem);
@@ -149,7 +154,7 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     c.ttid = threadIdx.x - c.team * p.team_threads;
     const uint32_t tb = team_block_bytes(p.n_slots);
     const uint32_t in_a = (uint32_t)(c.tables - smem) / tb;               // teams that fit below the tables
-    uint8_t* q = c.team < in_a ? smem + c.team * tb : c.tables + AES_TABLE_BYTES + (c.team - in_a) * tb;
+    uint8_t* q = c.team < in_a ? smem + c.team * tb : c.tables + aes_table_bytes(NT) + (c.team - in_a) * tb;
     c.rk = reinterpret_cast<uint32_t*>(q);
     c.claim = reinterpret_cast<volatile uint32_t*>(q + GC_RK_BYTES);
     c.slots = reinterpret_cast<uint4*>(q + GC_RK_BYTES + 16);
@@ -240,17 +245,16 @@ __device__ __forceinline__ NodeRegs load_row(const GcParams& p, uint32_t row, ui
 }
 
 // The node rows of a phase.  pipe[] holds this thread's records of rows `row` .. `row` +
-// GC_NODE_PIPE - 1; each step retires one and requests the record GC_NODE_PIPE rows ahead (the
-// row array ends with that many empty rows).  A team barrier follows the last row of a wave.
-template <bool GARBLE, bool FULL>
+// D - 1; each step retires one and requests the record D rows ahead (the row array ends with
+// GC_NODE_PIPE_MAX empty rows).  A team barrier follows the last row of a wave.
+template <bool GARBLE, bool FULL, uint32_t D>
 __device__ __forceinline__ void run_rows(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t n_rows,
-                                         uint32_t team, uint32_t ttid, uint32_t TT, NodeRegs (&pipe)[GC_NODE_PIPE],
-                                         uint32_t& row) {
+                                         uint32_t team, uint32_t ttid, uint32_t TT, NodeRegs (&pipe)[D], uint32_t& row) {
     for (uint32_t r = 0; r < n_rows; r++) {
         const NodeRegs cur = pipe[0];
 #pragma unroll
-        for (uint32_t d = 0; d + 1 < GC_NODE_PIPE; d++) pipe[d] = pipe[d + 1];
-        pipe[GC_NODE_PIPE - 1] = load_row(p, row + GC_NODE_PIPE, ttid);
+        for (uint32_t d = 0; d + 1 < D; d++) pipe[d] = pipe[d + 1];
+        pipe[D - 1] = load_row(p, row + D, ttid);
         run_node<GARBLE, FULL>(p, slots, R, inst, row * TT + ttid, cur);
         row++;
         if ((cur.lo.x >> 24) & NODE_WAVE_END) team_barrier(team, TT);
@@ -275,7 +279,7 @@ struct GarbleEnv {
 };
 
 // One pass of UU cipher tasks per thread: tasks (k0 + j)*TT + ttid.
-template <int NR, int MODE, int UU, int ILP, bool AND_ONLY>
+template <int NR, int MODE, int UU, int ILP, bool AND_ONLY, int NT>
 __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv& e, const Phase& ph, uint32_t ntask,
                                             uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP]) {
     static_assert(UU <= ILP, "pass wider than the record buffer");
@@ -300,7 +304,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
             K[j] = label_shl(x, 1);
             K[j].w3 ^= g.z + (k >> 1);
         }
-        aes_hash_multi<NR, UU>(lane, e.rk, K, H);
+        aes_hash_multi<NR, UU, NT>(lane, e.rk, K, H);
 #pragma unroll
         for (int j = 0; j < UU; j++) {
             const uint4 g = rec[j];
@@ -361,7 +365,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
         }
         K[j].w3 ^= tw;
     }
-    aes_hash_multi<NR, UU>(lane, e.rk, K, H);
+    aes_hash_multi<NR, UU, NT>(lane, e.rk, K, H);
 #pragma unroll
     for (int j = 0; j < UU; j++) {
         const Label h = H[j];
@@ -420,18 +424,19 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
     }
 }
 
-template <int NR, int MODE, int ILP, int MAXT>
+template <int NR, int MODE, int ILP, int MAXT, int NT>
 __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
+    constexpr uint32_t D = node_pipe(ILP, MAXT);
     constexpr bool FULL = MODE == GC_FULL;
     constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
-    const TeamCtx tc = team_ctx(smem, p);
-    aes_tables_to_smem(tc.tables);
+    const TeamCtx tc = team_ctx<NT>(smem, p);
+    aes_tables_to_smem<NT>(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
-        if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
+        if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
     uint4* const slots = tc.slots;
@@ -443,15 +448,15 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         const uint32_t inst = *tc.claim;
         if (inst >= p.batch) break;
         if (p.key_stride != 0 && ttid == 0)
-            aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+            aes_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Label R = label_from_mem(__ldg(p.r + inst));
         R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
         // plan records of the first phases load while the inputs do
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
-        NodeRegs pipe[GC_NODE_PIPE];
+        NodeRegs pipe[D];
         uint32_t row = 0;
 #pragma unroll
-        for (uint32_t d = 0; d < GC_NODE_PIPE; d++) pipe[d] = load_row(p, d, ttid);
+        for (uint32_t d = 0; d < D; d++) pipe[d] = load_row(p, d, ttid);
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
@@ -472,15 +477,17 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         }
         team_barrier(tc.team, TT);
         const GarbleEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, R, inst};
+        uint4 cur[ILP];
+        prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
 
         for (uint32_t pi = 0; pi < p.n_phases; pi++) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);  // two zero records of padding
-            uint4 cur[ILP];
-            prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
+            uint4 cur_n[ILP];                                  // first-pass records of the next phase
+            prefetch_cipher<true, ILP>(p, ph_n, 0, ttid, TT, cur_n);
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
-            run_rows<true, FULL>(p, slots, R, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
+            run_rows<true, FULL, D>(p, slots, R, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
             if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
             const uint32_t ntask = task_count<true>(ph);
@@ -494,14 +501,14 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                     prefetch_cipher<true, ILP>(p, ph, k0 + uu, ttid, TT, nxt);
                     const bool and_only = (k0 + uu) * TT <= and_tasks;
                     if (ILP >= 4 && uu == 4) {
-                        if (and_only) garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                        else garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        if (and_only) garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
                     } else if (ILP >= 2 && uu == 2) {
-                        if (and_only) garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                        else garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        if (and_only) garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
                     } else if (k0 * TT + (ttid & ~31u) < ntask) {
-                        if (and_only) garble_pass<NR, MODE, 1, ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                        else garble_pass<NR, MODE, 1, ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        if (and_only) garble_pass<NR, MODE, 1, ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
+                        else garble_pass<NR, MODE, 1, ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
                     }
                     k0 += uu;
 #pragma unroll
@@ -511,6 +518,8 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                 team_barrier(tc.team, TT);
             }
             ph = ph_n; ph_n = ph_nn;
+#pragma unroll
+            for (int j = 0; j < ILP; j++) cur[j] = cur_n[j];
         }
         // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
@@ -540,7 +549,7 @@ struct EvalEnv {
     uint32_t inst;
 };
 
-template <int NR, int MODE, int UU, int ILP, bool AND_ONLY>
+template <int NR, int MODE, int UU, int ILP, bool AND_ONLY, int NT>
 __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e, const Phase& ph, uint32_t ntask,
                                           uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP],
                                           const uint4 (&rowpre)[ILP], bool have_rows) {
@@ -565,7 +574,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
             K[j] = label_shl(x, 1);
             K[j].w3 ^= g.z + k;
         }
-        aes_hash_multi<NR, UU>(lane, e.rk, K, H);
+        aes_hash_multi<NR, UU, NT>(lane, e.rk, K, H);
 #pragma unroll
         for (int j = 0; j < UU; j++) {
             const uint4 g = rec[j];
@@ -619,7 +628,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
         // we ^= a when S(b) (eval.go:72-75): folded into the row term
         row[j] = row[j] ^ label_and_mask(a, mask_of((op[j] == OP_AND && k == 1) ? sB : 0u));
     }
-    aes_hash_multi<NR, UU>(lane, e.rk, K, H);
+    aes_hash_multi<NR, UU, NT>(lane, e.rk, K, H);
 #pragma unroll
     for (int j = 0; j < UU; j++) {
         const Label v = H[j] ^ row[j];                         // decrypt (garble.go:58-73) / half-gate
@@ -632,18 +641,19 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
     }
 }
 
-template <int NR, int MODE, int ILP, int MAXT>
+template <int NR, int MODE, int ILP, int MAXT, int NT>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
+    constexpr uint32_t D = node_pipe(ILP, MAXT);
     constexpr bool FULL = MODE == GC_FULL;
     constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
-    const TeamCtx tc = team_ctx(smem, p);
-    aes_tables_to_smem(tc.tables);
+    const TeamCtx tc = team_ctx<NT>(smem, p);
+    aes_tables_to_smem<NT>(tc.tables);
     __syncthreads();
     const AesLane lane = aes_lane(tc.tables);
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
-        if (ttid == 0) aes_expand_key(lane, p.keys, (int)p.keylen, tc.rk);
+        if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
     uint4* const slots = tc.slots;
@@ -655,12 +665,12 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         const uint32_t inst = *tc.claim;
         if (inst >= p.batch) break;
         if (p.key_stride != 0 && ttid == 0)
-            aes_expand_key(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+            aes_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
-        NodeRegs pipe[GC_NODE_PIPE];
+        NodeRegs pipe[D];
         uint32_t row = 0;
 #pragma unroll
-        for (uint32_t d = 0; d < GC_NODE_PIPE; d++) pipe[d] = load_row(p, d, ttid);
+        for (uint32_t d = 0; d < D; d++) pipe[d] = load_row(p, d, ttid);
         for (uint32_t k = ttid; k < p.n_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
             uint4 m;
@@ -690,7 +700,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             }
             uint4 cur_n[ILP];
             prefetch_cipher<false, ILP>(p, ph_n, 0, ttid, TT, cur_n);
-            run_rows<false, FULL>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
+            run_rows<false, FULL, D>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);
@@ -704,14 +714,14 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                     prefetch_cipher<false, ILP>(p, ph, k0 + uu, ttid, TT, nxt);
                     const bool and_only = (k0 + uu) * TT <= and_tasks;
                     if (ILP >= 4 && uu == 4) {
-                        if (and_only) eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
-                        else eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        if (and_only) eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        else eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     } else if (ILP >= 2 && uu == 2) {
-                        if (and_only) eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
-                        else eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        if (and_only) eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        else eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     } else if (k0 * TT + (ttid & ~31u) < ntask) {
-                        if (and_only) eval_pass<NR, MODE, 1, ILP, true>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
-                        else eval_pass<NR, MODE, 1, ILP, false>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        if (and_only) eval_pass<NR, MODE, 1, ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
+                        else eval_pass<NR, MODE, 1, ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     }
                     k0 += uu;
 #pragma unroll

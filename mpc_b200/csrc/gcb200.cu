@@ -19,7 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/gcb200.h"
-#include "gc_kernels.cuh"
+#include "gc_launch.hpp"
 #include "ot_kernels.cuh"
 #include "stream_kernels.cuh"
 #include "plan.hpp"
@@ -67,47 +67,6 @@ static cudaError_t opt_in(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemOptin);
 }
 
-// every (rounds, mode, ILP) instantiation of the gate kernels
-#define GC_FOR_ILP(M, NR, MODE) M(NR, MODE, 1, 1024) M(NR, MODE, 2, 512) M(NR, MODE, 2, 768) M(NR, MODE, 4, 256)
-#define GC_FOR_NR(M, MODE) GC_FOR_ILP(M, 10, MODE) GC_FOR_ILP(M, 12, MODE) GC_FOR_ILP(M, 14, MODE)
-static cudaError_t opt_in_gc() {
-    cudaError_t e = cudaSuccess;
-#define GC_OPT_G(NR, MODE, ILP, MAXT) if (e == cudaSuccess) e = opt_in(garble_kernel<NR, MODE, ILP, MAXT>);
-#define GC_OPT_E(NR, MODE, ILP, MAXT) if (e == cudaSuccess) e = opt_in(eval_kernel<NR, MODE, ILP, MAXT>);
-    GC_FOR_NR(GC_OPT_G, GC_PLAIN) GC_FOR_NR(GC_OPT_G, GC_FULL) GC_FOR_NR(GC_OPT_G, GC_STREAM)
-    GC_FOR_NR(GC_OPT_E, GC_PLAIN) GC_FOR_NR(GC_OPT_E, GC_FULL) GC_FOR_NR(GC_OPT_E, GC_STREAM)
-#undef GC_OPT_G
-#undef GC_OPT_E
-    return e;
-}
-
-template <int NR, int MODE>
-static void launch_garble(uint32_t ilp, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
-    if (ilp == 4) garble_kernel<NR, MODE, 4, 256><<<grid, block, smem, s>>>(p);
-    else if (ilp == 2 && block.x > 512) garble_kernel<NR, MODE, 2, 768><<<grid, block, smem, s>>>(p);
-    else if (ilp == 2) garble_kernel<NR, MODE, 2, 512><<<grid, block, smem, s>>>(p);
-    else garble_kernel<NR, MODE, 1, 1024><<<grid, block, smem, s>>>(p);
-}
-template <int NR, int MODE>
-static void launch_eval(uint32_t ilp, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
-    if (ilp == 4) eval_kernel<NR, MODE, 4, 256><<<grid, block, smem, s>>>(p);
-    else if (ilp == 2 && block.x > 512) eval_kernel<NR, MODE, 2, 768><<<grid, block, smem, s>>>(p);
-    else if (ilp == 2) eval_kernel<NR, MODE, 2, 512><<<grid, block, smem, s>>>(p);
-    else eval_kernel<NR, MODE, 1, 1024><<<grid, block, smem, s>>>(p);
-}
-template <int MODE>
-static void launch_garble_nr(uint32_t keylen, uint32_t ilp, dim3 g, dim3 b, size_t sm, cudaStream_t s, const GcParams& p) {
-    if (keylen == 16) launch_garble<10, MODE>(ilp, g, b, sm, s, p);
-    else if (keylen == 24) launch_garble<12, MODE>(ilp, g, b, sm, s, p);
-    else launch_garble<14, MODE>(ilp, g, b, sm, s, p);
-}
-template <int MODE>
-static void launch_eval_nr(uint32_t keylen, uint32_t ilp, dim3 g, dim3 b, size_t sm, cudaStream_t s, const GcParams& p) {
-    if (keylen == 16) launch_eval<10, MODE>(ilp, g, b, sm, s, p);
-    else if (keylen == 24) launch_eval<12, MODE>(ilp, g, b, sm, s, p);
-    else launch_eval<14, MODE>(ilp, g, b, sm, s, p);
-}
-
 // Where dynamic shared memory starts in the shared window (the AES tables are placed at
 // the next multiple of 64 KiB, see aes_core.cuh).
 __global__ void smem_base_probe(uint32_t* out) {
@@ -146,7 +105,8 @@ int select_device(DeviceInfo** out) {
         smem_base_probe<<<1, 32, 1024>>>(di->counters);
         CK(cudaMemcpy(&di->smem_base, di->counters, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         CK(cudaMemset(di->counters, 0, sizeof(uint32_t)));
-        CK(opt_in_gc());
+        CK(gc_opt_in_garble((int)kSmemOptin));
+        CK(gc_opt_in_eval((int)kSmemOptin));
         CK(opt_in(hash_half_kernel<10>)); CK(opt_in(hash_half_kernel<12>)); CK(opt_in(hash_half_kernel<14>));
         CK(opt_in(mitccrh_kernel));
         CK(opt_in(iknp_kernel<false, false>)); CK(opt_in(iknp_kernel<true, false>));
@@ -236,7 +196,7 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
     }
     ph.push_back(DevPhaseRec{});                        // the kernels read two records ahead
     ph.push_back(DevPhaseRec{});
-    rows.resize(rows.size() + (size_t)GC_NODE_PIPE * TT, NodeRec{});   // and GC_NODE_PIPE rows ahead
+    rows.resize(rows.size() + (size_t)GC_NODE_PIPE_MAX * TT, NodeRec{});   // and GC_NODE_PIPE_MAX rows ahead
     CK(upload(&dp->phases, ph));
     CK(upload(&dp->nodes, rows));
     CK(upload(&dp->crecs, plan.crecs));
@@ -249,46 +209,60 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
     return GCB_OK;
 }
 
-// Team geometry for a plan: how many instances one SM keeps resident, how many
-// threads work on each, and how many AES blocks a thread interleaves.
-// GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
-struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, stagger = 0; };
-static Geometry compute_geometry(uint32_t num_slots, uint32_t smem_base) {
-    Geometry g;
+// Team geometry for a plan: how many instances one SM keeps resident, how many threads work on
+// each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
+// GCB_NT / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
+struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0; };
+static size_t teams_that_fit(uint32_t num_slots, uint32_t smem_base, uint32_t nt) {
     // teams are packed below the 64 KiB-aligned tables first, then above them
     const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
     const size_t pad = table_pad(smem_base);
-    size_t n = pad / per_team + (kSmemOptin - pad - AES_TABLE_BYTES) / per_team;
+    return pad / per_team + (kSmemOptin - pad - (size_t)aes_table_bytes((int)nt)) / per_team;
+}
+// width = AES blocks per cipher level of the garbler (4 per AND / OR, 2 per INV), averaged.
+static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base) {
+    Geometry g;
+    const size_t n4 = teams_that_fit(num_slots, smem_base, 4), n2 = teams_that_fit(num_slots, smem_base, 2);
+    // Wide levels keep the shared-memory pipe busy with a few resident instances: four tables.
+    // Deep, narrow circuits (sha256: 39 blocks per level) are bound by the latency of each level,
+    // so the number of resident instances is what counts: two tables, twice the label space.
+    uint32_t nt = (n4 == 0 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
+    if (const char* e = getenv("GCB_NT")) { const int v = atoi(e); if (v == 2 || v == 4) nt = (uint32_t)v; }
+    size_t n = nt == 2 ? n2 : n4;
     if (n == 0) return g;
     if (n >= 32) n = 32; else if (n > 16) n = 16;
-    // measured on B200 (tools/tune_geometry.py, aes_128.circ): two interleaved AES blocks
-    // per thread and three-warp teams beat both deeper ILP and wider teams
-    uint32_t ilp = n <= 16 ? 2 : 1;
-    if (const char* e = getenv("GCB_ILP")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) ilp = (uint32_t)v; }
-    // threads per CTA: the 512-thread ILP-2 variant has 128 registers per thread and no spills
-    const uint32_t maxt = ilp == 4 ? 256 : ilp == 2 ? 512 : 1024;
+    // measured on B200 (tools/tune_geometry.py): two interleaved AES blocks per thread and
+    // three-warp teams for wide levels; one block per thread for narrow ones and one-warp teams
+    uint32_t ilp = (n > 16 || (nt == 2 && width < 128)) ? 1 : 2;
+    if (const char* e = getenv("GCB_ILP")) { const int v = atoi(e); if (v == 1 || v == 2) ilp = (uint32_t)v; }
+    // threads per CTA: the 512-thread variants have 128 registers per thread and no spills
+    const uint32_t maxt = (ilp == 1 && nt == 4) ? 1024 : 512;
     while (n * 32 > maxt) n--;                      // at least one warp per team
     uint32_t tt = 32u * (uint32_t)(maxt / 32 / n);
     if (tt > 96) tt = 96;
     if (n > 16) tt = 32;                            // named barriers: at most 16 multi-warp teams
     if (const char* e = getenv("GCB_TEAM_THREADS")) {
         const int v = atoi(e);
-        if (v >= 32 && v % 32 == 0 && (size_t)v * n <= (ilp == 2 ? 768u : maxt) && (v == 32 || n <= 16)) tt = (uint32_t)v;
+        if (v >= 32 && v % 32 == 0 && (size_t)v * n <= maxt && (v == 32 || n <= 16)) tt = (uint32_t)v;
     }
-    g.n_teams = (uint32_t)n; g.team_threads = tt; g.ilp = ilp;
+    g.n_teams = (uint32_t)n; g.team_threads = tt; g.ilp = ilp; g.nt = nt;
     g.stagger = n > 1 ? 100000 : 0;                 // teams start ~50 us apart
     if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
     return g;
 }
+static uint32_t plan_width(const Plan& plan) {
+    const size_t np = plan.phases.size();
+    return np ? (uint32_t)(plan.info.garble_hashes / np) : 0u;
+}
 void team_geometry(Plan& plan) {                    // what gcb_plan_get_info reports (typical device)
-    const Geometry g = compute_geometry(plan.info.num_slots, kAssumedSmemBase);
+    const Geometry g = compute_geometry(plan.info.num_slots, plan_width(plan), kAssumedSmemBase);
     plan.info.teams_per_sm = g.n_teams; plan.info.team_threads = g.team_threads;
     plan.ilp = g.ilp; plan.stagger = g.stagger;
 }
-size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams, uint32_t smem_base) {
+size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams, uint32_t nt, uint32_t smem_base) {
     const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
     const size_t pad = table_pad(smem_base), in_a = pad / per_team;
-    return pad + AES_TABLE_BYTES + (n_teams > in_a ? (n_teams - in_a) * per_team : 0);
+    return pad + (size_t)aes_table_bytes((int)nt) + (n_teams > in_a ? (n_teams - in_a) * per_team : 0);
 }
 
 // The plan a call runs on: the flattened one, or -- when the caller wants every wire
@@ -327,7 +301,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
                      cudaStream_t stream, const uint32_t* in_ids = nullptr, const uint32_t* out_ids = nullptr,
                      uint4* const* pages = nullptr) {
     const gcb_plan_info& in = plan.info;
-    const Geometry geo = compute_geometry(in.num_slots, di->smem_base);
+    const Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base);
     if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
     std::shared_ptr<DevicePlan> dp;
     int rc = plan_on_device(plan, device, geo.team_threads, &dp);
@@ -357,14 +331,12 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;
     const dim3 grid(want < (uint32_t)di->sm_count ? want : (uint32_t)di->sm_count);
     const dim3 block(p.n_teams * p.team_threads);
-    const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams, di->smem_base);
+    const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams, geo.nt, di->smem_base);
     const bool full = wires_full != nullptr;
-    if (pages && garble) launch_garble_nr<GC_STREAM>(keylen, geo.ilp, grid, block, smem, stream, p);
-    else if (pages) launch_eval_nr<GC_STREAM>(keylen, geo.ilp, grid, block, smem, stream, p);
-    else if (garble && full) launch_garble_nr<GC_FULL>(keylen, geo.ilp, grid, block, smem, stream, p);
-    else if (garble) launch_garble_nr<GC_PLAIN>(keylen, geo.ilp, grid, block, smem, stream, p);
-    else if (full) launch_eval_nr<GC_FULL>(keylen, geo.ilp, grid, block, smem, stream, p);
-    else launch_eval_nr<GC_PLAIN>(keylen, geo.ilp, grid, block, smem, stream, p);
+    const int mode = pages ? GC_STREAM : full ? GC_FULL : GC_PLAIN;
+    const GcVariant var{geo.ilp, geo.nt};
+    if (garble) gc_launch_garble(mode, keylen, var, grid, block, smem, stream, p);
+    else gc_launch_eval(mode, keylen, var, grid, block, smem, stream, p);
     CK(cudaGetLastError());
     return GCB_OK;
 }
@@ -536,7 +508,7 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     team_geometry(pl->p);
     if (pl->p.info.teams_per_sm == 0)
         return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; at most %zu fit on chip",
-                    pl->p.info.num_slots, (kSmemOptin - table_pad(kAssumedSmemBase) - AES_TABLE_BYTES - GC_RK_BYTES - 16) / 16);
+                    pl->p.info.num_slots, (kSmemOptin - table_pad(kAssumedSmemBase) - (size_t)aes_table_bytes(2) - GC_RK_BYTES - 16) / 16);
     pl->p.gates.assign(gates, gates + num_gates);
     *out = pl.release();
     return GCB_OK;

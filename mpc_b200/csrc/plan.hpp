@@ -81,7 +81,7 @@ struct DevPhaseRec {
     uint32_t pad[3];
 };
 static_assert(sizeof(DevPhaseRec) == 32, "DevPhaseRec must be 32 bytes");
-constexpr uint32_t GC_NODE_PIPE = 2;  // rows a thread keeps in flight ahead of the one it runs
+constexpr uint32_t GC_NODE_PIPE_MAX = 4;  // most rows any kernel variant keeps in flight ahead of the one it runs
 
 struct PlanSpec {
     const gcb_gate* gates = nullptr;
@@ -98,7 +98,7 @@ struct DevicePlan {                   // per (device, team width) copy of the ta
     int device = -1;
     uint32_t team_threads = 0;
     DevPhaseRec* phases = nullptr;    // + two zero records of padding
-    NodeRec* nodes = nullptr;         // rows of team_threads records + GC_NODE_PIPE empty rows
+    NodeRec* nodes = nullptr;         // rows of team_threads records + GC_NODE_PIPE_MAX empty rows
     GateRec* crecs = nullptr;
     uint32_t* nout_wire = nullptr;    // original output wire of each node record / ciphered gate
     uint32_t* cout_wire = nullptr;

@@ -1,6 +1,6 @@
 """Sweep the team geometry (GCB_ILP x GCB_TEAM_THREADS) of the gate kernels on one GPU.
 
-  python tools/tune_geometry.py [circuit] [batch] [keylen]
+  python tools/tune_geometry.py [circuit] [batch] [keylen] [ilp,team_threads,stagger[,tables] ...]
 
 Prints device time of garble and eval per configuration; every configuration's
 tables and output labels are compared with the first one's (they must be
@@ -41,9 +41,13 @@ def main():
     if len(sys.argv) > 4:
         configs = [tuple(int(x) for x in c.split(",")) for c in sys.argv[4:]]
     print(f"{name} batch={batch} keylen={klen}: slots/rows see plan; times in ms")
-    for ilp, tt, sg in configs:
-        for k in ("GCB_ILP", "GCB_TEAM_THREADS", "GCB_STAGGER"):
+    for cfg in configs:
+        ilp, tt, sg = cfg[:3]
+        nt = cfg[3] if len(cfg) > 3 else None
+        for k in ("GCB_ILP", "GCB_TEAM_THREADS", "GCB_STAGGER", "GCB_NT"):
             os.environ.pop(k, None)
+        if nt:
+            os.environ["GCB_NT"] = str(nt)
         if ilp:
             os.environ["GCB_ILP"] = str(ilp)
             os.environ["GCB_TEAM_THREADS"] = str(tt)
@@ -66,15 +70,6 @@ def main():
             torch.cuda.synchronize()
             if it:
                 best_g, best_e = min(best_g, e0.elapsed_time(e1)), min(best_e, e2.elapsed_time(e3))
-        for skip in (1, 2, 3):
-            os.environ["GCB_DEBUG_SKIP"] = str(skip)
-            ts = []
-            for it in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); eng.garble_dev(d_key, klen, 0, batch, d_r, d_l0, d_tab, d_io, stream=s); e1.record()
-                torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-            print(f"    garble with skip={skip} (1=no nodes, 2=no cipher, 3=neither): {min(ts):.3f} ms")
-        os.environ.pop("GCB_DEBUG_SKIP", None)
         eng.garble_dev(d_key, klen, 0, batch, d_r, d_l0, d_tab, d_io, stream=s)
         eng.eval_dev(d_key, klen, 0, batch, d_tab, d_in, d_out, stream=s)
         torch.cuda.synchronize()
@@ -83,7 +78,7 @@ def main():
             ref = sig
         ok = "same" if sig == ref else "DIFFERENT"
         n_and = circ.count(2)
-        print(f"ilp={ilp} tt={tt} stagger={sg}: teams={info.teams_per_sm} x {info.team_threads} slots={info.num_slots} "
+        print(f"ilp={ilp} tt={tt} stagger={sg} nt={nt}: teams={info.teams_per_sm} x {info.team_threads} slots={info.num_slots} "
               f"garble={best_g:.3f} eval={best_e:.3f} total={best_g + best_e:.3f} "
               f"-> {n_and * batch / (best_g + best_e) / 1e3:.1f} M AND/s  [{ok}]", flush=True)
 
