@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out.append(" ".join(cmd) + "\n" + text)
         failed |= proc.returncode != 0
     if not failed:
-        cmd = [nvcc, "-shared", "-o", SO] + [obj for _, obj, _ in jobs]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + [obj for _, obj, _ in jobs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         out.append(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         failed = r.returncode != 0

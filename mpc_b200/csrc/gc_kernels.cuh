@@ -244,20 +244,29 @@ __device__ __forceinline__ NodeRegs load_row(const GcParams& p, uint32_t row, ui
     return load_node(p.nodes, row * p.team_threads + ttid);
 }
 
-// The node rows of a phase.  pipe[] holds this thread's records of rows `row` .. `row` +
-// D - 1; each step retires one and requests the record D rows ahead (the row array ends with
-// GC_NODE_PIPE_MAX empty rows).  A team barrier follows the last row of a wave.
+// The node rows of a phase.  pipe[k] holds this thread's record of the next row whose index is
+// k mod D: running a row retires its register set and requests the record D rows ahead into the
+// same set (the row array ends with GC_NODE_PIPE_MAX empty rows).  The sets are addressed
+// statically -- rows run in aligned groups of D with warp-uniform guards -- because a pipeline that
+// shifts registers would copy the newest load right after issuing it and wait for it there.  A
+// team barrier follows the last row of a wave.
 template <bool GARBLE, bool FULL, uint32_t D>
 __device__ __forceinline__ void run_rows(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t n_rows,
                                          uint32_t team, uint32_t ttid, uint32_t TT, NodeRegs (&pipe)[D], uint32_t& row) {
-    for (uint32_t r = 0; r < n_rows; r++) {
-        const NodeRegs cur = pipe[0];
+    static_assert((D & (D - 1)) == 0, "pipeline depth must be a power of two");
+    const uint32_t end = row + n_rows;
+    while (row < end) {
+        const uint32_t k0 = row & (D - 1);
 #pragma unroll
-        for (uint32_t d = 0; d + 1 < D; d++) pipe[d] = pipe[d + 1];
-        pipe[D - 1] = load_row(p, row + D, ttid);
-        run_node<GARBLE, FULL>(p, slots, R, inst, row * TT + ttid, cur);
-        row++;
-        if ((cur.lo.x >> 24) & NODE_WAVE_END) team_barrier(team, TT);
+        for (uint32_t k = 0; k < D; k++) {
+            if (k >= k0 && row < end) {
+                const NodeRegs cur = pipe[k];
+                pipe[k] = load_row(p, row + D, ttid);
+                run_node<GARBLE, FULL>(p, slots, R, inst, row * TT + ttid, cur);
+                row++;
+                if ((cur.lo.x >> 24) & NODE_WAVE_END) team_barrier(team, TT);
+            }
+        }
     }
 }
 
