@@ -257,6 +257,49 @@ int gcb_mitccrh_hash(const gcb_label *seed, uint64_t gid_start, gcb_label *blks,
 int gcb_mitccrh_hash_dev(const gcb_label *seed_host, uint64_t gid_start, gcb_label *blks,
                          uint64_t nkeys, uint32_t h, void *stream);
 
+/* --------------------------------------------------- COT / ROT post-processing --- */
+/* Replace the per-batch loops that follow the IKNP extension in COT.Send / COT.Receive
+ * (ot/cot.go:157-181, :201-233) and ROT.Send / ROT.Receive (ot/rot.go:155-172, :192-197).
+ * OT number j is hashed under MiTCCRH key j of NewMITCCRH(seed, otBatchSize) (ot/cot.go:47,
+ * ot/mitccrh.go:61-128).  The _dev variants take device pointers (seed and delta stay host
+ * pointers), so the IKNP output never leaves HBM; `stream` is a cudaStream_t.
+ *   flags & GCB_COT_WIRE_BYTES: the message array is in the 16-byte SendLabel / ReceiveLabel
+ *   encoding (BE64(D0) || BE64(D1), ot/label.go:105-114) instead of Go memory order, so it can
+ *   be written to / read from the connection without a per-label conversion.
+ * gcb_cot_send:    msgs[2j] = H_j(q[j]) ^ wires[j].L0, msgs[2j+1] = H_j(q[j] ^ delta) ^ wires[j].L1
+ * gcb_cot_receive: result[j] = (choice[j] ? msgs[2j+1] : msgs[2j]) ^ H_j(t[j]); result may alias t
+ * gcb_rot_send:    wires[j] = {H_j(q[j]), H_j(q[j] ^ delta)}
+ * gcb_rot_receive: result[j] = H_j(t[j]); result may alias t */
+#define GCB_COT_WIRE_BYTES 1u
+int gcb_cot_send(const gcb_label *seed, const gcb_label *delta, const gcb_label *q, const gcb_wire *wires,
+                 uint64_t n, gcb_label *msgs, uint32_t flags);
+int gcb_cot_receive(const gcb_label *seed, const uint8_t *choice, const gcb_label *msgs, const gcb_label *t,
+                    uint64_t n, gcb_label *result, uint32_t flags);
+int gcb_rot_send(const gcb_label *seed, const gcb_label *delta, const gcb_label *q, uint64_t n, gcb_wire *wires);
+int gcb_rot_receive(const gcb_label *seed, const gcb_label *t, uint64_t n, gcb_label *result);
+int gcb_cot_send_dev(const gcb_label *seed, const gcb_label *delta, const gcb_label *q, const gcb_wire *wires,
+                     uint64_t n, gcb_label *msgs, uint32_t flags, void *stream);
+int gcb_cot_receive_dev(const gcb_label *seed, const uint8_t *choice, const gcb_label *msgs, const gcb_label *t,
+                        uint64_t n, gcb_label *result, uint32_t flags, void *stream);
+int gcb_rot_send_dev(const gcb_label *seed, const gcb_label *delta, const gcb_label *q, uint64_t n,
+                     gcb_wire *wires, void *stream);
+int gcb_rot_receive_dev(const gcb_label *seed, const gcb_label *t, uint64_t n, gcb_label *result, void *stream);
+
+/* ------------------------------------------- IKNP malicious-mode consistency sums --- */
+/* Replace the chi loops of IKNPSender.Send (ot/iknp.go:150-173) and IKNPReceiver.Receive
+ * (:408-451), i.e. prgLabels + vectorInnPrdtSumNoRed / mul128 (ot/gf128.go:14-27,
+ * ot/mul128_amd64.s): with chi_i = label number chi_start + i of the PRG keyed by seed2,
+ *   out[0], out[1] = XOR_i mul128(chi_i, labels[i])   (low, high 128 bits, no reduction)
+ *   out[2]         = XOR_{i : choice[i]} chi_i        (zero when choice is NULL: the sender)
+ * The caller XORs the sums of its Send/Receive result (chi_start 0) and of the 256 extra
+ * choice-vector OTs (chi_start n), then finishes the check as the reference does
+ * (:175-191 / :453-465).  _dev: labels and choice are device pointers, out is a host pointer;
+ * the call returns after the stream has produced the sums. */
+int gcb_iknp_check_sums(const gcb_label *seed2, uint64_t chi_start, const gcb_label *labels,
+                        const uint8_t *choice, uint64_t n, gcb_label out[3]);
+int gcb_iknp_check_sums_dev(const gcb_label *seed2, uint64_t chi_start, const gcb_label *labels,
+                            const uint8_t *choice, uint64_t n, gcb_label out[3], void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,16 @@ SYMBOLS = {
     "gcb_iknp_sender_expand_bits_dev": (_int, [_vp, _vp, _u64, _vp, _sz, _u64, _vp, _vp]),
     "gcb_mitccrh_hash": (_int, [C.POINTER(Label), _u64, _vp, _u64, _u32]),
     "gcb_mitccrh_hash_dev": (_int, [C.POINTER(Label), _u64, _vp, _u64, _u32, _vp]),
+    "gcb_cot_send": (_int, [C.POINTER(Label), C.POINTER(Label), _vp, _vp, _u64, _vp, _u32]),
+    "gcb_cot_receive": (_int, [C.POINTER(Label), _vp, _vp, _vp, _u64, _vp, _u32]),
+    "gcb_rot_send": (_int, [C.POINTER(Label), C.POINTER(Label), _vp, _u64, _vp]),
+    "gcb_rot_receive": (_int, [C.POINTER(Label), _vp, _u64, _vp]),
+    "gcb_cot_send_dev": (_int, [C.POINTER(Label), C.POINTER(Label), _vp, _vp, _u64, _vp, _u32, _vp]),
+    "gcb_cot_receive_dev": (_int, [C.POINTER(Label), _vp, _vp, _vp, _u64, _vp, _u32, _vp]),
+    "gcb_rot_send_dev": (_int, [C.POINTER(Label), C.POINTER(Label), _vp, _u64, _vp, _vp]),
+    "gcb_rot_receive_dev": (_int, [C.POINTER(Label), _vp, _u64, _vp, _vp]),
+    "gcb_iknp_check_sums": (_int, [C.POINTER(Label), _u64, _vp, _vp, _u64, _vp]),
+    "gcb_iknp_check_sums_dev": (_int, [C.POINTER(Label), _u64, _vp, _vp, _u64, _vp, _vp]),
 }
 
 _lib = None

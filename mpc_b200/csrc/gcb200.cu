@@ -1295,3 +1295,161 @@ int gcb_mitccrh_hash(const gcb_label* seed, uint64_t gid_start, gcb_label* blks,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------- COT / ROT post-processing ------
+template <int MODE>
+static int launch_cot(const gcb_label* seed, const gcb_label* delta, const void* data, const void* wires,
+                      const uint8_t* choice, const void* msgs_in, void* out, uint64_t n, uint32_t flags, void* stream) {
+    if (!seed || (n && (!data || !out))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    CotParams p{};
+    p.seed_d0 = seed->d0; p.seed_d1 = seed->d1;
+    if (delta) { p.delta_d0 = delta->d0; p.delta_d1 = delta->d1; }
+    p.data = reinterpret_cast<const uint4*>(data);
+    p.wires = reinterpret_cast<const uint4*>(wires);
+    p.flags = choice;
+    p.msgs_in = reinterpret_cast<const uint4*>(msgs_in);
+    p.out = reinterpret_cast<uint4*>(out);
+    p.n = n;
+    p.wire_bytes = (flags & GCB_COT_WIRE_BYTES) ? 1u : 0u;
+    static std::once_flag once;
+    static cudaError_t opt = cudaSuccess;
+    std::call_once(once, [] {
+        opt = opt_in(cot_kernel<COT_SEND>);
+        if (opt == cudaSuccess) opt = opt_in(cot_kernel<COT_RECEIVE>);
+        if (opt == cudaSuccess) opt = opt_in(cot_kernel<ROT_SEND>);
+        if (opt == cudaSuccess) opt = opt_in(cot_kernel<ROT_RECEIVE>);
+        if (opt == cudaSuccess) opt = opt_in(iknp_check_kernel);
+    });
+    CK(opt);
+    const uint64_t want = (n + 511) / 512;
+    const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
+    cot_kernel<MODE><<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+
+extern "C" {
+
+int gcb_cot_send_dev(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, const gcb_wire* wires,
+                     uint64_t n, gcb_label* msgs, uint32_t flags, void* stream) {
+    if (!delta || (n && !wires)) return fail(GCB_E_ARG, "null argument");
+    return launch_cot<COT_SEND>(seed, delta, q, wires, nullptr, nullptr, msgs, n, flags, stream);
+}
+int gcb_cot_receive_dev(const gcb_label* seed, const uint8_t* choice, const gcb_label* msgs, const gcb_label* t,
+                        uint64_t n, gcb_label* result, uint32_t flags, void* stream) {
+    if (n && (!choice || !msgs)) return fail(GCB_E_ARG, "null argument");
+    return launch_cot<COT_RECEIVE>(seed, nullptr, t, nullptr, choice, msgs, result, n, flags, stream);
+}
+int gcb_rot_send_dev(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, uint64_t n, gcb_wire* wires,
+                     void* stream) {
+    if (!delta) return fail(GCB_E_ARG, "null argument");
+    return launch_cot<ROT_SEND>(seed, delta, q, nullptr, nullptr, nullptr, wires, n, 0, stream);
+}
+int gcb_rot_receive_dev(const gcb_label* seed, const gcb_label* t, uint64_t n, gcb_label* result, void* stream) {
+    return launch_cot<ROT_RECEIVE>(seed, nullptr, t, nullptr, nullptr, nullptr, result, n, 0, stream);
+}
+
+// Host-pointer variants: one staging buffer per operand (these calls sit between network
+// round trips of the OT protocol; the bulk path keeps the labels on the device with _dev).
+struct Staged {
+    DevBuf b;
+    int up(const void* src, size_t bytes) {
+        CK(b.alloc(bytes));
+        if (src && bytes) CK(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+        return GCB_OK;
+    }
+};
+int gcb_cot_send(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, const gcb_wire* wires, uint64_t n,
+                 gcb_label* msgs, uint32_t flags) {
+    if (!seed || !delta || (n && (!q || !wires || !msgs))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    Staged dq, dw, dm;
+    if ((rc = dq.up(q, n * 16)) || (rc = dw.up(wires, n * 32)) || (rc = dm.up(nullptr, n * 32))) return rc;
+    if ((rc = gcb_cot_send_dev(seed, delta, dq.b.as<gcb_label>(), dw.b.as<gcb_wire>(), n, dm.b.as<gcb_label>(), flags, nullptr))) return rc;
+    CK(cudaMemcpy(msgs, dm.b.p, n * 32, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+int gcb_cot_receive(const gcb_label* seed, const uint8_t* choice, const gcb_label* msgs, const gcb_label* t, uint64_t n,
+                    gcb_label* result, uint32_t flags) {
+    if (!seed || (n && (!choice || !msgs || !t || !result))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    Staged dc, dm, dt;
+    if ((rc = dc.up(choice, n)) || (rc = dm.up(msgs, n * 32)) || (rc = dt.up(t, n * 16))) return rc;
+    if ((rc = gcb_cot_receive_dev(seed, dc.b.as<uint8_t>(), dm.b.as<gcb_label>(), dt.b.as<gcb_label>(), n, dt.b.as<gcb_label>(), flags, nullptr))) return rc;
+    CK(cudaMemcpy(result, dt.b.p, n * 16, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+int gcb_rot_send(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, uint64_t n, gcb_wire* wires) {
+    if (!seed || !delta || (n && (!q || !wires))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    Staged dq, dw;
+    if ((rc = dq.up(q, n * 16)) || (rc = dw.up(nullptr, n * 32))) return rc;
+    if ((rc = gcb_rot_send_dev(seed, delta, dq.b.as<gcb_label>(), n, dw.b.as<gcb_wire>(), nullptr))) return rc;
+    CK(cudaMemcpy(wires, dw.b.p, n * 32, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+int gcb_rot_receive(const gcb_label* seed, const gcb_label* t, uint64_t n, gcb_label* result) {
+    if (!seed || (n && (!t || !result))) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    Staged dt;
+    if ((rc = dt.up(t, n * 16))) return rc;
+    if ((rc = gcb_rot_receive_dev(seed, dt.b.as<gcb_label>(), n, dt.b.as<gcb_label>(), nullptr))) return rc;
+    CK(cudaMemcpy(result, dt.b.p, n * 16, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+// ------------------------------------------- IKNP malicious-mode consistency sums --
+int gcb_iknp_check_sums_dev(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
+                            uint64_t n, gcb_label out[3], void* stream) {
+    if (!seed2 || !out || (n && !labels)) return fail(GCB_E_ARG, "null argument");
+    memset(out, 0, 3 * sizeof(gcb_label));
+    if (n == 0) return GCB_OK;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t opt = cudaSuccess;
+    std::call_once(once, [] { opt = opt_in(iknp_check_kernel); });
+    CK(opt);
+    DevBuf acc;
+    CK(acc.alloc(12 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(acc.p, 0, 12 * sizeof(uint32_t), (cudaStream_t)stream));
+    CheckParams p{seed2->d0, seed2->d1, chi_start, reinterpret_cast<const uint4*>(labels), choice, n, acc.as<uint32_t>()};
+    const uint64_t want = (n + 511) / 512;
+    const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
+    iknp_check_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES + 512, (cudaStream_t)stream>>>(p);
+    CK(cudaGetLastError());
+    uint32_t w[12];
+    CK(cudaMemcpyAsync(w, acc.p, sizeof w, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < 3; k++) {
+        out[k].d0 = (uint64_t)w[4 * k] | ((uint64_t)w[4 * k + 1] << 32);
+        out[k].d1 = (uint64_t)w[4 * k + 2] | ((uint64_t)w[4 * k + 3] << 32);
+    }
+    return GCB_OK;
+}
+int gcb_iknp_check_sums(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
+                        uint64_t n, gcb_label out[3]) {
+    if (!seed2 || !out || (n && !labels)) return fail(GCB_E_ARG, "null argument");
+    if (n == 0) { memset(out, 0, 3 * sizeof(gcb_label)); return GCB_OK; }
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    Staged dl, dc;
+    if ((rc = dl.up(labels, n * 16))) return rc;
+    if (choice && (rc = dc.up(choice, n))) return rc;
+    return gcb_iknp_check_sums_dev(seed2, chi_start, dl.b.as<gcb_label>(), choice ? dc.b.as<uint8_t>() : nullptr, n, out, nullptr);
+}
+
+}  // extern "C"

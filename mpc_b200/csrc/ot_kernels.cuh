@@ -301,4 +301,150 @@ __global__ void __launch_bounds__(IKNP_CTA_THREADS, 1) iknp_kernel(const IknpPar
     }
 }
 
+// ------------------------------------------------- COT / ROT post-processing (K7) --
+// Replaces the per-batch loops of COT.Send / COT.Receive (ot/cot.go:157-181, :201-233) and
+// ROT.Send / ROT.Receive (ot/rot.go:155-172, :192-197): OT number j is hashed under MiTCCRH key
+// j (NewMITCCRH(seed, 8) hands out keys gid 0, 1, 2, ... eight per renewal; Hash(pad, 8, h) lets
+// key i encrypt blocks i*h .. i*h+h-1, ot/mitccrh.go:70-128), so the batches of eight are only
+// buffer management and every OT is independent: one thread per OT, one key schedule in
+// registers, one (receiver) or two (sender) blocks, the pad XORed with the payload on the way out.
+// The labels arrive straight from the IKNP kernel's output in HBM -- no PCIe round trip between
+// extension and hashing.
+enum : int { COT_SEND = 0, COT_RECEIVE = 1, ROT_SEND = 2, ROT_RECEIVE = 3 };
+struct CotParams {
+    uint64_t seed_d0, seed_d1;
+    uint64_t delta_d0, delta_d1;
+    const uint4* data;        // sender: q_j; receiver: t_j
+    const uint4* wires;       // COT_SEND: {L0, L1} per OT
+    const uint8_t* flags;     // COT_RECEIVE: choice per OT (Go []bool)
+    const uint4* msgs_in;     // COT_RECEIVE: the 2n labels taken off the wire
+    uint4* out;               // COT_SEND: 2n messages; COT_RECEIVE / ROT_RECEIVE: n labels; ROT_SEND: n wires {L0, L1}
+    uint64_t n;
+    uint32_t wire_bytes;      // 1: messages are in the SendLabel byte encoding (BE64(D0) || BE64(D1), ot/label.go:105-108)
+};
+// Label <-> the 16 bytes SendLabel / ReceiveLabel move (ot/io.go, ot/label.go:105-114)
+__device__ __forceinline__ uint4 label_to_wire(Label l) { return make_uint4(bswap32(l.w0), bswap32(l.w1), bswap32(l.w2), bswap32(l.w3)); }
+__device__ __forceinline__ Label label_from_wire(uint4 m) { return Label{bswap32(m.x), bswap32(m.y), bswap32(m.z), bswap32(m.w)}; }
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) cot_kernel(const CotParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
+    aes_tables_to_smem(smem);
+    __syncthreads();
+    const AesLane lane = aes_lane(smem);
+    const Label delta = Label{(uint32_t)(p.delta_d0 >> 32), (uint32_t)p.delta_d0, (uint32_t)(p.delta_d1 >> 32), (uint32_t)p.delta_d1};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const uint64_t d0 = p.seed_d0 ^ i;                 // key i = BE(seed ^ {D0: i}), mitccrh.go:72-86
+        uint32_t rk[44];
+        aes128_expand_regs(lane, (uint32_t)(d0 >> 32), (uint32_t)d0, (uint32_t)(p.seed_d1 >> 32), (uint32_t)p.seed_d1, rk);
+        const Label x = label_from_mem(__ldg(p.data + i));
+        uint32_t s0 = x.w0, s1 = x.w1, s2 = x.w2, s3 = x.w3;
+        aes128_encrypt_regs(lane, rk, s0, s1, s2, s3);
+        const Label h0 = Label{s0 ^ x.w0, s1 ^ x.w1, s2 ^ x.w2, s3 ^ x.w3};
+        if (MODE == ROT_RECEIVE) {                         // rot.go:192-197
+            p.out[i] = label_to_mem(h0);
+        } else if (MODE == COT_RECEIVE) {                  // cot.go:213-231
+            const uint4 m = __ldg(p.msgs_in + 2 * i + (p.flags[i] ? 1 : 0));
+            const Label r = p.wire_bytes ? label_from_wire(m) : label_from_mem(m);
+            p.out[i] = label_to_mem(r ^ h0);
+        } else {
+            const Label y = x ^ delta;                     // cot.go:163-165, rot.go:161-163
+            s0 = y.w0; s1 = y.w1; s2 = y.w2; s3 = y.w3;
+            aes128_encrypt_regs(lane, rk, s0, s1, s2, s3);
+            const Label h1 = Label{s0 ^ y.w0, s1 ^ y.w1, s2 ^ y.w2, s3 ^ y.w3};
+            if (MODE == COT_SEND) {                        // cot.go:168-177
+                const Label m0 = h0 ^ label_from_mem(__ldg(p.wires + 2 * i));
+                const Label m1 = h1 ^ label_from_mem(__ldg(p.wires + 2 * i + 1));
+                p.out[2 * i] = p.wire_bytes ? label_to_wire(m0) : label_to_mem(m0);
+                p.out[2 * i + 1] = p.wire_bytes ? label_to_wire(m1) : label_to_mem(m1);
+            } else {                                       // rot.go:166-169
+                p.out[2 * i] = label_to_mem(h0);
+                p.out[2 * i + 1] = label_to_mem(h1);
+            }
+        }
+    }
+}
+
+// ------------------------------------- malicious-mode consistency sums of IKNP (K8) --
+// Replaces the chi loops of IKNPSender.Send (ot/iknp.go:150-173) and IKNPReceiver.Receive
+// (:408-451) with vectorInnPrdtSumNoRed / mul128 (ot/gf128.go:14-27, ot/mul128_generic.go,
+// ot/mul128_amd64.s): chi_i is block chi_start + i of the AES-128-CTR stream keyed by seed2
+// (prgLabels :639-645), the sums are (lo, hi) ^= chi_i (x) l_i as 256-bit carry-less products and,
+// for the receiver, x ^= chi_i where the choice bit is set.  There is no carry-less multiply on
+// the GPU: a 32x32 product is 16 integer multiplies of operands with every fourth bit kept (the
+// partial sums of a bit position never exceed 8, so they cannot carry into the next kept bit),
+// which run on the FMA pipe beside the AES lookups.
+struct CheckParams {
+    uint64_t seed_d0, seed_d1; // seed2; the PRG key is BE(seed2) (newPrg, iknp.go:622-631)
+    uint64_t chi_start;
+    const uint4* labels;
+    const uint8_t* choice;    // nullable
+    uint64_t n;
+    uint32_t* acc;            // 12 words: lo (4), hi (4), x (4) as {D0 lo, D0 hi, D1 lo, D1 hi}; XOR-accumulated
+};
+__device__ __forceinline__ uint64_t clmul32(uint32_t x, uint32_t y) {
+    const uint32_t x0 = x & 0x11111111u, x1 = x & 0x22222222u, x2 = x & 0x44444444u, x3 = x & 0x88888888u;
+    const uint32_t y0 = y & 0x11111111u, y1 = y & 0x22222222u, y2 = y & 0x44444444u, y3 = y & 0x88888888u;
+    auto m = [](uint32_t a, uint32_t b) { return (uint64_t)a * b; };
+    const uint64_t z0 = m(x0, y0) ^ m(x1, y3) ^ m(x2, y2) ^ m(x3, y1);
+    const uint64_t z1 = m(x0, y1) ^ m(x1, y0) ^ m(x2, y3) ^ m(x3, y2);
+    const uint64_t z2 = m(x0, y2) ^ m(x1, y1) ^ m(x2, y0) ^ m(x3, y3);
+    const uint64_t z3 = m(x0, y3) ^ m(x1, y2) ^ m(x2, y1) ^ m(x3, y0);
+    return (z0 & 0x1111111111111111ull) | (z1 & 0x2222222222222222ull) | (z2 & 0x4444444444444444ull) |
+           (z3 & 0x8888888888888888ull);
+}
+// a, b: four 32-bit limbs, limb 0 = coefficients x^0..x^31 (Label.Bit numbering: D0 low word first);
+// r: eight limbs of the 256-bit product, XORed in.
+__device__ __forceinline__ void clmul128_acc(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t (&r)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t z = clmul32(a[i], b[j]);
+            r[i + j] ^= (uint32_t)z;
+            r[i + j + 1] ^= (uint32_t)(z >> 32);
+        }
+}
+__global__ void __launch_bounds__(512, 1) iknp_check_kernel(const CheckParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const smem = aes_align_tables(smem_raw);
+    uint32_t* rk = reinterpret_cast<uint32_t*>(smem + AES_TABLE_BYTES);
+    uint32_t* red = rk + 64;                               // 12 words of block-level accumulator
+    aes_tables_to_smem(smem);
+    if (threadIdx.x < 12) red[threadIdx.x] = 0;
+    __syncthreads();
+    const AesLane lane = aes_lane(smem);
+    if (threadIdx.x == 0) {
+        uint8_t* kb = reinterpret_cast<uint8_t*>(red + 16);
+        for (int b = 0; b < 8; b++) { kb[b] = (uint8_t)(p.seed_d0 >> (56 - 8 * b)); kb[8 + b] = (uint8_t)(p.seed_d1 >> (56 - 8 * b)); }
+        aes_expand_key(lane, kb, 16, rk);
+    }
+    __syncthreads();
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xs[4] = {0, 0, 0, 0};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const uint64_t ctr = p.chi_start + i;              // 128-bit big-endian counter, iv = 0 (newPrg :622-631)
+        uint32_t s0 = 0, s1 = 0, s2 = (uint32_t)(ctr >> 32), s3 = (uint32_t)ctr;
+        aes_encrypt_smem<10>(lane, rk, s0, s1, s2, s3);
+        // SetBytes (label.go:111-114): D0 = (s0, s1), D1 = (s2, s3); limbs in Label.Bit order
+        const uint32_t chi[4] = {s1, s0, s3, s2};
+        const uint4 lm = __ldg(p.labels + i);              // Go memory order: (lo D0, hi D0, lo D1, hi D1)
+        const uint32_t l[4] = {lm.x, lm.y, lm.z, lm.w};
+        clmul128_acc(chi, l, acc);
+        if (p.choice && p.choice[i]) { xs[0] ^= chi[0]; xs[1] ^= chi[1]; xs[2] ^= chi[2]; xs[3] ^= chi[3]; }
+    }
+    // warp XOR-reduction, then one shared and one global atomic per word
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+        uint32_t v = w < 8 ? acc[w] : xs[w - 8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicXor(red + w, v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 12 && red[threadIdx.x]) atomicXor(p.acc + threadIdx.x, red[threadIdx.x]);
+}
+
 }  // namespace gcb

@@ -16,7 +16,8 @@ from . import _lib
 from ._lib import GcbError, Label, check, ptr
 from .circuit_io import LABEL_DTYPE
 
-__all__ = ["IKNPSender", "IKNPReceiver", "MITCCRH", "u_size", "stream_advance", "GcbError"]
+__all__ = ["IKNPSender", "IKNPReceiver", "MITCCRH", "u_size", "stream_advance", "GcbError",
+           "cot_send", "cot_receive", "rot_send", "rot_receive", "iknp_check_sums", "mul128", "COT_WIRE_BYTES"]
 
 
 def u_size(n: int) -> int:
@@ -126,3 +127,86 @@ def mitccrh_hash_many(seed, gid_start: int, blks: np.ndarray, nkeys: int, h: int
     lab = Label(int(s["d0"][0]), int(s["d1"][0]))
     assert blks.dtype == LABEL_DTYPE and blks.flags["C_CONTIGUOUS"] and len(blks) == nkeys * h
     check(_lib.lib().gcb_mitccrh_hash(C.byref(lab), gid_start, ptr(blks), nkeys, h))
+
+
+# ---- COT / ROT post-processing and the malicious-mode check (ot/cot.go, ot/rot.go, ot/iknp.go) ----
+COT_WIRE_BYTES = 1
+
+
+def _label(x) -> Label:
+    s = np.asarray(x, dtype=LABEL_DTYPE).reshape(1)
+    return Label(int(s["d0"][0]), int(s["d1"][0]))
+
+
+def cot_send(seed, delta, q: np.ndarray, wires: np.ndarray, wire_bytes: bool = False) -> np.ndarray:
+    """The 2n messages COT.Send puts on the wire after the extension (ot/cot.go:157-181).
+    wire_bytes: return the SendLabel byte encoding (uint8[2n, 16]) instead of labels."""
+    from .circuit_io import WIRE_DTYPE
+    q = np.ascontiguousarray(q, dtype=LABEL_DTYPE)
+    wires = np.ascontiguousarray(wires, dtype=WIRE_DTYPE)
+    n = len(q)
+    assert len(wires) == n
+    msgs = np.zeros(max(2 * n, 1), dtype=LABEL_DTYPE)
+    s, d = _label(seed), _label(delta)
+    check(_lib.lib().gcb_cot_send(C.byref(s), C.byref(d), ptr(q), ptr(wires), n, ptr(msgs), COT_WIRE_BYTES if wire_bytes else 0))
+    msgs = msgs[: 2 * n]
+    return msgs.view(np.uint8).reshape(-1, 16) if wire_bytes else msgs
+
+
+def cot_receive(seed, choice: np.ndarray, msgs: np.ndarray, t: np.ndarray, wire_bytes: bool = False) -> np.ndarray:
+    """COT.Receive after the extension (ot/cot.go:201-233): result[j] = msgs[2j + b_j] ^ H_j(t_j)."""
+    t = np.ascontiguousarray(t, dtype=LABEL_DTYPE)
+    n = len(t)
+    choice = np.ascontiguousarray(choice, dtype=np.uint8)
+    msgs = np.ascontiguousarray(msgs)
+    assert msgs.nbytes == 32 * n and len(choice) == n
+    res = np.zeros(max(n, 1), dtype=LABEL_DTYPE)
+    s = _label(seed)
+    check(_lib.lib().gcb_cot_receive(C.byref(s), ptr(choice), ptr(msgs), ptr(t), n, ptr(res), COT_WIRE_BYTES if wire_bytes else 0))
+    return res[:n]
+
+
+def rot_send(seed, delta, q: np.ndarray) -> np.ndarray:
+    """ROT.Send after the extension (ot/rot.go:155-172): wires[j] = {H_j(q_j), H_j(q_j ^ delta)}."""
+    from .circuit_io import WIRE_DTYPE
+    q = np.ascontiguousarray(q, dtype=LABEL_DTYPE)
+    n = len(q)
+    wires = np.zeros(max(n, 1), dtype=WIRE_DTYPE)
+    s, d = _label(seed), _label(delta)
+    check(_lib.lib().gcb_rot_send(C.byref(s), C.byref(d), ptr(q), n, ptr(wires)))
+    return wires[:n]
+
+
+def rot_receive(seed, t: np.ndarray) -> np.ndarray:
+    """ROT.Receive after the extension (ot/rot.go:192-197): result[j] = H_j(t_j)."""
+    t = np.ascontiguousarray(t, dtype=LABEL_DTYPE)
+    n = len(t)
+    res = np.zeros(max(n, 1), dtype=LABEL_DTYPE)
+    s = _label(seed)
+    check(_lib.lib().gcb_rot_receive(C.byref(s), ptr(t), n, ptr(res)))
+    return res[:n]
+
+
+def iknp_check_sums(seed2, chi_start: int, labels: np.ndarray, choice=None):
+    """(lo, hi, x) sums of the malicious-mode check (ot/iknp.go:150-173, :408-451) as (d0, d1) tuples."""
+    labels = np.ascontiguousarray(labels, dtype=LABEL_DTYPE)
+    ch = None if choice is None else np.ascontiguousarray(choice, dtype=np.uint8)
+    out = np.zeros(3, dtype=LABEL_DTYPE)
+    s = _label(seed2)
+    check(_lib.lib().gcb_iknp_check_sums(C.byref(s), chi_start, ptr(labels) if len(labels) else None,
+                                          None if ch is None else ptr(ch), len(labels), ptr(out)))
+    return tuple((int(o["d0"]), int(o["d1"])) for o in out)
+
+
+def mul128(a, b):
+    """ot.mul128 (ot/mul128_generic.go): 256-bit carry-less product of two labels as ((lo.d0, lo.d1), (hi.d0, hi.d1)).
+    Host arithmetic on Python integers: one product per check, nothing to put on the device."""
+    def poly(l):
+        return int(l[0]) | (int(l[1]) << 64)
+    x, y, r = poly(a), poly(b), 0
+    while y:
+        low = y & -y
+        r ^= x * low
+        y ^= low
+    m = (1 << 64) - 1
+    return (r & m, (r >> 64) & m), ((r >> 128) & m, (r >> 192) & m)

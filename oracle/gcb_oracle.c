@@ -1040,3 +1040,27 @@ void orc_inner_product(const orc_label *a, const orc_label *b, uint64_t n, orc_l
     }
     *lo = r1; *hi = r2;
 }
+
+/* ======================================================================== */
+/* Malicious-mode consistency check of IKNP (ot/iknp.go:137-192 sender,       */
+/* :373-465 receiver): chi_i = prgLabels(newPrg(seed2)) in stream order, i.e.  */
+/* label number chi_start + i is keystream block chi_start + i read with       */
+/* SetBytes (big-endian); sums over `labels`: (lo, hi) ^= mul128(chi_i, l_i),  */
+/* and for the receiver x ^= chi_i where choice[i] is set (the And(select1) /  */
+/* And(select0) of :425-431).  out = {lo, hi, x}.  The 1024-label chunking of  */
+/* the reference is only buffer management: the stream is continuous.          */
+/* ======================================================================== */
+void orc_iknp_check_sums(orc_label seed2, uint64_t chi_start, const orc_label *labels,
+                         const uint8_t *choice, uint64_t n, orc_label out[3]) {
+    orc_label lo = {0, 0}, hi = {0, 0}, x = {0, 0};
+    for (uint64_t i = 0; i < n; i++) {
+        uint8_t buf[16];
+        orc_prg(seed2, (chi_start + i) * 16, buf, 16);
+        orc_label chi = {get_be64(buf), get_be64(buf + 8)};          /* SetBytes, label.go:111-114 */
+        orc_label l, h;
+        orc_mul128(chi, labels[i], &l, &h);
+        lo = lxor(lo, l); hi = lxor(hi, h);
+        if (choice && choice[i]) x = lxor(x, chi);
+    }
+    out[0] = lo; out[1] = hi; out[2] = x;
+}

@@ -174,6 +174,9 @@ void orc_rot_receive(orc_label *result, orc_label seed, uint64_t n);
 /* ---- GF(2^128) carry-less multiply (ot/mul128_ref.go, gf128.go:14) -------- */
 void orc_mul128(orc_label a, orc_label b, orc_label *lo, orc_label *hi);
 void orc_inner_product(const orc_label *a, const orc_label *b, uint64_t n, orc_label *lo, orc_label *hi);
+/* Sums of the malicious-mode check (ot/iknp.go:150-173, :408-451): out = {lo, hi, x}. */
+void orc_iknp_check_sums(orc_label seed2, uint64_t chi_start, const orc_label *labels,
+                         const uint8_t *choice, uint64_t n, orc_label out[3]);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,7 @@ def lib():
         L.orc_rot_receive.argtypes = [vp, _Label, u64]
         L.orc_mul128.argtypes = [_Label, _Label, C.POINTER(_Label), C.POINTER(_Label)]
         L.orc_inner_product.argtypes = [vp, vp, u64, C.POINTER(_Label), C.POINTER(_Label)]
+        L.orc_iknp_check_sums.argtypes = [_Label, u64, vp, vp, u64, vp]
         _lib = L
     return _lib
 
@@ -417,3 +418,12 @@ def inner_product(a: np.ndarray, b: np.ndarray):
     a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     lib().orc_inner_product(_p(a), _p(b), min(len(a), len(b)), C.byref(lo), C.byref(hi))
     return t(lo), t(hi)
+
+
+def iknp_check_sums(seed2, chi_start: int, labels: np.ndarray, choice=None):
+    """(lo, hi, x) of the malicious-mode check (ot/iknp.go:150-173, :408-451)."""
+    labels = np.ascontiguousarray(labels)
+    out = (_Label * 3)()
+    ch = None if choice is None else np.ascontiguousarray(choice, dtype=np.uint8)
+    lib().orc_iknp_check_sums(lab(seed2), chi_start, _p(labels), None if ch is None else _p(ch), len(labels), out)
+    return t(out[0]), t(out[1]), t(out[2])

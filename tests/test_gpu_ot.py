@@ -115,3 +115,85 @@ def test_iknp_bit_cot_bit_exact(n):
     o_s, _ = O.iknp_send_bits(ks, delta[0], 5, o_u, n)
     assert np.array_equal(s, o_s), "sender bits differ"
     assert rcv.pos == snd.pos == o_pos
+
+
+# ---- COT / ROT post-processing and the malicious-mode check on the device -------------
+def _rand_wires(tag, n):
+    from mpc_b200.circuit_io import WIRE_DTYPE
+    w = np.zeros(n, WIRE_DTYPE)
+    a, b = drbg_labels(tag + "/l0", n), drbg_labels(tag + "/l1", n)
+    w["l0"], w["l1"] = a, b
+    return w
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 64, 1000, 4096 + 5, (1 << 16) + 3])
+def test_cot_rot_bit_exact(n):
+    """COT.Send / Receive and ROT.Send / Receive after the extension (ot/cot.go:157-233,
+    ot/rot.go:155-197) against the oracle's batch-of-eight loops, incl. partial last batches."""
+    from mpc_b200.ot import cot_receive, cot_send, rot_receive, rot_send
+    k0, k1, delta, ks = _keys("cot")
+    b = (DRBG(f"cot/b/{n}").array(n) & 1).astype(np.uint8)
+    u, t = IKNPReceiver(k0, k1).receive(b)
+    q = IKNPSender(ks, delta).send(u, n)
+    seed = drbg_labels(f"cot/seed/{n}", 1)
+    wires = _rand_wires(f"cot/w/{n}", n)
+    msgs = cot_send(seed, delta, q, wires)
+    assert eq(msgs, O.cot_send(q, delta[0], seed[0], wires)), "COT messages differ"
+    got = cot_receive(seed, b, msgs, t)
+    assert eq(got, O.cot_receive(t, b, seed[0], msgs)), "COT results differ"
+    want = np.where(b.astype(bool), wires["l1"], wires["l0"])
+    assert eq(got, want), "COT does not deliver the chosen labels"
+    # SendLabel byte encoding on both sides (ot/label.go:105-114)
+    mb = cot_send(seed, delta, q, wires, wire_bytes=True)
+    be = np.stack([msgs["d0"].astype(">u8").view(np.uint8).reshape(-1, 8),
+                   msgs["d1"].astype(">u8").view(np.uint8).reshape(-1, 8)], axis=1).reshape(-1, 16)
+    assert eq(mb, be), "wire-byte messages differ"
+    assert eq(cot_receive(seed, b, mb, t, wire_bytes=True), want)
+    rw = rot_send(seed, delta, q)
+    assert eq(rw, O.rot_send(q, delta[0], seed[0])), "ROT wires differ"
+    rr = rot_receive(seed, t)
+    assert eq(rr, O.rot_receive(t, seed[0])), "ROT results differ"
+    assert eq(rr, np.where(b.astype(bool), rw["l1"], rw["l0"]))
+
+
+@pytest.mark.parametrize("n", [1, 2, 100, 1024, 1025, 5000, (1 << 16) + 77])
+def test_iknp_check_sums_bit_exact(n):
+    """prgLabels + vectorInnPrdtSumNoRed / mul128 sums (ot/iknp.go:150-173, :408-451) vs the oracle."""
+    from mpc_b200.ot import iknp_check_sums
+    labels = drbg_labels(f"chk/l/{n}", n)
+    choice = (DRBG(f"chk/b/{n}").array(n) & 1).astype(np.uint8)
+    seed2 = drbg_labels(f"chk/seed/{n}", 1)
+    for start in (0, 12345, (1 << 32) - 3):
+        assert iknp_check_sums(seed2, start, labels, choice) == O.iknp_check_sums(seed2[0], start, labels, choice)
+    lo, hi, x = iknp_check_sums(seed2, 9, labels)          # sender side: no choice vector
+    assert (lo, hi) == O.iknp_check_sums(seed2[0], 9, labels)[:2] and x == (0, 0)
+
+
+def test_iknp_malicious_check_full_size():
+    """The whole malicious-mode exchange at 2^20 OTs on the device: extension, the 256 choice-vector OTs,
+    both sides' sums, and the sender's verdict q ^ mul128(x, Delta) == t (ot/iknp.go:175-191)."""
+    from mpc_b200.ot import iknp_check_sums, mul128
+    n = 1 << 20
+    k0, k1, delta, ks = _keys("mal")
+    rcv, snd = IKNPReceiver(k0, k1), IKNPSender(ks, delta)
+    b = (DRBG("mal/b").array(n) & 1).astype(np.uint8)
+    bcv = (DRBG("mal/bcv").array(256) & 1).astype(np.uint8)
+    u, t = rcv.receive(b)
+    u2, t2 = rcv.receive(bcv)
+    q = snd.send(u, n)
+    q2 = snd.send(u2, 256)
+    seed2 = drbg_labels("mal/seed2", 1)
+
+    def fold(a, c):
+        return tuple((p[0] ^ r[0], p[1] ^ r[1]) for p, r in zip(a, c))
+    t0, t1, x = fold(iknp_check_sums(seed2, 0, t, b), iknp_check_sums(seed2, n, t2, bcv))
+    q0, q1, _ = fold(iknp_check_sums(seed2, 0, q), iknp_check_sums(seed2, n, q2))
+    d = (int(delta["d0"][0]), int(delta["d1"][0]))
+    r0, r1 = mul128(x, d)
+    assert mul128(x, d) == O.mul128(x, d)
+    assert (q0[0] ^ r0[0], q0[1] ^ r0[1]) == t0 and (q1[0] ^ r1[0], q1[1] ^ r1[1]) == t1
+    # a receiver that lies about one choice bit is caught
+    b[12345] ^= 1
+    c0, c1, cx = fold(iknp_check_sums(seed2, 0, t, b), iknp_check_sums(seed2, n, t2, bcv))
+    r0, r1 = mul128(cx, d)
+    assert ((q0[0] ^ r0[0], q0[1] ^ r0[1]), (q1[0] ^ r1[0], q1[1] ^ r1[1])) != (c0, c1)

@@ -524,3 +524,44 @@ def test_mul128_identities():
         lo, hi = O.mul128(x, y)
         assert lo[0] | (lo[1] << 64) | (hi[0] << 128) | (hi[1] << 192) == acc
         assert O.mul128(y, x) == (lo, hi)
+
+
+def test_iknp_malicious_check_sums_verify():
+    """ot/iknp.go:137-192 / :373-465: the sender's check q ^ mul128(x, Delta) == t must pass on the
+    sums of an honest run (n OTs + the 256 choice-vector OTs, one continuous chi stream), and fail
+    when a receiver label is off by one bit."""
+    k0, k1, delta = _iknp_keys("malicious")
+    dv = (delta[0] << 64) | delta[1]
+    ks = np.array([k1[i] if P.label_bit(dv, i) else k0[i] for i in range(128)], dtype=LABEL_DTYPE)
+    rng = np.random.default_rng(7)
+    for n in (1, 100, 1024, 1500):
+        b = rng.integers(0, 2, n).astype(np.uint8)
+        bcv = rng.integers(0, 2, 256).astype(np.uint8)
+        u, t, pos = O.iknp_receive(k0, k1, 0, b)
+        u2, t2, _ = O.iknp_receive(k0, k1, pos, bcv)
+        q, spos = O.iknp_send(ks, delta, 0, u, n)
+        q2, _ = O.iknp_send(ks, delta, spos, u2, 256)
+        seed2 = (int(rng.integers(0, 2**63)), int(rng.integers(0, 2**63)))
+
+        def fold(*parts):
+            acc = [(0, 0)] * 3
+            for p in parts:
+                acc = [(a[0] ^ c[0], a[1] ^ c[1]) for a, c in zip(acc, p)]
+            return acc
+        t0, t1, x = fold(O.iknp_check_sums(seed2, 0, t, b), O.iknp_check_sums(seed2, n, t2, bcv))
+        q0, q1, xs = fold(O.iknp_check_sums(seed2, 0, q), O.iknp_check_sums(seed2, n, q2))
+        assert xs == (0, 0)
+        r0, r1 = O.mul128(x, delta)                      # iknp.go:185-187
+        assert (q0[0] ^ r0[0], q0[1] ^ r0[1]) == t0 and (q1[0] ^ r1[0], q1[1] ^ r1[1]) == t1
+        bad = t.copy()
+        bad["d1"][n // 2] ^= 4
+        b0, b1, _ = fold(O.iknp_check_sums(seed2, 0, bad, b), O.iknp_check_sums(seed2, n, t2, bcv))
+        assert (b0, b1) != (t0, t1)
+    # the chi stream is prgLabels of newPrg(seed2): label i = SetBytes(AES_{BE(seed2)}(BE128(i)))
+    seed2 = (0x0123456789abcdef, 0x0fedcba987654321)
+    one = np.zeros(3, LABEL_DTYPE)
+    one["d0"] = 1                                     # chi_i * 1 = chi_i
+    lo, hi, x = O.iknp_check_sums(seed2, 5, one[:1], np.ones(1, np.uint8))
+    key = seed2[0].to_bytes(8, "big") + seed2[1].to_bytes(8, "big")
+    blk = P.Aes(key).enc(5)                           # OpenSSL: keystream block 5 of AES-128-CTR with zero IV
+    assert lo == x == (blk >> 64, blk & (2**64 - 1)) and hi == (0, 0)

@@ -77,6 +77,27 @@ def hash_half(n, klen):
     emit(path="hash_half", n=n, keylen=klen, ms=ms, hashes_per_s=n / ms * 1e3, achieved_gbs=gb / ms * 1e3, hbm_frac=gb / ms * 1e3 / PEAK)
 
 
+def cot(n):
+    """COT / ROT post-processing and the malicious-mode sums on labels that stay in HBM."""
+    seed, delta = Label(0x0123456789abcdef, 0xfedcba9876543210), Label(0x1111111111111111 | 1 << 63, 0x2222222222222222)
+    q, wires, msgs = rnd(n, 16), rnd(n, 32), torch.empty((2 * n, 16), dtype=torch.uint8, device=dev)
+    choice = torch.randint(0, 2, (n,), dtype=torch.uint8, device=dev)
+    res = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    out = np.zeros(6, dtype=np.uint64)
+    runs = (
+        ("cot_send", 80, 2, lambda: check(L.gcb_cot_send_dev(C.byref(seed), C.byref(delta), ptr(q), ptr(wires), n, ptr(msgs), 0, s))),
+        ("cot_receive", 33, 1, lambda: check(L.gcb_cot_receive_dev(C.byref(seed), ptr(choice), ptr(msgs), ptr(q), n, ptr(res), 0, s))),
+        ("rot_send", 48, 2, lambda: check(L.gcb_rot_send_dev(C.byref(seed), C.byref(delta), ptr(q), n, ptr(msgs), s))),
+        ("rot_receive", 32, 1, lambda: check(L.gcb_rot_receive_dev(C.byref(seed), ptr(q), n, ptr(res), s))),
+        ("iknp_check_sums", 17, 1, lambda: check(L.gcb_iknp_check_sums_dev(C.byref(seed), 0, ptr(q), ptr(choice), n, ptr(out), s))),
+    )
+    for name, bytes_per_ot, blocks, fn in runs:
+        ms = timeit(fn)
+        gb = bytes_per_ot * n / 1e9
+        emit(path=name, n=n, ms=ms, ot_per_s=n / ms * 1e3, aes_blocks_per_s=blocks * n / ms * 1e3, algorithmic_gb=gb,
+             achieved_gbs=gb / ms * 1e3, hbm_frac=gb / ms * 1e3 / PEAK)
+
+
 def garble_eval(name, batch, klen, per_instance):
     circ = load_circuit(name)
     eng = GarbleEngine(circ)
@@ -122,18 +143,20 @@ def streaming(name, batch, klen):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["iknp", "mitccrh", "hash", "gc", "stream"]
+    what = sys.argv[1:] or ["iknp", "mitccrh", "cot", "hash", "gc", "stream"]
     if "iknp" in what:
         iknp(1 << 24, 0); iknp(1 << 24, 17)
     if "mitccrh" in what:
         mitccrh(1 << 24, 1); mitccrh(1 << 24, 2)
+    if "cot" in what:
+        cot(1 << 24)
     if "hash" in what:
         hash_half(1 << 24, 16); hash_half(1 << 24, 32)
     if "gc" in what:
         garble_eval("aes_128", 4096, 16, False)
         garble_eval("aes_128", 4096, 32, True)
-        garble_eval("sha256", 1024, 16, False)
-        garble_eval("sha256xor", 1024, 32, True)
+        garble_eval("sha256", 1184, 16, False)
+        garble_eval("sha256xor", 1184, 32, True)
         garble_eval("mul64", 4096, 16, False)
     if "stream" in what:
         streaming("sha256", 256, 32)
