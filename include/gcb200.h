@@ -300,6 +300,28 @@ int gcb_iknp_check_sums(const gcb_label *seed2, uint64_t chi_start, const gcb_la
 int gcb_iknp_check_sums_dev(const gcb_label *seed2, uint64_t chi_start, const gcb_label *labels,
                             const uint8_t *choice, uint64_t n, gcb_label out[3], void *stream);
 
+/* ------------------------------------------- garbled tables in the wire format --- */
+/* The byte stream Garbler sends after Garble (circuit/garbler.go:69-82) and Evaluator parses
+ * before Eval (circuit/evaluator.go:40-66): SendUint32(NumGates), then for every gate in file
+ * order SendUint32(len(rows)) and the rows with SendLabel (16 bytes, BE64(D0) || BE64(D1)).
+ * These calls convert between that stream and the dense row slab of gcb_garble / gcb_eval for
+ * a whole batch, so the slab goes device -> pinned host -> socket with no per-label Go work
+ * (and sha2pc/encoding.go:363-440 can copy the same bytes).
+ *   wire bytes per instance = 4 + 4 * num_gates + 16 * num_rows   (gcb_tables_wire_size)
+ *   stride: bytes between instances in the wire buffer; a multiple of 16 that is at least
+ *   the wire size rounded up to 16, plus 16 for gcb_tables_from_wire (rows are read with
+ *   aligned 32-byte windows).
+ * gcb_tables_from_wire checks every count against the circuit ("wrong number of gates",
+ * GCB_E_CORRUPT on a row count that does not match the gate type) on the host copy; the _dev
+ * variants take device pointers, trust the counts and only move the rows. */
+int gcb_tables_wire_size(const gcb_plan *plan, size_t *bytes);
+int gcb_tables_to_wire(const gcb_plan *plan, uint32_t batch, const gcb_label *tables, uint8_t *dst, size_t stride);
+int gcb_tables_from_wire(const gcb_plan *plan, uint32_t batch, const uint8_t *src, size_t stride, gcb_label *tables);
+int gcb_tables_to_wire_dev(const gcb_plan *plan, uint32_t batch, const gcb_label *tables, uint8_t *dst,
+                           size_t stride, void *stream);
+int gcb_tables_from_wire_dev(const gcb_plan *plan, uint32_t batch, const uint8_t *src, size_t stride,
+                             gcb_label *tables, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

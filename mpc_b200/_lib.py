@@ -87,6 +87,11 @@ SYMBOLS = {
     "gcb_cot_receive_dev": (_int, [C.POINTER(Label), _vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "gcb_rot_send_dev": (_int, [C.POINTER(Label), C.POINTER(Label), _vp, _u64, _vp, _vp]),
     "gcb_rot_receive_dev": (_int, [C.POINTER(Label), _vp, _u64, _vp, _vp]),
+    "gcb_tables_wire_size": (_int, [_vp, C.POINTER(_sz)]),
+    "gcb_tables_to_wire": (_int, [_vp, _u32, _vp, _vp, _sz]),
+    "gcb_tables_from_wire": (_int, [_vp, _u32, _vp, _sz, _vp]),
+    "gcb_tables_to_wire_dev": (_int, [_vp, _u32, _vp, _vp, _sz, _vp]),
+    "gcb_tables_from_wire_dev": (_int, [_vp, _u32, _vp, _sz, _vp, _vp]),
     "gcb_iknp_check_sums": (_int, [C.POINTER(Label), _u64, _vp, _vp, _u64, _vp]),
     "gcb_iknp_check_sums_dev": (_int, [C.POINTER(Label), _u64, _vp, _vp, _u64, _vp, _vp]),
 }

@@ -190,6 +190,29 @@ class GarbleEngine:
         check(_lib.lib().gcb_eval(self._h, ptr(ka), kl, ks, batch, tp, ptr(in_labels), ptr(out_labels), None, 0))
         return out_labels
 
+    # ---- the garbled tables as Garbler sends them (circuit/garbler.go:69-82) --------
+    def tables_wire_size(self) -> int:
+        import ctypes as C
+        n = C.c_size_t()
+        check(_lib.lib().gcb_tables_wire_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def tables_to_wire(self, tables: np.ndarray) -> np.ndarray:
+        """[batch][rows] labels -> uint8[batch][wire_size]: u32 NumGates, then per gate u32 count + BE rows."""
+        tables = np.ascontiguousarray(tables, dtype=LABEL_DTYPE).reshape(-1, max(self.circ.num_rows, 1))
+        batch, n = len(tables), self.tables_wire_size()
+        out = np.zeros((batch, n), dtype=np.uint8)
+        check(_lib.lib().gcb_tables_to_wire(self._h, batch, ptr(tables), ptr(out), n))
+        return out
+
+    def tables_from_wire(self, wire: np.ndarray) -> np.ndarray:
+        """The inverse (circuit/evaluator.go:40-66); raises GcbError on a count that does not fit the circuit."""
+        wire = np.ascontiguousarray(wire, dtype=np.uint8)
+        batch, stride = wire.shape
+        tables = np.zeros((batch, max(self.circ.num_rows, 1)), dtype=LABEL_DTYPE)
+        check(_lib.lib().gcb_tables_from_wire(self._h, batch, ptr(wire), stride, ptr(tables)))
+        return tables[:, : self.circ.num_rows]
+
     # ---- batched, device-resident (torch tensors or raw device addresses) -------
     def garble_dev(self, keys_dev, keylen: int, key_stride: int, batch: int, r_dev, in_l0_dev, tables_dev,
                    io_wires_dev=None, wires_full_dev=None, stream: int = 0) -> None:

@@ -1453,3 +1453,128 @@ int gcb_iknp_check_sums(const gcb_label* seed2, uint64_t chi_start, const gcb_la
 }
 
 }  // extern "C"
+
+// ------------------------------------------- garbled tables in the wire format ------
+gcb::DevWireLayout::~DevWireLayout() {
+    if (tmpl) cudaFree(tmpl);
+    if (row_pos) cudaFree(row_pos);
+}
+static size_t tables_wire_bytes(const gcb_plan* plan) {
+    return 4 + 4 * (size_t)plan->p.info.num_gates + 16 * (size_t)plan->p.info.num_rows;
+}
+static void put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+static int wire_layout_on_device(const gcb_plan* plan, int device, std::shared_ptr<DevWireLayout>* out) {
+    std::lock_guard<std::mutex> lk(plan->wire_mu);
+    auto it = plan->wire_dev.find(device);
+    if (it != plan->wire_dev.end()) { *out = it->second; return GCB_OK; }
+    const Plan& pl = plan->p;
+    const size_t total = tables_wire_bytes(plan);
+    if (total > 0xfffffff0u) return fail(GCB_E_TOO_LARGE, "garbled tables exceed 4 GiB per instance");
+    std::vector<uint8_t> tmpl(((total + 15) & ~(size_t)15) + 16, 0);
+    std::vector<uint32_t> row_pos(pl.info.num_rows ? pl.info.num_rows : 1);
+    put_be32(tmpl.data(), pl.info.num_gates);                      // garbler.go:69
+    size_t pos = 4;
+    for (uint32_t g = 0; g < pl.info.num_gates; g++) {
+        const uint32_t r0 = pl.row_off[g], cnt = pl.row_off[g + 1] - r0;
+        put_be32(tmpl.data() + pos, cnt);                          // garbler.go:74
+        pos += 4;
+        for (uint32_t k = 0; k < cnt; k++, pos += 16) row_pos[r0 + k] = (uint32_t)pos;
+    }
+    auto dl = std::make_shared<DevWireLayout>();
+    CK(upload(&dl->tmpl, tmpl));
+    CK(upload(&dl->row_pos, row_pos));
+    plan->wire_dev[device] = dl;
+    *out = dl;
+    return GCB_OK;
+}
+
+extern "C" {
+
+int gcb_tables_wire_size(const gcb_plan* plan, size_t* bytes) {
+    if (!plan || !bytes) return fail(GCB_E_ARG, "null argument");
+    *bytes = tables_wire_bytes(plan);
+    return GCB_OK;
+}
+int gcb_tables_to_wire_dev(const gcb_plan* plan, uint32_t batch, const gcb_label* tables, uint8_t* dst, size_t stride,
+                           void* stream) {
+    if (!plan || (batch && (!dst || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
+    const size_t total = tables_wire_bytes(plan);
+    if ((stride & 15) || stride < ((total + 15) & ~(size_t)15)) return fail(GCB_E_BUFFER, "wire stride must be a multiple of 16 and at least %zu", (total + 15) & ~(size_t)15);
+    if (batch == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    std::shared_ptr<DevWireLayout> dl;
+    if ((rc = wire_layout_on_device(plan, tl_device, &dl))) return rc;
+    SerParams sp{dl->tmpl, (uint32_t)total, dl->row_pos, plan->p.info.num_rows, reinterpret_cast<const uint4*>(tables), dst, stride};
+    const dim3 grid((unsigned)((total + SER_TILE - 1) / SER_TILE), batch);
+    serialize_kernel<<<grid, SER_THREADS, 0, (cudaStream_t)stream>>>(sp);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+int gcb_tables_from_wire_dev(const gcb_plan* plan, uint32_t batch, const uint8_t* src, size_t stride, gcb_label* tables,
+                             void* stream) {
+    if (!plan || (batch && (!src || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
+    const size_t total = tables_wire_bytes(plan);
+    if ((stride & 15) || stride < ((total + 15) & ~(size_t)15) + 16) return fail(GCB_E_BUFFER, "wire stride must be a multiple of 16 and at least %zu", ((total + 15) & ~(size_t)15) + 16);
+    if (batch == 0 || plan->p.info.num_rows == 0) return GCB_OK;
+    DeviceInfo* di;
+    int rc = select_device(&di);
+    if (rc) return rc;
+    std::shared_ptr<DevWireLayout> dl;
+    if ((rc = wire_layout_on_device(plan, tl_device, &dl))) return rc;
+    DeserParams dp{src, stride, dl->row_pos, plan->p.info.num_rows, reinterpret_cast<uint4*>(tables), batch};
+    const size_t work = (size_t)batch * plan->p.info.num_rows;
+    const unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, (size_t)di->sm_count * 8);
+    deserialize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dp);
+    CK(cudaGetLastError());
+    return GCB_OK;
+}
+int gcb_tables_to_wire(const gcb_plan* plan, uint32_t batch, const gcb_label* tables, uint8_t* dst, size_t stride) {
+    if (!plan || (batch && (!dst || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
+    const size_t total = tables_wire_bytes(plan);
+    if (stride < total) return fail(GCB_E_BUFFER, "wire buffer too small: need %zu bytes per instance", total);
+    if (batch == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    const size_t rows_bytes = (size_t)batch * plan->p.info.num_rows * 16, s16 = (total + 15) & ~(size_t)15;
+    DevBuf dt, dw;
+    CK(dt.alloc(rows_bytes));
+    CK(dw.alloc((size_t)batch * s16));
+    if (rows_bytes) CK(cudaMemcpy(dt.p, tables, rows_bytes, cudaMemcpyHostToDevice));
+    if ((rc = gcb_tables_to_wire_dev(plan, batch, dt.as<gcb_label>(), dw.as<uint8_t>(), s16, nullptr))) return rc;
+    CK(cudaMemcpy2D(dst, stride, dw.p, s16, total, batch, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+int gcb_tables_from_wire(const gcb_plan* plan, uint32_t batch, const uint8_t* src, size_t stride, gcb_label* tables) {
+    if (!plan || (batch && (!src || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
+    const size_t total = tables_wire_bytes(plan);
+    if (stride < total) return fail(GCB_E_BUFFER, "wire buffer too small: need %zu bytes per instance", total);
+    // the counts the evaluator checks while it reads (evaluator.go:44-52, eval.go:55,87,103)
+    const Plan& pl = plan->p;
+    for (uint32_t b = 0; b < batch; b++) {
+        const uint8_t* q = src + (size_t)b * stride;
+        auto be32 = [](const uint8_t* x) { return ((uint32_t)x[0] << 24) | ((uint32_t)x[1] << 16) | ((uint32_t)x[2] << 8) | x[3]; };
+        if (be32(q) != pl.info.num_gates)
+            return fail(GCB_E_CORRUPT, "wrong number of gates: got %u, expected %u", be32(q), pl.info.num_gates);
+        size_t pos = 4;
+        for (uint32_t g = 0; g < pl.info.num_gates; g++) {
+            const uint32_t cnt = pl.row_off[g + 1] - pl.row_off[g];
+            if (be32(q + pos) != cnt)
+                return fail(GCB_E_CORRUPT, "corrupted circuit: gate %u has %u garbled rows, expected %u", g, be32(q + pos), cnt);
+            pos += 4 + (size_t)cnt * 16;
+        }
+    }
+    if (batch == 0 || pl.info.num_rows == 0) return GCB_OK;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    const size_t rows_bytes = (size_t)batch * pl.info.num_rows * 16, s16 = ((total + 15) & ~(size_t)15) + 16;
+    DevBuf dt, dw;
+    CK(dt.alloc(rows_bytes));
+    CK(dw.alloc((size_t)batch * s16));
+    CK(cudaMemcpy2D(dw.p, s16, src, stride, total, batch, cudaMemcpyHostToDevice));
+    if ((rc = gcb_tables_from_wire_dev(plan, batch, dw.as<uint8_t>(), s16, dt.as<gcb_label>(), nullptr))) return rc;
+    CK(cudaMemcpy(tables, dt.p, rows_bytes, cudaMemcpyDeviceToHost));
+    return GCB_OK;
+}
+
+}  // extern "C"

@@ -133,8 +133,22 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 
 }  // namespace gcb
 
+namespace gcb {
+// Byte layout of the garbled tables as Garbler sends them (circuit/garbler.go:69-82) and
+// Evaluator reads them (circuit/evaluator.go:40-66): u32 BE NumGates, then per gate in ORIGINAL
+// order a u32 BE row count followed by the rows as 16-byte big-endian labels.  The template holds
+// every count with the rows zeroed; row_pos[r] is the offset of slab row r.
+struct DevWireLayout {
+    uint8_t* tmpl = nullptr;
+    uint32_t* row_pos = nullptr;
+    ~DevWireLayout();
+};
+}  // namespace gcb
+
 struct gcb_plan {
     gcb::Plan p;                              // flattened free wires (the fast plan)
+    mutable std::mutex wire_mu;
+    mutable std::map<int, std::shared_ptr<gcb::DevWireLayout>> wire_dev;   // per device
     mutable std::mutex full_mu;
     mutable std::unique_ptr<gcb::Plan> full;  // every wire materialised (wires_full requests), built on demand
 };

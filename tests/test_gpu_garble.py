@@ -162,3 +162,45 @@ def test_fips197_kat_through_garble_eval():
     eng.eval(key, wires, g)
     ob = decode(g.Wires[-128:], wires[-128:])
     assert sum(int(b) << i for i, b in enumerate(ob)) == 0x69c4e0d86a7b0430d8cdb78070b4c55a
+
+
+def _wire_ref(circ, tables_one):
+    """numpy restatement of circuit/garbler.go:69-82 for one instance."""
+    out = bytearray(int(circ.num_gates).to_bytes(4, "big"))
+    off = circ.row_offsets()
+    for g in range(circ.num_gates):
+        rows = tables_one[off[g]: off[g + 1]]
+        out += len(rows).to_bytes(4, "big")
+        for r in rows:
+            out += int(r["d0"]).to_bytes(8, "big") + int(r["d1"]).to_bytes(8, "big")
+    return bytes(out)
+
+
+@pytest.mark.parametrize("name", ["add64", "aes_128", "mixed"])
+def test_tables_wire_format_round_trip(name):
+    """Garbler's table stream (garbler.go:69-82) and Evaluator's parse (evaluator.go:40-66) on the device."""
+    from conftest import mixed_circuit
+    circ = mixed_circuit(3) if name == "mixed" else load_circuit(name)
+    eng = GarbleEngine(circ)
+    batch = 5
+    keys, rand = garble_inputs(f"wire/{name}", batch, circ.num_inputs, 16)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, _ = eng.garble_batch(keys, r, l0)
+    wire = eng.tables_to_wire(tables)
+    assert wire.shape == (batch, 4 + 4 * circ.num_gates + 16 * circ.num_rows)
+    for b in (0, batch - 1):
+        assert wire[b].tobytes() == _wire_ref(circ, tables[b]), "wire bytes differ from the reference layout"
+    back = eng.tables_from_wire(wire)
+    assert eq(back, tables)
+    bad = wire.copy()
+    bad[1, 3] ^= 1                                       # NumGates
+    with pytest.raises(_lib.GcbError, match="wrong number of gates"):
+        eng.tables_from_wire(bad)
+    if circ.num_rows:
+        bad = wire.copy()
+        first = next(g for g in range(circ.num_gates) if circ.row_offsets()[g + 1] > circ.row_offsets()[g])
+        pos = 4 + 4 * first + 16 * int(circ.row_offsets()[first])
+        bad[2, pos + 3] ^= 1                             # row count of the first ciphered gate
+        with pytest.raises(_lib.GcbError, match="corrupted circuit") as e:
+            eng.tables_from_wire(bad)
+        assert e.value.rc == _lib.E_CORRUPT
