@@ -181,3 +181,47 @@ func MITCCRHHash(seed *Label, gidStart uint64, blks []Label, nkeys, h int) error
 	return lastError(C.gcb_mitccrh_hash((*C.gcb_label)(unsafe.Pointer(seed)), C.uint64_t(gidStart), lp(blks),
 		C.uint64_t(nkeys), C.uint32_t(h)))
 }
+
+// COT / ROT post-processing (ot/cot.go:157-233, ot/rot.go:155-197): OT j is hashed under MiTCCRH key j.
+// wireBytes: msgs is the SendLabel byte encoding, ready for conn.Write / filled by io.ReadFull.
+func COTSend(seed, delta *Label, q []Label, wires []Wire, msgs []byte) error {
+	return lastError(C.gcb_cot_send((*C.gcb_label)(unsafe.Pointer(seed)), (*C.gcb_label)(unsafe.Pointer(delta)), lp(q), wp(wires),
+		C.uint64_t(len(q)), (*C.gcb_label)(unsafe.Pointer(&msgs[0])), C.GCB_COT_WIRE_BYTES))
+}
+func COTReceive(seed *Label, flags []bool, msgs []byte, result []Label) error {
+	return lastError(C.gcb_cot_receive((*C.gcb_label)(unsafe.Pointer(seed)), (*C.uint8_t)(unsafe.Pointer(&flags[0])),
+		(*C.gcb_label)(unsafe.Pointer(&msgs[0])), lp(result), C.uint64_t(len(result)), lp(result), C.GCB_COT_WIRE_BYTES))
+}
+func ROTSend(seed, delta *Label, q []Label, wires []Wire) error {
+	return lastError(C.gcb_rot_send((*C.gcb_label)(unsafe.Pointer(seed)), (*C.gcb_label)(unsafe.Pointer(delta)), lp(q),
+		C.uint64_t(len(q)), wp(wires)))
+}
+func ROTReceive(seed *Label, result []Label) error {
+	return lastError(C.gcb_rot_receive((*C.gcb_label)(unsafe.Pointer(seed)), lp(result), C.uint64_t(len(result)), lp(result)))
+}
+
+// IKNPCheckSums replaces the chi loops of the malicious-mode check (ot/iknp.go:150-173, :408-451):
+// out = {lo, hi, x}; choice is nil on the sender side.
+func IKNPCheckSums(seed2 *Label, chiStart uint64, labels []Label, choice []bool) (out [3]Label, err error) {
+	var cp *C.uint8_t
+	if choice != nil {
+		cp = (*C.uint8_t)(unsafe.Pointer(&choice[0]))
+	}
+	err = lastError(C.gcb_iknp_check_sums((*C.gcb_label)(unsafe.Pointer(seed2)), C.uint64_t(chiStart), lp(labels), cp,
+		C.uint64_t(len(labels)), (*C.gcb_label)(unsafe.Pointer(&out[0]))))
+	return
+}
+
+// TablesToWire / TablesFromWire convert a batch of row slabs to and from the byte stream of
+// circuit/garbler.go:69-82 / circuit/evaluator.go:40-66 (stride = bytes per instance in wire).
+func (p *Plan) TablesWireSize() int {
+	var n C.size_t
+	C.gcb_tables_wire_size(p.h, &n)
+	return int(n)
+}
+func (p *Plan) TablesToWire(batch int, tables []Label, wire []byte, stride int) error {
+	return lastError(C.gcb_tables_to_wire(p.h, C.uint32_t(batch), lp(tables), (*C.uint8_t)(unsafe.Pointer(&wire[0])), C.size_t(stride)))
+}
+func (p *Plan) TablesFromWire(batch int, wire []byte, stride int, tables []Label) error {
+	return lastError(C.gcb_tables_from_wire(p.h, C.uint32_t(batch), (*C.uint8_t)(unsafe.Pointer(&wire[0])), C.size_t(stride), lp(tables)))
+}

@@ -73,3 +73,51 @@ func (m *MITCCRH) Hash(blks []Label, k, h int) {
 	}
 	m.keyUsed += k
 }
+
+// Send (ot/cot.go:136-181) with the per-batch MiTCCRH loop replaced by one call; the 2n messages
+// come back in the SendLabel encoding and go out with a single Write.
+func (cot *COT) Send(wires []Wire) error {
+	if cot.iknpS == nil {
+		return fmt.Errorf("not initialized as sender")
+	}
+	data, err := cot.iknpS.Send(len(wires), cot.malicious)
+	if err != nil {
+		return err
+	}
+	seed, err := NewLabel(cot.r)
+	if err != nil {
+		return err
+	}
+	var ld LabelData
+	if err := cot.io.SendLabel(seed, &ld); err != nil {
+		return err
+	}
+	if err := cot.io.Flush(); err != nil {
+		return err
+	}
+	msgs := make([]byte, 32*len(wires))
+	if err := gcb.COTSend((*gcb.Label)(unsafe.Pointer(&seed)), (*gcb.Label)(unsafe.Pointer(&cot.iknpS.Delta)),
+		unsafe.Slice((*gcb.Label)(unsafe.Pointer(&data[0])), len(data)),
+		unsafe.Slice((*gcb.Wire)(unsafe.Pointer(&wires[0])), len(wires)), msgs); err != nil {
+		return err
+	}
+	if err := cot.io.SendBytes(msgs); err != nil { // same bytes as 2n SendLabel calls
+		return err
+	}
+	return cot.io.Flush()
+}
+
+// The chi loop of IKNPSender.Send's malicious branch (ot/iknp.go:150-173): result first, then the
+// 256 choice-vector OTs on the same chi stream.
+func (s *IKNPSender) checkSums(seed2 Label, result, choiceVector []Label) (q0, q1 Label, err error) {
+	a, err := gcb.IKNPCheckSums((*gcb.Label)(unsafe.Pointer(&seed2)), 0,
+		unsafe.Slice((*gcb.Label)(unsafe.Pointer(&result[0])), len(result)), nil)
+	if err != nil {
+		return
+	}
+	b, err := gcb.IKNPCheckSums((*gcb.Label)(unsafe.Pointer(&seed2)), uint64(len(result)),
+		unsafe.Slice((*gcb.Label)(unsafe.Pointer(&choiceVector[0])), len(choiceVector)), nil)
+	q0 = Label{D0: a[0].D0 ^ b[0].D0, D1: a[0].D1 ^ b[0].D1}
+	q1 = Label{D0: a[1].D0 ^ b[1].D0, D1: a[1].D1 ^ b[1].D1}
+	return
+}
