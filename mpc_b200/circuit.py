@@ -320,7 +320,9 @@ class Streaming:
         reference writes into conn.WriteBuf for this sub-circuit."""
         i = np.ascontiguousarray(in_ids, dtype=np.uint32)
         o = np.ascontiguousarray(out_ids, dtype=np.uint32)
-        n = self.step_size(eng, i, o)
+        # upper bound of the record stream (1 + 3 * 4 header bytes per gate, 16 per row): no second
+        # pass over the gates just to size the buffer (step_size gives the exact figure when needed)
+        n = 13 * eng.circ.num_gates + 16 * eng.circ.num_rows
         buf = self._stream_buffer(max(n, 1))
         w, t0, t1 = C.c_size_t(), C.c_uint64(), C.c_uint64()
         check(_lib.lib().gcb_stream_garble(self._h, eng.handle, ptr(i) if len(i) else None, len(i),
@@ -364,8 +366,10 @@ class StreamEval:
 
     def circuit(self, stream: np.ndarray, ngates: int, ntmp: int, nwires: int) -> int:
         """Evaluate one OpCircuit body.  stream: uint8[batch, n] record bytes; returns bytes consumed."""
-        stream = np.ascontiguousarray(stream, dtype=np.uint8).reshape(self.batch, -1)
-        used = C.c_size_t()
-        check(_lib.lib().gcb_seval_circuit(self._h, ptr(stream), stream.shape[1], stream.shape[1], ngates, ntmp,
+        if not (isinstance(stream, np.ndarray) and stream.dtype == np.uint8 and stream.ndim == 2 and
+                len(stream) == self.batch and stream.strides[1] == 1):
+            stream = np.ascontiguousarray(stream, dtype=np.uint8).reshape(self.batch, -1)
+        used = C.c_size_t()               # rows of a wider buffer are passed by stride, not copied
+        check(_lib.lib().gcb_seval_circuit(self._h, stream.ctypes.data, stream.strides[0], stream.shape[1], ngates, ntmp,
                                            nwires, C.byref(used)))
         return int(used.value)

@@ -64,7 +64,7 @@ def main():
     plain = [bits[i].astype(np.uint8).tolist() for i in range(min(a.check, batch))]      # plaintext wire values by id
     plain = [dict(enumerate(p)) for p in plain]
     gates = stream_bytes = 0
-    t_g = t_e = 0.0
+    t_g = t_e = t_init = t_dev = 0.0
     first_streams = []
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -79,7 +79,8 @@ def main():
             blk += 1
             outs = list(range(next_id, next_id + 512)); next_id += 512
         ta = time.perf_counter()
-        buf, _, _ = st.garble(eng, ins, outs)
+        buf, ns_i, ns_g = st.garble(eng, ins, outs)
+        t_init += ns_i / 1e9; t_dev += ns_g / 1e9
         tb = time.perf_counter()
         if sev:
             sev.circuit(buf, circ.num_gates, circ.num_wires, next_id)
@@ -118,7 +119,7 @@ def main():
         wall, t_g, t_e = tt.tolist()
         print(json.dumps({"path": "stream_program", "n_gpus": world, "steps": a.steps, "batch_per_gpu": batch,
                           "gates_per_instance": gates // batch, "total_gates": gates * world,
-                          "stream_gb": stream_bytes * world / 1e9, "wall_s": wall, "garble_s": t_g, "eval_s": t_e,
+                          "stream_gb": stream_bytes * world / 1e9, "wall_s": wall, "garble_s": t_g, "garble_init_s": t_init, "garble_device_s": t_dev, "eval_s": t_e,
                           "m_gates_per_s": gates * world / wall / 1e6, "m_gates_per_s_garble_only": gates * world / t_g / 1e6,
                           "checks_ok": ok}), flush=True)
     if world > 1:
