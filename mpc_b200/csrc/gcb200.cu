@@ -211,7 +211,7 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
 
 // Team geometry for a plan: how many instances one SM keeps resident, how many threads work on
 // each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
-// GCB_NT / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
+// GCB_NT / GCB_TEAMS / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
 struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0; };
 static size_t teams_that_fit(uint32_t num_slots, uint32_t smem_base, uint32_t nt) {
     // teams are packed below the 64 KiB-aligned tables first, then above them
@@ -231,6 +231,7 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
     size_t n = nt == 2 ? n2 : n4;
     if (n == 0) return g;
     if (n >= 32) n = 32; else if (n > 16) n = 16;
+    if (const char* e = getenv("GCB_TEAMS")) { const int v = atoi(e); if (v >= 1 && (size_t)v <= n) n = (size_t)v; }
     // measured on B200 (tools/tune_geometry.py): two interleaved AES blocks per thread and
     // three-warp teams for wide levels; one block per thread for narrow ones and one-warp teams
     uint32_t ilp = (n > 16 || (nt == 2 && width < 128)) ? 1 : 2;

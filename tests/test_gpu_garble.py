@@ -204,3 +204,42 @@ def test_tables_wire_format_round_trip(name):
         with pytest.raises(_lib.GcbError, match="corrupted circuit") as e:
             eng.tables_from_wire(bad)
         assert e.value.rc == _lib.E_CORRUPT
+
+
+@pytest.mark.parametrize("variant", [dict(GCB_NT="4", GCB_ILP="2"), dict(GCB_NT="4", GCB_ILP="1"),
+                                     dict(GCB_NT="2", GCB_ILP="1"), dict(GCB_NT="2", GCB_ILP="2"),
+                                     dict(GCB_NT="2", GCB_ILP="1", GCB_TEAM_THREADS="32", GCB_TEAMS="3"),
+                                     dict(GCB_NT="4", GCB_ILP="2", GCB_TEAM_THREADS="64", GCB_STAGGER="0")])
+def test_every_kernel_variant_is_bit_exact(variant, monkeypatch):
+    """The geometry (resident T-tables, AES blocks per thread, team width, node rows in flight) must not change
+    a bit: every kernel variant, plain and full-wire mode, against the oracle on a circuit with all gate types
+    and on mul64 (deep carry chains: many waves per phase)."""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    for circ, batch in ((mixed_circuit(7, 2500, 48, 24), 7), (load_circuit("mul64"), 3)):
+        eng = GarbleEngine(circ)                                   # geometry is read when the plan is built
+        keys, rand = garble_inputs(f"variant/{circ.name}", batch, circ.num_inputs, 24)
+        r, l0 = rand_to_labels(rand, circ.num_inputs)
+        tables, io = eng.garble_batch(keys, r, l0)
+        _, o_tables, o_io = O.garble_batch(circ, keys, rand)
+        assert eq(tables, o_tables) and eq(io, o_io)
+        bits = np.random.default_rng(1).integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+        inl = select(io[:, : circ.num_inputs], bits)
+        out = eng.eval_batch(keys, tables, inl)
+        assert eq(out, O.eval_batch(circ, keys, o_tables, inl))
+        # full-wire mode (Garbled.Wires / Eval's in-place wires) through the single-instance mirror
+        key = DRBG(f"variant/key/{circ.name}").read(16)
+        rb = DRBG(f"variant/rand/{circ.name}").read(16 * (1 + circ.num_inputs))
+        g = eng.garble(rb, key)
+        _, o_wires, o_slab, _ = O.garble(circ, key, rb)
+        assert eq(g.Wires, o_wires) and eq(g.slab, o_slab), "full-wire garble differs"
+        wires = np.zeros(circ.num_wires, dtype=LABEL_DTYPE)
+        wires[: circ.num_inputs] = np.where(bits[0].astype(bool), g.Wires["l1"][: circ.num_inputs], g.Wires["l0"][: circ.num_inputs])
+        eng.eval(key, wires, g.Gates)
+        want = np.where(np.array(circ.compute_wires(bits[0].tolist()), dtype=bool), o_wires["l1"], o_wires["l0"]) \
+            if hasattr(circ, "compute_wires") else None
+        if want is not None:
+            assert eq(wires, want.astype(LABEL_DTYPE)), "full-wire eval differs"
+        else:
+            no = circ.num_outputs
+            assert np.array_equal(decode(g.Wires[-no:], wires[-no:]), circ.compute_bits(bits[0].tolist()))

@@ -190,3 +190,27 @@ def test_stream_eval_batch_and_malformed_stream():
     with pytest.raises(_lib.GcbError) as e:
         sev.circuit(bad, circ.num_gates, circ.num_wires, 264)
     assert e.value.rc == _lib.E_BADOP
+
+
+@pytest.mark.parametrize("variant", [dict(GCB_NT="4", GCB_ILP="2"), dict(GCB_NT="4", GCB_ILP="1"),
+                                     dict(GCB_NT="2", GCB_ILP="1"), dict(GCB_NT="2", GCB_ILP="2")])
+def test_streaming_under_every_kernel_variant(variant, monkeypatch):
+    """The streaming garbler and evaluator run the same gate kernels in wire-file mode: every variant
+    (resident T-tables x AES blocks per thread) emits the oracle's bytes and evaluates them back."""
+    from mpc_b200.circuit import StreamEval
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    circ = mixed_circuit(11, 1500, 40, 16)
+    key = DRBG("variant/stream").read(32)
+    in_ids, out_ids = list(range(40)), list(range(100, 116))
+    st, ost, eng = _run(circ, key, in_ids, out_ids, tag="variant/stream")
+    buf, _, _ = st.garble(eng, in_ids, out_ids)               # second step on the same ids: same bytes again
+    bits = np.random.default_rng(2).integers(0, 2, 40).astype(bool)
+    w = st.get_inputs(in_ids)[0]
+    sev = StreamEval(key, 1)
+    sev.set(in_ids, np.where(bits, w["l1"], w["l0"]).astype(LABEL_DTYPE).reshape(1, -1))
+    sev.circuit(buf, circ.num_gates, circ.num_wires, 116)
+    got = sev.get(out_ids)[0]
+    ow = st.get_inputs(out_ids)[0]
+    dec = np.where(got == ow["l1"], 1, np.where(got == ow["l0"], 0, 2))
+    assert np.array_equal(dec, circ.compute_bits(bits.astype(np.uint8).tolist()))

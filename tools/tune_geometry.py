@@ -1,6 +1,6 @@
 """Sweep the team geometry (GCB_ILP x GCB_TEAM_THREADS) of the gate kernels on one GPU.
 
-  python tools/tune_geometry.py [circuit] [batch] [keylen] [ilp,team_threads,stagger[,tables] ...]
+  python tools/tune_geometry.py [circuit] [batch] [keylen] [ilp,team_threads,stagger[,tables[,teams]] ...]
 
 Prints device time of garble and eval per configuration; every configuration's
 tables and output labels are compared with the first one's (they must be
@@ -44,10 +44,13 @@ def main():
     for cfg in configs:
         ilp, tt, sg = cfg[:3]
         nt = cfg[3] if len(cfg) > 3 else None
-        for k in ("GCB_ILP", "GCB_TEAM_THREADS", "GCB_STAGGER", "GCB_NT"):
+        teams = cfg[4] if len(cfg) > 4 else None
+        for k in ("GCB_ILP", "GCB_TEAM_THREADS", "GCB_STAGGER", "GCB_NT", "GCB_TEAMS"):
             os.environ.pop(k, None)
         if nt:
             os.environ["GCB_NT"] = str(nt)
+        if teams:
+            os.environ["GCB_TEAMS"] = str(teams)
         if ilp:
             os.environ["GCB_ILP"] = str(ilp)
             os.environ["GCB_TEAM_THREADS"] = str(tt)
