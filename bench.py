@@ -29,16 +29,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "million AND-gates/sec garble+eval (AES-128 circuit)"
 UNIT = "M AND-gates/s"
-BATCH = 4096
 E2E_PARTS = 16
 E2E_WORKERS = 2
 KEY = b"0123456789abcdef"            # circuit/garble_bench_test.go:34
-CIRCUIT = os.path.join(ROOT, "tests", "golden", "circuits", "aes_128.npz")
+CIRCUIT_DIR = os.path.join(ROOT, "tests", "golden", "circuits")
+# --circuit: the headline workload (aes_128, BASELINE.json configs[1]) or the second circuit BASELINE's
+# target names (sha256: 22,573 AND; batch = 8 resident instances x 148 SMs)
+WORKLOADS = {"aes_128": ("AES-128 circuit", 4096), "sha256": ("SHA-256 circuit", 1184)}
 
 
-def load_circuit():
+def load_circuit(name: str = "aes_128"):
     from mpc_b200.circuit_io import Circuit
-    return Circuit.load_npz(CIRCUIT, "aes_128")
+    return Circuit.load_npz(os.path.join(CIRCUIT_DIR, name + ".npz"), name)
 
 
 def synthetic_inputs(circ, batch: int, rank: int):
@@ -48,9 +50,13 @@ def synthetic_inputs(circ, batch: int, rank: int):
     from util import rand_to_labels
     nin = circ.num_inputs
     rand = np.empty((batch, 16 * (1 + nin)), dtype=np.uint8)
+    tag = "aes128" if circ.name == "aes_128" else circ.name
     for i in range(batch):
-        rand[i] = DRBG(f"aes128/{rank * batch + i}").array(16 * (1 + nin))
+        rand[i] = DRBG(f"{tag}/{rank * batch + i}").array(16 * (1 + nin))
     r, l0 = rand_to_labels(rand, nin)
+    if circ.name != "aes_128":                       # other circuits: seeded random plaintext inputs
+        bits = np.random.default_rng(1234 + rank).integers(0, 2, (batch, nin)).astype(np.uint8)
+        return rand, r, l0, bits
     pt_key = int.from_bytes(bytes(range(16)), "big")
     bits = np.zeros((batch, nin), dtype=np.uint8)
     kb = np.array([(pt_key >> b) & 1 for b in range(128)], dtype=np.uint8)
@@ -139,25 +145,28 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    circ = load_circuit()
+    circ = load_circuit(args.circuit)
     n_and = circ.count(2)
+    batch = args.batch or WORKLOADS[args.circuit][1]
     threads = os.cpu_count() or 1
     sample = max(threads * 8, 64)
     # size one step to roughly 1-2 s of wall time
     t = cpu_arm(circ, threads, sample, 1)[0]
-    sample = int(min(BATCH, max(sample, sample * 1.0 / max(t, 1e-3))))
+    sample = int(min(batch, max(sample, sample * 1.0 / max(t, 1e-3))))
     for _ in range(args.warmup):
         cpu_arm(circ, threads, sample, 1)
     times = cpu_arm(circ, threads, sample, args.steps)
     total = sum(times)
     value = n_and * sample * args.steps / total / 1e6
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.replace("AES-128 circuit", WORKLOADS[args.circuit][0]), "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u8 (AES-NI)",
         "data": "synthetic",
-        "config": {"workload": "aes_128.circ (6400 AND, 2087 INV, 28176 XOR) garble+eval",
-                   "batch_per_step": sample, "key": "shared 16-byte (AES-128)"},
+        "config": {"workload": f"{circ.name}.circ ({n_and} AND, {circ.count(4)} INV, {circ.count(0) + circ.count(1)} XOR) "
+                               f"garble+eval, batch {batch} per GPU",
+                   "batch_per_gpu": batch, "key": "shared 16-byte (AES-128)",
+                   "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} instances per step x {args.steps} steps, C oracle (AES-NI), "
                                    f"{threads} pthreads"},
@@ -191,10 +200,10 @@ def run_gcb(args):
     from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
 
     _lib.check(_lib.lib().gcb_set_device(local))
-    circ = load_circuit()
+    circ = load_circuit(args.circuit)
     eng = GarbleEngine(circ)
     nin, nout, rows, n_and = circ.num_inputs, circ.num_outputs, circ.num_rows, circ.count(2)
-    batch = BATCH
+    batch = args.batch or WORKLOADS[args.circuit][1]
     rand, r, l0, bits = synthetic_inputs(circ, batch, rank)
 
     def to_dev(a):
@@ -244,9 +253,12 @@ def run_gcb(args):
     ob = d_obits.cpu().numpy()
     enc = Cipher(algorithms.AES(bytes(range(16))), modes.ECB()).encryptor()
     for i in (0, 1, batch // 2, batch - 1):
-        want = int.from_bytes(enc.update((rank * batch + i).to_bytes(16, "big")), "big")
-        got = sum(int(b) << k for k, b in enumerate(ob[i]))
-        assert got == want, f"instance {i}: decoded output is not AES(key, index)"
+        if args.circuit == "aes_128":
+            want = int.from_bytes(enc.update((rank * batch + i).to_bytes(16, "big")), "big")
+            got = sum(int(b) << k for k, b in enumerate(ob[i]))
+            assert got == want, f"instance {i}: decoded output is not AES(key, index)"
+        else:                                        # plaintext evaluation of the same circuit file
+            assert np.array_equal(ob[i], circ.compute_bits(bits[i].tolist())), f"instance {i}: decoded output is wrong"
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -353,24 +365,25 @@ def run_gcb(args):
         if world == 1 and not args.no_cpu_baseline:
             sample = max(cores * 8, 64)
             t1 = cpu_arm(circ, cores, sample, 1)[0]
-            sample = int(min(BATCH, max(sample, sample * 1.5 / max(t1, 1e-3))))
+            sample = int(min(batch, max(sample, sample * 1.5 / max(t1, 1e-3))))
             ts = cpu_arm(circ, cores, sample, 3)
             cpu = {"value": n_and * sample / min(ts) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{sample} instances garble+eval, best of 3, C oracle (AES-NI), {cores} pthreads"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC.replace("AES-128 circuit", WORKLOADS[args.circuit][0]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 (AES T-tables, 128-bit label XOR)",
             "data": "synthetic",
-            "config": {"workload": "aes_128.circ (6400 AND, 2087 INV, 28176 XOR) garble+eval, batch 4096 per GPU",
+            "config": {"workload": f"{circ.name}.circ ({n_and} AND, {circ.count(4)} INV, {circ.count(0) + circ.count(1)} XOR) "
+                                   f"garble+eval, batch {batch} per GPU",
                        "batch_per_gpu": batch, "key": "shared 16-byte (AES-128)",
-                       "l2": "tables are 976 MB per step, larger than L2; no flush needed",
+                       "l2": f"tables are {batch * rows * 16 // 1000000} MB per step, larger than L2; no flush needed",
                        "kernel_ms": {"garble": g_ms, "eval": e_ms}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": gb * batch,
-                         "kernel": "garble_kernel<10,PLAIN,ILP2>",
+                         "kernel": f"garble_kernel<10,PLAIN> ({eng.info.teams_per_sm} teams x {eng.info.team_threads} threads per SM)",
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
-                         "note": "bound by the shared-memory pipe (AES T-table lookups, 82% busy in the ncu capture), "
+                         "note": "bound by the shared-memory pipe (AES T-table lookups, 83% busy in the ncu capture), "
                                  "not HBM: there is no AES instruction on the GPU; see DESIGN.md and profiles/"},
             "cpu_baseline": cpu,
             "e2e": None if args.no_e2e else {"value": total_and / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
@@ -393,6 +406,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gcb", choices=["gcb", "reference"])
+    ap.add_argument("--circuit", default="aes_128", choices=sorted(WORKLOADS), help="aes_128 = the headline workload")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: 4096 for aes_128, 1184 for sha256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")
     args = ap.parse_args()
