@@ -300,7 +300,12 @@ def run_gcb(args):
         # back (D2H) while the evaluator's tables of earlier parts stream in (H2D), as two parties
         # would; two workers per side hide the start-up latency of each blocking call.
         from concurrent.futures import ThreadPoolExecutor
-        parts = [slice(k * batch // E2E_PARTS, (k + 1) * batch // E2E_PARTS) for k in range(E2E_PARTS)]
+        # Sub-batches: as many as keep the PCIe time of one part well above the latency of garbling one
+        # instance (a part's kernel cannot finish sooner than that): ~1.2 us per dependency step of the plan.
+        lat_ms = eng.info.num_steps * 1.2e-3
+        pcie_ms = batch * (16 * rows + 32 * (nin + nout)) / 50e6
+        n_parts = int(max(2, min(E2E_PARTS, pcie_ms / (2 * lat_ms))))
+        parts = [slice(k * batch // n_parts, (k + 1) * batch // n_parts) for k in range(n_parts)]
 
         def garble_part(sl):
             _lib.check(L.gcb_set_device(local))
@@ -390,7 +395,7 @@ def run_gcb(args):
                     "h2d_bytes_per_step": int(world * batch * (16 * (1 + nin) + 16 * rows + 16 * nin)),
                     "d2h_bytes_per_step": int(world * batch * (16 * rows + 32 * (nin + nout) + 16 * nout)),
                     "ms_per_step": e2e_ms,
-                    "how": f"gcb_garble + gcb_eval on pinned host buffers, {E2E_PARTS} sub-batches, "
+                    "how": f"gcb_garble + gcb_eval on pinned host buffers, {n_parts} sub-batches, "
                            f"{E2E_WORKERS} garbler + {E2E_WORKERS} evaluator host threads"},
             "gpu_launches": 4 * args.steps,
             "clocks": clocks,

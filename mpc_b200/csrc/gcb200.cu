@@ -241,7 +241,7 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
     while (n * 32 > maxt) n--;                      // at least one warp per team
     uint32_t tt = 32u * (uint32_t)(maxt / 32 / n);
     if (tt > 96) tt = 96;
-    if (nt == 2 && ilp == 1 && width < 64) tt = 32; // very narrow levels: one-warp teams (no named barriers) measured best
+    if (nt == 2 && ilp == 1 && width < 64 && n >= 8) tt = 32;   // very narrow levels, many teams: one-warp teams (no named barriers) measured best
     if (n > 16) tt = 32;                            // named barriers: at most 16 multi-warp teams
     if (const char* e = getenv("GCB_TEAM_THREADS")) {
         const int v = atoi(e);
