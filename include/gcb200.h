@@ -322,6 +322,38 @@ int gcb_tables_to_wire_dev(const gcb_plan *plan, uint32_t batch, const gcb_label
 int gcb_tables_from_wire_dev(const gcb_plan *plan, uint32_t batch, const uint8_t *src, size_t stride,
                              gcb_label *tables, void *stream);
 
+/* --------------------------------------------------------- circuit front end --- */
+/* For callers that are not Go: the reference's circuit file formats, statistics and plaintext
+ * evaluation on the host (no device work), so that a file can become a plan and be checked
+ * through this ABI alone.  Go callers keep circuit.Parse and pass Circuit.Gates to gcb_plan_create.
+ *   gcb_circuit_parse     circuit.Parse on an in-memory file: GCB_FORMAT_BRISTOL follows
+ *                         circuit/parser.go:265-494, GCB_FORMAT_MPCLC follows :71-211; the "wire
+ *                         not set / not assigned" checks of the parser are applied to both
+ *   gcb_circuit_from_gates  the same object from a gate array (levels and statistics computed)
+ *   gcb_circuit_get_info  counts, IO.Size() of inputs / outputs, Stats[NumLevels] and
+ *                         Stats[MaxWidth] of AssignLevels(TargetYao), circuit/circuit.go:206-254;
+ *                         gcb_circuit_get_gates returns the gates with Level filled in
+ *   gcb_circuit_compute   Circuit.Compute (circuit/computer.go:15-91) on wire bits:
+ *                         in_bits [batch][num_inputs] of 0/1 -> out_bits [batch][num_outputs]
+ *   gcb_circuit_plan      gcb_plan_create on the parsed gates */
+typedef struct gcb_circuit gcb_circuit;
+enum { GCB_FORMAT_BRISTOL = 0, GCB_FORMAT_MPCLC = 1 };
+typedef struct {
+    uint32_t num_gates, num_wires, num_inputs, num_outputs, num_input_args, num_output_args;
+    uint32_t num_xor, num_xnor, num_and, num_or, num_inv;
+    uint32_t num_levels, max_width;
+} gcb_circuit_info;
+int gcb_circuit_parse(const void *data, size_t len, int format, gcb_circuit **out);
+int gcb_circuit_from_gates(const gcb_gate *gates, uint32_t num_gates, uint32_t num_wires, const uint32_t *inputs,
+                           uint32_t n_input_args, const uint32_t *outputs, uint32_t n_output_args,
+                           gcb_circuit **out);
+void gcb_circuit_destroy(gcb_circuit *circ);
+int gcb_circuit_get_info(const gcb_circuit *circ, gcb_circuit_info *info);
+int gcb_circuit_get_gates(const gcb_circuit *circ, gcb_gate *gates);
+int gcb_circuit_get_io(const gcb_circuit *circ, uint32_t *input_bits, uint32_t *output_bits);
+int gcb_circuit_compute(const gcb_circuit *circ, uint32_t batch, const uint8_t *in_bits, uint8_t *out_bits);
+int gcb_circuit_plan(const gcb_circuit *circ, gcb_plan **out);
+
 #ifdef __cplusplus
 }
 #endif

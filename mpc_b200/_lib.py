@@ -87,6 +87,14 @@ SYMBOLS = {
     "gcb_cot_receive_dev": (_int, [C.POINTER(Label), _vp, _vp, _vp, _u64, _vp, _u32, _vp]),
     "gcb_rot_send_dev": (_int, [C.POINTER(Label), C.POINTER(Label), _vp, _u64, _vp, _vp]),
     "gcb_rot_receive_dev": (_int, [C.POINTER(Label), _vp, _u64, _vp, _vp]),
+    "gcb_circuit_parse": (_int, [_vp, _sz, _int, C.POINTER(_vp)]),
+    "gcb_circuit_from_gates": (_int, [_vp, _u32, _u32, _vp, _u32, _vp, _u32, C.POINTER(_vp)]),
+    "gcb_circuit_destroy": (None, [_vp]),
+    "gcb_circuit_get_info": (_int, [_vp, _vp]),
+    "gcb_circuit_get_gates": (_int, [_vp, _vp]),
+    "gcb_circuit_get_io": (_int, [_vp, _vp, _vp]),
+    "gcb_circuit_compute": (_int, [_vp, _u32, _vp, _vp]),
+    "gcb_circuit_plan": (_int, [_vp, C.POINTER(_vp)]),
     "gcb_tables_wire_size": (_int, [_vp, C.POINTER(_sz)]),
     "gcb_tables_to_wire": (_int, [_vp, _u32, _vp, _vp, _sz]),
     "gcb_tables_from_wire": (_int, [_vp, _u32, _vp, _sz, _vp]),
