@@ -176,6 +176,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index: int):
+    """One process per GPU: run this rank's host threads, and so first-touch its pinned staging buffers, on
+    the NUMA node the GPU hangs off (sysfs numa_node / local_cpulist of the PCI function).  Without it the
+    host-pointer path of an 8-rank run crosses the socket interconnect for half of its DMA traffic.
+    Returns a short description for the JSON line; silently does nothing where sysfs has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:                       # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def run_gcb(args):
     import torch
     import torch.distributed as dist
@@ -192,6 +219,7 @@ def run_gcb(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -396,7 +424,8 @@ def run_gcb(args):
                     "d2h_bytes_per_step": int(world * batch * (16 * rows + 32 * (nin + nout) + 16 * nout)),
                     "ms_per_step": e2e_ms,
                     "how": f"gcb_garble + gcb_eval on pinned host buffers, {n_parts} sub-batches, "
-                           f"{E2E_WORKERS} garbler + {E2E_WORKERS} evaluator host threads"},
+                           f"{E2E_WORKERS} garbler + {E2E_WORKERS} evaluator host threads"
+                           + (f", ranks bound to their GPU's NUMA node ({numa['cpus']} cpus)" if numa else "")},
             "gpu_launches": 4 * args.steps,
             "clocks": clocks,
         }
