@@ -395,6 +395,10 @@ struct gcb_stream {
     // evaluator side: plans recovered from record streams, keyed by a hash of the gate headers
     struct EvalPlan { gcb::Plan plan; std::vector<uint32_t> in_ids, out_ids; };
     std::unordered_map<uint64_t, std::shared_ptr<EvalPlan>> eval_plans;
+    // permanent id -> canonical location of the call in progress: a flat array with an epoch stamp per
+    // entry (no clearing, no hashing: a sub-circuit touches its ids a few hundred thousand times)
+    std::vector<uint32_t> perm_loc, perm_epoch;
+    uint32_t epoch = 0;
     ~gcb_stream() {
         for (uint4* p : pages) if (p) cudaFree(p);
         if (cs) cudaStreamDestroy(cs);
@@ -819,13 +823,21 @@ int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, u
     const Plan& base = plan->p;
     const uint32_t nw = base.info.num_wires;
     if (nin > nw || nout > nw) return fail(GCB_E_ARG, "more wire ids than wires");
-    // initCircuit (stream_garble.go:102-114)
+    // initCircuit (stream_garble.go:102-114).  The byte layout of the record stream (every header,
+    // the offset of every row) is host work proportional to the gate count; when the caller's buffer
+    // is large enough for ANY id assignment (13 header bytes per gate at most) the gate kernel is
+    // launched first and the layout is built while it runs.
     StreamLayout lay;
     std::string err;
-    if ((rc = build_stream_layout(base.gates, nw, in, nin, out, nout, lay, err))) return fail(rc, "%s", err.c_str());
-    const size_t total = lay.tmpl.size();
-    if (written) *written = total;
-    if (total && (!dst || dst_stride < total)) return fail(GCB_E_BUFFER, "stream buffer too small: need %zu bytes per instance", total);
+    const size_t bound = 13 * base.gates.size() + 16 * (size_t)base.info.num_rows;
+    const bool late_layout = dst && dst_stride >= bound;
+    size_t total = 0;
+    if (!late_layout) {
+        if ((rc = build_stream_layout(base.gates, nw, in, nin, out, nout, lay, err))) return fail(rc, "%s", err.c_str());
+        total = lay.tmpl.size();
+        if (written) *written = total;
+        if (total && (!dst || dst_stride < total)) return fail(GCB_E_BUFFER, "stream buffer too small: need %zu bytes per instance", total);
+    }
     uint32_t mx = 0;
     for (uint32_t i = 0; i < nin; i++) mx = in[i] > mx ? in[i] : mx;
     for (uint32_t i = 0; i < nout; i++) mx = out[i] > mx ? out[i] : mx;
@@ -884,20 +896,13 @@ int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, u
         use = aliased.get();
     }
     const size_t n_rows = use->info.num_rows;
-    const size_t stride16 = (total + 15) & ~(size_t)15;
     const size_t nids = in_eff.size() + out_eff.size();
     if ((rc = grow(s->ids, s->ids_cap, (nids ? nids : 1) * 4))) return rc;
     if ((rc = grow(s->slab, s->slab_cap, (size_t)s->batch * n_rows * 16))) return rc;
-    if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
-    if ((rc = grow(s->tmpl, s->tmpl_cap, stride16 + 16))) return rc;
-    if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
     uint32_t* d_in = s->ids.as<uint32_t>();
     uint32_t* d_out = d_in + in_eff.size();
     if (!in_eff.empty()) CK(cudaMemcpyAsync(d_in, in_eff.data(), in_eff.size() * 4, cudaMemcpyHostToDevice, s->cs));
     if (!out_eff.empty()) CK(cudaMemcpyAsync(d_out, out_eff.data(), out_eff.size() * 4, cudaMemcpyHostToDevice, s->cs));
-    lay.tmpl.resize(stride16, 0);
-    if (total) CK(cudaMemcpyAsync(s->tmpl.p, lay.tmpl.data(), stride16, cudaMemcpyHostToDevice, s->cs));
-    if (n_rows) CK(cudaMemcpyAsync(s->row_pos.p, lay.row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
     const auto t_mid = clk::now();
 
     // the gate loop (stream_garble.go:179-190)
@@ -905,6 +910,19 @@ int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, u
                    s->r.as<gcb_label>(), nullptr, s->slab.as<gcb_label>(), nullptr, nullptr, s->cs, d_in, d_out,
                    reinterpret_cast<uint4* const*>(s->page_table.p));
     if (rc) return rc;
+    if (late_layout) {
+        rc = build_stream_layout(base.gates, nw, in, nin, out, nout, lay, err);
+        if (rc) { cudaStreamSynchronize(s->cs); return fail(rc, "%s", err.c_str()); }
+        total = lay.tmpl.size();
+        if (written) *written = total;
+    }
+    const size_t stride16 = (total + 15) & ~(size_t)15;
+    if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
+    if ((rc = grow(s->tmpl, s->tmpl_cap, stride16 + 16))) return rc;
+    if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
+    lay.tmpl.resize(stride16, 0);
+    if (total) CK(cudaMemcpyAsync(s->tmpl.p, lay.tmpl.data(), stride16, cudaMemcpyHostToDevice, s->cs));
+    if (n_rows) CK(cudaMemcpyAsync(s->row_pos.p, lay.row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
     if (total) {
         SerParams sp{s->tmpl.as<uint8_t>(), (uint32_t)total, s->row_pos.as<uint32_t>(), (uint32_t)n_rows,
                      s->slab.as<uint4>(), s->ser.as<uint8_t>(), stride16};
@@ -1008,6 +1026,15 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     DeviceInfo* di;
     int rc = select_device(&di);
     if (rc) return rc;
+    // the record bytes start moving to the device first: parsing the headers and recovering the plan
+    // on the host overlap the copy (2 GB per step in the config-5 stand-in)
+    const size_t stride16 = ((len + 15) & ~(size_t)15) + 16;
+    if (ngates && len) {
+        if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
+        CK(cudaMemcpy2DAsync(s->ser.p, stride16, src, s->batch > 1 ? src_stride : len, len, s->batch, cudaMemcpyHostToDevice, s->cs));
+    }
+    // on any error below the copy must have finished before the caller may reuse `src`
+    struct SyncOnExit { cudaStream_t cs; ~SyncOnExit() { cudaStreamSynchronize(cs); } } sync_on_exit{s->cs};
     // parse instance 0's headers
     std::vector<StreamGate> sg;
     std::vector<uint32_t> row_pos;
@@ -1021,14 +1048,15 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     // wire space of the recovered circuit: [permanent ids in order of first use | tmp wires].  The
     // plan depends only on this canonical form, not on the actual ids, so the steps of a program
     // that reuse a sub-circuit with fresh ids share one cached plan.
-    std::unordered_map<uint32_t, uint32_t> perm;
+    if (s->perm_loc.size() < nwires) { s->perm_loc.resize(nwires, 0); s->perm_epoch.resize(nwires, 0); }
+    if (++s->epoch == 0) { std::fill(s->perm_epoch.begin(), s->perm_epoch.end(), 0u); s->epoch = 1; }
+    const uint32_t epoch = s->epoch;
     std::vector<uint32_t> perm_ids;
     std::vector<uint8_t> first_is_read, written;
     auto perm_loc = [&](uint32_t id, bool is_read) {
-        auto f = perm.find(id);
-        if (f != perm.end()) { if (!is_read) written[f->second] = 1; return f->second; }
+        if (s->perm_epoch[id] == epoch) { const uint32_t l = s->perm_loc[id]; if (!is_read) written[l] = 1; return l; }
         const uint32_t l = (uint32_t)perm_ids.size();
-        perm.emplace(id, l); perm_ids.push_back(id);
+        s->perm_epoch[id] = epoch; s->perm_loc[id] = l; perm_ids.push_back(id);
         first_is_read.push_back(is_read); written.push_back(!is_read);
         return l;
     };
@@ -1042,6 +1070,8 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
         for (const auto& t : {std::pair<uint32_t, bool>{g.a, g.a_tmp}, {g.b, g.b_tmp}, {g.c, g.c_tmp}})
             if (t.second && t.first >= ntmp) return fail(GCB_E_WIRE, "tmp wire %u out of range (gate %zu)", t.first, i);
         if (!g.a_tmp && g.a >= nwires) return fail(GCB_E_WIRE, "wire %u out of range (gate %zu)", g.a, i);
+        if (g.op != OP_INV && !g.b_tmp && g.b >= nwires) return fail(GCB_E_WIRE, "wire %u out of range (gate %zu)", g.b, i);
+        if (!g.c_tmp && g.c >= nwires) return fail(GCB_E_WIRE, "wire %u out of range (gate %zu)", g.c, i);
         refs[i][0] = Ref{g.a_tmp ? g.a : perm_loc(g.a, true), (bool)g.a_tmp};
         refs[i][1] = g.op == OP_INV ? refs[i][0] : Ref{g.b_tmp ? g.b : perm_loc(g.b, true), (bool)g.b_tmp};
         refs[i][2] = Ref{g.c_tmp ? g.c : perm_loc(g.c, false), (bool)g.c_tmp};
@@ -1075,11 +1105,9 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = perm_ids[ep->in_ids[k]];
     for (size_t k = 0; k < out_ids.size(); k++) out_ids[k] = perm_ids[ep->out_ids[k]];
     const size_t n_rows = row_pos.size();
-    const size_t stride16 = ((len + 15) & ~(size_t)15) + 16;
     const size_t nids = in_ids.size() + out_ids.size();
     if ((rc = grow(s->ids, s->ids_cap, (nids ? nids : 1) * 4))) return rc;
     if ((rc = grow(s->slab, s->slab_cap, (size_t)s->batch * (n_rows ? n_rows : 1) * 16))) return rc;
-    if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
     if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
     uint32_t* d_in = s->ids.as<uint32_t>();
     uint32_t* d_out = d_in + in_ids.size();
@@ -1087,7 +1115,6 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     if (!out_ids.empty()) CK(cudaMemcpyAsync(d_out, out_ids.data(), out_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
     if (n_rows) {
         CK(cudaMemcpyAsync(s->row_pos.p, row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
-        CK(cudaMemcpy2DAsync(s->ser.p, stride16, src, s->batch > 1 ? src_stride : len, len, s->batch, cudaMemcpyHostToDevice, s->cs));
         DeserParams dp{s->ser.as<uint8_t>(), stride16, s->row_pos.as<uint32_t>(), (uint32_t)n_rows, s->slab.as<uint4>(), s->batch};
         deserialize_kernel<<<di->sm_count * 8, 256, 0, s->cs>>>(dp);
         CK(cudaGetLastError());

@@ -214,3 +214,34 @@ def test_streaming_under_every_kernel_variant(variant, monkeypatch):
     ow = st.get_inputs(out_ids)[0]
     dec = np.where(got == ow["l1"], 1, np.where(got == ow["l0"], 0, 2))
     assert np.array_equal(dec, circ.compute_bits(bits.astype(np.uint8).tolist()))
+
+
+def test_exact_size_buffer_and_too_small_buffer():
+    """gcb_stream_garble with a buffer of exactly step_size bytes (the layout is built before the launch)
+    gives the same bytes as the over-sized buffer path (layout built while the kernel runs); a buffer that is
+    too small is refused before anything is garbled."""
+    import ctypes as C
+    from mpc_b200 import _lib
+    from mpc_b200._lib import ptr
+    circ = mixed_circuit(13, 900, 32, 12)
+    key = DRBG("exact/key").read(16)
+    in_ids, out_ids = list(range(32)), list(range(50, 62))
+    rand = DRBG("exact/rand").read(16 * 33)
+    eng = GarbleEngine(circ)
+    want = O.Streaming(key, rand, in_ids).garble(circ, in_ids, out_ids)
+    st = Streaming.new(rand, key, in_ids)
+    n = st.step_size(eng, in_ids, out_ids)
+    assert n == len(want)
+    i32, o32 = np.array(in_ids, np.uint32), np.array(out_ids, np.uint32)
+    small = np.zeros((1, n - 1), np.uint8)
+    w, t0, t1 = C.c_size_t(), C.c_uint64(), C.c_uint64()
+    rc = _lib.lib().gcb_stream_garble(st._h, eng.handle, ptr(i32), 32, ptr(o32), 12, ptr(small), n - 1,
+                                      C.byref(w), C.byref(t0), C.byref(t1))
+    assert rc == _lib.E_BUFFER and int(w.value) == n
+    exact = np.zeros((1, n), np.uint8)
+    _lib.check(_lib.lib().gcb_stream_garble(st._h, eng.handle, ptr(i32), 32, ptr(o32), 12, ptr(exact), n,
+                                            C.byref(w), C.byref(t0), C.byref(t1)))
+    assert exact[0].tobytes() == want
+    st2 = Streaming.new(rand, key, in_ids)
+    buf, _, _ = st2.garble(eng, in_ids, out_ids)
+    assert buf[0].tobytes() == want
