@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                     if (ILP >= 4 && uu == 4) {
                         if (and_only) garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
                         else garble_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
-                    } else if (ILP >= 2 && uu == 2) {
+                    } else if (ILP >= 2 && uu == 2 && (k0 + 1) * TT + (ttid & ~31u) < ntask) {
                         if (and_only) garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
                         else garble_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur);
                     } else if (k0 * TT + (ttid & ~31u) < ntask) {
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                     if (ILP >= 4 && uu == 4) {
                         if (and_only) eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                         else eval_pass<NR, MODE, (ILP >= 4 ? 4 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
-                    } else if (ILP >= 2 && uu == 2) {
+                    } else if (ILP >= 2 && uu == 2 && (k0 + 1) * TT + (ttid & ~31u) < ntask) {
                         if (and_only) eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, true, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                         else eval_pass<NR, MODE, (ILP >= 2 ? 2 : 1), ILP, false, NT>(lane, env, ph, ntask, k0, ttid, TT, cur, rows, k0 == 0);
                     } else if (k0 * TT + (ttid & ~31u) < ntask) {

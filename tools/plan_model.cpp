@@ -121,6 +121,37 @@ int main(int argc, char** argv) {
             }
         }
     }
+    // AES warp-blocks (160 wavefronts each) per instance: the kernels' pass policy against a packing in
+    // which each warp takes a contiguous block of tasks and runs only the block slots it needs
+    {
+        uint64_t cur[2] = {0, 0}, packed[2] = {0, 0}, ideal[2] = {0, 0};
+        const uint32_t W = TT / 32;
+        for (const PhaseRec& ph : plan.phases)
+            for (int garble = 0; garble < 2; garble++) {
+                const uint32_t ntask = (garble ? 4 : 2) * ph.n_quad + (garble ? 2 : 1) * ph.n_inv;
+                if (!ntask) continue;
+                const uint32_t per_thread = (ntask + TT - 1) / TT;
+                for (uint32_t k0 = 0; k0 < per_thread;) {
+                    const uint32_t left = per_thread - k0, uu = left >= 2 ? 2 : 1;
+                    if (uu == 2) cur[garble] += 2 * W;
+                    else for (uint32_t w = 0; w < W; w++) cur[garble] += (k0 * TT + 32 * w < ntask);
+                    k0 += uu;
+                }
+                // packed: rounds of up to 64 tasks per warp (two slots), W warps
+                uint32_t rest = ntask;
+                while (rest) {
+                    for (uint32_t w = 0; w < W && rest; w++) {
+                        const uint32_t take = rest < 64 ? rest : 64;
+                        packed[garble] += (take + 31) / 32;
+                        rest -= take;
+                    }
+                }
+                ideal[garble] += (ntask + 31) / 32;
+            }
+        printf("AES warp-blocks per instance: garble now %llu packed %llu floor %llu ; eval now %llu packed %llu floor %llu\n",
+               (unsigned long long)cur[1], (unsigned long long)packed[1], (unsigned long long)ideal[1],
+               (unsigned long long)cur[0], (unsigned long long)packed[0], (unsigned long long)ideal[0]);
+    }
     auto pr = [](const char* n, const Acc& a) {
         printf("%-14s instr %8llu  wavefronts %8llu  ideal %8.0f  (x%.2f)\n", n, (unsigned long long)a.instr,
                (unsigned long long)a.wavefronts, a.ideal8 / 8.0, a.wavefronts / (a.ideal8 / 8.0 + 1e-9));
