@@ -38,8 +38,12 @@ constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-b
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
 // Node rows a thread keeps in flight ahead of the one it runs: the single-block 512-thread variant
 // (deep, narrow circuits: short rows, nothing else to hide the L2 latency behind) has the registers
-// for four, the others for two.
-__host__ __device__ constexpr uint32_t node_pipe(int ilp, int maxt) { return (ilp == 1 && maxt == 512) ? 4u : 2u; }
+// for four.  The two-block variants sit at the 128-register cap: eval keeps two rows in flight, garble
+// (four more words of state per block: R, the kept label) only one -- measured on aes_128 x 4096,
+// a deeper pipeline costs more in register shuffling than it hides (garble 4.08 -> 4.00 ms).
+__host__ __device__ constexpr uint32_t node_pipe(int ilp, int maxt, bool garble) {
+    return (ilp == 1 && maxt == 512) ? 4u : (ilp == 2 && garble) ? 1u : 2u;
+}
 
 struct GcParams {
     const uint4* phases;                  // DevPhaseRec[] (two uint4 each) followed by two zero records
@@ -435,7 +439,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
 
 template <int NR, int MODE, int ILP, int MAXT, int NT>
 __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
-    constexpr uint32_t D = node_pipe(ILP, MAXT);
+    constexpr uint32_t D = node_pipe(ILP, MAXT, true);
     constexpr bool FULL = MODE == GC_FULL;
     constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -486,13 +490,17 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         }
         team_barrier(tc.team, TT);
         const GarbleEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, R, inst};
+        // first-pass gate records: requested one phase ahead where the registers allow it (single-block
+        // variants), at the top of their own phase -- behind the node rows -- in the two-block variants
+        constexpr bool AHEAD = ILP == 1;
         uint4 cur[ILP];
-        prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
+        if (AHEAD) prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
 
         for (uint32_t pi = 0; pi < p.n_phases; pi++) {
             const Phase ph_nn = load_phase(p.phases, pi + 2);  // two zero records of padding
-            uint4 cur_n[ILP];                                  // first-pass records of the next phase
-            prefetch_cipher<true, ILP>(p, ph_n, 0, ttid, TT, cur_n);
+            uint4 cur_n[AHEAD ? ILP : 1];
+            if (AHEAD) prefetch_cipher<true, ILP>(p, ph_n, 0, ttid, TT, reinterpret_cast<uint4 (&)[ILP]>(cur_n));
+            else prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
@@ -527,8 +535,10 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                 team_barrier(tc.team, TT);
             }
             ph = ph_n; ph_n = ph_nn;
+            if (AHEAD) {
 #pragma unroll
-            for (int j = 0; j < ILP; j++) cur[j] = cur_n[j];
+                for (int j = 0; j < ILP; j++) cur[j] = cur_n[j];
+            }
         }
         // output wires (what circuit/garbler.go:153 and sha2pc/garbler.go:125 read)
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
@@ -652,7 +662,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
 
 template <int NR, int MODE, int ILP, int MAXT, int NT>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
-    constexpr uint32_t D = node_pipe(ILP, MAXT);
+    constexpr uint32_t D = node_pipe(ILP, MAXT, false);
     constexpr bool FULL = MODE == GC_FULL;
     constexpr bool STREAM = MODE == GC_STREAM;
     extern __shared__ __align__(16) uint8_t smem[];
