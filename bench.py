@@ -356,7 +356,7 @@ def run_gcb(args):
 
         e2e_step()
         h_in[:] = np.where(bits.astype(bool), h_io["l1"][:, :nin], h_io["l0"][:, :nin])
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(args.steps, 10))
         e2e_step()
         barrier()
         t0 = time.perf_counter()
