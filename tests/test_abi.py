@@ -111,3 +111,18 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(_lib.GcbError) as e:
         eng.garble(b"\1" * 48, b"\0" * 16)
     assert e.value.rc == _lib.E_CUDA
+
+
+def test_plan_refuses_a_circuit_whose_live_labels_do_not_fit_on_chip():
+    """More live wire labels than shared memory holds beside two T-tables: GCB_E_TOO_LARGE at plan creation
+    (host-only; no CPU fallback takes over)."""
+    import ctypes as C
+    from mpc_b200.circuit_io import parse_bristol
+    n = 6000
+    lines = [f"2 1 {i} {n + i} {2 * n + i} AND" for i in range(n)]
+    circ = parse_bristol(f"{n} {3 * n}\n2 {n} {n}\n1 {n}\n\n" + "\n".join(lines) + "\n", "toowide")
+    h = C.c_void_p()
+    gates = np.ascontiguousarray(circ.gates)
+    rc = _lib.lib().gcb_plan_create(_lib.ptr(gates), circ.num_gates, circ.num_wires, circ.num_inputs,
+                                    circ.num_outputs, C.byref(h))
+    assert rc == _lib.E_TOO_LARGE and b"live" in _lib.lib().gcb_last_error()

@@ -243,3 +243,32 @@ def test_every_kernel_variant_is_bit_exact(variant, monkeypatch):
         else:
             no = circ.num_outputs
             assert np.array_equal(decode(g.Wires[-no:], wires[-no:]), circ.compute_bits(bits[0].tolist()))
+
+
+def _wide_circuit(n_pairs: int):
+    """2 * n_pairs inputs, all live until the single AND level: out[i] = in[i] & in[n_pairs + i]."""
+    lines = [f"2 1 {i} {n_pairs + i} {2 * n_pairs + i} AND" for i in range(n_pairs)]
+    text = f"{n_pairs} {3 * n_pairs}\n2 {n_pairs} {n_pairs}\n1 {n_pairs}\n\n" + "\n".join(lines) + "\n"
+    from mpc_b200.circuit_io import parse_bristol
+    return parse_bristol(text, f"wide{n_pairs}")
+
+
+def test_circuit_that_only_fits_beside_two_tables():
+    """6,000 labels live at once do not fit beside four T-tables (one team's block must fit below or above the
+    tables: about 4,000 slots) but do beside two (about 6,400): the plan falls back to the two-table,
+    two-block variant and stays bit-exact."""
+    circ = _wide_circuit(2000)
+    eng = GarbleEngine(circ)
+    assert eng.info.num_slots >= 6000 and eng.info.teams_per_sm == 1
+    batch = 3
+    keys, rand = garble_inputs("wide", batch, circ.num_inputs, 16)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    _, o_tables, o_io = O.garble_batch(circ, keys, rand)
+    assert eq(tables, o_tables) and eq(io, o_io)
+    bits = np.random.default_rng(3).integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+    inl = select(io[:, : circ.num_inputs], bits)
+    out = eng.eval_batch(keys, tables, inl)
+    assert eq(out, O.eval_batch(circ, keys, o_tables, inl))
+    got = decode(io[:, circ.num_inputs:], out)
+    assert np.array_equal(got, bits[:, :2000] & bits[:, 2000:])
