@@ -54,6 +54,8 @@ struct GcParams {
     const uint2* live_in;                 // SlotRef[]
     const uint2* live_out;
     uint32_t n_phases, n_in, n_out, n_slots, n_rows, n_wires;
+    uint32_t n_smem;                      // wire slots held in shared memory (= n_slots unless the plan spills)
+    uint4* spill;                         // spilling variant: [grid * n_teams][n_slots - n_smem] labels in global memory
     const uint8_t* keys;
     uint32_t keylen, key_stride;
     uint32_t batch;
@@ -90,8 +92,25 @@ __device__ __forceinline__ void team_barrier(uint32_t team, uint32_t team_thread
     else asm volatile("bar.sync %0, %1;" ::"r"(team), "r"(team_threads) : "memory");
 }
 
-__device__ __forceinline__ Label lds_label(const uint4* slots, uint32_t s) { return label_from_mem(slots[s]); }
-__device__ __forceinline__ void sts_label(uint4* slots, uint32_t s, Label l) { slots[s] = label_to_mem(l); }
+// Where a team's wire labels live.  Normally all of them are in the team's slice of shared memory.  A
+// circuit that keeps more labels live than fit there (about 6,400 beside two tables) runs the SPILL
+// variant: slots below n_sm stay in shared memory -- the plan hands out low slot numbers first, so they
+// are the hot ones -- and the rest go to a per-team scratch in global memory (L2-resident; ordered
+// by the same team barriers, and written and read by this SM only).
+struct SlotsSmem {
+    uint4* sm;
+    __device__ __forceinline__ uint4 ldm(uint32_t s) const { return sm[s]; }
+    __device__ __forceinline__ void stm(uint32_t s, uint4 v) const { sm[s] = v; }
+};
+struct SlotsSpill {
+    uint4* sm;
+    uint4* gl;
+    uint32_t n_sm;
+    __device__ __forceinline__ uint4 ldm(uint32_t s) const { return s < n_sm ? sm[s] : gl[s - n_sm]; }
+    __device__ __forceinline__ void stm(uint32_t s, uint4 v) const { if (s < n_sm) sm[s] = v; else gl[s - n_sm] = v; }
+};
+template <class SL> __device__ __forceinline__ Label lds_label(const SL& slots, uint32_t s) { return label_from_mem(slots.ldm(s)); }
+template <class SL> __device__ __forceinline__ void sts_label(const SL& slots, uint32_t s, Label l) { slots.stm(s, label_to_mem(l)); }
 
 __device__ __forceinline__ Label shfl_xor_label(Label h, int m) {
     return Label{__shfl_xor_sync(0xffffffffu, h.w0, m), __shfl_xor_sync(0xffffffffu, h.w1, m),
@@ -156,13 +175,23 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     c.tables = aes_align_tables(smem);
     c.team = threadIdx.x / p.team_threads;
     c.ttid = threadIdx.x - c.team * p.team_threads;
-    const uint32_t tb = team_block_bytes(p.n_slots);
+    const uint32_t tb = team_block_bytes(p.n_smem);
     const uint32_t in_a = (uint32_t)(c.tables - smem) / tb;               // teams that fit below the tables
     uint8_t* q = c.team < in_a ? smem + c.team * tb : c.tables + aes_table_bytes(NT) + (c.team - in_a) * tb;
     c.rk = reinterpret_cast<uint32_t*>(q);
     c.claim = reinterpret_cast<volatile uint32_t*>(q + GC_RK_BYTES);
     c.slots = reinterpret_cast<uint4*>(q + GC_RK_BYTES + 16);
     return c;
+}
+
+template <bool SPILL>
+__device__ __forceinline__ auto team_slots(const TeamCtx& tc, const GcParams& p) {
+    if constexpr (SPILL) {
+        const size_t team_index = (size_t)blockIdx.x * p.n_teams + tc.team;
+        return SlotsSpill{tc.slots, p.spill + team_index * (p.n_slots - p.n_smem), p.n_smem};
+    } else {
+        return SlotsSmem{tc.slots};
+    }
 }
 
 // Gate index of cipher task t of a phase.  Garble: 4 tasks per AND/OR, 2 per INV;
@@ -214,8 +243,8 @@ __device__ __forceinline__ NodeRegs load_node(const uint4* nodes, uint32_t i) {
 // One node per thread: dst = XOR of the leaves (^ R for an odd number of XNORs on the way).
 // words: lo.x = dst | k<<16 | flags<<24 (NODE_PARITY / NODE_WAVE_END / NODE_ACTIVE); then 14 leaf
 // slots, two per word.
-template <bool GARBLE, bool FULL>
-__device__ __forceinline__ void run_node(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t index,
+template <bool GARBLE, bool FULL, class SL>
+__device__ __forceinline__ void run_node(const GcParams& p, const SL& slots, const Label R, uint32_t inst, uint32_t index,
                                          const NodeRegs& n) {
     const bool active = (n.lo.x >> 24) & NODE_ACTIVE;
     const uint32_t k = active ? (n.lo.x >> 16) & 0xff : 0u;
@@ -254,8 +283,8 @@ __device__ __forceinline__ NodeRegs load_row(const GcParams& p, uint32_t row, ui
 // statically -- rows run in aligned groups of D with warp-uniform guards -- because a pipeline that
 // shifts registers would copy the newest load right after issuing it and wait for it there.  A
 // team barrier follows the last row of a wave.
-template <bool GARBLE, bool FULL, uint32_t D>
-__device__ __forceinline__ void run_rows(const GcParams& p, uint4* slots, const Label R, uint32_t inst, uint32_t n_rows,
+template <bool GARBLE, bool FULL, uint32_t D, class SL>
+__device__ __forceinline__ void run_rows(const GcParams& p, const SL& slots, const Label R, uint32_t inst, uint32_t n_rows,
                                          uint32_t team, uint32_t ttid, uint32_t TT, NodeRegs (&pipe)[D], uint32_t& row) {
     static_assert((D & (D - 1)) == 0, "pipeline depth must be a power of two");
     const uint32_t end = row + n_rows;
@@ -282,9 +311,10 @@ __device__ __forceinline__ void stagger_start(uint32_t team, uint32_t stagger) {
 }
 
 // ------------------------------------------------------------------ garble ----
+template <class SL>
 struct GarbleEnv {
     GcParams const* p;
-    uint4* slots;
+    SL slots;
     const uint32_t* rk;
     uint4* tab;
     Label R;
@@ -292,13 +322,13 @@ struct GarbleEnv {
 };
 
 // One pass of UU cipher tasks per thread: tasks (k0 + j)*TT + ttid.
-template <int NR, int MODE, int UU, int ILP, bool AND_ONLY, int NT>
-__device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv& e, const Phase& ph, uint32_t ntask,
+template <int NR, int MODE, int UU, int ILP, bool AND_ONLY, int NT, class SL>
+__device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv<SL>& e, const Phase& ph, uint32_t ntask,
                                             uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP]) {
     static_assert(UU <= ILP, "pass wider than the record buffer");
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
-    uint4* const slots = e.slots;
+    const SL& slots = e.slots;
     const Label R = e.R;
     if constexpr (AND_ONLY) {
         // every task of the pass belongs to an AND gate: (a0,j0) (a1,j0) (b0,j1) (b1,j1) on four
@@ -437,7 +467,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
     }
 }
 
-template <int NR, int MODE, int ILP, int MAXT, int NT>
+template <int NR, int MODE, int ILP, int MAXT, int NT, bool SPILL>
 __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     constexpr uint32_t D = node_pipe(ILP, MAXT, true);
     constexpr bool FULL = MODE == GC_FULL;
@@ -452,7 +482,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
-    uint4* const slots = tc.slots;
+    const auto slots = team_slots<SPILL>(tc, p);
     stagger_start(tc.team, p.stagger);
 
     for (;;) {
@@ -476,7 +506,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             uint4 m;
             if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + ref.y), inst);
             else m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
-            slots[ref.x] = m;
+            slots.stm(ref.x, m);
             if (!STREAM && p.io) {
                 uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + ref.y) * 2;
                 w[0] = m;
@@ -489,7 +519,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             }
         }
         team_barrier(tc.team, TT);
-        const GarbleEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, R, inst};
+        const GarbleEnv<decltype(slots)> env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, R, inst};
         // first-pass gate records: requested one phase ahead where the registers allow it (single-block
         // variants), at the top of their own phase -- behind the node rows -- in the two-block variants
         constexpr bool AHEAD = ILP == 1;
@@ -544,7 +574,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
             for (uint32_t k = ttid; k < p.n_out; k += TT) {
                 const uint2 ref = __ldg(p.live_out + k);
-                *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots[ref.x];
+                *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots.ldm(ref.x);
             }
         } else if (p.io) {
             for (uint32_t k = ttid; k < p.n_out; k += TT) {
@@ -560,22 +590,23 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
 }
 
 // -------------------------------------------------------------------- eval ----
+template <class SL>
 struct EvalEnv {
     GcParams const* p;
-    uint4* slots;
+    SL slots;
     const uint32_t* rk;
     const uint4* tab;
     uint32_t inst;
 };
 
-template <int NR, int MODE, int UU, int ILP, bool AND_ONLY, int NT>
-__device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e, const Phase& ph, uint32_t ntask,
+template <int NR, int MODE, int UU, int ILP, bool AND_ONLY, int NT, class SL>
+__device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv<SL>& e, const Phase& ph, uint32_t ntask,
                                           uint32_t k0, uint32_t ttid, uint32_t TT, const uint4 (&rec)[ILP],
                                           const uint4 (&rowpre)[ILP], bool have_rows) {
     static_assert(UU <= ILP, "pass wider than the record buffer");
     constexpr bool FULL = MODE == GC_FULL;
     const GcParams& p = *e.p;
-    uint4* const slots = e.slots;
+    const SL& slots = e.slots;
     if constexpr (AND_ONLY) {
         // every task of the pass belongs to an AND gate: lane pair (a, j0) (b, j1), eval.go:52-78
         const uint32_t k = ttid & 1u;
@@ -660,7 +691,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv& e,
     }
 }
 
-template <int NR, int MODE, int ILP, int MAXT, int NT>
+template <int NR, int MODE, int ILP, int MAXT, int NT, bool SPILL>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     constexpr uint32_t D = node_pipe(ILP, MAXT, false);
     constexpr bool FULL = MODE == GC_FULL;
@@ -675,7 +706,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.team, TT);
     }
-    uint4* const slots = tc.slots;
+    const auto slots = team_slots<SPILL>(tc, p);
     stagger_start(tc.team, p.stagger);
 
     for (;;) {
@@ -695,11 +726,11 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             uint4 m;
             if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + ref.y), inst);    // StreamEval.Get, stream_evaluator.go:57-66
             else m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
-            slots[ref.x] = m;
+            slots.stm(ref.x, m);
             if (FULL) p.wires_full[(size_t)inst * p.n_wires + ref.y] = m;
         }
         team_barrier(tc.team, TT);
-        const EvalEnv env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, inst};
+        const EvalEnv<decltype(slots)> env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, inst};
         uint4 cur[ILP];
         prefetch_cipher<false, ILP>(p, ph, 0, ttid, TT, cur);
 
@@ -754,8 +785,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         }
         for (uint32_t k = ttid; k < p.n_out; k += TT) {
             const uint2 ref = __ldg(p.live_out + k);
-            if (STREAM) *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots[ref.x];   // StreamEval.Set
-            else p.io[(size_t)inst * p.n_out + ref.y] = slots[ref.x];
+            if (STREAM) *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots.ldm(ref.x);   // StreamEval.Set
+            else p.io[(size_t)inst * p.n_out + ref.y] = slots.ldm(ref.x);
         }
         team_barrier(tc.team, TT);
     }

@@ -212,7 +212,7 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
 // Team geometry for a plan: how many instances one SM keeps resident, how many threads work on
 // each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
 // GCB_NT / GCB_TEAMS / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
-struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0; };
+struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false; };
 static size_t teams_that_fit(uint32_t num_slots, uint32_t smem_base, uint32_t nt) {
     // teams are packed below the 64 KiB-aligned tables first, then above them
     const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
@@ -229,7 +229,17 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
     uint32_t nt = (n4 == 0 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
     if (const char* e = getenv("GCB_NT")) { const int v = atoi(e); if (v == 2 || v == 4) nt = (uint32_t)v; }
     size_t n = nt == 2 ? n2 : n4;
-    if (n == 0) return g;
+    g.n_smem = num_slots;
+    if (n == 0) {
+        // More live labels than one team's share of shared memory holds even beside two tables: one team
+        // per SM keeps the low (hot) slots in the region above the tables and spills the rest to a
+        // global-memory scratch (gc_kernels.cuh: SlotsSpill).
+        const size_t pad = table_pad(smem_base);
+        const size_t above = kSmemOptin - pad - (size_t)aes_table_bytes(2), region = above > pad ? above : pad;
+        g.n_teams = 1; g.team_threads = 256; g.ilp = 2; g.nt = 2; g.stagger = 0; g.spill = true;
+        g.n_smem = (uint32_t)((region - GC_RK_BYTES - 16) / 16);
+        return g;
+    }
     if (n >= 32) n = 32; else if (n > 16) n = 16;
     if (const char* e = getenv("GCB_TEAMS")) { const int v = atoi(e); if (v >= 1 && (size_t)v <= n) n = (size_t)v; }
     // measured on B200 (tools/tune_geometry.py): two interleaved AES blocks per thread and
@@ -333,12 +343,18 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;
     const dim3 grid(want < (uint32_t)di->sm_count ? want : (uint32_t)di->sm_count);
     const dim3 block(p.n_teams * p.team_threads);
-    const size_t smem = gc_smem_bytes(p.n_slots, p.n_teams, geo.nt, di->smem_base);
+    const size_t smem = gc_smem_bytes(geo.n_smem, p.n_teams, geo.nt, di->smem_base);
     const bool full = wires_full != nullptr;
     const int mode = pages ? GC_STREAM : full ? GC_FULL : GC_PLAIN;
-    const GcVariant var{geo.ilp, geo.nt};
+    const GcVariant var{geo.ilp, geo.nt, geo.spill};
+    p.n_smem = geo.n_smem;
+    if (geo.spill) {                                   // stream-ordered scratch: concurrent launches never share it
+        const size_t bytes = (size_t)grid.x * p.n_teams * (p.n_slots - p.n_smem) * 16;
+        CK(cudaMallocAsync(reinterpret_cast<void**>(&p.spill), bytes, stream));
+    }
     if (garble) gc_launch_garble(mode, keylen, var, grid, block, smem, stream, p);
     else gc_launch_eval(mode, keylen, var, grid, block, smem, stream, p);
+    if (geo.spill) CK(cudaFreeAsync(p.spill, stream));
     CK(cudaGetLastError());
     return GCB_OK;
 }

@@ -113,16 +113,28 @@ def test_no_cpu_fallback_without_a_device():
     assert e.value.rc == _lib.E_CUDA
 
 
-def test_plan_refuses_a_circuit_whose_live_labels_do_not_fit_on_chip():
-    """More live wire labels than shared memory holds beside two T-tables: GCB_E_TOO_LARGE at plan creation
-    (host-only; no CPU fallback takes over)."""
+def test_plan_limits_of_live_labels():
+    """A circuit that keeps more labels live than shared memory holds still gets a plan (the excess is spilled
+    to a global-memory scratch by a dedicated kernel variant); only the 16-bit slot numbering of the plan
+    records is a hard limit: GCB_E_TOO_LARGE at plan creation (host-only check)."""
     import ctypes as C
+    from mpc_b200._lib import PlanInfo
     from mpc_b200.circuit_io import parse_bristol
-    n = 6000
-    lines = [f"2 1 {i} {n + i} {2 * n + i} AND" for i in range(n)]
-    circ = parse_bristol(f"{n} {3 * n}\n2 {n} {n}\n1 {n}\n\n" + "\n".join(lines) + "\n", "toowide")
-    h = C.c_void_p()
-    gates = np.ascontiguousarray(circ.gates)
-    rc = _lib.lib().gcb_plan_create(_lib.ptr(gates), circ.num_gates, circ.num_wires, circ.num_inputs,
-                                    circ.num_outputs, C.byref(h))
-    assert rc == _lib.E_TOO_LARGE and b"live" in _lib.lib().gcb_last_error()
+
+    def plan(n):
+        lines = [f"2 1 {i} {n + i} {2 * n + i} AND" for i in range(n)]
+        circ = parse_bristol(f"{n} {3 * n}\n2 {n} {n}\n1 {n}\n\n" + "\n".join(lines) + "\n", "wide")
+        h = C.c_void_p()
+        gates = np.ascontiguousarray(circ.gates)
+        rc = _lib.lib().gcb_plan_create(_lib.ptr(gates), circ.num_gates, circ.num_wires, circ.num_inputs,
+                                        circ.num_outputs, C.byref(h))
+        return rc, h
+
+    rc, h = plan(6000)                                   # 18,000 live labels: spilling variant, one team per SM
+    assert rc == 0
+    info = PlanInfo()
+    _lib.check(_lib.lib().gcb_plan_get_info(h, C.byref(info)))
+    assert info.num_slots == 18000 and info.teams_per_sm == 1
+    _lib.lib().gcb_plan_destroy(h)
+    rc, h = plan(22000)                                  # 66,000 > 65,535
+    assert rc == _lib.E_TOO_LARGE and b"65535" in _lib.lib().gcb_last_error()

@@ -272,3 +272,29 @@ def test_circuit_that_only_fits_beside_two_tables():
     assert eq(out, O.eval_batch(circ, keys, o_tables, inl))
     got = decode(io[:, circ.num_inputs:], out)
     assert np.array_equal(got, bits[:, :2000] & bits[:, 2000:])
+
+
+@pytest.mark.parametrize("which", ["wide", "deep"])
+def test_circuit_that_spills_labels_to_global_memory(which):
+    """More live labels than fit on chip (12,000 in one AND level; 9,000 inputs that stay live through 20,000
+    gates of all types): the spilling variant keeps the low slots in shared memory and the rest in a
+    global-memory scratch, bit-exact in plain and full-wire mode."""
+    circ = _wide_circuit(4000) if which == "wide" else mixed_circuit(21, 20000, 9000, 64)
+    eng = GarbleEngine(circ)
+    assert eng.info.num_slots > 6400 and eng.info.teams_per_sm == 1
+    batch = 4
+    keys, rand = garble_inputs(f"spill/{which}", batch, circ.num_inputs, 32)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    _, o_tables, o_io = O.garble_batch(circ, keys, rand)
+    assert eq(tables, o_tables) and eq(io, o_io)
+    bits = np.random.default_rng(4).integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+    inl = select(io[:, : circ.num_inputs], bits)
+    out = eng.eval_batch(keys, tables, inl)
+    assert eq(out, O.eval_batch(circ, keys, o_tables, inl))
+    assert np.array_equal(decode(io[:, circ.num_inputs:], out)[0], circ.compute_bits(bits[0].tolist()))
+    key = DRBG(f"spill/key/{which}").read(16)
+    rb = DRBG(f"spill/rand/{which}").read(16 * (1 + circ.num_inputs))
+    g = eng.garble(rb, key)
+    _, o_wires, o_slab, _ = O.garble(circ, key, rb)
+    assert eq(g.Wires, o_wires) and eq(g.slab, o_slab), "full-wire garble differs"
