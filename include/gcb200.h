@@ -186,6 +186,15 @@ int gcb_stream_step_size(gcb_stream *s, const gcb_plan *plan, const uint32_t *in
 int gcb_stream_garble(gcb_stream *s, const gcb_plan *plan, const uint32_t *in, uint32_t nin,
                       const uint32_t *out, uint32_t nout, uint8_t *dst, size_t dst_stride,
                       size_t *written, uint64_t *ns_init, uint64_t *ns_garble);
+/* The same, split in two so that a caller can keep one step in flight: _begin queues the gate kernel, the
+ * serialiser and the copy into `dst` and returns; _wait(s, 1) returns when the bytes of every step but the
+ * one begun last are in place, _wait(s, 0) when all are.  The gate kernel of step k+1 then runs while the
+ * record bytes of step k are still crossing PCIe (the wire file is on the device, so step k+1 does not
+ * depend on that copy).  `dst` of a step must stay untouched until a _wait has covered it; a third _begin
+ * first waits for the first step's copy (two staging sets). */
+int gcb_stream_garble_begin(gcb_stream *s, const gcb_plan *plan, const uint32_t *in, uint32_t nin,
+                            const uint32_t *out, uint32_t nout, uint8_t *dst, size_t dst_stride, size_t *written);
+int gcb_stream_garble_wait(gcb_stream *s, uint32_t leave_in_flight);
 
 /* ------------------------------------------------------ streaming evaluator --- */
 /* Replaces circuit.StreamEval (circuit/stream_evaluator.go:29-96: NewStreamEval,

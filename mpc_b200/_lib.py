@@ -62,6 +62,8 @@ SYMBOLS = {
     "gcb_stream_step_size": (_int, [_vp, _vp, _vp, _u32, _vp, _u32, C.POINTER(_sz)]),
     "gcb_stream_garble": (_int, [_vp, _vp, _vp, _u32, _vp, _u32, _vp, _sz, C.POINTER(_sz),
                                  C.POINTER(_u64), C.POINTER(_u64)]),
+    "gcb_stream_garble_begin": (_int, [_vp, _vp, _vp, _u32, _vp, _u32, _vp, _sz, C.POINTER(_sz)]),
+    "gcb_stream_garble_wait": (_int, [_vp, _u32]),
     "gcb_seval_create": (_int, [_vp, _u32, _u32, _u32, C.POINTER(_vp)]),
     "gcb_seval_destroy": (None, [_vp]),
     "gcb_seval_set_wires": (_int, [_vp, _vp, _u32, _vp]),

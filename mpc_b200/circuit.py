@@ -278,24 +278,37 @@ class Streaming:
         if h:
             try:
                 _lib.lib().gcb_stream_destroy(h)
-                if getattr(self, "_buf_ptr", None):
-                    _lib.lib().gcb_host_free(self._buf_ptr)
-                    self._buf_ptr = None
+                for slot in self.__dict__.get("_ring", []):
+                    if slot[1]:
+                        _lib.lib().gcb_host_free(slot[1])
+                        slot[1] = None
             except Exception:
                 pass
 
+    #: page-locked output buffers used in turn (the Go side's conn.WriteBuf role): with 2 or more, the bytes of
+    #: step k stay valid while step k+1 is garbled, so a consumer (socket writer, evaluator) can run concurrently
+    stream_buffers = 1
+
     def _stream_buffer(self, n: int) -> np.ndarray:
-        """Page-locked [batch, n] byte buffer, kept across steps (the Go side's conn.WriteBuf role).
-        The returned array is overwritten by the next garble() call."""
+        """Page-locked [batch, n] byte buffer from a ring of ``stream_buffers`` buffers kept across steps.
+        The returned array is overwritten ``stream_buffers`` garble() calls later."""
         need = self.batch * n
-        if getattr(self, "_buf_cap", 0) < need:
-            if getattr(self, "_buf_ptr", None):
-                _lib.lib().gcb_host_free(self._buf_ptr)
-            self._buf_cap = need + need // 4
-            self._buf_ptr = _lib.lib().gcb_host_alloc(self._buf_cap)
-            if not self._buf_ptr:
+        ring = self.__dict__.setdefault("_ring", [])
+        turn = self.__dict__.get("_turn", 0)
+        self._turn = turn + 1
+        k = turn % max(1, int(self.stream_buffers))
+        while len(ring) <= k:
+            ring.append([0, None])                       # [capacity, address]
+        cap, addr = ring[k]
+        if cap < need:
+            if addr:
+                _lib.lib().gcb_host_free(addr)
+            cap = need + need // 4
+            addr = _lib.lib().gcb_host_alloc(cap)
+            if not addr:
                 raise GcbError(_lib.E_CUDA, _lib.lib().gcb_last_error().decode())
-        raw = (C.c_uint8 * need).from_address(self._buf_ptr)
+            ring[k] = [cap, addr]
+        raw = (C.c_uint8 * need).from_address(addr)
         return np.frombuffer(raw, dtype=np.uint8).reshape(self.batch, n)
 
     def get_inputs(self, ids) -> np.ndarray:
@@ -329,6 +342,23 @@ class Streaming:
                                            ptr(o) if len(o) else None, len(o), ptr(buf), buf.shape[1],
                                            C.byref(w), C.byref(t0), C.byref(t1)))
         return buf[:, : int(w.value)], int(t0.value), int(t1.value)
+
+
+    def garble_begin(self, eng: GarbleEngine, in_ids, out_ids) -> np.ndarray:
+        """Queue one Streaming.Garble step and return its output buffer, whose bytes are valid only after a
+        garble_wait() that covers it.  Set ``stream_buffers`` >= 2 (the buffers are handed out in turn)."""
+        i = np.ascontiguousarray(in_ids, dtype=np.uint32)
+        o = np.ascontiguousarray(out_ids, dtype=np.uint32)
+        n = 13 * eng.circ.num_gates + 16 * eng.circ.num_rows
+        buf = self._stream_buffer(max(n, 1))
+        w = C.c_size_t()
+        check(_lib.lib().gcb_stream_garble_begin(self._h, eng.handle, ptr(i) if len(i) else None, len(i),
+                                                 ptr(o) if len(o) else None, len(o), ptr(buf), buf.shape[1], C.byref(w)))
+        return buf[:, : int(w.value)]
+
+    def garble_wait(self, leave_in_flight: int = 0) -> None:
+        """0: every begun step's bytes are in place; 1: all but the step begun last."""
+        check(_lib.lib().gcb_stream_garble_wait(self._h, leave_in_flight))
 
 
 class StreamEval:

@@ -415,8 +415,22 @@ struct gcb_stream {
     // entry (no clearing, no hashing: a sub-circuit touches its ids a few hundred thousand times)
     std::vector<uint32_t> perm_loc, perm_epoch;
     uint32_t epoch = 0;
+    // evaluator side: the record bytes of call k+1 are copied in (stream ds, second staging buffer) while the
+    // kernel of call k runs (stream cs)
+    gcb::DevBuf ser2;
+    size_t ser2_cap = 0;
+    cudaStream_t ds = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_free[2] = {nullptr, nullptr};
+    bool ev_valid[2] = {false, false};
+    uint32_t ser_turn = 0;
+    uint8_t* stage[2] = {nullptr, nullptr};    // garbler side: page-locked staging of header templates / row offsets
+    size_t stage_cap[2] = {0, 0};
     ~gcb_stream() {
         for (uint4* p : pages) if (p) cudaFree(p);
+        for (uint8_t* h : stage) if (h) cudaFreeHost(h);
+        if (ev_h2d) cudaEventDestroy(ev_h2d);
+        for (cudaEvent_t e : ev_free) if (e) cudaEventDestroy(e);
+        if (ds) cudaStreamDestroy(ds);
         if (cs) cudaStreamDestroy(cs);
     }
 };
@@ -787,6 +801,7 @@ int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
 void gcb_stream_destroy(gcb_stream* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->ds) cudaStreamSynchronize(s->ds);
     if (s->cs) cudaStreamSynchronize(s->cs);
     delete s;
 }
@@ -825,9 +840,12 @@ int gcb_stream_step_size(gcb_stream* s, const gcb_plan* plan, const uint32_t* in
     return GCB_OK;
 }
 
-int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
-                      uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written, uint64_t* ns_init,
-                      uint64_t* ns_garble) {
+// Streaming.Garble for one sub-circuit.  wait = false (gcb_stream_garble_begin): everything is queued -- the gate
+// kernel and the serialiser on stream cs, the copy to `dst` on stream ds from one of two staging buffers -- and
+// the call returns; the next step's kernel then runs while this step's bytes are still crossing PCIe.
+static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
+                              uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written, uint64_t* ns_init,
+                              uint64_t* ns_garble, bool wait) {
     using clk = std::chrono::steady_clock;
     const auto t_start = clk::now();
     if (!s || !plan || (nin && !in) || (nout && !out)) return fail(GCB_E_ARG, "null argument");
@@ -933,24 +951,75 @@ int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, u
         if (written) *written = total;
     }
     const size_t stride16 = (total + 15) & ~(size_t)15;
-    if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
+    if (!s->ds) {
+        CK(cudaStreamCreateWithFlags(&s->ds, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+        for (cudaEvent_t& e : s->ev_free) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint32_t cur = s->ser_turn++ & 1u;                 // staging buffers used in turn
+    DevBuf& ser = cur ? s->ser2 : s->ser;
+    size_t& ser_cap = cur ? s->ser2_cap : s->ser_cap;
+    if ((rc = grow(ser, ser_cap, (size_t)s->batch * stride16))) return rc;
     if ((rc = grow(s->tmpl, s->tmpl_cap, stride16 + 16))) return rc;
     if ((rc = grow(s->row_pos, s->row_pos_cap, (n_rows ? n_rows : 1) * 4))) return rc;
-    lay.tmpl.resize(stride16, 0);
-    if (total) CK(cudaMemcpyAsync(s->tmpl.p, lay.tmpl.data(), stride16, cudaMemcpyHostToDevice, s->cs));
-    if (n_rows) CK(cudaMemcpyAsync(s->row_pos.p, lay.row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
+    // header template and row offsets go through page-locked staging (two sets, like the buffers above): a
+    // copy from pageable memory would hold this thread until the stream has drained up to it
+    const size_t stage_bytes = stride16 + (n_rows ? n_rows : 1) * 4;
+    if (s->stage_cap[cur] < stage_bytes) {
+        if (s->stage[cur]) { CK(cudaStreamSynchronize(s->cs)); cudaFreeHost(s->stage[cur]); s->stage[cur] = nullptr; s->stage_cap[cur] = 0; }
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&s->stage[cur]), stage_bytes + stage_bytes / 4, cudaHostAllocDefault));
+        s->stage_cap[cur] = stage_bytes + stage_bytes / 4;
+    }
+    if (s->ev_valid[cur]) CK(cudaEventSynchronize(s->ev_free[cur]));   // the copy that last used this set (two calls ago) is done
+    uint8_t* h_tmpl = s->stage[cur];
+    uint32_t* h_rows = reinterpret_cast<uint32_t*>(s->stage[cur] + stride16);
+    memcpy(h_tmpl, lay.tmpl.data(), total);
+    memset(h_tmpl + total, 0, stride16 - total);
+    if (n_rows) memcpy(h_rows, lay.row_pos.data(), n_rows * 4);
+    if (total) CK(cudaMemcpyAsync(s->tmpl.p, h_tmpl, stride16, cudaMemcpyHostToDevice, s->cs));
+    if (n_rows) CK(cudaMemcpyAsync(s->row_pos.p, h_rows, n_rows * 4, cudaMemcpyHostToDevice, s->cs));
     if (total) {
         SerParams sp{s->tmpl.as<uint8_t>(), (uint32_t)total, s->row_pos.as<uint32_t>(), (uint32_t)n_rows,
-                     s->slab.as<uint4>(), s->ser.as<uint8_t>(), stride16};
+                     s->slab.as<uint4>(), ser.as<uint8_t>(), stride16};
         const dim3 grid((unsigned)((total + SER_TILE - 1) / SER_TILE), s->batch);
         serialize_kernel<<<grid, SER_THREADS, 0, s->cs>>>(sp);
         CK(cudaGetLastError());
-        CK(cudaMemcpy2DAsync(dst, dst_stride, s->ser.p, stride16, total, s->batch, cudaMemcpyDeviceToHost, s->cs));
+        CK(cudaEventRecord(s->ev_h2d, s->cs));
+        CK(cudaStreamWaitEvent(s->ds, s->ev_h2d, 0));
+        CK(cudaMemcpy2DAsync(dst, dst_stride, ser.p, stride16, total, s->batch, cudaMemcpyDeviceToHost, s->ds));
     }
-    CK(cudaStreamSynchronize(s->cs));
+    CK(cudaEventRecord(s->ev_free[cur], s->ds));
+    s->ev_valid[cur] = true;
+    if (wait) { CK(cudaStreamSynchronize(s->ds)); CK(cudaStreamSynchronize(s->cs)); }
     const auto t_end = clk::now();
     if (ns_init) *ns_init = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_mid - t_start).count();
     if (ns_garble) *ns_garble = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_end - t_mid).count();
+    return GCB_OK;
+}
+
+int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
+                      uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written, uint64_t* ns_init,
+                      uint64_t* ns_garble) {
+    return stream_garble_impl(s, plan, in, nin, out, nout, dst, dst_stride, written, ns_init, ns_garble, true);
+}
+int gcb_stream_garble_begin(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
+                            uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written) {
+    return stream_garble_impl(s, plan, in, nin, out, nout, dst, dst_stride, written, nullptr, nullptr, false);
+}
+int gcb_stream_garble_wait(gcb_stream* s, uint32_t leave_in_flight) {
+    if (!s) return fail(GCB_E_ARG, "null argument");
+    if (leave_in_flight > 1) return fail(GCB_E_ARG, "at most one step can stay in flight");
+    std::lock_guard<std::mutex> lk(s->mu);
+    tl_device = s->device;
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    if (leave_in_flight == 1) {                       // everything but the step begun last
+        const uint32_t prev = s->ser_turn & 1u;       // the set the step before the last one used
+        if (s->ser_turn >= 2 && s->ev_valid[prev]) CK(cudaEventSynchronize(s->ev_free[prev]));
+        return GCB_OK;
+    }
+    if (s->ds) CK(cudaStreamSynchronize(s->ds));
+    CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
 }
 
@@ -982,6 +1051,7 @@ int gcb_seval_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, 
 void gcb_seval_destroy(gcb_seval* s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->ds) cudaStreamSynchronize(s->ds);
     if (s->cs) cudaStreamSynchronize(s->cs);
     delete s;
 }
@@ -1045,12 +1115,25 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     // the record bytes start moving to the device first: parsing the headers and recovering the plan
     // on the host overlap the copy (2 GB per step in the config-5 stand-in)
     const size_t stride16 = ((len + 15) & ~(size_t)15) + 16;
-    if (ngates && len) {
-        if ((rc = grow(s->ser, s->ser_cap, (size_t)s->batch * stride16))) return rc;
-        CK(cudaMemcpy2DAsync(s->ser.p, stride16, src, s->batch > 1 ? src_stride : len, len, s->batch, cudaMemcpyHostToDevice, s->cs));
+    if (!s->ds) {
+        CK(cudaStreamCreateWithFlags(&s->ds, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming));
+        for (cudaEvent_t& e : s->ev_free) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    // on any error below the copy must have finished before the caller may reuse `src`
-    struct SyncOnExit { cudaStream_t cs; ~SyncOnExit() { cudaStreamSynchronize(cs); } } sync_on_exit{s->cs};
+    // Two staging buffers used in turn, the copy on its own stream: the call returns when ITS bytes are on
+    // the device (the caller may reuse `src`) while its kernel is still queued or running, so the copy of
+    // the next call overlaps it.  Readers of the wire file (gcb_seval_get_wires) are ordered on stream cs.
+    const uint32_t cur = s->ser_turn++ & 1u;
+    DevBuf& ser = cur ? s->ser2 : s->ser;
+    size_t& ser_cap = cur ? s->ser2_cap : s->ser_cap;
+    if (ngates && len) {
+        if ((rc = grow(ser, ser_cap, (size_t)s->batch * stride16))) return rc;
+        if (s->ev_valid[cur]) CK(cudaStreamWaitEvent(s->ds, s->ev_free[cur], 0));   // its previous reader has run
+        CK(cudaMemcpy2DAsync(ser.p, stride16, src, s->batch > 1 ? src_stride : len, len, s->batch, cudaMemcpyHostToDevice, s->ds));
+        CK(cudaEventRecord(s->ev_h2d, s->ds));
+    }
+    // on every path out of this call the copy has finished before the caller may reuse `src`
+    struct SyncOnExit { cudaStream_t st; ~SyncOnExit() { cudaStreamSynchronize(st); } } sync_on_exit{s->ds};
     // parse instance 0's headers
     std::vector<StreamGate> sg;
     std::vector<uint32_t> row_pos;
@@ -1131,16 +1214,18 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     if (!out_ids.empty()) CK(cudaMemcpyAsync(d_out, out_ids.data(), out_ids.size() * 4, cudaMemcpyHostToDevice, s->cs));
     if (n_rows) {
         CK(cudaMemcpyAsync(s->row_pos.p, row_pos.data(), n_rows * 4, cudaMemcpyHostToDevice, s->cs));
-        DeserParams dp{s->ser.as<uint8_t>(), stride16, s->row_pos.as<uint32_t>(), (uint32_t)n_rows, s->slab.as<uint4>(), s->batch};
+        CK(cudaStreamWaitEvent(s->cs, s->ev_h2d, 0));
+        DeserParams dp{ser.as<uint8_t>(), stride16, s->row_pos.as<uint32_t>(), (uint32_t)n_rows, s->slab.as<uint4>(), s->batch};
         deserialize_kernel<<<di->sm_count * 8, 256, 0, s->cs>>>(dp);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(s->ev_free[cur], s->cs));
+        s->ev_valid[cur] = true;
     }
     rc = launch_gc(false, ep->plan, di, s->device, s->keys.as<uint8_t>(), s->keylen, s->key_stride, s->batch, nullptr,
                    nullptr, s->slab.as<gcb_label>(), nullptr, nullptr, s->cs, d_in, d_out,
                    reinterpret_cast<uint4* const*>(s->page_table.p));
     if (rc) return rc;
-    CK(cudaStreamSynchronize(s->cs));
-    return GCB_OK;
+    return GCB_OK;                          // sync_on_exit waits for the copy; the kernel completes on stream cs
 }
 
 // ------------------------------------------------------------------- IKNP -------

@@ -124,7 +124,9 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         return lv;
     };
 
-    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out) -> int {
+    // emit = false: only the figures the policies are compared on (slots, steps); the records (and the
+    // leaf ordering, the expensive part) are produced once, for the schedule that won
+    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out, bool emit) -> int {
         // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
         // free gate of a later phase, or by the caller afterwards
         std::vector<uint8_t> required(ng, keep_all ? 1 : 0);
@@ -333,6 +335,12 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             err = msg;
             return GCB_E_TOO_LARGE;
         }
+        if (!emit) {
+            out.info = gcb_plan_info{};
+            out.info.num_slots = next_slot;
+            out.info.num_steps = (uint32_t)nsteps;
+            return GCB_OK;
+        }
         out.live_out.clear();
         for (size_t k = 0; k < spec.live_out.size(); k++)
             out.live_out.push_back(SlotRef{slot[(size_t)out_def[k]], (uint32_t)k});
@@ -360,9 +368,10 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             };
             NodeRec best[8], cand[8];
             std::copy(q, q + n, best);
-            int best_cost = cost_of(best);
+            int best_cost = cost_of(best), floor_cost = 0;       // one wavefront per leaf position at least
+            for (size_t i = 0; i < n; i++) floor_cost = std::max<int>(floor_cost, q[i].k);
             uint32_t rng = 0x9e3779b9u;
-            for (int trial = 0; trial < 12; trial++) {
+            for (int trial = 0; trial < 6 && best_cost > floor_cost; trial++) {
                 std::copy(q, q + n, cand);
                 uint16_t pool[8][NODE_MAX_FANIN];
                 int left[8];
@@ -461,29 +470,24 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
     };
 
     // ---- try the schedules and keep the one that needs the fewest wire slots
-    int best_rc = GCB_OK;
     {
-        Plan best;
-        bool have = false;
+        int best_policy = -1, best_rc = GCB_OK;
+        uint32_t best_slots = 0, best_steps = 0;
         std::string first_err;
-        for (int policy = 0; policy < 3; policy++) {
-            std::vector<uint32_t> ph = policy == 0 ? asap : alap_levels(policy == 2);
+        for (int policy = 0; policy < (keep_all ? 1 : 3); policy++) {      // the full-wire plan keeps the simple schedule
             Plan cand;
-            cand.row_off = plan.row_off; cand.ops = plan.ops;
-            const int rc = schedule(ph, cand);
-            if (rc != GCB_OK) { if (!have && first_err.empty()) { first_err = err; best_rc = rc; } continue; }
-            if (!have || cand.info.num_slots < best.info.num_slots ||
-                (cand.info.num_slots == best.info.num_slots && cand.info.num_steps < best.info.num_steps)) {
-                best.info = cand.info; best.ilp = cand.ilp; best.stagger = cand.stagger;
-                best.phases.swap(cand.phases); best.waves.swap(cand.waves); best.nodes.swap(cand.nodes);
-                best.crecs.swap(cand.crecs); best.nout_wire.swap(cand.nout_wire); best.cout_wire.swap(cand.cout_wire);
-                best.live_in.swap(cand.live_in); best.live_out.swap(cand.live_out);
-                best.node_loads = cand.node_loads;
-                have = true;
+            const int rc = schedule(policy == 0 ? asap : alap_levels(policy == 2), cand, false);
+            if (rc != GCB_OK) { if (best_policy < 0 && first_err.empty()) { first_err = err; best_rc = rc; } continue; }
+            if (best_policy < 0 || cand.info.num_slots < best_slots ||
+                (cand.info.num_slots == best_slots && cand.info.num_steps < best_steps)) {
+                best_policy = policy; best_slots = cand.info.num_slots; best_steps = cand.info.num_steps;
             }
-            if (keep_all) break;                     // the full-wire plan keeps the simple schedule
         }
-        if (!have) { err = first_err; return best_rc; }
+        if (best_policy < 0) { err = first_err; return best_rc; }
+        Plan best;
+        best.row_off = plan.row_off; best.ops = plan.ops;
+        const int rc = schedule(best_policy == 0 ? asap : alap_levels(best_policy == 2), best, true);
+        if (rc != GCB_OK) return rc;
         plan.info = best.info;
         plan.phases.swap(best.phases); plan.waves.swap(best.waves); plan.nodes.swap(best.nodes);
         plan.crecs.swap(best.crecs); plan.nout_wire.swap(best.nout_wire); plan.cout_wire.swap(best.cout_wire);

@@ -245,3 +245,32 @@ def test_exact_size_buffer_and_too_small_buffer():
     st2 = Streaming.new(rand, key, in_ids)
     buf, _, _ = st2.garble(eng, in_ids, out_ids)
     assert buf[0].tobytes() == want
+
+
+def test_garble_begin_wait_keeps_a_step_in_flight():
+    """gcb_stream_garble_begin / _wait: chained steps issued back to back (the second begun before the first
+    one's bytes were waited for) give the oracle's bytes and wire file, exactly like the blocking call."""
+    circ = load_circuit("add64")
+    key = DRBG("async").read(16)
+    ins = list(range(100, 228))
+    rand = DRBG("async/r").read(16 * (1 + 128))
+    st, ost, eng = Streaming.new(rand, key, ins), O.Streaming(key, rand, ins), GarbleEngine(circ)
+    st.stream_buffers = 3
+    steps = [
+        (ins, list(range(300, 364))),
+        (list(range(300, 364)) + list(range(100, 164)), list(range(400, 464))),
+        (list(range(400, 464)) + list(range(164, 228)), list(range(500, 564))),
+        (list(range(500, 564)) + list(range(300, 364)), list(range(600, 664))),
+    ]
+    bufs = []
+    for k, (i, o) in enumerate(steps):
+        bufs.append(st.garble_begin(eng, i, o))
+        st.garble_wait(1)                                   # everything but the newest step is in place
+        if k:
+            assert bufs[k - 1][0].tobytes() == ost.garble(circ, *steps[k - 1])
+    st.garble_wait(0)
+    assert bufs[-1][0].tobytes() == ost.garble(circ, *steps[-1])
+    ids = list(range(600, 664))
+    got = st.get_inputs(ids)[0]
+    for k, wid in enumerate(ids):
+        assert _wire_tuple(got[k]) == ost.get_input(wid)
