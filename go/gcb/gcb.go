@@ -225,3 +225,17 @@ func (p *Plan) TablesToWire(batch int, tables []Label, wire []byte, stride int) 
 func (p *Plan) TablesFromWire(batch int, wire []byte, stride int, tables []Label) error {
 	return lastError(C.gcb_tables_from_wire(p.h, C.uint32_t(batch), (*C.uint8_t)(unsafe.Pointer(&wire[0])), C.size_t(stride), lp(tables)))
 }
+
+// GarbleBegin / GarbleWait split Stream.Garble so that one step stays in flight: the kernel of step k+1
+// runs while the record bytes of step k cross PCIe.  dst must stay untouched until a GarbleWait covers it.
+func (s *Stream) GarbleBegin(p *Plan, in, out []uint32, dst []byte) (n int, err error) {
+	var w C.size_t
+	err = lastError(C.gcb_stream_garble_begin(s.h, p.h, u32p(in), C.uint32_t(len(in)), u32p(out), C.uint32_t(len(out)),
+		(*C.uint8_t)(unsafe.Pointer(&dst[0])), C.size_t(len(dst)), &w))
+	return int(w), err
+}
+
+// GarbleWait(0): every begun step is complete; GarbleWait(1): all but the one begun last.
+func (s *Stream) GarbleWait(leaveInFlight int) error {
+	return lastError(C.gcb_stream_garble_wait(s.h, C.uint32_t(leaveInFlight)))
+}
