@@ -227,7 +227,9 @@ func (p *Plan) TablesFromWire(batch int, wire []byte, stride int, tables []Label
 }
 
 // GarbleBegin / GarbleWait split Stream.Garble so that one step stays in flight: the kernel of step k+1
-// runs while the record bytes of step k cross PCIe.  dst must stay untouched until a GarbleWait covers it.
+// runs while the record bytes of step k cross PCIe.  dst must be page-locked C memory from HostAlloc (the copy
+// outlives the call, so Go-managed memory is not allowed here by the cgo pointer rules) and must stay untouched
+// until a GarbleWait covers it.
 func (s *Stream) GarbleBegin(p *Plan, in, out []uint32, dst []byte) (n int, err error) {
 	var w C.size_t
 	err = lastError(C.gcb_stream_garble_begin(s.h, p.h, u32p(in), C.uint32_t(len(in)), u32p(out), C.uint32_t(len(out)),
