@@ -1,6 +1,6 @@
 // plan_model.cpp -- host-only model of the shared-memory traffic of a plan.
 //
-// Builds the plan of a circuit (tools/_build/<name>.gates, written by tools/plan_model.py)
+// Builds the plan of a circuit (tools/_build/<name>.gates, written by tools/dump_gates.py)
 // with the product's plan compiler and counts, for a given team width, the shared-memory
 // wavefronts the gate kernels spend on wire labels: a 128-bit access is served one quarter
 // warp at a time, and a quarter warp takes as many wavefronts as the largest number of
