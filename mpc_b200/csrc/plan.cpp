@@ -405,7 +405,36 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                         if (pick_cost >= 0) { seen[ns++] = leaf; cnt[leaf & 7]++; }
                     }
                 }
-                const int c = cost_of(cand);
+                int c = cost_of(cand);
+                // local search: swap two leaf positions of one node while that lowers the cost of the two
+                // positions it touches
+                auto pos_cost = [&](int j) {
+                    uint32_t seen[8]; int ns = 0, cnt[8] = {0}, worst = 0;
+                    for (size_t i = 0; i < n; i++) {
+                        if (j >= cand[i].k) continue;
+                        bool dup = false;
+                        for (int x = 0; x < ns; x++) dup |= seen[x] == cand[i].leaf[j];
+                        if (dup) continue;
+                        seen[ns++] = cand[i].leaf[j];
+                        worst = std::max(worst, ++cnt[cand[i].leaf[j] & 7]);
+                    }
+                    return worst;
+                };
+                for (int pass = 0; pass < 4 && c > floor_cost; pass++) {
+                    bool improved = false;
+                    for (size_t i = 0; i < n; i++)
+                        for (int j1 = 0; j1 < cand[i].k; j1++)
+                            for (int j2 = j1 + 1; j2 < cand[i].k; j2++) {
+                                if ((cand[i].leaf[j1] & 7) == (cand[i].leaf[j2] & 7)) continue;
+                                const int before = pos_cost(j1) + pos_cost(j2);
+                                if (before <= 2) continue;
+                                std::swap(cand[i].leaf[j1], cand[i].leaf[j2]);
+                                const int after = pos_cost(j1) + pos_cost(j2);
+                                if (after < before) { c += after - before; improved = true; }
+                                else std::swap(cand[i].leaf[j1], cand[i].leaf[j2]);
+                            }
+                    if (!improved) break;
+                }
                 if (c < best_cost) { best_cost = c; std::copy(cand, cand + n, best); }
             }
             std::copy(best, best + n, q);

@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
            plan.waves.size(), plan.nodes.size(), plan.node_loads);
 
     Acc node_ld, node_st, g_ld, g_st, e_ld, e_st;
-    uint64_t barriers = 0, garble_passes = 0, eval_passes = 0, node_iters = 0;
+    uint64_t barriers = 0, garble_passes = 0, eval_passes = 0, node_iters = 0, node_floor = 0;
     std::vector<int> ls(32);
     for (const PhaseRec& ph : plan.phases) {
         const uint32_t nw = ph.n_waves & 0x7fffffffu;
@@ -88,6 +88,11 @@ int main(int argc, char** argv) {
                             if (j < wr.count && k < plan.nodes[wr.first + j].k) ls[l] = plan.nodes[wr.first + j].leaf[k];
                         }
                         node_ld.add(ls);
+                        for (int q = 0; q < 4; q++) {          // floor: one wavefront per quarter warp with an active lane
+                            bool any = false;
+                            for (int l = 0; l < 8; l++) any |= ls[q * 8 + l] >= 0;
+                            node_floor += any;
+                        }
                     }
                     for (int l = 0; l < 32; l++) {
                         const uint32_t j = base + wb + l;
@@ -157,6 +162,7 @@ int main(int argc, char** argv) {
                (unsigned long long)a.wavefronts, a.ideal8 / 8.0, a.wavefronts / (a.ideal8 / 8.0 + 1e-9));
     };
     pr("node loads", node_ld); pr("node stores", node_st);
+    printf("node loads floor (one wavefront per active quarter warp and leaf position): %llu\n", (unsigned long long)node_floor);
     pr("garble loads", g_ld); pr("garble stores", g_st);
     pr("eval loads", e_ld); pr("eval stores", e_st);
     printf("barriers %llu  node warp-iterations %llu  cipher warp-passes garble %llu eval %llu\n",
