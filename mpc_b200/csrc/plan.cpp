@@ -2,6 +2,7 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <functional>
 #include <iterator>
@@ -247,18 +248,49 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             if (last[k] < 0) release(slot[k]);                         // never read, not live-out
             else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
         }
-        auto take_slot = [&](size_t d, uint32_t want) {
-            want &= 7;
+        // Readers: the eight nodes of a quarter warp read leaf j in one instruction, and (XOR commutes)
+        // each node's leaves can be put in any order; an order without bank conflicts exists exactly
+        // when no bank group holds more of the quarter's leaves than its longest node has leaves
+        // (edge colouring of the node x bank-group multigraph).  So the bank group of a value is chosen
+        // to keep the leaves of the quarters that will read it balanced: quarter_load[q][b] counts the
+        // leaves of quarter q already placed in group b.
+        std::vector<std::vector<uint32_t>> readers(ndefs);
+        std::vector<std::array<uint16_t, 8>> quarter_load;
+        for (uint32_t p = 0; p < n_phases; p++) {
+            // nodes sorted by (wave, fan-in descending) so that the lanes of a warp do similar work
+            std::stable_sort(phase_nodes[p].begin(), phase_nodes[p].end(), [](const Node& x, const Node& y) {
+                if (x.wave != y.wave) return x.wave < y.wave;
+                return x.leaves.size() > y.leaves.size();
+            });
+            uint32_t pos = 0, wave = 0;
+            for (const Node& nd : phase_nodes[p]) {
+                if (nd.wave != wave) { wave = nd.wave; pos = 0; }
+                if ((pos & 7) == 0) quarter_load.push_back(std::array<uint16_t, 8>{});
+                const uint32_t q = (uint32_t)quarter_load.size() - 1;
+                for (uint32_t l : nd.leaves) readers[l].push_back(q);
+                pos++;
+            }
+        }
+        auto place = [&](size_t d) { for (uint32_t q : readers[d]) quarter_load[q][slot[d] & 7]++; };
+        for (size_t k = 0; k < ninit; k++) place(k);
+        // The store of the value is one lane of a quarter warp too: store_used counts the bank groups
+        // the lanes before it in the same quarter (`lane` & 7 == 0 starts a new one) have taken.
+        uint16_t store_used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        auto take_slot = [&](size_t d, uint32_t lane) {
+            if ((lane & 7) == 0) std::fill(store_used, store_used + 8, (uint16_t)0);
             int from = -1;
-            if (!free_slots[want].empty()) from = (int)want;
-            else {
-                uint32_t lowest = 0xffffffffu;
-                for (int b = 0; b < 8; b++)
-                    if (!free_slots[b].empty() && *free_slots[b].begin() < lowest) { lowest = *free_slots[b].begin(); from = b; }
+            uint32_t best = 0xffffffffu;
+            for (int b = 0; b < 8; b++) {
+                if (free_slots[b].empty()) continue;
+                uint32_t cost = 4u * store_used[b];
+                for (uint32_t q : readers[d]) cost += 2u * quarter_load[q][b];
+                if (cost < best) { best = cost; from = b; }
             }
             if (from < 0) slot[d] = next_slot++;
             else { slot[d] = *free_slots[from].begin(); free_slots[from].erase(free_slots[from].begin()); }
             if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+            store_used[slot[d] & 7]++;
+            place(d);
         };
         // Order of the ciphered gates of a level: AND/OR first, then INV (the kernels give 4 / 2
         // tasks to each); inside a class, gates are grouped so that the lanes of a quarter warp
@@ -310,11 +342,6 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                 }
             };
             for (uint32_t p = 0; p < n_phases; p++) {
-                // nodes sorted by (wave, fan-in descending) so that the lanes of a warp do similar work
-                std::stable_sort(phase_nodes[p].begin(), phase_nodes[p].end(), [](const Node& x, const Node& y) {
-                    if (x.wave != y.wave) return x.wave < y.wave;
-                    return x.leaves.size() > y.leaves.size();
-                });
                 size_t pos = 0;
                 for (uint32_t w = 0; w < n_waves[p]; w++, s++) {
                     advance();
