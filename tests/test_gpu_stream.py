@@ -274,3 +274,24 @@ def test_garble_begin_wait_keeps_a_step_in_flight():
     got = st.get_inputs(ids)[0]
     for k, wid in enumerate(ids):
         assert _wire_tuple(got[k]) == ost.get_input(wid)
+
+
+def test_streaming_step_that_spills_labels():
+    """A sub-circuit with more live labels than fit on chip (9,000 inputs kept live through 12,000 gates of all
+    types) through the streaming garbler and evaluator: the spilling kernel variant in wire-file mode."""
+    from mpc_b200.circuit import StreamEval
+    circ = mixed_circuit(31, 12000, 9000, 32)
+    key = DRBG("spill/stream").read(16)
+    in_ids, out_ids = list(range(9000)), list(range(20000, 20032))
+    st, ost, eng = _run(circ, key, in_ids, out_ids, tag="spill/stream")
+    assert eng.info.num_slots > 6400
+    buf, _, _ = st.garble(eng, in_ids, out_ids)
+    bits = np.random.default_rng(6).integers(0, 2, 9000).astype(bool)
+    w = st.get_inputs(in_ids)[0]
+    sev = StreamEval(key, 1)
+    sev.set(in_ids, np.where(bits, w["l1"], w["l0"]).astype(LABEL_DTYPE).reshape(1, -1))
+    sev.circuit(buf, circ.num_gates, circ.num_wires, 20032)
+    got = sev.get(out_ids)[0]
+    ow = st.get_inputs(out_ids)[0]
+    dec = np.where(got == ow["l1"], 1, np.where(got == ow["l0"], 0, 2))
+    assert np.array_equal(dec, circ.compute_bits(bits.astype(np.uint8).tolist()))
