@@ -71,6 +71,19 @@ int gcb_device_count(void);
 void *gcb_host_alloc(size_t bytes);
 void gcb_host_free(void *p);
 
+/* Device buffers and streams for callers without a CUDA binding of their own (Go): what the _dev
+ * entry points take.  Keeping the operands of consecutive calls on the device -- IKNP expansion ->
+ * COT post-processing, garble -> wire format -> eval -- removes the PCIe round trips between them.
+ * A stream handle is a cudaStream_t (NULL = the default stream); copies are asynchronous on the
+ * stream when the host side is page-locked (gcb_host_alloc), and gcb_dev_sync waits for it. */
+void *gcb_dev_alloc(size_t bytes);
+void gcb_dev_free(void *p);
+int gcb_dev_upload(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int gcb_dev_download(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int gcb_dev_stream_create(void **stream);
+void gcb_dev_stream_destroy(void *stream);
+int gcb_dev_sync(void *stream);
+
 /* ------------------------------------------------------------------ plans --- */
 /* A plan is the compiled, immutable form of one circuit.Circuit: gates grouped
  * into dependency steps, with the static per-gate tweak ids (the `id` counter of

@@ -44,6 +44,13 @@ SYMBOLS = {
     "gcb_device_count": (_int, []),
     "gcb_host_alloc": (_vp, [_sz]),
     "gcb_host_free": (None, [_vp]),
+    "gcb_dev_alloc": (_vp, [_sz]),
+    "gcb_dev_free": (None, [_vp]),
+    "gcb_dev_upload": (_int, [_vp, _vp, _sz, _vp]),
+    "gcb_dev_download": (_int, [_vp, _vp, _sz, _vp]),
+    "gcb_dev_stream_create": (_int, [C.POINTER(_vp)]),
+    "gcb_dev_stream_destroy": (None, [_vp]),
+    "gcb_dev_sync": (_int, [_vp]),
     "gcb_plan_create": (_int, [_vp, _u32, _u32, _u32, _u32, C.POINTER(_vp)]),
     "gcb_plan_destroy": (None, [_vp]),
     "gcb_plan_get_info": (_int, [_vp, C.POINTER(PlanInfo)]),

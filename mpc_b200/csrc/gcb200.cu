@@ -526,6 +526,47 @@ void* gcb_host_alloc(size_t bytes) {
 }
 void gcb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+void* gcb_dev_alloc(size_t bytes) {
+    if (select_device(nullptr)) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        fail(GCB_E_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void gcb_dev_free(void* p) { if (p) cudaFree(p); }
+int gcb_dev_upload(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    if (bytes && (!dst_dev || !src_host)) return fail(GCB_E_ARG, "null argument");
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    if (bytes) CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return GCB_OK;
+}
+int gcb_dev_download(void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+    if (bytes && (!dst_host || !src_dev)) return fail(GCB_E_ARG, "null argument");
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    if (bytes) CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return GCB_OK;
+}
+int gcb_dev_stream_create(void** stream) {
+    if (!stream) return fail(GCB_E_ARG, "null argument");
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream = st;
+    return GCB_OK;
+}
+void gcb_dev_stream_destroy(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+int gcb_dev_sync(void* stream) {
+    int rc = select_device(nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return GCB_OK;
+}
+
 // ------------------------------------------------------------------ plans -------
 int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wires, uint32_t num_inputs,
                     uint32_t num_outputs, gcb_plan** out) {

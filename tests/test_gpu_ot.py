@@ -197,3 +197,49 @@ def test_iknp_malicious_check_full_size():
     c0, c1, cx = fold(iknp_check_sums(seed2, 0, t, b), iknp_check_sums(seed2, n, t2, bcv))
     r0, r1 = mul128(cx, d)
     assert ((q0[0] ^ r0[0], q0[1] ^ r0[1]), (q1[0] ^ r1[0], q1[1] ^ r1[1])) != (c0, c1)
+
+
+def test_cot_chain_stays_on_the_device_through_the_c_abi_alone():
+    """IKNP expansion -> COT post-processing on both sides with every intermediate label left in HBM, using
+    only C-ABI calls (gcb_dev_alloc / upload / download, the _dev entry points and one library stream) --
+    what a Go caller without a CUDA binding does.  The receiver ends up with the chosen wire labels."""
+    import ctypes as C
+    from mpc_b200._lib import Label, check, ptr
+    from mpc_b200.ot import stream_advance, u_size
+    L = _lib.lib()
+    n = 5000
+    k0, k1, delta, ks = _keys("chain")
+    b = (DRBG("chain/b").array(n) & 1).astype(np.uint8)
+    wires = _rand_wires("chain/w", n)
+    seed = drbg_labels("chain/seed", 1)
+    st = C.c_void_p()
+    check(L.gcb_dev_stream_create(C.byref(st)))
+
+    def dev(nbytes, src=None):
+        p = L.gcb_dev_alloc(nbytes)
+        assert p
+        if src is not None:
+            check(L.gcb_dev_upload(p, ptr(np.ascontiguousarray(src)), nbytes, st))
+        return p
+
+    d_k0, d_k1, d_ks, d_delta = dev(2048, k0), dev(2048, k1), dev(2048, ks), dev(16, delta)
+    d_b, d_w = dev(n, b), dev(32 * n, wires)
+    ul = u_size(n)
+    d_u, d_t, d_q, d_msgs, d_res = dev(ul), dev(16 * n), dev(16 * n), dev(32 * n), dev(16 * n)
+    s_lab, d_lab = Label(int(seed["d0"][0]), int(seed["d1"][0])), Label(int(delta["d0"][0]), int(delta["d1"][0]))
+    check(L.gcb_iknp_receiver_expand_dev(d_k0, d_k1, 0, d_b, n, d_u, d_t, st))
+    check(L.gcb_iknp_sender_expand_dev(d_ks, d_delta, 0, d_u, ul, n, d_q, st))
+    check(L.gcb_cot_send_dev(C.byref(s_lab), C.byref(d_lab), d_q, d_w, n, d_msgs, 0, st))
+    check(L.gcb_cot_receive_dev(C.byref(s_lab), d_b, d_msgs, d_t, n, d_res, 0, st))
+    res = np.zeros(n, dtype=LABEL_DTYPE)
+    check(L.gcb_dev_download(ptr(res), d_res, 16 * n, st))
+    check(L.gcb_dev_sync(st))
+    assert eq(res, np.where(b.astype(bool), wires["l1"], wires["l0"]))
+    # and the host-pointer calls agree with the chain (same OT numbering, same seed)
+    u, t = IKNPReceiver(k0, k1).receive(b)
+    q = IKNPSender(ks, delta).send(u, n)
+    from mpc_b200.ot import cot_receive, cot_send
+    assert eq(cot_receive(seed, b, cot_send(seed, delta, q, wires), t), res)
+    for p in (d_k0, d_k1, d_ks, d_delta, d_b, d_w, d_u, d_t, d_q, d_msgs, d_res):
+        L.gcb_dev_free(p)
+    L.gcb_dev_stream_destroy(st)
