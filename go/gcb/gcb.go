@@ -241,3 +241,14 @@ func (s *Stream) GarbleBegin(p *Plan, in, out []uint32, dst []byte) (n int, err 
 func (s *Stream) GarbleWait(leaveInFlight int) error {
 	return lastError(C.gcb_stream_garble_wait(s.h, C.uint32_t(leaveInFlight)))
 }
+
+// Device buffers and streams (the operands of the _dev entry points) for callers without a CUDA binding.
+func DevAlloc(n int) unsafe.Pointer { return C.gcb_dev_alloc(C.size_t(n)) }
+func DevFree(p unsafe.Pointer)      { C.gcb_dev_free(p) }
+func DevUpload(dst unsafe.Pointer, src []byte, stream unsafe.Pointer) error {
+	return lastError(C.gcb_dev_upload(dst, unsafe.Pointer(&src[0]), C.size_t(len(src)), stream))
+}
+func DevDownload(dst []byte, src unsafe.Pointer, stream unsafe.Pointer) error {
+	return lastError(C.gcb_dev_download(unsafe.Pointer(&dst[0]), src, C.size_t(len(dst)), stream))
+}
+func DevSync(stream unsafe.Pointer) error { return lastError(C.gcb_dev_sync(stream)) }
