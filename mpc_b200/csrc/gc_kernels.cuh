@@ -390,8 +390,11 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
         const uint32_t sa = g[j].x & 0xffff, sb = g[j].x >> 16;
         op[j] = active ? ((g[j].y >> 16) & 0xff) : 0xffu;
         kk[j] = k; gidx[j] = gi;
-        a0[j] = lds_label(slots, sa);
-        const Label b0 = lds_label(slots, sb);
+        // idle lanes of a partly filled pass read nothing (their zero record would name slot 0, which a
+        // gate of this level may be writing)
+        a0[j] = Label{0, 0, 0, 0};
+        Label b0 = Label{0, 0, 0, 0};
+        if (active) { a0[j] = lds_label(slots, sa); b0 = lds_label(slots, sb); }
         const uint32_t pa = label_s(a0[j]), pb = label_s(b0);
         pp[j] = 2 * pa + pb;
         uint32_t tw = g[j].z;
@@ -655,8 +658,8 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv<SL>
         const uint32_t sa = g[j].x & 0xffff, sb = g[j].x >> 16;
         op[j] = act[j] ? ((g[j].y >> 16) & 0xff) : 0xffu;
         kk[j] = k; gidx[j] = gi;
-        const Label a = lds_label(slots, sa);
-        const Label b = lds_label(slots, sb);
+        Label a = Label{0, 0, 0, 0}, b = Label{0, 0, 0, 0};     // idle lanes read nothing (see garble_pass)
+        if (act[j]) { a = lds_label(slots, sa); b = lds_label(slots, sb); }
         const uint32_t sA = label_s(a), sB = label_s(b);
         // the garbled row this task may need, fetched before the AES so the HBM
         // latency hides behind the rounds

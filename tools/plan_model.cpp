@@ -126,6 +126,28 @@ int main(int argc, char** argv) {
             }
         }
     }
+    // invariant the kernels rely on: the reads and writes of one step (a wave, a cipher level) are unordered,
+    // so no slot may be read and written in the same step
+    {
+        uint64_t bad = 0;
+        for (size_t pi = 0; pi < plan.phases.size(); pi++) {
+            const PhaseRec& ph = plan.phases[pi];
+            const uint32_t nw = ph.n_waves & 0x7fffffffu;
+            for (uint32_t w = 0; w < nw; w++) {
+                const WaveRec& wr = plan.waves[ph.wave_first + w];
+                std::vector<uint8_t> rd(65536, 0);
+                for (uint32_t j = 0; j < wr.count; j++)
+                    for (uint32_t k = 0; k < plan.nodes[wr.first + j].k; k++) rd[plan.nodes[wr.first + j].leaf[k]] = 1;
+                for (uint32_t j = 0; j < wr.count; j++)
+                    if (rd[plan.nodes[wr.first + j].dst]) { bad++; printf("phase %zu wave %u: node %u writes slot %u that the wave reads\n", pi, w, j, plan.nodes[wr.first + j].dst); }
+            }
+            std::vector<uint8_t> rd(65536, 0);
+            for (uint32_t g = 0; g < ph.n_quad + ph.n_inv; g++) { rd[plan.crecs[ph.cipher_first + g].a] = 1; rd[plan.crecs[ph.cipher_first + g].b] = 1; }
+            for (uint32_t g = 0; g < ph.n_quad + ph.n_inv; g++)
+                if (rd[plan.crecs[ph.cipher_first + g].c]) { bad++; if (bad < 20) printf("phase %zu cipher level: gate %u writes slot %u that the level reads\n", pi, g, plan.crecs[ph.cipher_first + g].c); }
+        }
+        printf("same-step read/write overlaps: %llu\n", (unsigned long long)bad);
+    }
     // AES warp-blocks (160 wavefronts each) per instance: the kernels' pass policy against a packing in
     // which each warp takes a contiguous block of tasks and runs only the block slots it needs
     {
