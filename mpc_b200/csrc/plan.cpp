@@ -9,6 +9,7 @@
 #include <limits>
 #include <queue>
 #include <set>
+#include <thread>
 
 namespace gcb {
 
@@ -127,7 +128,8 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 
     // emit = false: only the figures the policies are compared on (slots, steps); the records (and the
     // leaf ordering, the expensive part) are produced once, for the schedule that won
-    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out, bool emit) -> int {
+    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out, bool emit, std::string& err) -> int {
+        char msg[160];
         // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
         // free gate of a later phase, or by the caller afterwards
         std::vector<uint8_t> required(ng, keep_all ? 1 : 0);
@@ -525,24 +527,37 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         return GCB_OK;
     };
 
-    // ---- try the schedules and keep the one that needs the fewest wire slots
+    // ---- try the schedules and keep the one that needs the fewest wire slots (the three trials are
+    // independent and run on their own threads: the compiler is on the critical path of the first use of a
+    // circuit, e.g. a streaming evaluator that meets a new sub-circuit)
     {
         int best_policy = -1, best_rc = GCB_OK;
         uint32_t best_slots = 0, best_steps = 0;
         std::string first_err;
-        for (int policy = 0; policy < (keep_all ? 1 : 3); policy++) {      // the full-wire plan keeps the simple schedule
-            Plan cand;
-            const int rc = schedule(policy == 0 ? asap : alap_levels(policy == 2), cand, false);
-            if (rc != GCB_OK) { if (best_policy < 0 && first_err.empty()) { first_err = err; best_rc = rc; } continue; }
-            if (best_policy < 0 || cand.info.num_slots < best_slots ||
-                (cand.info.num_slots == best_slots && cand.info.num_steps < best_steps)) {
-                best_policy = policy; best_slots = cand.info.num_slots; best_steps = cand.info.num_steps;
+        const int n_policies = keep_all ? 1 : 3;          // the full-wire plan keeps the simple schedule
+        Plan cand[3];
+        int rcs[3] = {GCB_OK, GCB_OK, GCB_OK};
+        std::string errs[3];
+        auto trial = [&](int policy) {
+            rcs[policy] = schedule(policy == 0 ? asap : alap_levels(policy == 2), cand[policy], false, errs[policy]);
+        };
+        {
+            std::vector<std::thread> workers;
+            for (int policy = 1; policy < n_policies; policy++) workers.emplace_back(trial, policy);
+            trial(0);
+            for (std::thread& t : workers) t.join();
+        }
+        for (int policy = 0; policy < n_policies; policy++) {
+            if (rcs[policy] != GCB_OK) { if (best_policy < 0 && first_err.empty()) { first_err = errs[policy]; best_rc = rcs[policy]; } continue; }
+            if (best_policy < 0 || cand[policy].info.num_slots < best_slots ||
+                (cand[policy].info.num_slots == best_slots && cand[policy].info.num_steps < best_steps)) {
+                best_policy = policy; best_slots = cand[policy].info.num_slots; best_steps = cand[policy].info.num_steps;
             }
         }
         if (best_policy < 0) { err = first_err; return best_rc; }
         Plan best;
         best.row_off = plan.row_off; best.ops = plan.ops;
-        const int rc = schedule(best_policy == 0 ? asap : alap_levels(best_policy == 2), best, true);
+        const int rc = schedule(best_policy == 0 ? asap : alap_levels(best_policy == 2), best, true, err);
         if (rc != GCB_OK) return rc;
         plan.info = best.info;
         plan.phases.swap(best.phases); plan.waves.swap(best.waves); plan.nodes.swap(best.nodes);

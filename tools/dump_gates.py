@@ -2,7 +2,7 @@
 u32 num_gates, num_wires, num_inputs, num_outputs, then num_gates 20-byte circuit.Gate records.
 
   python tools/dump_gates.py [circuit ...]          -> tools/_build/<circuit>.gates
-  g++ -O2 -std=c++17 -I include -o tools/_build/plan_model tools/plan_model.cpp mpc_b200/csrc/plan.cpp
+  g++ -O2 -std=c++17 -pthread -I include -o tools/_build/plan_model tools/plan_model.cpp mpc_b200/csrc/plan.cpp
   tools/_build/plan_model tools/_build/aes_128.gates 96
 """
 import os

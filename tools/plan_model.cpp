@@ -6,7 +6,7 @@
 // warp at a time, and a quarter warp takes as many wavefronts as the largest number of
 // distinct 16-byte words that fall into the same group of four banks (word index mod 8).
 //
-//   g++ -O2 -std=c++17 -I include -o tools/_build/plan_model tools/plan_model.cpp mpc_b200/csrc/plan.cpp
+//   g++ -O2 -std=c++17 -pthread -I include -o tools/_build/plan_model tools/plan_model.cpp mpc_b200/csrc/plan.cpp
 //   tools/_build/plan_model tools/_build/aes_128.gates 96
 #include <cstdio>
 #include <cstdlib>
