@@ -80,17 +80,17 @@ func (c *Circuit) Eval(key []byte, wires []ot.Label, garbled [][]ot.Label) error
 		switch c.Gates[i].Op {
 		case AND:
 			if len(rows) != 2 {
-				return fmt.Errorf("corrupted ciruit: AND row length: expected %d, got %d", 2, len(rows))
+				return fmt.Errorf("corrupted ciruit: AND row length: %d", len(rows))
 			}
 			slab = append(slab, rows...)
 		case OR:
 			if len(rows) < 3 {
-				return fmt.Errorf("corrupted circuit: index %d >= row len %d", 2, len(rows))
+				return fmt.Errorf("corrupted circuit: index %d >= row %d", 2, len(rows))
 			}
 			slab = append(slab, rows[:3]...)
 		case INV:
 			if len(rows) < 1 {
-				return fmt.Errorf("corrupted circuit: index %d >= row len %d", 0, len(rows))
+				return fmt.Errorf("corrupted circuit: index %d >= row %d", 0, len(rows))
 			}
 			slab = append(slab, rows[0])
 		}

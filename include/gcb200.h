@@ -58,9 +58,22 @@ const char *gcb_last_error(void);
 const char *gcb_version(void);
 
 /* Device selection.  cgo calls may arrive on any OS thread, so every entry point
- * re-selects its device; gcb_set_device changes the calling thread's choice
- * (default: device 0, or LOCAL_RANK when set). */
+ * re-selects its device.
+ *   gcb_set_devices(ids, n)  the process-wide engine setting of SURVEY.md section 8(b): the devices the
+ *                            library may use (n = 0 clears it).  Entry points whose work splits into
+ *                            independent units -- host-pointer gcb_garble / gcb_eval (and _begin) by
+ *                            contiguous blocks of instances, gcb_iknp_*_expand by 512-row chunk ranges,
+ *                            gcb_mitccrh_hash / gcb_cot_* / gcb_rot_* by OT ranges, and the _dev forms of
+ *                            garble / eval with GCB_FLAG_FANOUT -- fan one call out over all of them
+ *                            (circuit/garble.go:285-299 is the loop being parallelised); everything else
+ *                            runs on ids[0].  Results are byte-identical to a one-device call.
+ *   gcb_set_device(d)        the calling thread's override: d >= 0 pins this thread's calls to one
+ *                            device, -1 returns it to the process-wide setting.
+ * Default with neither set: device LOCAL_RANK if that variable is set, else device 0.
+ * gcb_get_devices: the devices a call of this thread would use (returns their number). */
 int gcb_set_device(int device);
+int gcb_set_devices(const int *ids, int n);
+int gcb_get_devices(int *ids, int cap);
 int gcb_device_count(void);
 
 /* Page-locked host memory.  Replaces the per-circuit scratch pool of
@@ -116,6 +129,10 @@ int gcb_plan_row_offsets(const gcb_plan *plan, uint32_t *row_off);
 
 /* ----------------------------------------------------------- garble / eval --- */
 #define GCB_FLAG_NONE 0u
+/* gcb_garble_dev / gcb_eval_dev only: the operands live on the calling thread's device; the batch is
+ * split over the gcb_set_devices list, inputs scattered and results gathered with peer copies over
+ * NVLink, sliced behind the kernels and ordered against `stream` (no wires_full). */
+#define GCB_FLAG_FANOUT 1u
 
 /* Replaces (*Circuit).Garble(rand, key) (circuit/garble.go:248-308), batched.
  *   keys       : key bytes; key_stride 0 = one key shared by the batch, else
@@ -145,6 +162,23 @@ int gcb_garble(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint3
 int gcb_eval(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
              uint32_t batch, const gcb_label *tables, const gcb_label *in_labels,
              gcb_label *out_labels, gcb_label *wires_full, uint32_t flags);
+
+/* The same calls split in two, so that ONE host thread keeps the copy engines and the SMs of every selected
+ * device busy: _begin queues the whole call -- input copies, kernels slice by slice, result copies -- and
+ * returns; gcb_job_wait blocks until the results are in the caller's buffers, frees the job and returns its
+ * status (gcb_job_done polls: 1 = finished).  Every buffer must stay valid and untouched until the wait; Go
+ * callers pass gcb_host_alloc memory (C memory: the cgo pointer rules do not apply to it), which is also
+ * what makes the copies truly asynchronous -- pageable memory is staged with a host memcpy inside _begin
+ * (inputs) and inside the wait (results).  Many jobs may be in flight; they complete in any order. */
+typedef struct gcb_job gcb_job;
+int gcb_garble_begin(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
+                     uint32_t batch, const gcb_label *r, const gcb_label *in_l0, gcb_label *tables,
+                     gcb_wire *io_wires, gcb_wire *wires_full, uint32_t flags, gcb_job **job);
+int gcb_eval_begin(const gcb_plan *plan, const uint8_t *keys, uint32_t keylen, uint32_t key_stride,
+                   uint32_t batch, const gcb_label *tables, const gcb_label *in_labels,
+                   gcb_label *out_labels, gcb_label *wires_full, uint32_t flags, gcb_job **job);
+int gcb_job_wait(gcb_job *job);
+int gcb_job_done(gcb_job *job);
 
 /* Device-resident variants (all pointers are device pointers; asynchronous on
  * `stream`).  Used for throughput measurement and multi-stage pipelines. */

@@ -41,6 +41,8 @@ SYMBOLS = {
     "gcb_last_error": (C.c_char_p, []),
     "gcb_version": (C.c_char_p, []),
     "gcb_set_device": (_int, [_int]),
+    "gcb_set_devices": (_int, [_vp, _int]),
+    "gcb_get_devices": (_int, [_vp, _int]),
     "gcb_device_count": (_int, []),
     "gcb_host_alloc": (_vp, [_sz]),
     "gcb_host_free": (None, [_vp]),
@@ -57,6 +59,10 @@ SYMBOLS = {
     "gcb_plan_row_offsets": (_int, [_vp, _vp]),
     "gcb_garble": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u32]),
     "gcb_eval": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32]),
+    "gcb_garble_begin": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "gcb_eval_begin": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, C.POINTER(_vp)]),
+    "gcb_job_wait": (_int, [_vp]),
+    "gcb_job_done": (_int, [_vp]),
     "gcb_garble_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "gcb_eval_dev": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp]),
     "gcb_select_labels_dev": (_int, [_vp, _sz, _vp, _vp, _u32, _u32, _vp]),

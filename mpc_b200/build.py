@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libgcb200.so")
 SOURCES = ["gcb200.cu", "gc_garble.cu", "gc_eval.cu", "plan.cpp", "circuit_host.cpp"]
-HEADERS = ["aes_core.cuh", "gc_kernels.cuh", "ot_kernels.cuh", "stream_kernels.cuh", "plan.hpp", "hostpipe.hpp",
+HEADERS = ["aes_core.cuh", "gc_kernels.cuh", "ot_kernels.cuh", "stream_kernels.cuh", "plan.hpp", "async.hpp",
            "gc_launch.hpp", "../../include/gcb200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -141,9 +141,9 @@ class GarbleEngine:
                 rows = garbled[i]
                 n = 0 if rows is None else len(rows)
                 if op == AND and n != 2:
-                    raise GcbError(_lib.E_CORRUPT, f"corrupted ciruit: AND row length: expected 2, got {n}")
+                    raise GcbError(_lib.E_CORRUPT, f"corrupted ciruit: AND row length: {n}")
                 if op in (OR, INV) and n < need[op]:
-                    raise GcbError(_lib.E_CORRUPT, f"corrupted circuit: index {need[op] - 1} >= row len {n}")
+                    raise GcbError(_lib.E_CORRUPT, f"corrupted circuit: index {need[op] - 1} >= row {n}")
                 if op in need:
                     parts.append(np.asarray(rows[: need[op]], dtype=LABEL_DTYPE))
             slab = np.concatenate(parts) if parts else np.zeros(0, dtype=LABEL_DTYPE)

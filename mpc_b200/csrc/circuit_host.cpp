@@ -183,6 +183,7 @@ int parse_mpclc(const uint8_t* p, size_t len, gcb_circuit& c) {
 extern "C" {
 
 int gcb_circuit_parse(const void* data, size_t len, int format, gcb_circuit** out) {
+    GCB_TRY
     if (!out || (!data && len)) return fail(GCB_E_ARG, "null argument");
     *out = nullptr;
     auto* c = new gcb_circuit();
@@ -193,9 +194,11 @@ int gcb_circuit_parse(const void* data, size_t len, int format, gcb_circuit** ou
     if (rc) { delete c; return rc; }
     *out = c;
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_circuit_from_gates(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wires, const uint32_t* inputs,
                            uint32_t n_input_args, const uint32_t* outputs, uint32_t n_output_args, gcb_circuit** out) {
+    GCB_TRY
     if (!out || (!gates && num_gates) || (!inputs && n_input_args) || (!outputs && n_output_args))
         return fail(GCB_E_ARG, "null argument");
     *out = nullptr;
@@ -208,10 +211,12 @@ int gcb_circuit_from_gates(const gcb_gate* gates, uint32_t num_gates, uint32_t n
     if (rc) { delete c; return rc; }
     *out = c;
     return GCB_OK;
+    GCB_CATCH
 }
 void gcb_circuit_destroy(gcb_circuit* c) { delete c; }
 
 int gcb_circuit_get_info(const gcb_circuit* c, gcb_circuit_info* info) {
+    GCB_TRY
     if (!c || !info) return fail(GCB_E_ARG, "null argument");
     *info = gcb_circuit_info{};
     info->num_gates = (uint32_t)c->gates.size();
@@ -222,19 +227,25 @@ int gcb_circuit_get_info(const gcb_circuit* c, gcb_circuit_info* info) {
     info->num_or = c->count[OP_OR]; info->num_inv = c->count[OP_INV];
     info->num_levels = c->num_levels; info->max_width = c->max_width;
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_circuit_get_gates(const gcb_circuit* c, gcb_gate* gates) {
+    GCB_TRY
     if (!c || (!gates && !c->gates.empty())) return fail(GCB_E_ARG, "null argument");
     if (!c->gates.empty()) memcpy(gates, c->gates.data(), c->gates.size() * sizeof(gcb_gate));
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_circuit_get_io(const gcb_circuit* c, uint32_t* input_bits, uint32_t* output_bits) {
+    GCB_TRY
     if (!c) return fail(GCB_E_ARG, "null argument");
     if (input_bits && !c->inputs.empty()) memcpy(input_bits, c->inputs.data(), c->inputs.size() * 4);
     if (output_bits && !c->outputs.empty()) memcpy(output_bits, c->outputs.data(), c->outputs.size() * 4);
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_circuit_compute(const gcb_circuit* c, uint32_t batch, const uint8_t* in_bits, uint8_t* out_bits) {
+    GCB_TRY
     if (!c || (batch && ((!in_bits && c->num_inputs) || (!out_bits && c->num_outputs)))) return fail(GCB_E_ARG, "null argument");
     std::vector<uint8_t> w(c->num_wires);
     for (uint32_t b = 0; b < batch; b++) {
@@ -254,10 +265,13 @@ int gcb_circuit_compute(const gcb_circuit* c, uint32_t batch, const uint8_t* in_
         if (c->num_outputs) memcpy(out_bits + (size_t)b * c->num_outputs, w.data() + (c->num_wires - c->num_outputs), c->num_outputs);
     }
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_circuit_plan(const gcb_circuit* c, gcb_plan** out) {
+    GCB_TRY
     if (!c) return fail(GCB_E_ARG, "null argument");
     return gcb_plan_create(c->gates.data(), (uint32_t)c->gates.size(), c->num_wires, c->num_inputs, c->num_outputs, out);
+    GCB_CATCH
 }
 
 }  // extern "C"

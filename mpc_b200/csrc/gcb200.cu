@@ -2,6 +2,7 @@
 // selection, plan upload, kernel launches and the host-buffer staging paths.
 // There is no CPU fallback in this file: without a CUDA device every compute
 // entry point fails with GCB_E_CUDA.
+#include <algorithm>
 #include <array>
 #include <atomic>
 #include <chrono>
@@ -23,7 +24,7 @@
 #include "ot_kernels.cuh"
 #include "stream_kernels.cuh"
 #include "plan.hpp"
-#include "hostpipe.hpp"
+#include "async.hpp"
 
 namespace gcb {
 
@@ -76,11 +77,27 @@ __global__ void smem_base_probe(uint32_t* out) {
 constexpr uint32_t kAssumedSmemBase = 1024;
 static uint32_t table_pad(uint32_t smem_base) { return ((smem_base + 0xffffu) & ~0xffffu) - smem_base; }
 
-int select_device(DeviceInfo** out) {
-    if (tl_device < 0) {
-        const char* lr = getenv("LOCAL_RANK");
-        tl_device = lr ? atoi(lr) : 0;
-    }
+// Which device(s) a call runs on.  A thread that called gcb_set_device(d >= 0) uses d.  Otherwise the
+// process-wide list of gcb_set_devices applies: calls that can split their work (host-pointer garble /
+// eval / IKNP / MiTCCRH, and the _dev forms with GCB_FLAG_FANOUT) spread it over the whole list, all
+// others run on its first entry.  With neither set: LOCAL_RANK, else device 0.
+static std::mutex g_devlist_mu;
+static std::shared_ptr<const std::vector<int>> g_devlist;
+static int default_device() {
+    static const int d = [] { const char* lr = getenv("LOCAL_RANK"); return lr ? atoi(lr) : 0; }();
+    return d;
+}
+static std::vector<int> call_devices() {
+    if (tl_device >= 0) return {tl_device};
+    std::shared_ptr<const std::vector<int>> l;
+    { std::lock_guard<std::mutex> lk(g_devlist_mu); l = g_devlist; }
+    if (l && !l->empty()) return *l;
+    return {default_device()};
+}
+static int current_device() { return call_devices()[0]; }
+
+// Makes `device` current for the calling thread and returns its per-device state (created on first use).
+int use_device(int device, DeviceInfo** out) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -88,16 +105,16 @@ int select_device(DeviceInfo** out) {
         return fail(GCB_E_CUDA, "no CUDA device available (%s); this library has no CPU path",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
-    if (tl_device >= count) return fail(GCB_E_CUDA, "device %d out of range (%d devices)", tl_device, count);
-    CK(cudaSetDevice(tl_device));
+    if (device < 0 || device >= count) return fail(GCB_E_CUDA, "device %d out of range (%d devices)", device, count);
+    CK(cudaSetDevice(device));
     std::lock_guard<std::mutex> lk(g_dev_mu);
-    auto& slot = g_devs[tl_device];
+    auto& slot = g_devs[device];
     if (!slot) {
         auto di = std::make_unique<DeviceInfo>();
         cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, tl_device));
+        CK(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10)
-            return fail(GCB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", tl_device,
+            return fail(GCB_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                         prop.major, prop.minor);
         di->sm_count = prop.multiProcessorCount;
         CK(cudaMalloc(&di->counters, kCounterRing * sizeof(uint32_t)));
@@ -111,10 +128,19 @@ int select_device(DeviceInfo** out) {
         CK(opt_in(mitccrh_kernel));
         CK(opt_in(iknp_kernel<false, false>)); CK(opt_in(iknp_kernel<true, false>));
         CK(opt_in(iknp_kernel<false, true>)); CK(opt_in(iknp_kernel<true, true>));
+        CK(opt_in(cot_kernel<COT_SEND>)); CK(opt_in(cot_kernel<COT_RECEIVE>));
+        CK(opt_in(cot_kernel<ROT_SEND>)); CK(opt_in(cot_kernel<ROT_RECEIVE>));
+        CK(opt_in(iknp_check_kernel));
         slot = std::move(di);
     }
     if (out) *out = slot.get();
     return GCB_OK;
+}
+// The calling thread's device (see call_devices); remembered in tl_cur for the code that follows.
+static thread_local int tl_cur = 0;
+int select_device(DeviceInfo** out) {
+    tl_cur = current_device();
+    return use_device(tl_cur, out);
 }
 
 // A zeroed claim counter for one launch on `stream`.
@@ -409,8 +435,14 @@ struct gcb_stream {
     size_t slab_cap = 0, ser_cap = 0, ids_cap = 0, tmpl_cap = 0, row_pos_cap = 0, wires_cap = 0;
     std::mutex mu;
     // evaluator side: plans recovered from record streams, keyed by a hash of the gate headers
-    struct EvalPlan { gcb::Plan plan; std::vector<uint32_t> in_ids, out_ids; };
+    // `canon`: the canonical gate list (op | tmp flags, three canonical locations per gate) the plan was built
+    // from.  The headers come from the peer and the hash is not collision resistant, so a hit is only used
+    // after the whole list compared equal.
+    struct EvalPlan { gcb::Plan plan; std::vector<uint32_t> in_ids, out_ids, canon; uint32_t ntmp = 0, np = 0; };
     std::unordered_map<uint64_t, std::shared_ptr<EvalPlan>> eval_plans;
+    // garbler side: plans built for aliased in / out ids, keyed by the plan and the aliasing pattern
+    struct AliasPlan { uint64_t plan_uid; std::vector<uint32_t> loc; std::unique_ptr<gcb::Plan> plan; std::vector<uint32_t> in_locs, out_locs; };
+    std::vector<std::shared_ptr<AliasPlan>> alias_plans;
     // permanent id -> canonical location of the call in progress: a flat array with an epoch stamp per
     // entry (no clearing, no hashing: a sub-circuit touches its ids a few hundred thousand times)
     std::vector<uint32_t> perm_loc, perm_epoch;
@@ -468,28 +500,376 @@ static int ensure_wires(gcb_stream* s, uint32_t max_id) {
     return GCB_OK;
 }
 
-// Staging pipes are pooled per device and checked out for the duration of one host-pointer
-// call, so that repeated Garble / Eval calls -- from any host thread -- reuse warm arenas
-// and streams instead of re-allocating them.
-struct PipeLease {
-    int device;
-    std::unique_ptr<HostPipe> pipe;
-    PipeLease(int dev);
-    ~PipeLease();
-    HostPipe& operator*() { return *pipe; }
+// ------------------------------------------------------------------ jobs -------
+// Host-pointer garble / eval as asynchronous jobs (async.hpp).
+static ResPool g_res_pool;
+
+static int lease_res(int device, std::unique_ptr<JobRes>* out) {
+    cudaError_t e = cudaSuccess;
+    *out = g_res_pool.lease(device, &e);
+    if (!*out) return cuda_fail(e, "stream creation");
+    return GCB_OK;
+}
+
+// One operand of a staged call: `per` bytes per instance at host address `host` (already offset to the
+// part's first instance); per == 0 marks an operand that is absent.
+struct Operand {
+    uint8_t* host = nullptr;
+    size_t per = 0;
+    bool pinned = false;
+    size_t dev_off = 0, pin_off = 0;
+    uint8_t* dev(const JobRes& r, size_t inst) const { return r.dev.base + dev_off + inst * per; }
 };
-static std::mutex g_pipe_mu;
-static std::map<int, std::vector<std::unique_ptr<HostPipe>>> g_pipe_pool;
-PipeLease::PipeLease(int dev) : device(dev) {
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    auto& v = g_pipe_pool[dev];
-    if (!v.empty()) { pipe = std::move(v.back()); v.pop_back(); }
-    else pipe = std::make_unique<HostPipe>();
+static Operand operand(const void* host, size_t per) {
+    Operand o;
+    o.host = static_cast<uint8_t*>(const_cast<void*>(host));
+    o.per = host ? per : 0;
+    return o;
 }
-PipeLease::~PipeLease() {
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    g_pipe_pool[device].push_back(std::move(pipe));
+
+// Instances per slice: whole kernel waves (`wave` = instances the device holds at once), about 64 MB of
+// traffic, so that the copies of one slice hide behind the kernel and copies of its neighbours.
+static uint32_t slice_instances(size_t per_inst, uint32_t batch, uint32_t wave) {
+    constexpr size_t kSliceBytes = 64u << 20;
+    if (wave == 0) wave = 1;
+    size_t n = kSliceBytes / (per_inst ? per_inst : 1) / wave * wave;
+    if (n < wave) n = wave;
+    return n >= batch ? batch : (uint32_t)n;
 }
+
+// Queue one part of a garble (garble = true) or eval call on `device`: `batch` instances whose operands
+// start at the given host addresses.  ins / outs: per-instance operands; `key` is the shared key (key_stride
+// == 0) or null.  Returns with everything queued on the part's streams.
+// peer.home >= 0: the operands are DEVICE buffers on device peer.home (the fan-out of a _dev call): copies become
+// peer copies over NVLink, start once `after` (recorded on the caller's stream) has completed, and `done` is
+// recorded behind the last one.
+struct PeerMode { int home = -1; cudaEvent_t after = nullptr; cudaEvent_t* done = nullptr; };
+static int begin_part(bool garble, const Plan& plan, int device, const uint8_t* key, uint32_t keylen, uint32_t key_stride,
+                      uint32_t batch, std::vector<Operand>& ins, std::vector<Operand>& outs, JobPart* part,
+                      const PeerMode& peer = PeerMode()) {
+    DeviceInfo* di;
+    int rc = use_device(device, &di);
+    if (rc) return rc;
+    if ((rc = lease_res(device, &part->res))) return rc;
+    JobRes& r = *part->res;
+    r.dev.used = r.pin.used = 0; r.ev_used = 0;
+    size_t per_inst = 0;
+    const size_t key_pin = r.pin.take(64), key_dev = r.dev.take(64);      // the shared key always goes through pinned staging
+    for (std::vector<Operand>* v : {&ins, &outs})
+        for (Operand& o : *v) {
+            if (!o.per) continue;
+            o.pinned = peer.home >= 0 || is_pinned(o.host);
+            o.dev_off = r.dev.take((size_t)batch * o.per);
+            if (!o.pinned) o.pin_off = r.pin.take((size_t)batch * o.per);
+            per_inst += o.per;
+        }
+    cudaError_t e;
+    if ((e = r.dev.reserve(r.dev.used)) != cudaSuccess) return cuda_fail(e, "device staging allocation");
+    if ((e = r.pin.reserve(r.pin.used)) != cudaSuccess) return cuda_fail(e, "pinned staging allocation");
+    auto copy_in = [&](void* dst, const void* src, size_t n) {
+        return peer.home >= 0 ? cudaMemcpyPeerAsync(dst, device, src, peer.home, n, r.h2d)
+                              : cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, r.h2d);
+    };
+    auto copy_out = [&](void* dst, const void* src, size_t n) {
+        return peer.home >= 0 ? cudaMemcpyPeerAsync(dst, peer.home, src, device, n, r.d2h)
+                              : cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, r.d2h);
+    };
+    if (peer.after) CK(cudaStreamWaitEvent(r.h2d, peer.after, 0));
+    if (key && peer.home >= 0) CK(copy_in(r.dev.base + key_dev, key, keylen));
+    else if (key) {
+        memcpy(r.pin.base + key_pin, key, keylen);
+        CK(copy_in(r.dev.base + key_dev, r.pin.base + key_pin, keylen));
+    }
+    const gcb_plan_info& in = plan.info;
+    const uint32_t wave = (in.teams_per_sm ? in.teams_per_sm : 1) * (uint32_t)di->sm_count;
+    const uint32_t slice = slice_instances(per_inst, batch, wave);
+    for (uint32_t b0 = 0; b0 < batch; b0 += slice) {
+        const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
+        for (const Operand& o : ins) {
+            if (!o.per) continue;
+            const size_t off = (size_t)b0 * o.per, n = (size_t)nb * o.per;
+            const uint8_t* src = o.host + off;
+            if (!o.pinned) { memcpy(r.pin.base + o.pin_off + off, src, n); src = r.pin.base + o.pin_off + off; }
+            CK(copy_in(r.dev.base + o.dev_off + off, src, n));
+        }
+        cudaEvent_t ev_in, ev_k;
+        CK(r.event(&ev_in)); CK(r.event(&ev_k));
+        CK(cudaEventRecord(ev_in, r.h2d));
+        CK(cudaStreamWaitEvent(r.k, ev_in, 0));
+        // operand order (see gcb_garble_begin / gcb_eval_begin): garble ins = {keys, r, l0}, outs = {tables, io, full};
+        // eval ins = {keys, tables, in_labels}, outs = {out_labels, full}
+        const uint8_t* dk = key ? r.dev.base + key_dev : ins[0].dev(r, b0);
+        if (garble)
+            rc = launch_gc(true, plan, di, device, dk, keylen, key_stride, nb, (const gcb_label*)ins[1].dev(r, b0),
+                           ins[2].per ? (const gcb_label*)ins[2].dev(r, b0) : nullptr,
+                           outs[0].per ? (gcb_label*)outs[0].dev(r, b0) : nullptr, outs[1].per ? outs[1].dev(r, b0) : nullptr,
+                           outs[2].per ? outs[2].dev(r, b0) : nullptr, r.k);
+        else
+            rc = launch_gc(false, plan, di, device, dk, keylen, key_stride, nb, nullptr,
+                           ins[2].per ? (const gcb_label*)ins[2].dev(r, b0) : nullptr,
+                           ins[1].per ? (gcb_label*)ins[1].dev(r, b0) : nullptr, outs[0].per ? outs[0].dev(r, b0) : nullptr,
+                           outs[1].per ? outs[1].dev(r, b0) : nullptr, r.k);
+        if (rc) return rc;
+        CK(cudaEventRecord(ev_k, r.k));
+        CK(cudaStreamWaitEvent(r.d2h, ev_k, 0));
+        for (const Operand& o : outs) {
+            if (!o.per) continue;
+            const size_t off = (size_t)b0 * o.per, n = (size_t)nb * o.per;
+            uint8_t* dst = o.pinned ? o.host + off : r.pin.base + o.pin_off + off;
+            CK(copy_out(dst, r.dev.base + o.dev_off + off, n));
+            if (!o.pinned) {
+                cudaEvent_t ready;
+                CK(r.event(&ready));
+                CK(cudaEventRecord(ready, r.d2h));
+                part->late.push_back(LateCopy{o.host + off, dst, n, ready});
+            }
+        }
+    }
+    if (peer.done) {
+        CK(r.event(peer.done));
+        CK(cudaEventRecord(*peer.done, r.d2h));
+    }
+    return GCB_OK;
+}
+
+// Waits for every part, finishes the copies into pageable memory, returns the resources.  The first error wins,
+// but every part is drained: afterwards nothing refers to the caller's buffers.
+static int finish_job(gcb_job* job) {
+    int rc = GCB_OK;
+    for (JobPart& part : job->parts) {
+        if (!part.res) continue;
+        JobRes& r = *part.res;
+        cudaSetDevice(r.device);
+        for (const LateCopy& c : part.late) {
+            cudaError_t e = cudaEventSynchronize(c.ready);
+            if (e != cudaSuccess) { if (!rc) rc = cuda_fail(e, "result copy"); break; }
+            memcpy(c.dst, c.src, c.bytes);
+        }
+        cudaError_t e = r.quiesce();
+        if (e != cudaSuccess && !rc) rc = cuda_fail(e, "job completion");
+        g_res_pool.give_back(std::move(part.res));
+    }
+    job->parts.clear();
+    return rc;
+}
+
+// Per-device share of a host-pointer call above which the blocking entry points go through the device in
+// several rounds (the staging arena of one round stays below this).
+constexpr size_t kMaxPartBytes = (size_t)24 << 30;
+
+static int garble_begin_impl(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                             const gcb_label* r, const gcb_label* in_l0, gcb_label* tables, gcb_wire* io_wires,
+                             gcb_wire* wires_full, gcb_job* job) {
+    const Plan* use;
+    int rc = plan_for(plan, wires_full != nullptr, &use);
+    if (rc) return rc;
+    const gcb_plan_info& in = use->info;
+    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
+    std::vector<int> devs = call_devices();
+    const uint32_t nd = (uint32_t)std::min<size_t>(devs.size(), batch);
+    job->parts.resize(nd);
+    for (uint32_t d = 0; d < nd; d++) {
+        uint64_t lo, hi;
+        share_range(batch, d, nd, &lo, &hi);
+        std::vector<Operand> ins = {operand(key_stride ? keys + lo * key_stride : nullptr, key_stride),
+                                    operand(r + lo, 16), operand(nin ? in_l0 + lo * nin : nullptr, nin * 16)};
+        std::vector<Operand> outs = {operand(rows ? tables + lo * rows : nullptr, rows * 16),
+                                     operand(io_wires ? io_wires + lo * (nin + nout) : nullptr, (nin + nout) * 32),
+                                     operand(wires_full ? wires_full + lo * nw : nullptr, nw * 32)};
+        if ((rc = begin_part(true, *use, devs[d], key_stride ? nullptr : keys, keylen, key_stride, (uint32_t)(hi - lo), ins, outs,
+                             &job->parts[d])))
+            return rc;
+    }
+    return GCB_OK;
+}
+
+static int eval_begin_impl(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                           const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels, gcb_label* wires_full,
+                           gcb_job* job) {
+    const Plan* use;
+    int rc = plan_for(plan, wires_full != nullptr, &use);
+    if (rc) return rc;
+    const gcb_plan_info& in = use->info;
+    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
+    std::vector<int> devs = call_devices();
+    const uint32_t nd = (uint32_t)std::min<size_t>(devs.size(), batch);
+    job->parts.resize(nd);
+    for (uint32_t d = 0; d < nd; d++) {
+        uint64_t lo, hi;
+        share_range(batch, d, nd, &lo, &hi);
+        std::vector<Operand> ins = {operand(key_stride ? keys + lo * key_stride : nullptr, key_stride),
+                                    operand(rows ? tables + lo * rows : nullptr, rows * 16),
+                                    operand(nin ? in_labels + lo * nin : nullptr, nin * 16)};
+        std::vector<Operand> outs = {operand(nout ? out_labels + lo * nout : nullptr, nout * 16),
+                                     operand(wires_full ? wires_full + lo * nw : nullptr, nw * 16)};
+        if ((rc = begin_part(false, *use, devs[d], key_stride ? nullptr : keys, keylen, key_stride, (uint32_t)(hi - lo), ins, outs,
+                             &job->parts[d])))
+            return rc;
+    }
+    return GCB_OK;
+}
+
+// ---- fan-out of a device-resident call (GCB_FLAG_FANOUT) ------------------------------------
+// The operands live on the calling thread's device (`home`).  Every other device of the gcb_set_devices list
+// takes a contiguous block of instances: its inputs are scattered to it and its results gathered back with peer
+// copies over NVLink, slice by slice behind the kernels, all ordered against the caller's stream by events -- the
+// call only enqueues.  This is the "scatter input labels, gather garbled tables" exchange of the batch split
+// (SURVEY.md section 8e); there is no collective because no rank needs another rank's data.
+static std::mutex g_peer_mu;
+static std::map<std::pair<int, int>, bool> g_peer_on;
+static void enable_peer(int a, int b) {                      // best effort: without it the copies are staged by the driver
+    std::lock_guard<std::mutex> lk(g_peer_mu);
+    for (const auto& pr : {std::make_pair(a, b), std::make_pair(b, a)}) {
+        if (g_peer_on.count(pr)) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, pr.first, pr.second);
+        if (can) {
+            cudaSetDevice(pr.first);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(pr.second, 0);
+            if (e != cudaSuccess) cudaGetLastError();            // already enabled, or refused
+        }
+        g_peer_on[pr] = can != 0;
+    }
+}
+struct FanoutCleanup { std::vector<std::unique_ptr<JobRes>> res; };
+static void CUDART_CB fanout_done(void* p) {
+    std::unique_ptr<FanoutCleanup> c(static_cast<FanoutCleanup*>(p));
+    for (auto& r : c->res) g_res_pool.retire(std::move(r));
+}
+// run_home(lo, hi): queue the home device's own block on the caller's stream.
+template <class RunHome>
+static int fanout_dev(bool garble, const Plan& plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                      const std::vector<Operand>& ins0, const std::vector<Operand>& outs0, cudaStream_t stream, RunHome run_home) {
+    const int home = tl_cur;
+    std::vector<int> devs;
+    { std::lock_guard<std::mutex> lk(g_devlist_mu); if (g_devlist) devs = *g_devlist; }
+    devs.erase(std::remove(devs.begin(), devs.end(), home), devs.end());
+    devs.insert(devs.begin(), home);
+    const uint32_t nd = (uint32_t)std::min<size_t>(devs.size(), batch);
+    if (nd <= 1) return run_home(0, batch);
+    DeviceInfo* di;
+    int rc = use_device(home, &di);
+    if (rc) return rc;
+    auto cleanup = std::make_unique<FanoutCleanup>();
+    std::unique_ptr<JobRes> home_res;                          // only for its events
+    if ((rc = lease_res(home, &home_res))) return rc;
+    home_res->ev_used = 0;
+    cudaEvent_t ready;
+    CK(home_res->event(&ready));
+    CK(cudaEventRecord(ready, stream));
+    std::vector<cudaEvent_t> done(nd, nullptr);
+    for (uint32_t d = 1; d < nd && !rc; d++) {
+        uint64_t lo, hi;
+        share_range(batch, d, nd, &lo, &hi);
+        enable_peer(home, devs[d]);
+        std::vector<Operand> ins = ins0, outs = outs0;
+        for (std::vector<Operand>* v : {&ins, &outs})
+            for (Operand& o : *v) if (o.per) o.host += lo * o.per;
+        JobPart part;
+        PeerMode pm;
+        pm.home = home; pm.after = ready; pm.done = &done[d];
+        rc = begin_part(garble, plan, devs[d], key_stride ? nullptr : keys, keylen, key_stride, (uint32_t)(hi - lo), ins, outs, &part, pm);
+        if (part.res) cleanup->res.push_back(std::move(part.res));
+    }
+    if (!rc) rc = use_device(home, &di);
+    uint64_t lo, hi;
+    share_range(batch, 0, nd, &lo, &hi);
+    if (!rc) rc = run_home((uint32_t)lo, (uint32_t)hi);
+    cudaSetDevice(home);
+    for (uint32_t d = 1; d < nd; d++)
+        if (done[d]) cudaStreamWaitEvent(stream, done[d], 0);
+    cleanup->res.push_back(std::move(home_res));
+    if (rc) {                                                  // drain what was queued, then give the parts back
+        for (auto& r : cleanup->res) { cudaSetDevice(r->device); r->quiesce(); g_res_pool.give_back(std::move(r)); }
+        cudaSetDevice(home);
+        return rc;
+    }
+    CK(cudaLaunchHostFunc(stream, fanout_done, cleanup.release()));
+    return GCB_OK;
+}
+
+// ---- simple staged calls (IKNP, MiTCCRH, COT / ROT, hashes, wire format) ---------------------
+// One part per device on the part's kernel stream: inputs up, the _dev entry point, results down.  The parts
+// of all devices are queued before any is waited for.
+struct DeviceScope {                                   // the _dev entry points run on the calling thread's device
+    int saved;
+    explicit DeviceScope(int d) : saved(tl_device) { tl_device = d; }
+    ~DeviceScope() { tl_device = saved; }
+};
+struct HostOp {
+    const void* src;          // copied to the device before the kernel (null: none)
+    void* dst;                // copied back after it (null: none)
+    size_t bytes;
+    void* dptr = nullptr;
+    size_t dev_off = 0, pin_off = 0;
+    bool pinned = false;
+    const void* host() const { return src ? src : dst; }
+};
+static int stage_begin(int device, std::vector<HostOp*> ops, JobPart* part) {
+    int rc = use_device(device, nullptr);
+    if (rc) return rc;
+    if ((rc = lease_res(device, &part->res))) return rc;
+    JobRes& r = *part->res;
+    r.dev.used = r.pin.used = 0; r.ev_used = 0;
+    for (HostOp* o : ops) {
+        o->pinned = o->host() && is_pinned(o->host());
+        o->dev_off = r.dev.take(o->bytes ? o->bytes : 16);
+        if (!o->pinned) o->pin_off = r.pin.take(o->bytes ? o->bytes : 16);
+    }
+    cudaError_t e;
+    if ((e = r.dev.reserve(r.dev.used)) != cudaSuccess) return cuda_fail(e, "device staging allocation");
+    if ((e = r.pin.reserve(r.pin.used ? r.pin.used : 16)) != cudaSuccess) return cuda_fail(e, "pinned staging allocation");
+    for (HostOp* o : ops) {
+        o->dptr = r.dev.base + o->dev_off;
+        if (!o->src || !o->bytes) continue;
+        const void* h = o->src;
+        if (!o->pinned) { memcpy(r.pin.base + o->pin_off, o->src, o->bytes); h = r.pin.base + o->pin_off; }
+        CK(cudaMemcpyAsync(o->dptr, h, o->bytes, cudaMemcpyHostToDevice, r.k));
+    }
+    return GCB_OK;
+}
+static int stage_end(std::vector<HostOp*> ops, JobPart* part) {
+    JobRes& r = *part->res;
+    for (HostOp* o : ops) {
+        if (!o->dst || !o->bytes) continue;
+        void* h = o->pinned ? o->dst : (void*)(r.pin.base + o->pin_off);
+        CK(cudaMemcpyAsync(h, o->dptr, o->bytes, cudaMemcpyDeviceToHost, r.k));
+        if (!o->pinned) {
+            cudaEvent_t ready;
+            CK(r.event(&ready));
+            CK(cudaEventRecord(ready, r.k));
+            part->late.push_back(LateCopy{o->dst, static_cast<const uint8_t*>(h), o->bytes, ready});
+        }
+    }
+    return GCB_OK;
+}
+// Runs body(device, lo, hi, part) for every device's block of `units`, then waits for all parts.
+template <class Body>
+static int fan_out(uint64_t units, Body body) {
+    const std::vector<int> devs = call_devices();
+    const uint32_t nd = (uint32_t)std::min<uint64_t>(devs.size(), units ? units : 1);
+    gcb_job job;
+    job.parts.resize(nd);
+    int rc = GCB_OK;
+    for (uint32_t d = 0; d < nd && !rc; d++) {
+        uint64_t lo, hi;
+        share_range(units, d, nd, &lo, &hi);
+        DeviceScope scope(devs[d]);
+        rc = body(devs[d], lo, hi, &job.parts[d]);
+    }
+    const std::string msg = tl_err;
+    const int rc2 = finish_job(&job);
+    if (rc) { tl_err = msg; return rc; }
+    return rc2;
+}
+
+// Instances one round of a blocking call may take so that no device's staging exceeds kMaxPartBytes.
+static uint32_t round_instances(size_t per_inst, uint32_t batch) {
+    const size_t nd = call_devices().size();
+    const size_t n = kMaxPartBytes / (per_inst ? per_inst : 1) * (nd ? nd : 1);
+    return n >= batch ? batch : (uint32_t)(n ? n : 1);
+}
+
 
 }  // namespace gcb
 
@@ -502,14 +882,43 @@ const char* gcb_last_error(void) { return tl_err.c_str(); }
 const char* gcb_version(void) { return "gcb200 0.1 (sm_100a)"; }
 
 int gcb_set_device(int device) {
-    if (device < 0) return fail(GCB_E_ARG, "negative device index");
-    tl_device = device;
+    GCB_TRY
+    tl_device = device < 0 ? -1 : device;                   // -1: back to the process-wide choice
     return GCB_OK;
+    GCB_CATCH
+}
+int gcb_set_devices(const int* ids, int n) {
+    GCB_TRY
+    if (n < 0 || (n > 0 && !ids)) return fail(GCB_E_ARG, "bad device list");
+    int count = 0;
+    if (n > 0 && (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)) {
+        cudaGetLastError();
+        return fail(GCB_E_CUDA, "no CUDA device available; this library has no CPU path");
+    }
+    auto l = std::make_shared<std::vector<int>>();
+    for (int i = 0; i < n; i++) {
+        if (ids[i] < 0 || ids[i] >= count) return fail(GCB_E_ARG, "device %d out of range (%d devices)", ids[i], count);
+        for (int v : *l) if (v == ids[i]) return fail(GCB_E_ARG, "device %d listed twice", ids[i]);
+        l->push_back(ids[i]);
+    }
+    std::lock_guard<std::mutex> lk(g_devlist_mu);
+    g_devlist = n ? l : nullptr;
+    return GCB_OK;
+    GCB_CATCH
+}
+int gcb_get_devices(int* ids, int cap) {
+    GCB_TRY
+    const std::vector<int> d = call_devices();
+    for (int i = 0; i < cap && i < (int)d.size(); i++) if (ids) ids[i] = d[i];
+    return (int)d.size();
+    GCB_CATCH
 }
 int gcb_device_count(void) {
+    GCB_TRY
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+    GCB_CATCH
 }
 
 // Page-locked host memory for the slabs the Go side pools per circuit
@@ -537,20 +946,25 @@ void* gcb_dev_alloc(size_t bytes) {
 }
 void gcb_dev_free(void* p) { if (p) cudaFree(p); }
 int gcb_dev_upload(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+    GCB_TRY
     if (bytes && (!dst_dev || !src_host)) return fail(GCB_E_ARG, "null argument");
     int rc = select_device(nullptr);
     if (rc) return rc;
     if (bytes) CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_dev_download(void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+    GCB_TRY
     if (bytes && (!dst_host || !src_dev)) return fail(GCB_E_ARG, "null argument");
     int rc = select_device(nullptr);
     if (rc) return rc;
     if (bytes) CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_dev_stream_create(void** stream) {
+    GCB_TRY
     if (!stream) return fail(GCB_E_ARG, "null argument");
     int rc = select_device(nullptr);
     if (rc) return rc;
@@ -558,18 +972,22 @@ int gcb_dev_stream_create(void** stream) {
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     *stream = st;
     return GCB_OK;
+    GCB_CATCH
 }
 void gcb_dev_stream_destroy(void* stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
 int gcb_dev_sync(void* stream) {
+    GCB_TRY
     int rc = select_device(nullptr);
     if (rc) return rc;
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return GCB_OK;
+    GCB_CATCH
 }
 
 // ------------------------------------------------------------------ plans -------
 int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wires, uint32_t num_inputs,
                     uint32_t num_outputs, gcb_plan** out) {
+    GCB_TRY
     if (!out) return fail(GCB_E_ARG, "null plan output pointer");
     *out = nullptr;
     if (!gates && num_gates) return fail(GCB_E_ARG, "null gate array");
@@ -579,6 +997,8 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     for (uint32_t i = 0; i < num_inputs; i++) spec.live_in.push_back(i);
     for (uint32_t i = 0; i < num_outputs; i++) spec.live_out.push_back(num_wires - num_outputs + i);
     auto pl = std::make_unique<gcb_plan>();
+    static std::atomic<uint64_t> next_uid{1};
+    pl->uid = next_uid.fetch_add(1);
     std::string err;
     int rc = build_plan(spec, pl->p, err);
     if (rc) return fail(rc, "%s", err.c_str());
@@ -589,24 +1009,29 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     pl->p.gates.assign(gates, gates + num_gates);
     *out = pl.release();
     return GCB_OK;
+    GCB_CATCH
 }
 void gcb_plan_destroy(gcb_plan* plan) { delete plan; }
 int gcb_plan_get_info(const gcb_plan* plan, gcb_plan_info* info) {
+    GCB_TRY
     if (!plan || !info) return fail(GCB_E_ARG, "null argument");
     *info = plan->p.info;
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_plan_row_offsets(const gcb_plan* plan, uint32_t* row_off) {
+    GCB_TRY
     if (!plan || !row_off) return fail(GCB_E_ARG, "null argument");
     memcpy(row_off, plan->p.row_off.data(), plan->p.row_off.size() * sizeof(uint32_t));
     return GCB_OK;
+    GCB_CATCH
 }
 
 // ----------------------------------------------------------- garble / eval ------
 int gcb_garble_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
                    uint32_t batch, const gcb_label* r, const gcb_label* in_l0, gcb_label* tables,
                    gcb_wire* io_wires, gcb_wire* wires_full, uint32_t flags, void* stream) {
-    (void)flags;
+    GCB_TRY
     if (!plan || !keys || !r || (!in_l0 && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows))
         return fail(GCB_E_ARG, "null argument");
     int rc = check_keylen(keylen);
@@ -617,14 +1042,26 @@ int gcb_garble_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, u
     if ((rc = select_device(&di))) return rc;
     const Plan* use;
     if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
-    return launch_gc(true, *use, di, tl_device, keys, keylen, key_stride, batch, r, in_l0, tables, io_wires,
+    if (flags & GCB_FLAG_FANOUT) {
+        if (wires_full) return fail(GCB_E_ARG, "GCB_FLAG_FANOUT does not produce wires_full");
+        const size_t nin = use->info.num_inputs, nout = use->info.num_outputs, rows = use->info.num_rows;
+        const std::vector<Operand> ins = {operand(key_stride ? keys : nullptr, key_stride), operand(r, 16), operand(nin ? in_l0 : nullptr, nin * 16)};
+        const std::vector<Operand> outs = {operand(rows ? tables : nullptr, rows * 16), operand(io_wires, (nin + nout) * 32), operand(nullptr, 0)};
+        return fanout_dev(true, *use, keys, keylen, key_stride, batch, ins, outs, (cudaStream_t)stream, [&](uint32_t lo, uint32_t hi) -> int {
+            return launch_gc(true, *use, di, tl_cur, key_stride ? keys + (size_t)lo * key_stride : keys, keylen, key_stride, hi - lo, r + lo,
+                             in_l0 ? in_l0 + (size_t)lo * nin : nullptr, tables ? tables + (size_t)lo * rows : nullptr,
+                             io_wires ? io_wires + (size_t)lo * (nin + nout) : nullptr, nullptr, (cudaStream_t)stream);
+        });
+    }
+    return launch_gc(true, *use, di, tl_cur, keys, keylen, key_stride, batch, r, in_l0, tables, io_wires,
                      wires_full, (cudaStream_t)stream);
+    GCB_CATCH
 }
 
 int gcb_eval_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
                  const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels,
                  gcb_label* wires_full, uint32_t flags, void* stream) {
-    (void)flags;
+    GCB_TRY
     if (!plan || !keys || (!in_labels && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows) ||
         (!out_labels && plan->p.info.num_outputs))
         return fail(GCB_E_ARG, "null argument");
@@ -636,109 +1073,162 @@ int gcb_eval_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uin
     if ((rc = select_device(&di))) return rc;
     const Plan* use;
     if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
-    return launch_gc(false, *use, di, tl_device, keys, keylen, key_stride, batch, nullptr, in_labels,
+    if (flags & GCB_FLAG_FANOUT) {
+        if (wires_full) return fail(GCB_E_ARG, "GCB_FLAG_FANOUT does not produce wires_full");
+        const size_t nin = use->info.num_inputs, nout = use->info.num_outputs, rows = use->info.num_rows;
+        const std::vector<Operand> ins = {operand(key_stride ? keys : nullptr, key_stride), operand(rows ? tables : nullptr, rows * 16),
+                                          operand(nin ? in_labels : nullptr, nin * 16)};
+        const std::vector<Operand> outs = {operand(nout ? out_labels : nullptr, nout * 16), operand(nullptr, 0)};
+        return fanout_dev(false, *use, keys, keylen, key_stride, batch, ins, outs, (cudaStream_t)stream, [&](uint32_t lo, uint32_t hi) -> int {
+            return launch_gc(false, *use, di, tl_cur, key_stride ? keys + (size_t)lo * key_stride : keys, keylen, key_stride, hi - lo, nullptr,
+                             in_labels ? in_labels + (size_t)lo * nin : nullptr, const_cast<gcb_label*>(tables ? tables + (size_t)lo * rows : nullptr),
+                             out_labels ? out_labels + (size_t)lo * nout : nullptr, nullptr, (cudaStream_t)stream);
+        });
+    }
+    return launch_gc(false, *use, di, tl_cur, keys, keylen, key_stride, batch, nullptr, in_labels,
                      const_cast<gcb_label*>(tables), out_labels, wires_full, (cudaStream_t)stream);
+    GCB_CATCH
 }
 
-// Host-buffer variants: the batch is cut into slices that move through pinned
-// staging on three streams' worth of overlap (H2D of slice i+1, kernel of slice
-// i, D2H of slice i-1 proceed concurrently).
-int gcb_garble(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
-               const gcb_label* r, const gcb_label* in_l0, gcb_label* tables, gcb_wire* io_wires,
-               gcb_wire* wires_full, uint32_t flags) {
+// Host-buffer variants.  gcb_garble / gcb_eval = _begin + gcb_job_wait; a batch whose staging would not fit one
+// arena per device goes through in rounds.
+static int check_garble_args(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
+                             const gcb_label* r, const gcb_label* in_l0, const gcb_label* tables) {
     if (!plan || !keys || !r || (!in_l0 && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows))
         return fail(GCB_E_ARG, "null argument");
     int rc = check_keylen(keylen);
     if (rc) return rc;
-    if (batch == 0) return GCB_OK;
-    DeviceInfo* di;
-    if ((rc = select_device(&di))) return rc;
-    const Plan* use;
-    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
-    const gcb_plan_info& in = use->info;
-    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
-    PipeLease lease(tl_device);
-    HostPipe& pipe = *lease;
-    if ((rc = pipe.init())) return rc;
-    const size_t per_inst = 16 + nin * 16 + rows * 16 + (io_wires ? (nin + nout) * 32 : 0) +
-                            (wires_full ? nw * 32 : 0) + (key_stride ? key_stride : 0);
-    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm ? in.teams_per_sm : 1);
-    for (uint32_t b0 = 0, k = 0; b0 < batch; b0 += slice, k++) {
-        const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
-        HostPipe::Slot& s = pipe.slot(k);
-        if ((rc = s.begin())) return rc;
-        // the key(s) travel with every slice: no per-call device allocation (cudaFree would
-        // synchronise the whole device and serialise concurrent callers)
-        const uint8_t* dk = nullptr;
-        if (key_stride) rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk);
-        else rc = s.in(keys, keylen, (const void**)&dk);
-        if (rc) return rc;
-        const gcb_label *dr, *dl0 = nullptr;
-        if ((rc = s.in(r + b0, (size_t)nb * 16, (const void**)&dr))) return rc;
-        if (nin && (rc = s.in(in_l0 + (size_t)b0 * nin, (size_t)nb * nin * 16, (const void**)&dl0))) return rc;
-        gcb_label* dt = nullptr;
-        gcb_wire *dio = nullptr, *dwf = nullptr;
-        if ((rc = s.out(tables + (size_t)b0 * rows, (size_t)nb * rows * 16, (void**)&dt))) return rc;
-        if (io_wires && (rc = s.out(io_wires + (size_t)b0 * (nin + nout), (size_t)nb * (nin + nout) * 32, (void**)&dio)))
-            return rc;
-        if (wires_full && (rc = s.out(wires_full + (size_t)b0 * nw, (size_t)nb * nw * 32, (void**)&dwf))) return rc;
-        if ((rc = s.upload())) return rc;
-        rc = launch_gc(true, *use, di, tl_device, dk, keylen, key_stride, nb, dr, dl0, dt, dio, dwf, s.compute);
-        if (rc) return rc;
-        if ((rc = s.download())) return rc;
-    }
-    (void)flags;
-    return pipe.finish();
+    if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
+    return GCB_OK;
 }
-
-int gcb_eval(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
-             const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels, gcb_label* wires_full,
-             uint32_t flags) {
+static int check_eval_args(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
+                           const gcb_label* tables, const gcb_label* in_labels, const gcb_label* out_labels) {
     if (!plan || !keys || (!in_labels && plan->p.info.num_inputs) || (!tables && plan->p.info.num_rows) ||
         (!out_labels && plan->p.info.num_outputs))
         return fail(GCB_E_ARG, "null argument");
     int rc = check_keylen(keylen);
     if (rc) return rc;
-    if (batch == 0) return GCB_OK;
-    DeviceInfo* di;
-    if ((rc = select_device(&di))) return rc;
-    const Plan* use;
-    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
-    const gcb_plan_info& in = use->info;
-    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
-    PipeLease lease(tl_device);
-    HostPipe& pipe = *lease;
-    if ((rc = pipe.init())) return rc;
-    const size_t per_inst = nin * 16 + rows * 16 + nout * 16 + (wires_full ? nw * 16 : 0) + key_stride;
-    const uint32_t slice = pipe.slice_for(per_inst, batch, in.teams_per_sm ? in.teams_per_sm : 1);
-    for (uint32_t b0 = 0, k = 0; b0 < batch; b0 += slice, k++) {
-        const uint32_t nb = batch - b0 < slice ? batch - b0 : slice;
-        HostPipe::Slot& s = pipe.slot(k);
-        if ((rc = s.begin())) return rc;
-        // the key(s) travel with every slice: no per-call device allocation (cudaFree would
-        // synchronise the whole device and serialise concurrent callers)
-        const uint8_t* dk = nullptr;
-        if (key_stride) rc = s.in(keys + (size_t)b0 * key_stride, (size_t)nb * key_stride, (const void**)&dk);
-        else rc = s.in(keys, keylen, (const void**)&dk);
-        if (rc) return rc;
-        const gcb_label *dt = nullptr, *dil = nullptr;
-        if (rows && (rc = s.in(tables + (size_t)b0 * rows, (size_t)nb * rows * 16, (const void**)&dt))) return rc;
-        if (nin && (rc = s.in(in_labels + (size_t)b0 * nin, (size_t)nb * nin * 16, (const void**)&dil))) return rc;
-        gcb_label *dol = nullptr, *dwf = nullptr;
-        if (nout && (rc = s.out(out_labels + (size_t)b0 * nout, (size_t)nb * nout * 16, (void**)&dol))) return rc;
-        if (wires_full && (rc = s.out(wires_full + (size_t)b0 * nw, (size_t)nb * nw * 16, (void**)&dwf))) return rc;
-        if ((rc = s.upload())) return rc;
-        rc = launch_gc(false, *use, di, tl_device, dk, keylen, key_stride, nb, nullptr, dil,
-                       const_cast<gcb_label*>(dt), dol, dwf, s.compute);
-        if (rc) return rc;
-        if ((rc = s.download())) return rc;
-    }
+    if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
+    return GCB_OK;
+}
+
+int gcb_garble_begin(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                     const gcb_label* r, const gcb_label* in_l0, gcb_label* tables, gcb_wire* io_wires,
+                     gcb_wire* wires_full, uint32_t flags, gcb_job** job) {
+    GCB_TRY
     (void)flags;
-    return pipe.finish();
+    if (!job) return fail(GCB_E_ARG, "null job output pointer");
+    *job = nullptr;
+    int rc = check_garble_args(plan, keys, keylen, key_stride, r, in_l0, tables);
+    if (rc) return rc;
+    auto j = std::make_unique<gcb_job>();
+    if (batch && (rc = garble_begin_impl(plan, keys, keylen, key_stride, batch, r, in_l0, tables, io_wires, wires_full, j.get()))) {
+        const std::string msg = tl_err;                    // keep the first error over whatever the drain reports
+        finish_job(j.get());
+        tl_err = msg;
+        return rc;
+    }
+    *job = j.release();
+    return GCB_OK;
+    GCB_CATCH
+}
+
+int gcb_eval_begin(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+                   const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels, gcb_label* wires_full,
+                   uint32_t flags, gcb_job** job) {
+    GCB_TRY
+    (void)flags;
+    if (!job) return fail(GCB_E_ARG, "null job output pointer");
+    *job = nullptr;
+    int rc = check_eval_args(plan, keys, keylen, key_stride, tables, in_labels, out_labels);
+    if (rc) return rc;
+    auto j = std::make_unique<gcb_job>();
+    if (batch && (rc = eval_begin_impl(plan, keys, keylen, key_stride, batch, tables, in_labels, out_labels, wires_full, j.get()))) {
+        const std::string msg = tl_err;
+        finish_job(j.get());
+        tl_err = msg;
+        return rc;
+    }
+    *job = j.release();
+    return GCB_OK;
+    GCB_CATCH
+}
+
+int gcb_job_wait(gcb_job* job) {
+    GCB_TRY
+    if (!job) return fail(GCB_E_ARG, "null job");
+    std::unique_ptr<gcb_job> j(job);
+    return finish_job(j.get());
+    GCB_CATCH
+}
+
+int gcb_job_done(gcb_job* job) {
+    GCB_TRY
+    if (!job) return 1;
+    for (JobPart& part : job->parts) {
+        if (!part.res) continue;
+        cudaSetDevice(part.res->device);
+        for (cudaStream_t st : {part.res->h2d, part.res->k, part.res->d2h}) {
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaErrorNotReady) return 0;
+            if (e != cudaSuccess) return 1;              // gcb_job_wait reports it
+        }
+    }
+    return 1;
+    GCB_CATCH
+}
+
+int gcb_garble(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+               const gcb_label* r, const gcb_label* in_l0, gcb_label* tables, gcb_wire* io_wires,
+               gcb_wire* wires_full, uint32_t flags) {
+    GCB_TRY
+    int rc = check_garble_args(plan, keys, keylen, key_stride, r, in_l0, tables);
+    if (rc || batch == 0) return rc;
+    const gcb_plan_info& in = plan->p.info;
+    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
+    const size_t per_inst = 16 + nin * 16 + rows * 16 + (io_wires ? (nin + nout) * 32 : 0) + (wires_full ? nw * 32 : 0) + key_stride;
+    const uint32_t round = round_instances(per_inst, batch);
+    for (uint32_t b0 = 0; b0 < batch; b0 += round) {
+        const uint32_t nb = batch - b0 < round ? batch - b0 : round;
+        gcb_job* job = nullptr;
+        rc = gcb_garble_begin(plan, key_stride ? keys + (size_t)b0 * key_stride : keys, keylen, key_stride, nb, r + b0,
+                              in_l0 ? in_l0 + (size_t)b0 * nin : nullptr, tables ? tables + (size_t)b0 * rows : nullptr,
+                              io_wires ? io_wires + (size_t)b0 * (nin + nout) : nullptr,
+                              wires_full ? wires_full + (size_t)b0 * nw : nullptr, flags, &job);
+        if (rc) return rc;
+        if ((rc = gcb_job_wait(job))) return rc;
+    }
+    return GCB_OK;
+    GCB_CATCH
+}
+
+int gcb_eval(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch,
+             const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels, gcb_label* wires_full,
+             uint32_t flags) {
+    GCB_TRY
+    int rc = check_eval_args(plan, keys, keylen, key_stride, tables, in_labels, out_labels);
+    if (rc || batch == 0) return rc;
+    const gcb_plan_info& in = plan->p.info;
+    const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
+    const size_t per_inst = nin * 16 + rows * 16 + nout * 16 + (wires_full ? nw * 16 : 0) + key_stride;
+    const uint32_t round = round_instances(per_inst, batch);
+    for (uint32_t b0 = 0; b0 < batch; b0 += round) {
+        const uint32_t nb = batch - b0 < round ? batch - b0 : round;
+        gcb_job* job = nullptr;
+        rc = gcb_eval_begin(plan, key_stride ? keys + (size_t)b0 * key_stride : keys, keylen, key_stride, nb,
+                            tables ? tables + (size_t)b0 * rows : nullptr, in_labels ? in_labels + (size_t)b0 * nin : nullptr,
+                            out_labels ? out_labels + (size_t)b0 * nout : nullptr,
+                            wires_full ? wires_full + (size_t)b0 * nw : nullptr, flags, &job);
+        if (rc) return rc;
+        if ((rc = gcb_job_wait(job))) return rc;
+    }
+    return GCB_OK;
+    GCB_CATCH
 }
 
 int gcb_select_labels_dev(const gcb_wire* wires, size_t wire_stride, const uint8_t* bits, gcb_label* out,
                           uint32_t batch, uint32_t n, void* stream) {
+    GCB_TRY
     if (!wires || !bits || !out) return fail(GCB_E_ARG, "null argument");
     if (!batch || !n) return GCB_OK;
     DeviceInfo* di;
@@ -748,9 +1238,11 @@ int gcb_select_labels_dev(const gcb_wire* wires, size_t wire_stride, const uint8
         reinterpret_cast<const uint4*>(wires), wire_stride, bits, reinterpret_cast<uint4*>(out), batch, n);
     CK(cudaGetLastError());
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_decode_bits_dev(const gcb_wire* wires, size_t wire_stride, const gcb_label* labels, uint8_t* bits,
                         uint32_t batch, uint32_t n, void* stream) {
+    GCB_TRY
     if (!wires || !bits || !labels) return fail(GCB_E_ARG, "null argument");
     if (!batch || !n) return GCB_OK;
     DeviceInfo* di;
@@ -760,12 +1252,14 @@ int gcb_decode_bits_dev(const gcb_wire* wires, size_t wire_stride, const gcb_lab
         reinterpret_cast<const uint4*>(wires), wire_stride, reinterpret_cast<const uint4*>(labels), bits, batch, n);
     CK(cudaGetLastError());
     return GCB_OK;
+    GCB_CATCH
 }
 
 // ------------------------------------------------------------- gate hashes ------
 // key: DEVICE pointer in the _dev variant.
 int gcb_hash_half_dev(const uint8_t* key, uint32_t keylen, const gcb_label* x, uint32_t tweak0, gcb_label* out,
                       uint64_t n, void* stream) {
+    GCB_TRY
     if (!key || (n && (!x || !out))) return fail(GCB_E_ARG, "null argument");
     int rc = check_keylen(keylen);
     if (rc) return rc;
@@ -782,27 +1276,31 @@ int gcb_hash_half_dev(const uint8_t* key, uint32_t keylen, const gcb_label* x, u
     else hash_half_kernel<14><<<grid, 1024, smem, s>>>(p);
     CK(cudaGetLastError());
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_hash_half(const uint8_t* key, uint32_t keylen, const gcb_label* x, uint32_t tweak0, gcb_label* out,
                   uint64_t n) {
+    GCB_TRY
     if (!key || (n && (!x || !out))) return fail(GCB_E_ARG, "null argument");
     int rc = check_keylen(keylen);
     if (rc) return rc;
     if (n == 0) return GCB_OK;
-    if ((rc = select_device(nullptr))) return rc;
-    DevBuf dk, dx, dout;
-    CK(dk.alloc(keylen)); CK(dx.alloc(n * 16)); CK(dout.alloc(n * 16));
-    CK(cudaMemcpy(dk.p, key, keylen, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dx.p, x, n * 16, cudaMemcpyHostToDevice));
-    if ((rc = gcb_hash_half_dev(dk.as<uint8_t>(), keylen, dx.as<gcb_label>(), tweak0, dout.as<gcb_label>(), n, nullptr)))
-        return rc;
-    CK(cudaMemcpy(out, dout.p, n * 16, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(n, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        HostOp k{key, nullptr, keylen}, xi{x + lo, nullptr, (size_t)(hi - lo) * 16}, o{nullptr, out + lo, (size_t)(hi - lo) * 16};
+        int rc = stage_begin(dev, {&k, &xi, &o}, part);
+        if (rc) return rc;
+        if ((rc = gcb_hash_half_dev((const uint8_t*)k.dptr, keylen, (const gcb_label*)xi.dptr, tweak0 + (uint32_t)lo, (gcb_label*)o.dptr,
+                                    hi - lo, part->res->k)))
+            return rc;
+        return stage_end({&o}, part);
+    });
+    GCB_CATCH
 }
 
 // --------------------------------------------------------------- streaming ------
 int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch, const gcb_label* r,
                       const uint32_t* input_ids, uint32_t ninputs, const gcb_label* in_l0, gcb_stream** out) {
+    GCB_TRY
     if (!out) return fail(GCB_E_ARG, "null stream output pointer");
     *out = nullptr;
     if (!keys || !r || (ninputs && (!input_ids || !in_l0)) || batch == 0) return fail(GCB_E_ARG, "null argument");
@@ -812,7 +1310,7 @@ int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
     auto s = std::make_unique<gcb_stream>();
-    s->device = tl_device; s->batch = batch; s->keylen = keylen; s->key_stride = key_stride;
+    s->device = tl_cur; s->batch = batch; s->keylen = keylen; s->key_stride = key_stride;
     CK(cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking));
     const size_t kb = key_stride ? (size_t)key_stride * batch : keylen;
     CK(s->keys.alloc(kb));
@@ -838,6 +1336,7 @@ int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
     CK(cudaStreamSynchronize(s->cs));
     *out = s.release();
     return GCB_OK;
+    GCB_CATCH
 }
 void gcb_stream_destroy(gcb_stream* s) {
     if (!s) return;
@@ -848,12 +1347,12 @@ void gcb_stream_destroy(gcb_stream* s) {
 }
 
 int gcb_stream_get_wires(gcb_stream* s, const uint32_t* ids, uint32_t n, gcb_wire* wires) {
+    GCB_TRY
     if (!s || (n && (!ids || !wires))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
     std::lock_guard<std::mutex> lk(s->mu);
-    tl_device = s->device;
     DeviceInfo* di;
-    int rc = select_device(&di);
+    int rc = use_device(s->device, &di);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++)
         if (((size_t)ids[i] >> WF_PAGE_SHIFT) >= s->pages.size())
@@ -868,10 +1367,12 @@ int gcb_stream_get_wires(gcb_stream* s, const uint32_t* ids, uint32_t n, gcb_wir
     CK(cudaMemcpyAsync(wires, s->wires.p, (size_t)s->batch * n * 32, cudaMemcpyDeviceToHost, s->cs));
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
+    GCB_CATCH
 }
 
 int gcb_stream_step_size(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
                          uint32_t nout, size_t* bytes) {
+    GCB_TRY
     if (!s || !plan || !bytes || (nin && !in) || (nout && !out)) return fail(GCB_E_ARG, "null argument");
     StreamLayout lay;
     std::string err;
@@ -879,6 +1380,7 @@ int gcb_stream_step_size(gcb_stream* s, const gcb_plan* plan, const uint32_t* in
     if (rc) return fail(rc, "%s", err.c_str());
     *bytes = lay.tmpl.size();
     return GCB_OK;
+    GCB_CATCH
 }
 
 // Streaming.Garble for one sub-circuit.  wait = false (gcb_stream_garble_begin): everything is queued -- the gate
@@ -891,9 +1393,8 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
     const auto t_start = clk::now();
     if (!s || !plan || (nin && !in) || (nout && !out)) return fail(GCB_E_ARG, "null argument");
     std::lock_guard<std::mutex> lk(s->mu);
-    tl_device = s->device;
     DeviceInfo* di;
-    int rc = select_device(&di);
+    int rc = use_device(s->device, &di);
     if (rc) return rc;
     const Plan& base = plan->p;
     const uint32_t nw = base.info.num_wires;
@@ -933,7 +1434,7 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
             alias = gt.out < nin || (first_out < nin);
         }
     }
-    std::unique_ptr<Plan> aliased;
+    std::shared_ptr<gcb_stream::AliasPlan> aliased;
     std::vector<uint32_t> in_eff(in, in + nin), out_eff(out, out + nout);
     const Plan* use = &base;
     if (alias) {
@@ -964,11 +1465,24 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
         in_eff = ids;
         out_eff.clear();
         for (uint32_t l = 0; l < np; l++) if (written_loc[l]) { spec.live_out.push_back(l); out_eff.push_back(ids[l]); }
-        aliased = std::make_unique<Plan>();
-        if ((rc = build_plan(spec, *aliased, err))) return fail(rc, "%s", err.c_str());
-        team_geometry(*aliased);
-        if (aliased->info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", aliased->info.num_slots);
-        use = aliased.get();
+        // The plan depends on the aliasing PATTERN (spec.loc numbers locations by first appearance), not on the ids:
+        // the steps of a program that reuse a sub-circuit with the same pattern share one compiled plan, which also
+        // stays alive in the cache while its kernel runs (no implicit device synchronisation on return).
+        for (const auto& c : s->alias_plans)
+            if (c->plan_uid == plan->uid && c->loc == spec.loc) { aliased = c; break; }
+        if (!aliased) {
+            auto ap = std::make_shared<gcb_stream::AliasPlan>();
+            ap->plan_uid = plan->uid;
+            ap->plan = std::make_unique<Plan>();
+            if ((rc = build_plan(spec, *ap->plan, err))) return fail(rc, "%s", err.c_str());
+            team_geometry(*ap->plan);
+            if (ap->plan->info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ap->plan->info.num_slots);
+            ap->loc = spec.loc;
+            if (s->alias_plans.size() >= 16) s->alias_plans.erase(s->alias_plans.begin());
+            s->alias_plans.push_back(ap);
+            aliased = ap;
+        }
+        use = aliased->plan.get();
     }
     const size_t n_rows = use->info.num_rows;
     const size_t nids = in_eff.size() + out_eff.size();
@@ -1041,18 +1555,22 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
 int gcb_stream_garble(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
                       uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written, uint64_t* ns_init,
                       uint64_t* ns_garble) {
+    GCB_TRY
     return stream_garble_impl(s, plan, in, nin, out, nout, dst, dst_stride, written, ns_init, ns_garble, true);
+    GCB_CATCH
 }
 int gcb_stream_garble_begin(gcb_stream* s, const gcb_plan* plan, const uint32_t* in, uint32_t nin, const uint32_t* out,
                             uint32_t nout, uint8_t* dst, size_t dst_stride, size_t* written) {
+    GCB_TRY
     return stream_garble_impl(s, plan, in, nin, out, nout, dst, dst_stride, written, nullptr, nullptr, false);
+    GCB_CATCH
 }
 int gcb_stream_garble_wait(gcb_stream* s, uint32_t leave_in_flight) {
+    GCB_TRY
     if (!s) return fail(GCB_E_ARG, "null argument");
     if (leave_in_flight > 1) return fail(GCB_E_ARG, "at most one step can stay in flight");
     std::lock_guard<std::mutex> lk(s->mu);
-    tl_device = s->device;
-    int rc = select_device(nullptr);
+    int rc = use_device(s->device, nullptr);
     if (rc) return rc;
     if (leave_in_flight == 1) {                       // everything but the step begun last
         const uint32_t prev = s->ser_turn & 1u;       // the set the step before the last one used
@@ -1062,6 +1580,7 @@ int gcb_stream_garble_wait(gcb_stream* s, uint32_t leave_in_flight) {
     if (s->ds) CK(cudaStreamSynchronize(s->ds));
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
+    GCB_CATCH
 }
 
 // ------------------------------------------------------- streaming evaluator ----
@@ -1072,6 +1591,7 @@ struct gcb_seval : gcb_stream {};
 extern "C" {
 
 int gcb_seval_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, uint32_t batch, gcb_seval** out) {
+    GCB_TRY
     if (!out) return fail(GCB_E_ARG, "null output pointer");
     *out = nullptr;
     if (!keys || batch == 0) return fail(GCB_E_ARG, "null argument");
@@ -1080,7 +1600,7 @@ int gcb_seval_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, 
     if (key_stride && key_stride < keylen) return fail(GCB_E_ARG, "key_stride smaller than keylen");
     if ((rc = select_device(nullptr))) return rc;
     auto s = std::make_unique<gcb_seval>();
-    s->device = tl_device; s->batch = batch; s->keylen = keylen; s->key_stride = key_stride;
+    s->device = tl_cur; s->batch = batch; s->keylen = keylen; s->key_stride = key_stride;
     CK(cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking));
     const size_t kb = key_stride ? (size_t)key_stride * batch : keylen;
     CK(s->keys.alloc(kb));
@@ -1088,6 +1608,7 @@ int gcb_seval_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride, 
     CK(cudaStreamSynchronize(s->cs));
     *out = s.release();
     return GCB_OK;
+    GCB_CATCH
 }
 void gcb_seval_destroy(gcb_seval* s) {
     if (!s) return;
@@ -1099,12 +1620,12 @@ void gcb_seval_destroy(gcb_seval* s) {
 
 // StreamEval.Set / SetInputs (stream_evaluator.go:68-96): labels [batch][n].
 int gcb_seval_set_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, const gcb_label* labels) {
+    GCB_TRY
     if (!s || (n && (!ids || !labels))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
     std::lock_guard<std::mutex> lk(s->mu);
-    tl_device = s->device;
     DeviceInfo* di;
-    int rc = select_device(&di);
+    int rc = use_device(s->device, &di);
     if (rc) return rc;
     uint32_t mx = 0;
     for (uint32_t i = 0; i < n; i++) mx = ids[i] > mx ? ids[i] : mx;
@@ -1118,15 +1639,16 @@ int gcb_seval_set_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, const gcb
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
+    GCB_CATCH
 }
 // StreamEval.Get (stream_evaluator.go:57-66): labels [batch][n].
 int gcb_seval_get_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, gcb_label* labels) {
+    GCB_TRY
     if (!s || (n && (!ids || !labels))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
     std::lock_guard<std::mutex> lk(s->mu);
-    tl_device = s->device;
     DeviceInfo* di;
-    int rc = select_device(&di);
+    int rc = use_device(s->device, &di);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; i++)
         if (((size_t)ids[i] >> WF_PAGE_SHIFT) >= s->pages.size()) return fail(GCB_E_WIRE, "wire %u not allocated", ids[i]);
@@ -1139,6 +1661,7 @@ int gcb_seval_get_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, gcb_label
     CK(cudaMemcpyAsync(labels, s->wires.p, (size_t)s->batch * n * 16, cudaMemcpyDeviceToHost, s->cs));
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
+    GCB_CATCH
 }
 
 // The gate loop of StreamEvaluator for one OpCircuit body (stream_evaluator.go:270-432).
@@ -1146,12 +1669,12 @@ int gcb_seval_get_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, gcb_label
 // instances carry the same gate headers: same circuit, same wire ids; only the rows differ).
 int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_t len, uint32_t ngates,
                       uint32_t ntmp, uint32_t nwires, size_t* consumed) {
+    GCB_TRY
     if (!s || (ngates && !src)) return fail(GCB_E_ARG, "null argument");
     if (src_stride < len && s->batch > 1) return fail(GCB_E_ARG, "src_stride smaller than len");
     std::lock_guard<std::mutex> lk(s->mu);
-    tl_device = s->device;
     DeviceInfo* di;
-    int rc = select_device(&di);
+    int rc = use_device(s->device, &di);
     if (rc) return rc;
     // the record bytes start moving to the device first: parsing the headers and recovering the plan
     // on the host overlap the copy (2 GB per step in the config-5 stand-in)
@@ -1202,6 +1725,8 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     };
     struct Ref { uint32_t loc; bool tmp; };
     std::vector<std::array<Ref, 3>> refs(sg.size());
+    std::vector<uint32_t> canon;
+    canon.reserve(sg.size() * 4);
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
     mix(ntmp);
@@ -1215,13 +1740,16 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
         refs[i][0] = Ref{g.a_tmp ? g.a : perm_loc(g.a, true), (bool)g.a_tmp};
         refs[i][1] = g.op == OP_INV ? refs[i][0] : Ref{g.b_tmp ? g.b : perm_loc(g.b, true), (bool)g.b_tmp};
         refs[i][2] = Ref{g.c_tmp ? g.c : perm_loc(g.c, false), (bool)g.c_tmp};
-        mix(g.op | (g.a_tmp << 8) | (g.b_tmp << 9) | (g.c_tmp << 10));
+        const uint32_t head = g.op | (g.a_tmp << 8) | (g.b_tmp << 9) | (g.c_tmp << 10);
+        mix(head);
         mix(refs[i][0].loc); mix(refs[i][1].loc); mix(refs[i][2].loc);
+        canon.push_back(head); canon.push_back(refs[i][0].loc); canon.push_back(refs[i][1].loc); canon.push_back(refs[i][2].loc);
     }
     const uint32_t np = (uint32_t)perm_ids.size();
     std::shared_ptr<gcb_stream::EvalPlan> ep;
     auto it = s->eval_plans.find(h);
-    if (it != s->eval_plans.end()) ep = it->second;
+    if (it != s->eval_plans.end() && it->second->ntmp == ntmp && it->second->np == np && it->second->canon == canon)
+        ep = it->second;
     else {
         std::vector<gcb_gate> gates(sg.size());
         for (size_t i = 0; i < sg.size(); i++) {
@@ -1238,8 +1766,10 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
         if ((rc = build_plan(spec, ep->plan, err))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
         team_geometry(ep->plan);
         if (ep->plan.info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ep->plan.info.num_slots);
-        if (s->eval_plans.size() > 64) s->eval_plans.clear();
-        s->eval_plans.emplace(h, ep);
+        ep->canon.swap(canon);
+        ep->ntmp = ntmp; ep->np = np;
+        if (s->eval_plans.size() > 32) s->eval_plans.clear();
+        s->eval_plans[h] = ep;                          // replaces a colliding entry
     }
     std::vector<uint32_t> in_ids(ep->in_ids.size()), out_ids(ep->out_ids.size());
     for (size_t k = 0; k < in_ids.size(); k++) in_ids[k] = perm_ids[ep->in_ids[k]];
@@ -1267,6 +1797,7 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
                    reinterpret_cast<uint4* const*>(s->page_table.p));
     if (rc) return rc;
     return GCB_OK;                          // sync_on_exit waits for the copy; the kernel completes on stream cs
+    GCB_CATCH
 }
 
 // ------------------------------------------------------------------- IKNP -------
@@ -1302,6 +1833,7 @@ static int launch_iknp(bool receiver, bool bits, const IknpParams& p0, void* str
 int gcb_iknp_receiver_expand_dev(const gcb_label* k0, const gcb_label* k1, uint64_t stream_pos,
                                  const uint8_t* choice, uint64_t n, uint8_t* u_out, gcb_label* labels,
                                  void* stream) {
+    GCB_TRY
     if (!k0 || !k1 || (n && (!choice || !u_out || !labels))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
     if (reinterpret_cast<uintptr_t>(u_out) & 15) return fail(GCB_E_ARG, "u_out must be 16-byte aligned");
@@ -1310,9 +1842,11 @@ int gcb_iknp_receiver_expand_dev(const gcb_label* k0, const gcb_label* k1, uint6
     p.stream_pos = stream_pos; p.choice = choice; p.u_out = u_out;
     p.labels = reinterpret_cast<uint4*>(labels); p.n = n;
     return launch_iknp(true, false, p, stream);
+    GCB_CATCH
 }
 int gcb_iknp_sender_expand_dev(const gcb_label* k, const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
                                size_t u_len, uint64_t n, gcb_label* labels, void* stream) {
+    GCB_TRY
     if (!k || !delta || (n && (!u || !labels))) return fail(GCB_E_ARG, "null argument");
     if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
                                                  (unsigned long long)n);
@@ -1322,45 +1856,49 @@ int gcb_iknp_sender_expand_dev(const gcb_label* k, const gcb_label* delta, uint6
     p.k0 = reinterpret_cast<const uint4*>(k); p.delta = reinterpret_cast<const uint4*>(delta);
     p.stream_pos = stream_pos; p.u_in = u; p.labels = reinterpret_cast<uint4*>(labels); p.n = n;
     return launch_iknp(false, false, p, stream);
+    GCB_CATCH
 }
 
+// Host-pointer variants: rows split by 512-row chunk ranges over the selected devices (the CTR
+// keystream is random access, so a range only needs its byte offset into the column streams).
+static uint64_t iknp_chunks(uint64_t n) { return (n + IKNP_CHUNK_ROWS - 1) / IKNP_CHUNK_ROWS; }
 int gcb_iknp_receiver_expand(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
                              const uint8_t* choice, uint64_t n, uint8_t* u_out, gcb_label* labels) {
+    GCB_TRY
     if (!k0 || !k1 || (n && (!choice || !u_out || !labels))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    const size_t ul = gcb_iknp_u_size(n);
-    DevBuf dk, dc, du, dl;
-    CK(dk.alloc(256 * 16)); CK(dc.alloc(n)); CK(du.alloc(ul)); CK(dl.alloc(n * 16));
-    CK(cudaMemcpy(dk.p, k0, 128 * 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dk.as<gcb_label>() + 128, k1, 128 * 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dc.p, choice, n, cudaMemcpyHostToDevice));
-    rc = gcb_iknp_receiver_expand_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, dc.as<uint8_t>(), n,
-                                      du.as<uint8_t>(), dl.as<gcb_label>(), nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpy(u_out, du.p, ul, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(labels, dl.p, n * 16, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(iknp_chunks(n), [&](int dev, uint64_t clo, uint64_t chi, JobPart* part) -> int {
+        const uint64_t lo = clo * IKNP_CHUNK_ROWS, hi = std::min<uint64_t>(n, chi * IKNP_CHUNK_ROWS), m = hi - lo;
+        HostOp a{k0, nullptr, 128 * 16}, b{k1, nullptr, 128 * 16}, c{choice + lo, nullptr, (size_t)m};
+        HostOp u{nullptr, u_out + clo * 64 * 128, gcb_iknp_u_size(m)}, l{nullptr, labels + lo, (size_t)m * 16};
+        int rc = stage_begin(dev, {&a, &b, &c, &u, &l}, part);
+        if (rc) return rc;
+        if ((rc = gcb_iknp_receiver_expand_dev((const gcb_label*)a.dptr, (const gcb_label*)b.dptr, stream_pos + clo * 64,
+                                               (const uint8_t*)c.dptr, m, (uint8_t*)u.dptr, (gcb_label*)l.dptr, part->res->k)))
+            return rc;
+        return stage_end({&u, &l}, part);
+    });
+    GCB_CATCH
 }
 int gcb_iknp_sender_expand(const gcb_label k[128], const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
                            size_t u_len, uint64_t n, gcb_label* labels) {
+    GCB_TRY
     if (!k || !delta || (n && (!u || !labels))) return fail(GCB_E_ARG, "null argument");
     if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
                                                  (unsigned long long)n);
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    DevBuf dk, du, dl;
-    CK(dk.alloc(129 * 16)); CK(du.alloc(u_len)); CK(dl.alloc(n * 16));
-    CK(cudaMemcpy(dk.p, k, 128 * 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dk.as<gcb_label>() + 128, delta, 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(du.p, u, u_len, cudaMemcpyHostToDevice));
-    rc = gcb_iknp_sender_expand_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, du.as<uint8_t>(), u_len,
-                                    n, dl.as<gcb_label>(), nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpy(labels, dl.p, n * 16, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(iknp_chunks(n), [&](int dev, uint64_t clo, uint64_t chi, JobPart* part) -> int {
+        const uint64_t lo = clo * IKNP_CHUNK_ROWS, hi = std::min<uint64_t>(n, chi * IKNP_CHUNK_ROWS), m = hi - lo;
+        HostOp a{k, nullptr, 128 * 16}, d{delta, nullptr, 16}, ui{u + clo * 64 * 128, nullptr, gcb_iknp_u_size(m)};
+        HostOp l{nullptr, labels + lo, (size_t)m * 16};
+        int rc = stage_begin(dev, {&a, &d, &ui, &l}, part);
+        if (rc) return rc;
+        if ((rc = gcb_iknp_sender_expand_dev((const gcb_label*)a.dptr, (const gcb_label*)d.dptr, stream_pos + clo * 64,
+                                             (const uint8_t*)ui.dptr, ui.bytes, m, (gcb_label*)l.dptr, part->res->k)))
+            return rc;
+        return stage_end({&l}, part);
+    });
+    GCB_CATCH
 }
 
 // Bit-COT variants: ReceiveBits / SendBits (ot/iknp.go:554-620, 259-310).  choices / result are
@@ -1368,6 +1906,7 @@ int gcb_iknp_sender_expand(const gcb_label k[128], const gcb_label* delta, uint6
 int gcb_iknp_receiver_expand_bits_dev(const gcb_label* k0, const gcb_label* k1, uint64_t stream_pos,
                                       const uint64_t* choices, uint64_t n, uint8_t* u_out, uint64_t* result,
                                       void* stream) {
+    GCB_TRY
     if (!k0 || !k1 || (n && (!choices || !u_out || !result))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
     if (reinterpret_cast<uintptr_t>(u_out) & 15) return fail(GCB_E_ARG, "u_out must be 16-byte aligned");
@@ -1377,9 +1916,11 @@ int gcb_iknp_receiver_expand_bits_dev(const gcb_label* k0, const gcb_label* k1, 
     p.stream_pos = stream_pos; p.choice_bits = reinterpret_cast<const uint32_t*>(choices); p.u_out = u_out;
     p.result_bits = reinterpret_cast<uint32_t*>(result); p.n = n;
     return launch_iknp(true, true, p, stream);
+    GCB_CATCH
 }
 int gcb_iknp_sender_expand_bits_dev(const gcb_label* k, const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
                                     size_t u_len, uint64_t n, uint64_t* result, void* stream) {
+    GCB_TRY
     if (!k || !delta || (n && (!u || !result))) return fail(GCB_E_ARG, "null argument");
     if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
                                                  (unsigned long long)n);
@@ -1390,53 +1931,57 @@ int gcb_iknp_sender_expand_bits_dev(const gcb_label* k, const gcb_label* delta, 
     p.k0 = reinterpret_cast<const uint4*>(k); p.delta = reinterpret_cast<const uint4*>(delta);
     p.stream_pos = stream_pos; p.u_in = u; p.result_bits = reinterpret_cast<uint32_t*>(result); p.n = n;
     return launch_iknp(false, true, p, stream);
+    GCB_CATCH
 }
 int gcb_iknp_receiver_expand_bits(const gcb_label k0[128], const gcb_label k1[128], uint64_t stream_pos,
                                   const uint64_t* choices, uint64_t n, uint8_t* u_out, uint64_t* result) {
+    GCB_TRY
     if (!k0 || !k1 || (n && (!choices || !u_out || !result))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    const size_t ul = gcb_iknp_u_size(n), words = (n + 63) / 64;
-    // the reference reads whole 64-bit choice words per full 8-byte row group: round the copy up to the chunk
-    const size_t cwords = ((n + 511) / 512) * 8;
-    DevBuf dk, dc, du, dr;
-    CK(dk.alloc(256 * 16)); CK(dc.alloc(cwords * 8)); CK(du.alloc(ul)); CK(dr.alloc(words * 8));
-    CK(cudaMemset(dc.p, 0, cwords * 8));
-    CK(cudaMemcpy(dk.p, k0, 128 * 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dk.as<gcb_label>() + 128, k1, 128 * 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dc.p, choices, words * 8, cudaMemcpyHostToDevice));
-    rc = gcb_iknp_receiver_expand_bits_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, dc.as<uint64_t>(), n,
-                                           du.as<uint8_t>(), dr.as<uint64_t>(), nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpy(u_out, du.p, ul, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(result, dr.p, words * 8, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    const uint64_t words = (n + 63) / 64;
+    return fan_out(iknp_chunks(n), [&](int dev, uint64_t clo, uint64_t chi, JobPart* part) -> int {
+        const uint64_t lo = clo * IKNP_CHUNK_ROWS, hi = std::min<uint64_t>(n, chi * IKNP_CHUNK_ROWS), m = hi - lo;
+        // the reference reads whole 64-bit choice words per full 8-byte row group: the range's words, zero-padded
+        // to the end of its last chunk
+        const uint64_t w0 = lo / 64, cwords = (chi - clo) * 8, have = std::min<uint64_t>(cwords, words - w0);
+        std::vector<uint64_t> cw(cwords, 0);
+        memcpy(cw.data(), choices + w0, have * 8);
+        HostOp a{k0, nullptr, 128 * 16}, b{k1, nullptr, 128 * 16}, c{cw.data(), nullptr, (size_t)cwords * 8};
+        HostOp u{nullptr, u_out + clo * 64 * 128, gcb_iknp_u_size(m)}, r{nullptr, result + w0, (size_t)((m + 63) / 64) * 8};
+        int rc = stage_begin(dev, {&a, &b, &c, &u, &r}, part);      // cw is pageable: copied into staging right here
+        if (rc) return rc;
+        if ((rc = gcb_iknp_receiver_expand_bits_dev((const gcb_label*)a.dptr, (const gcb_label*)b.dptr, stream_pos + clo * 64,
+                                                    (const uint64_t*)c.dptr, m, (uint8_t*)u.dptr, (uint64_t*)r.dptr, part->res->k)))
+            return rc;
+        return stage_end({&u, &r}, part);
+    });
+    GCB_CATCH
 }
 int gcb_iknp_sender_expand_bits(const gcb_label k[128], const gcb_label* delta, uint64_t stream_pos, const uint8_t* u,
                                 size_t u_len, uint64_t n, uint64_t* result) {
+    GCB_TRY
     if (!k || !delta || (n && (!u || !result))) return fail(GCB_E_ARG, "null argument");
     if (u_len != gcb_iknp_u_size(n)) return fail(GCB_E_CHUNK, "invalid chunk size: %zu bytes for %llu OTs", u_len,
                                                  (unsigned long long)n);
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    const size_t words = (n + 63) / 64;
-    DevBuf dk, du, dr;
-    CK(dk.alloc(129 * 16)); CK(du.alloc(u_len)); CK(dr.alloc(words * 8));
-    CK(cudaMemcpy(dk.p, k, 128 * 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dk.as<gcb_label>() + 128, delta, 16, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(du.p, u, u_len, cudaMemcpyHostToDevice));
-    rc = gcb_iknp_sender_expand_bits_dev(dk.as<gcb_label>(), dk.as<gcb_label>() + 128, stream_pos, du.as<uint8_t>(), u_len, n,
-                                         dr.as<uint64_t>(), nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpy(result, dr.p, words * 8, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(iknp_chunks(n), [&](int dev, uint64_t clo, uint64_t chi, JobPart* part) -> int {
+        const uint64_t lo = clo * IKNP_CHUNK_ROWS, hi = std::min<uint64_t>(n, chi * IKNP_CHUNK_ROWS), m = hi - lo;
+        HostOp a{k, nullptr, 128 * 16}, d{delta, nullptr, 16}, ui{u + clo * 64 * 128, nullptr, gcb_iknp_u_size(m)};
+        HostOp r{nullptr, result + lo / 64, (size_t)((m + 63) / 64) * 8};
+        int rc = stage_begin(dev, {&a, &d, &ui, &r}, part);
+        if (rc) return rc;
+        if ((rc = gcb_iknp_sender_expand_bits_dev((const gcb_label*)a.dptr, (const gcb_label*)d.dptr, stream_pos + clo * 64,
+                                                  (const uint8_t*)ui.dptr, ui.bytes, m, (uint64_t*)r.dptr, part->res->k)))
+            return rc;
+        return stage_end({&r}, part);
+    });
+    GCB_CATCH
 }
 
 // ----------------------------------------------------------------- MiTCCRH ------
 int gcb_mitccrh_hash_dev(const gcb_label* seed_host, uint64_t gid_start, gcb_label* blks, uint64_t nkeys, uint32_t h,
                          void* stream) {
+    GCB_TRY
     if (!seed_host || (nkeys && !blks)) return fail(GCB_E_ARG, "null argument");
     if (h == 0 || h > 64) return fail(GCB_E_ARG, "MITCCRH.Hash: invalid H %u", h);   // mitccrh.go:94-102 panics
     if (nkeys == 0) return GCB_OK;
@@ -1449,20 +1994,21 @@ int gcb_mitccrh_hash_dev(const gcb_label* seed_host, uint64_t gid_start, gcb_lab
     mitccrh_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
     CK(cudaGetLastError());
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_mitccrh_hash(const gcb_label* seed, uint64_t gid_start, gcb_label* blks, uint64_t nkeys, uint32_t h) {
+    GCB_TRY
     if (!seed || (nkeys && !blks)) return fail(GCB_E_ARG, "null argument");
     if (h == 0 || h > 64) return fail(GCB_E_ARG, "MITCCRH.Hash: invalid H %u", h);
     if (nkeys == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    DevBuf db;
-    const size_t bytes = (size_t)nkeys * h * 16;
-    CK(db.alloc(bytes));
-    CK(cudaMemcpy(db.p, blks, bytes, cudaMemcpyHostToDevice));
-    if ((rc = gcb_mitccrh_hash_dev(seed, gid_start, db.as<gcb_label>(), nkeys, h, nullptr))) return rc;
-    CK(cudaMemcpy(blks, db.p, bytes, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(nkeys, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        HostOp b{blks + lo * h, blks + lo * h, (size_t)(hi - lo) * h * 16};       // in place
+        int rc = stage_begin(dev, {&b}, part);
+        if (rc) return rc;
+        if ((rc = gcb_mitccrh_hash_dev(seed, gid_start + lo, (gcb_label*)b.dptr, hi - lo, h, part->res->k))) return rc;
+        return stage_end({&b}, part);
+    });
+    GCB_CATCH
 }
 
 }  // extern "C"
@@ -1470,7 +2016,8 @@ int gcb_mitccrh_hash(const gcb_label* seed, uint64_t gid_start, gcb_label* blks,
 // ------------------------------------------------- COT / ROT post-processing ------
 template <int MODE>
 static int launch_cot(const gcb_label* seed, const gcb_label* delta, const void* data, const void* wires,
-                      const uint8_t* choice, const void* msgs_in, void* out, uint64_t n, uint32_t flags, void* stream) {
+                      const uint8_t* choice, const void* msgs_in, void* out, uint64_t n, uint32_t flags, void* stream,
+                      uint64_t first = 0) {
     if (!seed || (n && (!data || !out))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
     DeviceInfo* di;
@@ -1485,17 +2032,8 @@ static int launch_cot(const gcb_label* seed, const gcb_label* delta, const void*
     p.msgs_in = reinterpret_cast<const uint4*>(msgs_in);
     p.out = reinterpret_cast<uint4*>(out);
     p.n = n;
+    p.first = first;
     p.wire_bytes = (flags & GCB_COT_WIRE_BYTES) ? 1u : 0u;
-    static std::once_flag once;
-    static cudaError_t opt = cudaSuccess;
-    std::call_once(once, [] {
-        opt = opt_in(cot_kernel<COT_SEND>);
-        if (opt == cudaSuccess) opt = opt_in(cot_kernel<COT_RECEIVE>);
-        if (opt == cudaSuccess) opt = opt_in(cot_kernel<ROT_SEND>);
-        if (opt == cudaSuccess) opt = opt_in(cot_kernel<ROT_RECEIVE>);
-        if (opt == cudaSuccess) opt = opt_in(iknp_check_kernel);
-    });
-    CK(opt);
     const uint64_t want = (n + 511) / 512;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
     cot_kernel<MODE><<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
@@ -1507,120 +2045,162 @@ extern "C" {
 
 int gcb_cot_send_dev(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, const gcb_wire* wires,
                      uint64_t n, gcb_label* msgs, uint32_t flags, void* stream) {
+    GCB_TRY
     if (!delta || (n && !wires)) return fail(GCB_E_ARG, "null argument");
     return launch_cot<COT_SEND>(seed, delta, q, wires, nullptr, nullptr, msgs, n, flags, stream);
+    GCB_CATCH
 }
 int gcb_cot_receive_dev(const gcb_label* seed, const uint8_t* choice, const gcb_label* msgs, const gcb_label* t,
                         uint64_t n, gcb_label* result, uint32_t flags, void* stream) {
+    GCB_TRY
     if (n && (!choice || !msgs)) return fail(GCB_E_ARG, "null argument");
     return launch_cot<COT_RECEIVE>(seed, nullptr, t, nullptr, choice, msgs, result, n, flags, stream);
+    GCB_CATCH
 }
 int gcb_rot_send_dev(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, uint64_t n, gcb_wire* wires,
                      void* stream) {
+    GCB_TRY
     if (!delta) return fail(GCB_E_ARG, "null argument");
     return launch_cot<ROT_SEND>(seed, delta, q, nullptr, nullptr, nullptr, wires, n, 0, stream);
+    GCB_CATCH
 }
 int gcb_rot_receive_dev(const gcb_label* seed, const gcb_label* t, uint64_t n, gcb_label* result, void* stream) {
+    GCB_TRY
     return launch_cot<ROT_RECEIVE>(seed, nullptr, t, nullptr, nullptr, nullptr, result, n, 0, stream);
+    GCB_CATCH
 }
 
-// Host-pointer variants: one staging buffer per operand (these calls sit between network
-// round trips of the OT protocol; the bulk path keeps the labels on the device with _dev).
-struct Staged {
-    DevBuf b;
-    int up(const void* src, size_t bytes) {
-        CK(b.alloc(bytes));
-        if (src && bytes) CK(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
-        return GCB_OK;
-    }
-};
+// Host-pointer variants: OT ranges split over the selected devices (each OT is independent: MiTCCRH key number =
+// OT number); the bulk path keeps the labels on the device with _dev.
 int gcb_cot_send(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, const gcb_wire* wires, uint64_t n,
                  gcb_label* msgs, uint32_t flags) {
+    GCB_TRY
     if (!seed || !delta || (n && (!q || !wires || !msgs))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    Staged dq, dw, dm;
-    if ((rc = dq.up(q, n * 16)) || (rc = dw.up(wires, n * 32)) || (rc = dm.up(nullptr, n * 32))) return rc;
-    if ((rc = gcb_cot_send_dev(seed, delta, dq.b.as<gcb_label>(), dw.b.as<gcb_wire>(), n, dm.b.as<gcb_label>(), flags, nullptr))) return rc;
-    CK(cudaMemcpy(msgs, dm.b.p, n * 32, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(n, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dq{q + lo, nullptr, m * 16}, dw{wires + lo, nullptr, m * 32}, dm{nullptr, msgs + 2 * lo, m * 32};
+        int rc = stage_begin(dev, {&dq, &dw, &dm}, part);
+        if (rc) return rc;
+        if ((rc = launch_cot<COT_SEND>(seed, delta, dq.dptr, dw.dptr, nullptr, nullptr, dm.dptr, m, flags, part->res->k, lo))) return rc;
+        return stage_end({&dm}, part);
+    });
+    GCB_CATCH
 }
 int gcb_cot_receive(const gcb_label* seed, const uint8_t* choice, const gcb_label* msgs, const gcb_label* t, uint64_t n,
                     gcb_label* result, uint32_t flags) {
+    GCB_TRY
     if (!seed || (n && (!choice || !msgs || !t || !result))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    Staged dc, dm, dt;
-    if ((rc = dc.up(choice, n)) || (rc = dm.up(msgs, n * 32)) || (rc = dt.up(t, n * 16))) return rc;
-    if ((rc = gcb_cot_receive_dev(seed, dc.b.as<uint8_t>(), dm.b.as<gcb_label>(), dt.b.as<gcb_label>(), n, dt.b.as<gcb_label>(), flags, nullptr))) return rc;
-    CK(cudaMemcpy(result, dt.b.p, n * 16, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(n, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dc{choice + lo, nullptr, m}, dm{msgs + 2 * lo, nullptr, m * 32}, dt{t + lo, result + lo, m * 16};
+        int rc = stage_begin(dev, {&dc, &dm, &dt}, part);
+        if (rc) return rc;
+        if ((rc = launch_cot<COT_RECEIVE>(seed, nullptr, dt.dptr, nullptr, (const uint8_t*)dc.dptr, dm.dptr, dt.dptr, m, flags, part->res->k, lo)))
+            return rc;
+        return stage_end({&dt}, part);
+    });
+    GCB_CATCH
 }
 int gcb_rot_send(const gcb_label* seed, const gcb_label* delta, const gcb_label* q, uint64_t n, gcb_wire* wires) {
+    GCB_TRY
     if (!seed || !delta || (n && (!q || !wires))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    Staged dq, dw;
-    if ((rc = dq.up(q, n * 16)) || (rc = dw.up(nullptr, n * 32))) return rc;
-    if ((rc = gcb_rot_send_dev(seed, delta, dq.b.as<gcb_label>(), n, dw.b.as<gcb_wire>(), nullptr))) return rc;
-    CK(cudaMemcpy(wires, dw.b.p, n * 32, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(n, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dq{q + lo, nullptr, m * 16}, dw{nullptr, wires + lo, m * 32};
+        int rc = stage_begin(dev, {&dq, &dw}, part);
+        if (rc) return rc;
+        if ((rc = launch_cot<ROT_SEND>(seed, delta, dq.dptr, nullptr, nullptr, nullptr, dw.dptr, m, 0, part->res->k, lo))) return rc;
+        return stage_end({&dw}, part);
+    });
+    GCB_CATCH
 }
 int gcb_rot_receive(const gcb_label* seed, const gcb_label* t, uint64_t n, gcb_label* result) {
+    GCB_TRY
     if (!seed || (n && (!t || !result))) return fail(GCB_E_ARG, "null argument");
     if (n == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    Staged dt;
-    if ((rc = dt.up(t, n * 16))) return rc;
-    if ((rc = gcb_rot_receive_dev(seed, dt.b.as<gcb_label>(), n, dt.b.as<gcb_label>(), nullptr))) return rc;
-    CK(cudaMemcpy(result, dt.b.p, n * 16, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    return fan_out(n, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dt{t + lo, result + lo, m * 16};
+        int rc = stage_begin(dev, {&dt}, part);
+        if (rc) return rc;
+        if ((rc = launch_cot<ROT_RECEIVE>(seed, nullptr, dt.dptr, nullptr, nullptr, nullptr, dt.dptr, m, 0, part->res->k, lo))) return rc;
+        return stage_end({&dt}, part);
+    });
+    GCB_CATCH
 }
 
 // ------------------------------------------- IKNP malicious-mode consistency sums --
-int gcb_iknp_check_sums_dev(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
-                            uint64_t n, gcb_label out[3], void* stream) {
-    if (!seed2 || !out || (n && !labels)) return fail(GCB_E_ARG, "null argument");
-    memset(out, 0, 3 * sizeof(gcb_label));
-    if (n == 0) return GCB_OK;
+// acc: 12 zeroed device words, XOR-accumulated
+static int check_sums_enqueue(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
+                              uint64_t n, uint32_t* acc, cudaStream_t stream) {
     DeviceInfo* di;
     int rc = select_device(&di);
     if (rc) return rc;
-    static std::once_flag once;
-    static cudaError_t opt = cudaSuccess;
-    std::call_once(once, [] { opt = opt_in(iknp_check_kernel); });
-    CK(opt);
-    DevBuf acc;
-    CK(acc.alloc(12 * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(acc.p, 0, 12 * sizeof(uint32_t), (cudaStream_t)stream));
-    CheckParams p{seed2->d0, seed2->d1, chi_start, reinterpret_cast<const uint4*>(labels), choice, n, acc.as<uint32_t>()};
+    CheckParams p{seed2->d0, seed2->d1, chi_start, reinterpret_cast<const uint4*>(labels), choice, n, acc};
     const uint64_t want = (n + 511) / 512;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
-    iknp_check_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES + 512, (cudaStream_t)stream>>>(p);
+    iknp_check_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES + 512, stream>>>(p);
     CK(cudaGetLastError());
-    uint32_t w[12];
-    CK(cudaMemcpyAsync(w, acc.p, sizeof w, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int k = 0; k < 3; k++) {
-        out[k].d0 = (uint64_t)w[4 * k] | ((uint64_t)w[4 * k + 1] << 32);
-        out[k].d1 = (uint64_t)w[4 * k + 2] | ((uint64_t)w[4 * k + 3] << 32);
-    }
     return GCB_OK;
 }
-int gcb_iknp_check_sums(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
-                        uint64_t n, gcb_label out[3]) {
+static void sums_from_words(const uint32_t* w, gcb_label out[3]) {
+    for (int k = 0; k < 3; k++) {
+        out[k].d0 ^= (uint64_t)w[4 * k] | ((uint64_t)w[4 * k + 1] << 32);
+        out[k].d1 ^= (uint64_t)w[4 * k + 2] | ((uint64_t)w[4 * k + 3] << 32);
+    }
+}
+int gcb_iknp_check_sums_dev(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
+                            uint64_t n, gcb_label out[3], void* stream) {
+    GCB_TRY
     if (!seed2 || !out || (n && !labels)) return fail(GCB_E_ARG, "null argument");
-    if (n == 0) { memset(out, 0, 3 * sizeof(gcb_label)); return GCB_OK; }
+    memset(out, 0, 3 * sizeof(gcb_label));
+    if (n == 0) return GCB_OK;
     int rc = select_device(nullptr);
     if (rc) return rc;
-    Staged dl, dc;
-    if ((rc = dl.up(labels, n * 16))) return rc;
-    if (choice && (rc = dc.up(choice, n))) return rc;
-    return gcb_iknp_check_sums_dev(seed2, chi_start, dl.b.as<gcb_label>(), choice ? dc.b.as<uint8_t>() : nullptr, n, out, nullptr);
+    uint32_t* acc = nullptr;
+    CK(cudaMallocAsync(reinterpret_cast<void**>(&acc), 12 * sizeof(uint32_t), (cudaStream_t)stream));
+    CK(cudaMemsetAsync(acc, 0, 12 * sizeof(uint32_t), (cudaStream_t)stream));
+    rc = check_sums_enqueue(seed2, chi_start, labels, choice, n, acc, (cudaStream_t)stream);
+    uint32_t w[12] = {0};
+    if (!rc) CK(cudaMemcpyAsync(w, acc, sizeof w, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaFreeAsync(acc, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (rc) return rc;
+    sums_from_words(w, out);
+    return GCB_OK;
+    GCB_CATCH
+}
+// Host-pointer variant: OT ranges over the selected devices; the partial sums are XORed on the host (SURVEY.md 8e:
+// "gather 32 B per rank and fold on host" -- NCCL has no XOR reduction).
+int gcb_iknp_check_sums(const gcb_label* seed2, uint64_t chi_start, const gcb_label* labels, const uint8_t* choice,
+                        uint64_t n, gcb_label out[3]) {
+    GCB_TRY
+    if (!seed2 || !out || (n && !labels)) return fail(GCB_E_ARG, "null argument");
+    memset(out, 0, 3 * sizeof(gcb_label));
+    if (n == 0) return GCB_OK;
+    const size_t nd = call_devices().size();
+    std::vector<std::array<uint32_t, 12>> partial(nd ? nd : 1);
+    for (auto& w : partial) w.fill(0);
+    uint32_t next = 0;
+    int rc = fan_out(n, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dl{labels + lo, nullptr, m * 16}, dc{choice ? choice + lo : nullptr, nullptr, choice ? m : 0};
+        HostOp acc{nullptr, partial[next++].data(), 12 * sizeof(uint32_t)};
+        int rc = stage_begin(dev, {&dl, &dc, &acc}, part);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(acc.dptr, 0, 12 * sizeof(uint32_t), part->res->k));
+        if ((rc = check_sums_enqueue(seed2, chi_start + lo, (const gcb_label*)dl.dptr, choice ? (const uint8_t*)dc.dptr : nullptr, m,
+                                     (uint32_t*)acc.dptr, part->res->k)))
+            return rc;
+        return stage_end({&acc}, part);
+    });
+    if (rc) return rc;
+    for (const auto& w : partial) sums_from_words(w.data(), out);
+    return GCB_OK;
+    GCB_CATCH
 }
 
 }  // extern "C"
@@ -1662,12 +2242,15 @@ static int wire_layout_on_device(const gcb_plan* plan, int device, std::shared_p
 extern "C" {
 
 int gcb_tables_wire_size(const gcb_plan* plan, size_t* bytes) {
+    GCB_TRY
     if (!plan || !bytes) return fail(GCB_E_ARG, "null argument");
     *bytes = tables_wire_bytes(plan);
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_tables_to_wire_dev(const gcb_plan* plan, uint32_t batch, const gcb_label* tables, uint8_t* dst, size_t stride,
                            void* stream) {
+    GCB_TRY
     if (!plan || (batch && (!dst || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
     const size_t total = tables_wire_bytes(plan);
     if ((stride & 15) || stride < ((total + 15) & ~(size_t)15)) return fail(GCB_E_BUFFER, "wire stride must be a multiple of 16 and at least %zu", (total + 15) & ~(size_t)15);
@@ -1675,15 +2258,17 @@ int gcb_tables_to_wire_dev(const gcb_plan* plan, uint32_t batch, const gcb_label
     int rc = select_device(nullptr);
     if (rc) return rc;
     std::shared_ptr<DevWireLayout> dl;
-    if ((rc = wire_layout_on_device(plan, tl_device, &dl))) return rc;
+    if ((rc = wire_layout_on_device(plan, tl_cur, &dl))) return rc;
     SerParams sp{dl->tmpl, (uint32_t)total, dl->row_pos, plan->p.info.num_rows, reinterpret_cast<const uint4*>(tables), dst, stride};
     const dim3 grid((unsigned)((total + SER_TILE - 1) / SER_TILE), batch);
     serialize_kernel<<<grid, SER_THREADS, 0, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError());
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_tables_from_wire_dev(const gcb_plan* plan, uint32_t batch, const uint8_t* src, size_t stride, gcb_label* tables,
                              void* stream) {
+    GCB_TRY
     if (!plan || (batch && (!src || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
     const size_t total = tables_wire_bytes(plan);
     if ((stride & 15) || stride < ((total + 15) & ~(size_t)15) + 16) return fail(GCB_E_BUFFER, "wire stride must be a multiple of 16 and at least %zu", ((total + 15) & ~(size_t)15) + 16);
@@ -1692,31 +2277,36 @@ int gcb_tables_from_wire_dev(const gcb_plan* plan, uint32_t batch, const uint8_t
     int rc = select_device(&di);
     if (rc) return rc;
     std::shared_ptr<DevWireLayout> dl;
-    if ((rc = wire_layout_on_device(plan, tl_device, &dl))) return rc;
+    if ((rc = wire_layout_on_device(plan, tl_cur, &dl))) return rc;
     DeserParams dp{src, stride, dl->row_pos, plan->p.info.num_rows, reinterpret_cast<uint4*>(tables), batch};
     const size_t work = (size_t)batch * plan->p.info.num_rows;
     const unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, (size_t)di->sm_count * 8);
     deserialize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dp);
     CK(cudaGetLastError());
     return GCB_OK;
+    GCB_CATCH
 }
 int gcb_tables_to_wire(const gcb_plan* plan, uint32_t batch, const gcb_label* tables, uint8_t* dst, size_t stride) {
+    GCB_TRY
     if (!plan || (batch && (!dst || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
     const size_t total = tables_wire_bytes(plan);
     if (stride < total) return fail(GCB_E_BUFFER, "wire buffer too small: need %zu bytes per instance", total);
     if (batch == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    const size_t rows_bytes = (size_t)batch * plan->p.info.num_rows * 16, s16 = (total + 15) & ~(size_t)15;
-    DevBuf dt, dw;
-    CK(dt.alloc(rows_bytes));
-    CK(dw.alloc((size_t)batch * s16));
-    if (rows_bytes) CK(cudaMemcpy(dt.p, tables, rows_bytes, cudaMemcpyHostToDevice));
-    if ((rc = gcb_tables_to_wire_dev(plan, batch, dt.as<gcb_label>(), dw.as<uint8_t>(), s16, nullptr))) return rc;
-    CK(cudaMemcpy2D(dst, stride, dw.p, s16, total, batch, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    const size_t rows = plan->p.info.num_rows, s16 = (total + 15) & ~(size_t)15;
+    return fan_out(batch, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dt{rows ? tables + lo * rows : nullptr, nullptr, m * rows * 16}, dw{nullptr, nullptr, m * s16};
+        int rc = stage_begin(dev, {&dt, &dw}, part);
+        if (rc) return rc;
+        if ((rc = gcb_tables_to_wire_dev(plan, (uint32_t)m, (const gcb_label*)dt.dptr, (uint8_t*)dw.dptr, s16, part->res->k))) return rc;
+        // rows of `total` bytes at the caller's stride (pageable or pinned: the 2-D copy handles both)
+        CK(cudaMemcpy2DAsync(dst + lo * stride, stride, dw.dptr, s16, total, m, cudaMemcpyDeviceToHost, part->res->k));
+        return GCB_OK;
+    });
+    GCB_CATCH
 }
 int gcb_tables_from_wire(const gcb_plan* plan, uint32_t batch, const uint8_t* src, size_t stride, gcb_label* tables) {
+    GCB_TRY
     if (!plan || (batch && (!src || (!tables && plan->p.info.num_rows)))) return fail(GCB_E_ARG, "null argument");
     const size_t total = tables_wire_bytes(plan);
     if (stride < total) return fail(GCB_E_BUFFER, "wire buffer too small: need %zu bytes per instance", total);
@@ -1736,16 +2326,17 @@ int gcb_tables_from_wire(const gcb_plan* plan, uint32_t batch, const uint8_t* sr
         }
     }
     if (batch == 0 || pl.info.num_rows == 0) return GCB_OK;
-    int rc = select_device(nullptr);
-    if (rc) return rc;
-    const size_t rows_bytes = (size_t)batch * pl.info.num_rows * 16, s16 = ((total + 15) & ~(size_t)15) + 16;
-    DevBuf dt, dw;
-    CK(dt.alloc(rows_bytes));
-    CK(dw.alloc((size_t)batch * s16));
-    CK(cudaMemcpy2D(dw.p, s16, src, stride, total, batch, cudaMemcpyHostToDevice));
-    if ((rc = gcb_tables_from_wire_dev(plan, batch, dw.as<uint8_t>(), s16, dt.as<gcb_label>(), nullptr))) return rc;
-    CK(cudaMemcpy(tables, dt.p, rows_bytes, cudaMemcpyDeviceToHost));
-    return GCB_OK;
+    const size_t rows = pl.info.num_rows, s16 = ((total + 15) & ~(size_t)15) + 16;
+    return fan_out(batch, [&](int dev, uint64_t lo, uint64_t hi, JobPart* part) -> int {
+        const size_t m = (size_t)(hi - lo);
+        HostOp dw{nullptr, nullptr, m * s16}, dt{nullptr, tables + lo * rows, m * rows * 16};
+        int rc = stage_begin(dev, {&dw, &dt}, part);
+        if (rc) return rc;
+        CK(cudaMemcpy2DAsync(dw.dptr, s16, src + lo * stride, stride, total, m, cudaMemcpyHostToDevice, part->res->k));
+        if ((rc = gcb_tables_from_wire_dev(plan, (uint32_t)m, (const uint8_t*)dw.dptr, s16, (gcb_label*)dt.dptr, part->res->k))) return rc;
+        return stage_end({&dt}, part);
+    });
+    GCB_CATCH
 }
 
 }  // extern "C"

@@ -320,6 +320,7 @@ struct CotParams {
     const uint4* msgs_in;     // COT_RECEIVE: the 2n labels taken off the wire
     uint4* out;               // COT_SEND: 2n messages; COT_RECEIVE / ROT_RECEIVE: n labels; ROT_SEND: n wires {L0, L1}
     uint64_t n;
+    uint64_t first;           // number of the first OT of this launch (a row-range shard): OT i uses MiTCCRH key first + i
     uint32_t wire_bytes;      // 1: messages are in the SendLabel byte encoding (BE64(D0) || BE64(D1), ot/label.go:105-108)
 };
 // Label <-> the 16 bytes SendLabel / ReceiveLabel move (ot/io.go, ot/label.go:105-114)
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) cot_kernel(const CotParams p) {
     const Label delta = Label{(uint32_t)(p.delta_d0 >> 32), (uint32_t)p.delta_d0, (uint32_t)(p.delta_d1 >> 32), (uint32_t)p.delta_d1};
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
-        const uint64_t d0 = p.seed_d0 ^ i;                 // key i = BE(seed ^ {D0: i}), mitccrh.go:72-86
+        const uint64_t d0 = p.seed_d0 ^ (p.first + i);     // key j = BE(seed ^ {D0: j}), mitccrh.go:72-86
         uint32_t rk[44];
         aes128_expand_regs(lane, (uint32_t)(d0 >> 32), (uint32_t)d0, (uint32_t)(p.seed_d1 >> 32), (uint32_t)p.seed_d1, rk);
         const Label x = label_from_mem(__ldg(p.data + i));

@@ -542,10 +542,18 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             rcs[policy] = schedule(policy == 0 ? asap : alap_levels(policy == 2), cand[policy], false, errs[policy]);
         };
         {
-            std::vector<std::thread> workers;
-            for (int policy = 1; policy < n_policies; policy++) workers.emplace_back(trial, policy);
-            trial(0);
-            for (std::thread& t : workers) t.join();
+            // joined on every path out of this scope (an exception in trial(0) or in thread creation must not
+            // leave joinable threads behind: that would terminate the process)
+            struct Joiner {
+                std::vector<std::thread> v;
+                ~Joiner() { for (std::thread& t : v) if (t.joinable()) t.join(); }
+            } workers;
+            auto guarded = [&](int policy) {
+                try { trial(policy); }
+                catch (const std::exception& e) { rcs[policy] = GCB_E_TOO_LARGE; errs[policy] = e.what(); }
+            };
+            for (int policy = 1; policy < n_policies; policy++) workers.v.emplace_back(guarded, policy);
+            guarded(0);
         }
         for (int policy = 0; policy < n_policies; policy++) {
             if (rcs[policy] != GCB_OK) { if (best_policy < 0 && first_err.empty()) { first_err = errs[policy]; best_rc = rcs[policy]; } continue; }
@@ -575,6 +583,9 @@ namespace gcb {
 int parse_stream(const uint8_t* buf, size_t len, uint32_t ngates, std::vector<StreamGate>& gates,
                  std::vector<uint32_t>& row_pos, size_t* consumed, std::string& err) {
     gates.clear(); row_pos.clear();
+    // the count comes from the peer: a record is at least 5 bytes (INV with 16-bit ids), so a count the
+    // buffer cannot hold is rejected before anything is sized by it
+    if ((uint64_t)ngates * 5 > (uint64_t)len) { err = "record stream truncated"; return GCB_E_BUFFER; }
     gates.reserve(ngates);
     size_t pos = 0;
     auto need = [&](size_t n) { return pos + n <= len; };

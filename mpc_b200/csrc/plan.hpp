@@ -9,10 +9,20 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/gcb200.h"
+
+namespace gcb { int fail(int code, const char* fmt, ...); }
+// Exceptions must not cross the C boundary (a cgo caller would terminate).
+#define GCB_TRY try {
+#define GCB_CATCH                                                                                             \
+    } catch (const std::bad_alloc&) { return gcb::fail(GCB_E_TOO_LARGE, "out of host memory"); }              \
+    catch (const std::exception& ex_) { return gcb::fail(GCB_E_ARG, "internal error: %s", ex_.what()); }      \
+    catch (...) { return gcb::fail(GCB_E_ARG, "internal error"); }
 
 namespace gcb {
 
@@ -146,6 +156,7 @@ struct DevWireLayout {
 }  // namespace gcb
 
 struct gcb_plan {
+    uint64_t uid = 0;                         // unique per created plan (caches must not trust a recycled address)
     gcb::Plan p;                              // flattened free wires (the fast plan)
     mutable std::mutex wire_mu;
     mutable std::map<int, std::shared_ptr<gcb::DevWireLayout>> wire_dev;   // per device

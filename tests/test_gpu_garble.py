@@ -91,7 +91,7 @@ def test_eval_error_paths_match_reference():
     gates = list(g.Gates)
     inv_i = int(np.nonzero(circ.gates["op"] == 4)[0][0])
     gates[inv_i] = None
-    with pytest.raises(_lib.GcbError, match="index 0 >= row len 0"):
+    with pytest.raises(_lib.GcbError, match="index 0 >= row 0"):
         eng.eval(key, wires, gates)
     with pytest.raises(_lib.GcbError, match="invalid key size"):
         eng.eval(b"x" * 17, wires, g)
