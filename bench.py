@@ -2,21 +2,30 @@
 """Headline benchmark: million AND-gates/s garbled + evaluated on the AES-128
 Bristol circuit, batch 4096 per GPU (BASELINE.json configs[1]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gcb|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gcb|reference] [--no-extra]
 
 One step = garble the whole batch, select the evaluator's input labels,
 evaluate the whole batch, decode the outputs.  `value` is measured with every
-input resident in HBM; `e2e` goes through the host-pointer C ABI (gcb_garble /
-gcb_eval on pinned host buffers, copies inside the timed region).  The
-reference arm times the CPU oracle (the C restatement of the reference's Go
-loops, AES-NI) on all host cores.  Prints ONE JSON line on rank 0.
+input resident in HBM; `e2e` goes through the host-pointer C ABI
+(gcb_garble_begin / gcb_eval_begin / gcb_job_wait on page-locked host buffers,
+one host thread, copies inside the timed region).  The reference arm times the
+CPU oracle (the C restatement of the reference's Go loops, AES-NI) on all host
+cores.  Prints ONE JSON line on rank 0.
+
+`extra` in the same line carries the other BASELINE.json configurations, each
+timed at this N with its own algorithmic bytes and HBM fraction: aes_128 with
+per-instance 32-byte keys (the production key shape), sha256.circ x 1184,
+IKNP 2^24 (sender + receiver), one streaming sha256 step, the >= 10^8-gate
+streaming program (config 5 stand-in), a copy-only PCIe probe (the floor of the
+e2e figure on this box with N ranks copying at once) and, at N = 1, the latency
+of the unchanged batch = 1 call next to one CPU thread.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -26,11 +35,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "million AND-gates/sec garble+eval (AES-128 circuit)"
 UNIT = "M AND-gates/s"
 E2E_PARTS = 16
-E2E_WORKERS = 2
 KEY = b"0123456789abcdef"            # circuit/garble_bench_test.go:34
 CIRCUIT_DIR = os.path.join(ROOT, "tests", "golden", "circuits")
 # --circuit: the headline workload (aes_128, BASELINE.json configs[1]) or the second circuit BASELINE's
@@ -41,6 +50,17 @@ WORKLOADS = {"aes_128": ("AES-128 circuit", 4096), "sha256": ("SHA-256 circuit",
 def load_circuit(name: str = "aes_128"):
     from mpc_b200.circuit_io import Circuit
     return Circuit.load_npz(os.path.join(CIRCUIT_DIR, name + ".npz"), name)
+
+
+def workload_name(circ, batch: int) -> str:
+    return (f"{circ.name}.circ ({circ.count(2)} AND, {circ.count(4)} INV, {circ.count(0) + circ.count(1)} XOR) "
+            f"garble+eval, batch {batch} per GPU")
+
+
+def config_of(circ, batch: int) -> dict:
+    """The `config` object: identical keys and values in both arms."""
+    return {"workload": workload_name(circ, batch), "batch_per_gpu": batch, "key": "shared 16-byte (AES-128)",
+            "l2": f"tables are {batch * circ.num_rows * 16 // 1000000} MB per step, larger than L2; no flush needed"}
 
 
 def synthetic_inputs(circ, batch: int, rank: int):
@@ -73,6 +93,22 @@ def algorithmic_bytes(circ):
     garble = 16 * (1 + nin) + 16 * rows + 32 * (nin + nout)
     evalb = 16 * rows + 16 * nin + 16 * nout
     return garble, evalb
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(circuit: str, kernel: str):
+    """DRAM bytes per launch of this circuit's kernel from the committed ncu capture, or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[circuit][kernel]["dram_bytes"]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -159,14 +195,11 @@ def run_reference(args):
     total = sum(times)
     value = n_and * sample * args.steps / total / 1e6
     line = {
-        "impl": "reference", "metric": METRIC.replace("AES-128 circuit", WORKLOADS[args.circuit][0]), "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "impl": "reference", "metric": METRIC.replace("AES-128 circuit", WORKLOADS[args.circuit][0]), "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u8 (AES-NI)",
         "data": "synthetic",
-        "config": {"workload": f"{circ.name}.circ ({n_and} AND, {circ.count(4)} INV, {circ.count(0) + circ.count(1)} XOR) "
-                               f"garble+eval, batch {batch} per GPU",
-                   "batch_per_gpu": batch, "key": "shared 16-byte (AES-128)",
-                   "sample_per_step": sample},
+        "config": config_of(circ, batch),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} instances per step x {args.steps} steps, C oracle (AES-NI), "
                                    f"{threads} pthreads"},
@@ -178,9 +211,8 @@ def run_reference(args):
 
 def bind_to_gpu_numa_node(index: int):
     """One process per GPU: run this rank's host threads, and so first-touch its pinned staging buffers, on
-    the NUMA node the GPU hangs off (sysfs numa_node / local_cpulist of the PCI function).  Without it the
-    host-pointer path of an 8-rank run crosses the socket interconnect for half of its DMA traffic.
-    Returns a short description for the JSON line; silently does nothing where sysfs has no answer."""
+    the NUMA node the GPU hangs off (sysfs numa_node / local_cpulist of the PCI function).  Returns a short
+    description for the JSON line; does nothing where sysfs has no answer (single-node VMs)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -203,13 +235,357 @@ def bind_to_gpu_numa_node(index: int):
         return None
 
 
+def host_topology():
+    """What the box offers the host-pointer path: NUMA nodes and cores."""
+    nodes = []
+    try:
+        for d in sorted(os.listdir("/sys/devices/system/node")):
+            if d.startswith("node") and d[4:].isdigit():
+                nodes.append(int(d[4:]))
+    except Exception:
+        pass
+    return {"numa_nodes": len(nodes) or None, "cpus": os.cpu_count()}
+
+
+# ------------------------------------------------------------------------------------------------
+class Bench:
+    """Per-rank state shared by the headline loop and the extras."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from mpc_b200 import _lib
+        self._lib, self.L = _lib, _lib.lib()
+        _lib.check(self.L.gcb_set_device(self.local))
+        self.stream = torch.cuda.current_stream()
+        self.s = self.stream.cuda_stream
+        self.peak, self.peak_source = measured_peak()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor([float(v) for v in values], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def to_dev(self, a):
+        return self.torch.from_numpy(a.view(np.uint8).reshape(a.shape + (-1,)) if a.dtype.fields else a).to(self.dev)
+
+    def launches(self) -> int:
+        return int(self.L.gcb_launch_count())
+
+
+def device_loop(b: Bench, circ, eng, batch: int, keys, steps: int, warmup: int, sampler=None):
+    """Garble + select + eval + decode, device-resident, `steps` times.  keys: bytes (one shared key) or
+    uint8[batch, keylen] (per-instance keys).  Returns timings (max over ranks) and the device tensors."""
+    from mpc_b200.circuit import decode_bits_dev, select_labels_dev
+    torch = b.torch
+    nin, nout, rows = circ.num_inputs, circ.num_outputs, circ.num_rows
+    rand, r, l0, bits = synthetic_inputs(circ, batch, b.rank)
+    if isinstance(keys, bytes):
+        d_key, klen, kstride = torch.frombuffer(bytearray(keys), dtype=torch.uint8).to(b.dev), len(keys), 0
+    else:
+        d_key, klen, kstride = b.to_dev(np.ascontiguousarray(keys)), keys.shape[1], keys.shape[1]
+    d_r, d_l0, d_bits = b.to_dev(r), b.to_dev(l0), b.to_dev(bits)
+    d_tab = torch.empty((batch, rows, 16), dtype=torch.uint8, device=b.dev)
+    d_io = torch.empty((batch, nin + nout, 32), dtype=torch.uint8, device=b.dev)
+    d_in = torch.empty((batch, nin, 16), dtype=torch.uint8, device=b.dev)
+    d_out = torch.empty((batch, nout, 16), dtype=torch.uint8, device=b.dev)
+    d_obits = torch.empty((batch, nout), dtype=torch.uint8, device=b.dev)
+    kern = {"garble": [], "eval": []}
+
+    def step(timed: bool):
+        e = [b.ev() for _ in range(4)] if timed else None
+        if timed: e[0].record(b.stream)
+        eng.garble_dev(d_key, klen, kstride, batch, d_r, d_l0, d_tab, d_io, stream=b.s)
+        if timed: e[1].record(b.stream)
+        select_labels_dev(d_io, nin + nout, d_bits, d_in, batch, nin, stream=b.s)
+        if timed: e[2].record(b.stream)
+        eng.eval_dev(d_key, klen, kstride, batch, d_tab, d_in, d_out, stream=b.s)
+        if timed: e[3].record(b.stream)
+        if timed:
+            kern["garble"].append((e[0], e[1])); kern["eval"].append((e[2], e[3]))
+        # output wires are a strided view of io_wires: decode takes the wire stride
+        decode_bits_dev(d_io.data_ptr() + nin * 32, nin + nout, d_out, d_obits, batch, nout, stream=b.s)
+
+    for _ in range(max(warmup, 3)):
+        step(False)
+    b.barrier()
+    # correctness of what is being timed: decoded outputs equal the plaintext function of the inputs
+    ob = d_obits.cpu().numpy()
+    if circ.name == "aes_128":
+        from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+        enc = Cipher(algorithms.AES(bytes(range(16))), modes.ECB()).encryptor()
+        for i in (0, 1, batch // 2, batch - 1):
+            want = int.from_bytes(enc.update((b.rank * batch + i).to_bytes(16, "big")), "big")
+            got = sum(int(x) << k for k, x in enumerate(ob[i]))
+            assert got == want, f"instance {i}: decoded output is not AES(key, index)"
+    else:
+        for i in (0, batch - 1):
+            assert np.array_equal(ob[i], circ.compute_bits(bits[i].tolist())), f"instance {i}: decoded output is wrong"
+    if sampler:
+        sampler.start()
+    b.barrier()
+    n0 = b.launches()
+    t0, t1 = b.ev(), b.ev()
+    t0.record(b.stream)
+    for _ in range(steps):
+        step(True)
+    t1.record(b.stream)
+    b.barrier()
+    n1 = b.launches()
+    ms = t0.elapsed_time(t1)
+    g_ms = float(np.mean([x.elapsed_time(y) for x, y in kern["garble"]]))
+    e_ms = float(np.mean([x.elapsed_time(y) for x, y in kern["eval"]]))
+    ms, g_ms, e_ms = b.max_over_ranks([ms, g_ms, e_ms])
+    return {"ms": ms, "garble_ms": g_ms, "eval_ms": e_ms, "launches": n1 - n0,
+            "inputs": (r, l0, bits), "dev": (d_tab, d_out, d_io)}
+
+
+def roofline_of(b: Bench, circ, eng, batch: int, g_ms: float, e_ms: float, nr: int):
+    gb, eb = algorithmic_bytes(circ)
+    ach_g, ach_e = gb * batch / (g_ms * 1e-3) / 1e9, eb * batch / (e_ms * 1e-3) / 1e9
+    geo = f"{eng.info.teams_per_sm} teams x {eng.info.team_threads} threads per SM"
+    return {"bound": "hbm", "achieved": ach_g, "peak": b.peak, "unit": "GB/s", "frac": ach_g / b.peak,
+            "traffic": ncu_traffic(circ.name, "garble_kernel"), "algorithmic_bytes": gb * batch,
+            "kernel": f"garble_kernel<NR={nr},PLAIN> ({geo})", "kernel_ms": g_ms,
+            "eval": {"achieved": ach_e, "frac": ach_e / b.peak, "algorithmic_bytes": eb * batch, "kernel_ms": e_ms,
+                     "traffic": ncu_traffic(circ.name, "eval_kernel"), "kernel": f"eval_kernel<NR={nr},PLAIN> ({geo})"},
+            "peak_source": b.peak_source,
+            "note": "bound by the shared-memory pipe (AES T-table lookups), not HBM: there is no AES instruction on the "
+                    "GPU; see DESIGN.md section 4 and profiles/"}
+
+
+def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinned: bool):
+    """The call a user makes, from ONE host thread: gcb_garble_begin on every part, then per part
+    gcb_job_wait -> gcb_eval_begin, then the eval waits.  Host buffers; copies inside the timed region."""
+    from mpc_b200.circuit import host_alloc, host_free
+    from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
+    nin, nout, rows = circ.num_inputs, circ.num_outputs, circ.num_rows
+    r, l0, bits = inputs
+    alloc = host_alloc if pinned else (lambda shape, dt: np.zeros(shape, dtype=dt))
+    h_r, h_l0 = alloc((batch,), LABEL_DTYPE), alloc((batch, nin), LABEL_DTYPE)
+    h_tab, h_io = alloc((batch, rows), LABEL_DTYPE), alloc((batch, nin + nout), WIRE_DTYPE)
+    h_in, h_out = alloc((batch, nin), LABEL_DTYPE), alloc((batch, nout), LABEL_DTYPE)
+    h_r[:] = r
+    h_l0[:] = l0
+    n_parts = max(1, min(E2E_PARTS, batch // 64))
+    parts = [slice(k * batch // n_parts, (k + 1) * batch // n_parts) for k in range(n_parts)]
+
+    def step():
+        gj = [eng.garble_begin(KEY, h_r[sl], h_l0[sl], h_tab[sl], h_io[sl]) for sl in parts]
+        ej = []
+        for j, sl in zip(gj, parts):
+            j.wait()                                  # this part's tables are on the host: its evaluation may start
+            ej.append(eng.eval_begin(KEY, h_tab[sl], h_in[sl], h_out[sl]))
+        for j in ej:
+            j.wait()
+
+    step()
+    h_in[:] = np.where(bits.astype(bool), h_io["l1"][:, :nin], h_io["l0"][:, :nin])
+    step()
+    b.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    b.torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    d_tab, d_out, _ = ref_dev
+    ok = h_out.tobytes() == d_out.cpu().numpy().tobytes() and h_tab.tobytes() == d_tab.cpu().numpy().tobytes()
+    assert ok, "host-pointer path and device-resident path disagree"
+    if pinned:
+        for a in (h_r, h_l0, h_tab, h_io, h_in, h_out):
+            host_free(a)
+    return sec, n_parts
+
+
+def pcie_probe(b: Bench, h2d_bytes: int, d2h_bytes: int, reps: int = 5):
+    """Copy-only floor of the e2e step on this box: every rank moves the step's bytes host->device and
+    device->host at the same time (page-locked memory, two streams), all ranks at once."""
+    torch = b.torch
+    h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=b.dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=b.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up: bool, down: bool):
+        b.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    run(True, True)
+    both, up, down = run(True, True), run(True, False), run(False, True)
+    both, up, down = b.max_over_ranks([both, up, down])
+    return {"both_ms": both * 1e3, "h2d_alone_gbs_per_gpu": h2d_bytes / up / 1e9, "d2h_alone_gbs_per_gpu": d2h_bytes / down / 1e9,
+            "both_gbs_per_gpu_each_way": (h2d_bytes + d2h_bytes) / 2 / both / 1e9,
+            "box_total_gbs": (h2d_bytes + d2h_bytes) * b.world / both / 1e9,
+            "how": f"{b.world} rank(s) at once, {h2d_bytes / 1e9:.2f} GB up + {d2h_bytes / 1e9:.2f} GB down per rank, "
+                   f"pinned memory, two streams, mean of {reps}"}
+
+
+def extra_iknp(b: Bench, n: int = 1 << 24):
+    """BASELINE config 4: IKNP expansion of 2^24 OTs, receiver then sender on the receiver's U, labels in HBM."""
+    torch, L, check, ptr = b.torch, b.L, b._lib.check, b._lib.ptr
+    rnd = lambda *shape: torch.randint(0, 256, shape, dtype=torch.uint8, device=b.dev)
+    k0, k1, delta = rnd(128, 16), rnd(128, 16), rnd(1, 16)
+    choice = torch.randint(0, 2, (n,), dtype=torch.uint8, device=b.dev)
+    ul = L.gcb_iknp_u_size(n)
+    u = torch.empty(ul, dtype=torch.uint8, device=b.dev)
+    t_lab = torch.empty((n, 16), dtype=torch.uint8, device=b.dev)
+    q_lab = torch.empty((n, 16), dtype=torch.uint8, device=b.dev)
+    out = {}
+    for pos in (0, 17):
+        recv = lambda: check(L.gcb_iknp_receiver_expand_dev(ptr(k0), ptr(k1), pos, ptr(choice), n, ptr(u), ptr(t_lab), b.s))
+        send = lambda: check(L.gcb_iknp_sender_expand_dev(ptr(k0), ptr(delta), pos, ptr(u), ul, n, ptr(q_lab), b.s))
+        for name, fn, blocks in (("receiver", recv, 2), ("sender", send, 1)):
+            for _ in range(3):
+                fn()
+            b.barrier()
+            e0, e1 = b.ev(), b.ev()
+            e0.record(b.stream)
+            for _ in range(5):
+                fn()
+            e1.record(b.stream)
+            b.barrier()
+            ms = b.max_over_ranks([e0.elapsed_time(e1) / 5])[0]
+            gb = 32.0 * n / 1e9
+            out[f"{name}_pos{pos}"] = {"ms": ms, "m_ot_per_s": n * b.world / ms / 1e3, "aes_blocks_per_ot": blocks,
+                                       "algorithmic_bytes": int(32 * n), "achieved_gbs": gb / ms * 1e3, "hbm_frac": gb / ms * 1e3 / b.peak}
+    out["workload"] = f"IKNP expansion of 2^24 OTs per GPU (transpose + AES-CTR column PRG), stream positions 0 and 17"
+    return out
+
+
+def extra_stream_step(b: Bench, batch: int = 256):
+    """BASELINE config 3: sha256.circ as one Streaming.Garble step (gate kernel + record serialisation + D2H of the
+    byte stream), then the streaming evaluator on those bytes."""
+    from mpc_b200.circuit import GarbleEngine, StreamEval, Streaming
+    from mpc_b200.circuit_io import LABEL_DTYPE
+    circ = load_circuit("sha256")
+    eng = GarbleEngine(circ)
+    rng = np.random.default_rng(77 + b.rank)
+    nin = circ.num_inputs
+    r = rng.integers(0, 2**63, (batch, 2), dtype=np.uint64).view(LABEL_DTYPE).reshape(batch)
+    l0 = rng.integers(0, 2**63, (batch, nin, 2), dtype=np.uint64).view(LABEL_DTYPE).reshape(batch, nin)
+    ids = list(range(nin))
+    st = Streaming(bytes(32), r, ids, l0)
+    sev = StreamEval(bytes(32), batch)
+    w = st.get_inputs(ids)
+    sev.set(ids, w["l0"].astype(LABEL_DTYPE))
+    outs = list(range(nin, nin + circ.num_outputs))
+    nbytes = 0
+    tg = te = 0.0
+    for k in range(5):
+        b.barrier()
+        t0 = time.perf_counter()
+        buf, _, _ = st.garble(eng, ids, outs)
+        t1 = time.perf_counter()
+        sev.circuit(buf, circ.num_gates, circ.num_wires, nin + circ.num_outputs)
+        sev.get(outs[:1])                              # ordered behind the eval kernel
+        t2 = time.perf_counter()
+        if k >= 2:
+            tg += (t1 - t0) / 3
+            te += (t2 - t1) / 3
+        nbytes = buf.shape[1]
+    tg, te = b.max_over_ranks([tg, te])
+    gates = circ.num_gates * batch * b.world
+    return {"workload": f"sha256.circ as one streaming step, batch {batch} per GPU, 32-byte key; record stream to / from host memory",
+            "stream_bytes_per_instance": int(nbytes), "garble_ms": tg * 1e3, "eval_ms": te * 1e3,
+            "m_gates_per_s_garble": gates / tg / 1e6, "m_gates_per_s_eval": gates / te / 1e6,
+            "pcie_gbs_garble": nbytes * batch / tg / 1e9, "pcie_gbs_eval": nbytes * batch / te / 1e9}
+
+
+def extra_stream_program(b: Bench, batch: int):
+    """BASELINE config 5 stand-in at >= 10^8 gates per instance (tools/stream_program.py)."""
+    import stream_program as sp
+    steps = sp.steps_for_gates(1e8)
+    res = sp.run_program(steps, batch, check=1, warm=4, rank=b.rank, oracle_steps=1 if b.rank == 0 else 0,
+                         sync=(b.dist.barrier if b.world > 1 else None))
+    wall, tg, te, bad = b.max_over_ranks([res["wall_s"], res["garble_s"], res["eval_s"], 0.0 if res["checks_ok"] else 1.0])
+    g = res["timed_gates"] * b.world
+    return {"workload": f"{steps} steps of sha512.circ / mul64.circ chained through permanent wires (stand-in for ed25519 "
+                        f"sign.mpcl, which needs the Go MPCL compiler), batch {batch} per GPU, garbler + evaluator",
+            "gates_per_instance": res["gates_per_instance"], "timed_gates_per_instance": res["timed_gates_per_instance"],
+            "total_gates_timed": g, "stream_gb": res["stream_bytes"] * b.world / 1e9, "wall_s": wall,
+            "m_gates_per_s": g / wall / 1e6, "m_and_per_s": g / wall / 1e6 * (3 * 57947 + 4033) / (3 * 349617 + 13675),
+            "pcie_gbs_each_way": res["stream_bytes"] * b.world / wall / 1e9, "checks_ok": bad == 0.0}
+
+
+def extra_latency(b: Bench):
+    """The unchanged drop-in call: batch = 1 gcb_garble (with the full Wires array) + gcb_eval from host buffers,
+    wall clock, next to the oracle on ONE thread (the reference's execution model, circuit/garble_bench_test.go:38-64)."""
+    from mpc_b200.circuit import GarbleEngine
+    from mpc_b200.circuit_io import LABEL_DTYPE
+    from mpc_b200.drbg import DRBG
+    from oracle import pyoracle as O
+    out = {}
+    for name in ("sha256xor", "aes_128"):
+        circ = load_circuit(name)
+        eng = GarbleEngine(circ)
+        key = bytes(range(32))
+        rand = DRBG(f"lat/{name}").read(16 * (1 + circ.num_inputs))
+
+        def gpu_once():
+            g = eng.garble(rand, key)
+            wires = np.zeros(circ.num_wires, dtype=LABEL_DTYPE)
+            wires[: circ.num_inputs] = g.Wires["l0"][: circ.num_inputs]
+            eng.eval(key, wires, g)
+
+        def cpu_once():
+            _, o_wires, o_slab, o_off = O.garble(circ, key, rand)
+            O.eval_(circ, key, np.ascontiguousarray(o_wires["l0"][: circ.num_inputs]), o_slab, o_off)
+
+        res = {}
+        for tag, fn in (("gpu_ms", gpu_once), ("cpu_1thread_ms", cpu_once)):
+            fn(); fn()
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+            res[tag] = 1e3 * float(np.median(ts))
+        # the throughput form of the same call: how many instances one call needs before the GPU wins
+        from util import garble_inputs, rand_to_labels
+        for nb in (8, 64):
+            keys, rr = garble_inputs(f"lat/{name}/{nb}", nb, circ.num_inputs, 32)
+            r, l0 = rand_to_labels(rr, circ.num_inputs)
+            eng.garble_batch(keys[0].tobytes(), r, l0)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                tables, io = eng.garble_batch(keys[0].tobytes(), r, l0)
+            res[f"gpu_garble_batch{nb}_ms_per_instance"] = 1e3 * (time.perf_counter() - t0) / 3 / nb
+        out[name] = res
+    out["note"] = ("batch = 1, host buffers, wall clock incl. copies; gpu = gcb_garble(wires_full) + gcb_eval(wires_full) as the "
+                   "Go binding's Garble / Eval call them; cpu = the C oracle on one thread")
+    return out
+
+
 def run_gcb(args):
     import torch
-    import torch.distributed as dist
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus > 1 and world == 1:
         # convenience: `python bench.py --gpus N` re-launches itself under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
@@ -217,179 +593,81 @@ def run_gcb(args):
         os.execv(sys.executable, cmd)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    b = Bench(args)
+    rank, world = b.rank, b.world
+    from mpc_b200.circuit import GarbleEngine
 
-    from mpc_b200 import _lib
-    from mpc_b200.circuit import GarbleEngine, decode_bits_dev, select_labels_dev
-    from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
-
-    _lib.check(_lib.lib().gcb_set_device(local))
     circ = load_circuit(args.circuit)
     eng = GarbleEngine(circ)
     nin, nout, rows, n_and = circ.num_inputs, circ.num_outputs, circ.num_rows, circ.count(2)
     batch = args.batch or WORKLOADS[args.circuit][1]
-    rand, r, l0, bits = synthetic_inputs(circ, batch, rank)
 
-    def to_dev(a):
-        return torch.from_numpy(a.view(np.uint8).reshape(a.shape + (-1,)) if a.dtype.fields else a).to(dev)
+    sampler = ClockSampler(b.local) if rank == 0 else None
+    head = device_loop(b, circ, eng, batch, KEY, args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if sampler else None
+    ms, g_ms, e_ms = head["ms"], head["garble_ms"], head["eval_ms"]
 
-    d_key = torch.frombuffer(bytearray(KEY), dtype=torch.uint8).to(dev)
-    d_r, d_l0, d_bits = to_dev(r), to_dev(l0), to_dev(bits)
-    d_tab = torch.empty((batch, rows, 16), dtype=torch.uint8, device=dev)
-    d_io = torch.empty((batch, nin + nout, 32), dtype=torch.uint8, device=dev)
-    d_in = torch.empty((batch, nin, 16), dtype=torch.uint8, device=dev)
-    d_out = torch.empty((batch, nout, 16), dtype=torch.uint8, device=dev)
-    d_obits = torch.empty((batch, nout), dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
-    s = stream.cuda_stream
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    kern = {"garble": [], "eval": []}
-
-    def step(timed: bool):
-        e0, e1, e2, e3 = (ev(), ev(), ev(), ev()) if timed else (None,) * 4
-        if timed: e0.record(stream)
-        eng.garble_dev(d_key, 16, 0, batch, d_r, d_l0, d_tab, d_io, stream=s)
-        if timed: e1.record(stream)
-        select_labels_dev(d_io, nin + nout, d_bits, d_in, batch, nin, stream=s)
-        if timed: e2.record(stream)
-        eng.eval_dev(d_key, 16, 0, batch, d_tab, d_in, d_out, stream=s)
-        if timed: e3.record(stream)
-        if timed:
-            kern["garble"].append((e0, e1)); kern["eval"].append((e2, e3))
-
-    # output wires are a strided view of io_wires: decode takes the wire stride
-    def decode():
-        base = d_io.data_ptr() + nin * 32
-        decode_bits_dev(base, nin + nout, d_out, d_obits, batch, nout, stream=s)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step(False); decode()
-    barrier()
-    # correctness of what is being timed: decoded outputs equal OpenSSL AES of the instance index
-    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
-    ob = d_obits.cpu().numpy()
-    enc = Cipher(algorithms.AES(bytes(range(16))), modes.ECB()).encryptor()
-    for i in (0, 1, batch // 2, batch - 1):
-        if args.circuit == "aes_128":
-            want = int.from_bytes(enc.update((rank * batch + i).to_bytes(16, "big")), "big")
-            got = sum(int(b) << k for k, b in enumerate(ob[i]))
-            assert got == want, f"instance {i}: decoded output is not AES(key, index)"
-        else:                                        # plaintext evaluation of the same circuit file
-            assert np.array_equal(ob[i], circ.compute_bits(bits[i].tolist())), f"instance {i}: decoded output is wrong"
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    t_start, t_end = ev(), ev()
-    t_start.record(stream)
-    for _ in range(args.steps):
-        step(True); decode()
-    t_end.record(stream)
-    barrier()
-    ms = t_start.elapsed_time(t_end)
-    clocks = sampler.stop() if rank == 0 else None
-    g_ms = float(np.mean([a.elapsed_time(b) for a, b in kern["garble"]]))
-    e_ms = float(np.mean([a.elapsed_time(b) for a, b in kern["eval"]]))
-
-    e2e_s = float("nan")
+    h2d = batch * (16 * (1 + nin) + 16 * rows + 16 * nin)
+    d2h = batch * (16 * rows + 32 * (nin + nout) + 16 * nout)
+    e2e = None
     if not args.no_e2e:
-        # ---- e2e: host-pointer C ABI, pinned host buffers, copies inside the timed region
-        L = _lib.lib()
-
-        def pinned(shape, dtype):
-            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
-            p = L.gcb_host_alloc(max(n, 1))
-            assert p, "gcb_host_alloc failed"
-            import ctypes as C
-            arr = np.frombuffer((C.c_uint8 * n).from_address(p), dtype=dtype).reshape(shape)
-            return arr, p
-
-        h_r, p1 = pinned((batch,), LABEL_DTYPE); h_r[:] = r
-        h_l0, p2 = pinned((batch, nin), LABEL_DTYPE); h_l0[:] = l0
-        h_tab, p3 = pinned((batch, rows), LABEL_DTYPE)
-        h_io, p4 = pinned((batch, nin + nout), WIRE_DTYPE)
-        h_in, p5 = pinned((batch, nin), LABEL_DTYPE)
-        h_out, p6 = pinned((batch, nout), LABEL_DTYPE)
-
-        # The call a user makes: gcb_garble / gcb_eval on host buffers.  The batch goes through in
-        # E2E_PARTS sub-batches on two small thread pools -- the garbler's tables of part i stream
-        # back (D2H) while the evaluator's tables of earlier parts stream in (H2D), as two parties
-        # would; two workers per side hide the start-up latency of each blocking call.
-        from concurrent.futures import ThreadPoolExecutor
-        # Sub-batches: as many as keep the PCIe time of one part well above the latency of garbling one
-        # instance (a part's kernel cannot finish sooner than that): ~1.2 us per dependency step of the plan.
-        lat_ms = eng.info.num_steps * 1.2e-3
-        pcie_ms = batch * (16 * rows + 32 * (nin + nout)) / 50e6
-        n_parts = int(max(2, min(E2E_PARTS, pcie_ms / (2 * lat_ms))))
-        parts = [slice(k * batch // n_parts, (k + 1) * batch // n_parts) for k in range(n_parts)]
-
-        def garble_part(sl):
-            _lib.check(L.gcb_set_device(local))
-            eng.garble_batch(KEY, h_r[sl], h_l0[sl], tables=h_tab[sl], io_wires=h_io[sl])
-
-        def eval_part(sl):
-            _lib.check(L.gcb_set_device(local))
-            eng.eval_batch(KEY, h_tab[sl], h_in[sl], out_labels=h_out[sl])
-
-        gpool, epool = ThreadPoolExecutor(E2E_WORKERS), ThreadPoolExecutor(E2E_WORKERS)
-
-        def e2e_step():
-            gfs = [gpool.submit(garble_part, sl) for sl in parts]
-            efs = []
-            for f, sl in zip(gfs, parts):
-                f.result()                      # re-raises worker exceptions
-                efs.append(epool.submit(eval_part, sl))
-            for f in efs:
-                f.result()
-
-        e2e_step()
-        h_in[:] = np.where(bits.astype(bool), h_io["l1"][:, :nin], h_io["l0"][:, :nin])
         e2e_steps = max(2, min(args.steps, 10))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        ok_e2e = h_out.tobytes() == d_out.cpu().numpy().tobytes() and h_tab.tobytes() == d_tab.cpu().numpy().tobytes()
-        assert ok_e2e, "host-pointer path and device-resident path disagree"
-        gpool.shutdown(); epool.shutdown()
-        for p in (p1, p2, p3, p4, p5, p6):
-            L.gcb_host_free(p)
+        sec, n_parts = e2e_loop(b, circ, eng, batch, head["inputs"], head["dev"], e2e_steps, pinned=True)
+        e2e_ms = b.max_over_ranks([sec * 1e3])[0]
+        e2e = {"value": n_and * batch * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(world * h2d), "d2h_bytes_per_step": int(world * d2h), "ms_per_step": e2e_ms,
+               "how": f"gcb_garble_begin / gcb_eval_begin / gcb_job_wait on page-locked host buffers (gcb_host_alloc), "
+                      f"{n_parts} parts in flight, ONE host thread per GPU"
+                      + (f", ranks bound to their GPU's NUMA node ({b.numa['cpus']} cpus)" if b.numa else "")}
 
-    # max over ranks
-    tt = torch.tensor([ms, e2e_s * 1e3, g_ms, e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, g_ms, e_ms = tt.tolist()
+    extra = {}
+    if not args.no_extra:
+        t_extra = time.perf_counter()
+        probe = pcie_probe(b, h2d, d2h)
+        extra["pcie_probe"] = probe
+        if e2e:
+            e2e["pcie_floor_ms"] = probe["both_ms"]
+            e2e["frac_of_pcie_floor"] = probe["both_ms"] / e2e["ms_per_step"]
+            sec, _ = e2e_loop(b, circ, eng, batch, head["inputs"], head["dev"], 2, pinned=False)
+            p_ms = b.max_over_ranks([sec * 1e3])[0]
+            extra["e2e_pageable"] = {"value": n_and * batch * world / (p_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": p_ms,
+                                     "how": "the same calls on pageable (malloc) host buffers: one extra host memcpy each way, "
+                                            "done by the calling thread"}
+        del head["dev"]
+        torch.cuda.empty_cache()
+        # key shape (ii) of SURVEY 8d: per-instance random 32-byte keys (circuit/garbler.go:47-53, sha2pc/garbler.go:96-101)
+        keys32 = np.random.default_rng(99 + rank).integers(0, 256, (batch, 32), dtype=np.uint8)
+        k32 = device_loop(b, circ, eng, batch, keys32, max(3, args.steps // 3), 3)
+        steps32 = max(3, args.steps // 3)
+        extra["aes_128_keys32"] = {
+            "workload": workload_name(circ, batch) + ", per-instance random 32-byte keys (AES-256, 14 rounds, key schedule per instance)",
+            "value": n_and * batch * world * steps32 / (k32["ms"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": k32["ms"] / steps32,
+            "roofline": roofline_of(b, circ, eng, batch, k32["garble_ms"], k32["eval_ms"], 14)}
+        del k32
+        torch.cuda.empty_cache()
+        sha = load_circuit("sha256")
+        sha_eng = GarbleEngine(sha)
+        sb = WORKLOADS["sha256"][1]
+        steps_s = max(3, args.steps // 3)
+        sh = device_loop(b, sha, sha_eng, sb, KEY, steps_s, 3)
+        extra["sha256"] = {
+            "workload": workload_name(sha, sb) + ", shared 16-byte key",
+            "value": sha.count(2) * sb * world * steps_s / (sh["ms"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": sh["ms"] / steps_s,
+            "roofline": roofline_of(b, sha, sha_eng, sb, sh["garble_ms"], sh["eval_ms"], 10)}
+        del sh
+        torch.cuda.empty_cache()
+        extra["iknp_2p24"] = extra_iknp(b)
+        torch.cuda.empty_cache()
+        extra["stream_sha256_step"] = extra_stream_step(b)
+        torch.cuda.empty_cache()
+        extra["stream_program"] = extra_stream_program(b, args.program_batch)
+        torch.cuda.empty_cache()
+        if world == 1:
+            extra["latency_batch1"] = extra_latency(b)
+        extra["host"] = host_topology()
+        extra["seconds"] = time.perf_counter() - t_extra
 
     if rank == 0:
-        gb, eb = algorithmic_bytes(circ)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = gb * batch / (g_ms * 1e-3) / 1e9
-        traffic = None                              # DRAM bytes per launch from the committed ncu capture
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["garble_kernel"]["dram_bytes"]
-        except Exception:
-            pass
         total_and = n_and * batch * world
         value = total_and * args.steps / (ms * 1e-3) / 1e6
         cores = os.cpu_count() or 1
@@ -403,35 +681,21 @@ def run_gcb(args):
             cpu = {"value": n_and * sample / min(ts) / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{sample} instances garble+eval, best of 3, C oracle (AES-NI), {cores} pthreads"}
         line = {
-            "metric": METRIC.replace("AES-128 circuit", WORKLOADS[args.circuit][0]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC.replace("AES-128 circuit", WORKLOADS[args.circuit][0]), "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 (AES T-tables, 128-bit label XOR)",
             "data": "synthetic",
-            "config": {"workload": f"{circ.name}.circ ({n_and} AND, {circ.count(4)} INV, {circ.count(0) + circ.count(1)} XOR) "
-                                   f"garble+eval, batch {batch} per GPU",
-                       "batch_per_gpu": batch, "key": "shared 16-byte (AES-128)",
-                       "l2": f"tables are {batch * rows * 16 // 1000000} MB per step, larger than L2; no flush needed",
-                       "kernel_ms": {"garble": g_ms, "eval": e_ms}},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": gb * batch,
-                         "kernel": f"garble_kernel<10,PLAIN> ({eng.info.teams_per_sm} teams x {eng.info.team_threads} threads per SM)",
-                         "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
-                         "note": "bound by the shared-memory pipe (AES T-table lookups, 83% busy in the ncu capture), "
-                                 "not HBM: there is no AES instruction on the GPU; see DESIGN.md and profiles/"},
+            "config": config_of(circ, batch),
+            "roofline": roofline_of(b, circ, eng, batch, g_ms, e_ms, 10),
             "cpu_baseline": cpu,
-            "e2e": None if args.no_e2e else {"value": total_and / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
-                    "h2d_bytes_per_step": int(world * batch * (16 * (1 + nin) + 16 * rows + 16 * nin)),
-                    "d2h_bytes_per_step": int(world * batch * (16 * rows + 32 * (nin + nout) + 16 * nout)),
-                    "ms_per_step": e2e_ms,
-                    "how": f"gcb_garble + gcb_eval on pinned host buffers, {n_parts} sub-batches, "
-                           f"{E2E_WORKERS} garbler + {E2E_WORKERS} evaluator host threads"
-                           + (f", ranks bound to their GPU's NUMA node ({numa['cpus']} cpus)" if numa else "")},
-            "gpu_launches": 4 * args.steps,
+            "e2e": e2e,
+            "gpu_launches": head["launches"],
             "clocks": clocks,
+            "extra": extra or None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        b.dist.destroy_process_group()
 
 
 def main():
@@ -442,8 +706,10 @@ def main():
     ap.add_argument("--impl", default="gcb", choices=["gcb", "reference"])
     ap.add_argument("--circuit", default="aes_128", choices=sorted(WORKLOADS), help="aes_128 = the headline workload")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: 4096 for aes_128, 1184 for sha256)")
+    ap.add_argument("--program-batch", type=int, default=148, help="instances per GPU of the streaming program in `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configurations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

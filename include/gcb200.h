@@ -56,6 +56,9 @@ typedef enum {
 
 const char *gcb_last_error(void);
 const char *gcb_version(void);
+/* Diagnostic: kernels this library has launched in this process so far (bench.py reports the difference
+ * over its timed region as `gpu_launches`). */
+uint64_t gcb_launch_count(void);
 
 /* Device selection.  cgo calls may arrive on any OS thread, so every entry point
  * re-selects its device.

@@ -40,6 +40,7 @@ _vp, _u32, _u64, _sz, _int = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c
 SYMBOLS = {
     "gcb_last_error": (C.c_char_p, []),
     "gcb_version": (C.c_char_p, []),
+    "gcb_launch_count": (_u64, []),
     "gcb_set_device": (_int, [_int]),
     "gcb_set_devices": (_int, [_vp, _int]),
     "gcb_get_devices": (_int, [_vp, _int]),

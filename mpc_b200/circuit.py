@@ -23,7 +23,95 @@ from . import _lib
 from ._lib import GcbError, PlanInfo, check, ptr
 from .circuit_io import AND, INV, LABEL_DTYPE, OR, WIRE_DTYPE, Circuit
 
-__all__ = ["Garbled", "GarbleEngine", "Streaming", "StreamEval", "GcbError"]
+__all__ = ["Garbled", "GarbleEngine", "Streaming", "StreamEval", "GcbError", "Job", "set_devices", "get_devices",
+           "host_alloc", "host_free"]
+
+
+def set_devices(ids) -> None:
+    """gcb_set_devices: the devices host-pointer calls fan out over (empty = back to the default)."""
+    arr = (C.c_int * len(ids))(*ids)
+    check(_lib.lib().gcb_set_devices(arr, len(ids)))
+
+
+def get_devices() -> List[int]:
+    arr = (C.c_int * 64)()
+    n = _lib.lib().gcb_get_devices(arr, 64)
+    return [int(arr[i]) for i in range(min(n, 64))]
+
+
+def host_alloc(shape, dtype) -> np.ndarray:
+    """Page-locked array from gcb_host_alloc (what the Go side's pooled slabs become); free with host_free."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = _lib.lib().gcb_host_alloc(max(n, 1))
+    if not p:
+        raise GcbError(_lib.E_CUDA, _lib.lib().gcb_last_error().decode())
+    arr = np.frombuffer((C.c_uint8 * max(n, 1)).from_address(p), dtype=np.uint8)[:n].view(dtype).reshape(shape)
+    _host_blocks[arr.ctypes.data] = p
+    return arr
+
+
+_host_blocks = {}
+
+
+def host_free(arr: np.ndarray) -> None:
+    p = _host_blocks.pop(arr.ctypes.data, None)
+    if p:
+        _lib.lib().gcb_host_free(p)
+
+
+class HostCircuit:
+    """The C++ circuit front end (gcb_circuit_*) over a parsed circuit: Circuit.Compute on wire bits
+    (circuit/computer.go:15-91) for whole batches, on the host."""
+
+    def __init__(self, circ: Circuit):
+        self.circ = circ
+        gates = np.ascontiguousarray(circ.gates)
+        ins = np.asarray(circ.inputs, dtype=np.uint32)
+        outs = np.asarray(circ.outputs, dtype=np.uint32)
+        h = C.c_void_p()
+        check(_lib.lib().gcb_circuit_from_gates(ptr(gates), circ.num_gates, circ.num_wires, ptr(ins), len(ins),
+                                                ptr(outs), len(outs), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().gcb_circuit_destroy(h)
+            except Exception:
+                pass
+
+    def compute_bits(self, in_bits: np.ndarray) -> np.ndarray:
+        """uint8[batch, num_inputs] of 0/1 -> uint8[batch, num_outputs]."""
+        b = np.ascontiguousarray(in_bits, dtype=np.uint8).reshape(-1, self.circ.num_inputs)
+        out = np.zeros((len(b), self.circ.num_outputs), dtype=np.uint8)
+        check(_lib.lib().gcb_circuit_compute(self._h, len(b), ptr(b), ptr(out)))
+        return out
+
+
+class Job:
+    """A queued gcb_garble_begin / gcb_eval_begin call.  ``wait()`` blocks until the results are in the caller's
+    buffers; the arrays handed to the begin call are kept alive until then."""
+
+    def __init__(self, handle, keep):
+        self._h, self._keep = handle, keep
+
+    def done(self) -> bool:
+        return self._h is None or bool(_lib.lib().gcb_job_done(self._h))
+
+    def wait(self) -> None:
+        h, self._h = self._h, None
+        if h:
+            try:
+                check(_lib.lib().gcb_job_wait(h))
+            finally:
+                self._keep = None
+
+    def __del__(self):
+        try:
+            self.wait()
+        except Exception:
+            pass
 
 
 def _read(rand, n: int) -> bytes:
@@ -74,6 +162,9 @@ def _key_args(keys, batch: int):
     if keys.ndim != 2 or keys.shape[0] != batch:
         raise ValueError("keys must be bytes or uint8[batch, keylen]")
     return keys, keys.shape[1], keys.shape[1]
+
+
+FLAG_FANOUT = 1
 
 
 class GarbleEngine:
@@ -190,6 +281,33 @@ class GarbleEngine:
         check(_lib.lib().gcb_eval(self._h, ptr(ka), kl, ks, batch, tp, ptr(in_labels), ptr(out_labels), None, 0))
         return out_labels
 
+    # ---- the same, split in two (one host thread keeps every selected device and both PCIe directions busy) ----
+    def garble_begin(self, keys, r: np.ndarray, in_l0: np.ndarray, tables: np.ndarray,
+                     io_wires: Optional[np.ndarray] = None) -> Job:
+        """Queue a batched Garble; buffers must be C-contiguous and stay untouched until ``Job.wait()``."""
+        c = self.circ
+        batch = len(r)
+        ka, kl, ks = _key_args(keys, batch)
+        for a in (r, in_l0, tables, io_wires):
+            assert a is None or a.flags["C_CONTIGUOUS"], "begin calls take contiguous arrays (no hidden copies)"
+        h = C.c_void_p()
+        check(_lib.lib().gcb_garble_begin(self._h, ptr(ka), kl, ks, batch, ptr(r), ptr(in_l0) if c.num_inputs else None,
+                                          ptr(tables) if c.num_rows else ptr(np.zeros(1, LABEL_DTYPE)),
+                                          ptr(io_wires) if io_wires is not None else None, None, 0, C.byref(h)))
+        return Job(h, (ka, r, in_l0, tables, io_wires))
+
+    def eval_begin(self, keys, tables: np.ndarray, in_labels: np.ndarray, out_labels: np.ndarray) -> Job:
+        c = self.circ
+        batch = len(in_labels)
+        ka, kl, ks = _key_args(keys, batch)
+        for a in (tables, in_labels, out_labels):
+            assert a.flags["C_CONTIGUOUS"], "begin calls take contiguous arrays (no hidden copies)"
+        h = C.c_void_p()
+        check(_lib.lib().gcb_eval_begin(self._h, ptr(ka), kl, ks, batch,
+                                        ptr(tables) if c.num_rows else ptr(np.zeros(1, LABEL_DTYPE)), ptr(in_labels),
+                                        ptr(out_labels), None, 0, C.byref(h)))
+        return Job(h, (ka, tables, in_labels, out_labels))
+
     # ---- the garbled tables as Garbler sends them (circuit/garbler.go:69-82) --------
     def tables_wire_size(self) -> int:
         import ctypes as C
@@ -215,15 +333,16 @@ class GarbleEngine:
 
     # ---- batched, device-resident (torch tensors or raw device addresses) -------
     def garble_dev(self, keys_dev, keylen: int, key_stride: int, batch: int, r_dev, in_l0_dev, tables_dev,
-                   io_wires_dev=None, wires_full_dev=None, stream: int = 0) -> None:
+                   io_wires_dev=None, wires_full_dev=None, stream: int = 0, flags: int = 0) -> None:
+        """flags = FLAG_FANOUT: split the batch over the set_devices list (operands stay on this device)."""
         check(_lib.lib().gcb_garble_dev(self._h, ptr(keys_dev), keylen, key_stride, batch, ptr(r_dev),
                                         ptr(in_l0_dev), ptr(tables_dev), ptr(io_wires_dev),
-                                        ptr(wires_full_dev), 0, stream))
+                                        ptr(wires_full_dev), flags, stream))
 
     def eval_dev(self, keys_dev, keylen: int, key_stride: int, batch: int, tables_dev, in_labels_dev,
-                 out_labels_dev, wires_full_dev=None, stream: int = 0) -> None:
+                 out_labels_dev, wires_full_dev=None, stream: int = 0, flags: int = 0) -> None:
         check(_lib.lib().gcb_eval_dev(self._h, ptr(keys_dev), keylen, key_stride, batch, ptr(tables_dev),
-                                      ptr(in_labels_dev), ptr(out_labels_dev), ptr(wires_full_dev), 0, stream))
+                                      ptr(in_labels_dev), ptr(out_labels_dev), ptr(wires_full_dev), flags, stream))
 
 
 def select_labels_dev(wires_dev, wire_stride: int, bits_dev, out_dev, batch: int, n: int, stream: int = 0):

@@ -41,6 +41,9 @@ int fail(int code, const char* fmt, ...) {
     tl_err = buf;
     return code;
 }
+// Kernels this library has launched (every launch site checks cudaGetLastError through launched()).
+static std::atomic<uint64_t> g_launches{0};
+static cudaError_t launched() { g_launches++; return cudaGetLastError(); }
 static int cuda_fail(cudaError_t e, const char* what) {
     return fail(GCB_E_CUDA, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
 }
@@ -381,7 +384,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     if (garble) gc_launch_garble(mode, keylen, var, grid, block, smem, stream, p);
     else gc_launch_eval(mode, keylen, var, grid, block, smem, stream, p);
     if (geo.spill) CK(cudaFreeAsync(p.spill, stream));
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
 }
 
@@ -879,7 +882,8 @@ using namespace gcb;
 extern "C" {
 
 const char* gcb_last_error(void) { return tl_err.c_str(); }
-const char* gcb_version(void) { return "gcb200 0.1 (sm_100a)"; }
+const char* gcb_version(void) { return "gcb200 0.2 (sm_100a)"; }
+uint64_t gcb_launch_count(void) { return g_launches.load(); }
 
 int gcb_set_device(int device) {
     GCB_TRY
@@ -1236,7 +1240,7 @@ int gcb_select_labels_dev(const gcb_wire* wires, size_t wire_stride, const uint8
     if (rc) return rc;
     select_labels_kernel<<<di->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(wires), wire_stride, bits, reinterpret_cast<uint4*>(out), batch, n);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
     GCB_CATCH
 }
@@ -1250,7 +1254,7 @@ int gcb_decode_bits_dev(const gcb_wire* wires, size_t wire_stride, const gcb_lab
     if (rc) return rc;
     decode_bits_kernel<<<di->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(wires), wire_stride, reinterpret_cast<const uint4*>(labels), bits, batch, n);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
     GCB_CATCH
 }
@@ -1274,7 +1278,7 @@ int gcb_hash_half_dev(const uint8_t* key, uint32_t keylen, const gcb_label* x, u
     if (keylen == 16) hash_half_kernel<10><<<grid, 1024, smem, s>>>(p);
     else if (keylen == 24) hash_half_kernel<12><<<grid, 1024, smem, s>>>(p);
     else hash_half_kernel<14><<<grid, 1024, smem, s>>>(p);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
     GCB_CATCH
 }
@@ -1318,7 +1322,7 @@ int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
     CK(s->r.alloc((size_t)batch * 16));
     CK(cudaMemcpyAsync(s->r.p, r, (size_t)batch * 16, cudaMemcpyHostToDevice, s->cs));
     force_s_kernel<<<(batch + 255) / 256, 256, 0, s->cs>>>(s->r.as<uint4>(), batch);
-    CK(cudaGetLastError());
+    CK(launched());
     if (ninputs) {
         uint32_t mx = 0;
         for (uint32_t i = 0; i < ninputs; i++) mx = input_ids[i] > mx ? input_ids[i] : mx;
@@ -1330,7 +1334,7 @@ int gcb_stream_create(const uint8_t* keys, uint32_t keylen, uint32_t key_stride,
         CK(cudaMemcpyAsync(dl0.p, in_l0, (size_t)batch * ninputs * 16, cudaMemcpyHostToDevice, s->cs));
         wf_set_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
                                                            s->ids.as<uint32_t>(), ninputs, dl0.as<uint4>(), batch);
-        CK(cudaGetLastError());
+        CK(launched());
         CK(cudaStreamSynchronize(s->cs));
     }
     CK(cudaStreamSynchronize(s->cs));
@@ -1363,7 +1367,7 @@ int gcb_stream_get_wires(gcb_stream* s, const uint32_t* ids, uint32_t n, gcb_wir
     wf_get_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
                                                        s->ids.as<uint32_t>(), n, s->r.as<uint4>(),
                                                        s->wires.as<uint4>(), s->batch);
-    CK(cudaGetLastError());
+    CK(launched());
     CK(cudaMemcpyAsync(wires, s->wires.p, (size_t)s->batch * n * 32, cudaMemcpyDeviceToHost, s->cs));
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
@@ -1538,7 +1542,7 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
                      s->slab.as<uint4>(), ser.as<uint8_t>(), stride16};
         const dim3 grid((unsigned)((total + SER_TILE - 1) / SER_TILE), s->batch);
         serialize_kernel<<<grid, SER_THREADS, 0, s->cs>>>(sp);
-        CK(cudaGetLastError());
+        CK(launched());
         CK(cudaEventRecord(s->ev_h2d, s->cs));
         CK(cudaStreamWaitEvent(s->ds, s->ev_h2d, 0));
         CK(cudaMemcpy2DAsync(dst, dst_stride, ser.p, stride16, total, s->batch, cudaMemcpyDeviceToHost, s->ds));
@@ -1636,7 +1640,7 @@ int gcb_seval_set_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, const gcb
     CK(cudaMemcpyAsync(s->wires.p, labels, (size_t)s->batch * n * 16, cudaMemcpyHostToDevice, s->cs));
     wf_set_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
                                                        s->ids.as<uint32_t>(), n, s->wires.as<uint4>(), s->batch);
-    CK(cudaGetLastError());
+    CK(launched());
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
     GCB_CATCH
@@ -1657,7 +1661,7 @@ int gcb_seval_get_wires(gcb_seval* s, const uint32_t* ids, uint32_t n, gcb_label
     CK(cudaMemcpyAsync(s->ids.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, s->cs));
     wf_get_labels_kernel<<<di->sm_count * 4, 256, 0, s->cs>>>(reinterpret_cast<uint4* const*>(s->page_table.p),
                                                               s->ids.as<uint32_t>(), n, s->wires.as<uint4>(), s->batch);
-    CK(cudaGetLastError());
+    CK(launched());
     CK(cudaMemcpyAsync(labels, s->wires.p, (size_t)s->batch * n * 16, cudaMemcpyDeviceToHost, s->cs));
     CK(cudaStreamSynchronize(s->cs));
     return GCB_OK;
@@ -1788,7 +1792,7 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
         CK(cudaStreamWaitEvent(s->cs, s->ev_h2d, 0));
         DeserParams dp{ser.as<uint8_t>(), stride16, s->row_pos.as<uint32_t>(), (uint32_t)n_rows, s->slab.as<uint4>(), s->batch};
         deserialize_kernel<<<di->sm_count * 8, 256, 0, s->cs>>>(dp);
-        CK(cudaGetLastError());
+        CK(launched());
         CK(cudaEventRecord(s->ev_free[cur], s->cs));
         s->ev_valid[cur] = true;
     }
@@ -1826,7 +1830,7 @@ static int launch_iknp(bool receiver, bool bits, const IknpParams& p0, void* str
     else if (receiver) iknp_kernel<true, false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
     else if (bits) iknp_kernel<false, true><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
     else iknp_kernel<false, false><<<grid, IKNP_CTA_THREADS, smem, s>>>(p);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
 }
 
@@ -1992,7 +1996,7 @@ int gcb_mitccrh_hash_dev(const gcb_label* seed_host, uint64_t gid_start, gcb_lab
     const uint64_t want = (nkeys + 511) / 512;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
     mitccrh_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
     GCB_CATCH
 }
@@ -2037,7 +2041,7 @@ static int launch_cot(const gcb_label* seed, const gcb_label* delta, const void*
     const uint64_t want = (n + 511) / 512;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
     cot_kernel<MODE><<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES, (cudaStream_t)stream>>>(p);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
 }
 
@@ -2143,7 +2147,7 @@ static int check_sums_enqueue(const gcb_label* seed2, uint64_t chi_start, const 
     const uint64_t want = (n + 511) / 512;
     const dim3 grid((unsigned)(want < (uint64_t)di->sm_count ? want : (uint64_t)di->sm_count));
     iknp_check_kernel<<<grid, 512, table_pad(di->smem_base) + AES_TABLE_BYTES + 512, stream>>>(p);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
 }
 static void sums_from_words(const uint32_t* w, gcb_label out[3]) {
@@ -2262,7 +2266,7 @@ int gcb_tables_to_wire_dev(const gcb_plan* plan, uint32_t batch, const gcb_label
     SerParams sp{dl->tmpl, (uint32_t)total, dl->row_pos, plan->p.info.num_rows, reinterpret_cast<const uint4*>(tables), dst, stride};
     const dim3 grid((unsigned)((total + SER_TILE - 1) / SER_TILE), batch);
     serialize_kernel<<<grid, SER_THREADS, 0, (cudaStream_t)stream>>>(sp);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
     GCB_CATCH
 }
@@ -2282,7 +2286,7 @@ int gcb_tables_from_wire_dev(const gcb_plan* plan, uint32_t batch, const uint8_t
     const size_t work = (size_t)batch * plan->p.info.num_rows;
     const unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, (size_t)di->sm_count * 8);
     deserialize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dp);
-    CK(cudaGetLastError());
+    CK(launched());
     return GCB_OK;
     GCB_CATCH
 }

@@ -105,3 +105,20 @@ def test_iknp_2_24(pos):
         assert eq(u[8192 * c0: 8192 * c0 + len(o_u)], o_u) and eq(t[lo:lo + rows], o_t)
         o_q, _ = O.iknp_send(ks, delta[0], pos + 64 * c0, o_u, rows)
         assert eq(q[lo:lo + rows], o_q)
+
+
+def test_stream_program_over_1e8_gates():
+    """BASELINE config 5 at its stated size (>= 10^8 gates per program instance, compiler/ssa/streamer.go:664-699,
+    benchmarks.md:677-703) for a small batch: 377 chained sha512 / mul64 steps through the streaming garbler and
+    evaluator; the first record streams equal the oracle's bytes, and the final state of the evaluator decodes to
+    the plaintext evaluation of the whole program."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import stream_program as sp
+    steps = sp.steps_for_gates(1e8)
+    assert steps >= 300
+    torch.cuda.set_device(0)
+    res = sp.run_program(steps, batch=3, check=2, warm=2, oracle_steps=2)
+    assert res["gates_per_instance"] >= 100_000_000
+    assert res["checks_ok"]
