@@ -32,6 +32,9 @@ import time
 
 import numpy as np
 
+# more hardware work queues than the default 8, before the CUDA context exists: the job API keeps 8 library
+# streams busy beside the caller's own
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

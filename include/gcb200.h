@@ -118,6 +118,8 @@ typedef struct {
     uint32_t team_threads;
     uint32_t garble_hashes;   /* AES blocks per garbled instance (4/AND, 4/OR, 2/INV) */
     uint32_t eval_hashes;     /* AES blocks per evaluated instance (2/AND, 1/OR, 1/INV) */
+    uint32_t garble_passes;   /* warp passes of 32 AES blocks the cipher levels start, garbler ... */
+    uint32_t eval_passes;     /* ... and evaluator (>= hashes / 32: a level pays for whole passes) */
 } gcb_plan_info;
 
 /* Replaces: the per-circuit preparation Circuit.Garble does lazily

@@ -3,10 +3,10 @@
 // and MiTCCRH host calls).
 //
 // A call becomes a JOB: one part per selected device (gcb_set_devices), each part cut into slices of
-// whole kernel waves.  Everything is queued on the part's three streams -- inputs host->device on
+// whole kernel waves.  Everything is queued on three of the device's streams -- inputs host->device on
 // `h2d`, the kernel of a slice on `k` behind its inputs, results device->host on `d2h` behind the
-// kernel -- and the call returns; gcb_job_wait() blocks until the results are in the caller's
-// buffers.  One host thread therefore keeps the copy engines of every device busy in both
+// kernel, ordered by events -- and the call returns; gcb_job_wait() blocks until the results are in the
+// caller's buffers.  One host thread therefore keeps the copy engines of every device busy in both
 // directions.  Page-locked user memory (gcb_host_alloc) is DMA'd in place; pageable memory goes
 // through a pinned arena with one extra host memcpy each way (inputs inside begin, results inside
 // wait).  Streams, events and arenas are pooled per device and reused by later calls.
@@ -57,21 +57,40 @@ inline bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-// What one part of a job holds while it is in flight.
+// The streams of one device, shared by every job on it.  Few on purpose: the hardware has a limited number
+// of work queues per context (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default), and streams that share a queue block
+// one another -- with three private streams per job, a result copy waiting for its kernel held up the input
+// copies of other jobs queued behind it.  Bulk copies of the two directions have their own streams per job
+// class (garble: small inputs up, tables down; eval: tables up, small results down), so neither class waits
+// behind the other's bulk transfers; kernels rotate over four streams so that short launches overlap.
+struct StreamSet {
+    cudaStream_t h2d[2] = {nullptr, nullptr}, d2h[2] = {nullptr, nullptr}, k[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t next_k = 0;
+    cudaError_t init() {
+        cudaError_t e;
+        for (cudaStream_t* s : {&h2d[0], &h2d[1], &d2h[0], &d2h[1], &k[0], &k[1], &k[2], &k[3]})
+            if ((e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+};
+
+// What one part of a job holds while it is in flight: its slice of the device's streams, events, staging arenas.
 struct JobRes {
     int device = -1;
-    cudaStream_t h2d = nullptr, k = nullptr, d2h = nullptr;
+    cudaStream_t h2d = nullptr, k = nullptr, d2h = nullptr;      // assigned from the device's StreamSet at lease time
     std::vector<cudaEvent_t> events;
     size_t ev_used = 0;
+    cudaEvent_t tail[3] = {nullptr, nullptr, nullptr};             // behind everything this part queued on h2d / k / d2h
+    bool sealed = false;
     Arena dev, pin;
 
     cudaError_t init(int dev_index) {
         device = dev_index;
         pin.pinned_host = true;
         cudaError_t e;
-        if ((e = cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        if ((e = cudaStreamCreateWithFlags(&k, cudaStreamNonBlocking)) != cudaSuccess) return e;
-        return cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking);
+        for (cudaEvent_t& t : tail)
+            if ((e = cudaEventCreateWithFlags(&t, cudaEventDisableTiming)) != cudaSuccess) return e;
+        return cudaSuccess;
     }
     cudaError_t event(cudaEvent_t* out) {
         if (ev_used == events.size()) {
@@ -83,38 +102,78 @@ struct JobRes {
         *out = events[ev_used++];
         return cudaSuccess;
     }
-    // Everything queued has run (or failed): nothing refers to caller memory any more.
+    // Marks the end of what this part queued (the streams are shared: later work of other jobs must not be waited for).
+    cudaError_t seal() {
+        cudaError_t e = cudaSuccess, r;
+        const cudaStream_t st[3] = {h2d, k, d2h};
+        for (int i = 0; i < 3; i++)
+            if (st[i] && (r = cudaEventRecord(tail[i], st[i])) != cudaSuccess && e == cudaSuccess) e = r;
+        sealed = true;
+        return e;
+    }
+    // Everything this part queued has run (or failed): nothing refers to caller memory any more.
     cudaError_t quiesce() {
         cudaError_t e = cudaSuccess, r;
-        for (cudaStream_t s : {h2d, k, d2h})
-            if (s && (r = cudaStreamSynchronize(s)) != cudaSuccess && e == cudaSuccess) e = r;
-        ev_used = 0; dev.used = 0; pin.used = 0;
+        if (!sealed) e = seal();
+        for (cudaEvent_t t : tail)
+            if (t && (r = cudaEventSynchronize(t)) != cudaSuccess && e == cudaSuccess) e = r;
+        ev_used = 0; dev.used = 0; pin.used = 0; sealed = false;
         return e;
     }
     ~JobRes() {
         if (device >= 0) cudaSetDevice(device);
-        for (cudaStream_t s : {h2d, k, d2h}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+        if (sealed) for (cudaEvent_t t : tail) if (t) cudaEventSynchronize(t);
+        for (cudaEvent_t t : tail) if (t) cudaEventDestroy(t);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
     }
 };
 
 class ResPool {
 public:
-    std::unique_ptr<JobRes> lease(int device, cudaError_t* err) {
+    // cls: 0 = garble-like (bulk results), 1 = eval-like (bulk inputs).  want: device staging bytes the part needs;
+    // the pooled entry that fits best is taken, and a new arena is sized for the largest request seen so far, so that
+    // the pool converges to arenas any part can use (growing one costs a cudaFree, i.e. a device-wide synchronisation).
+    std::unique_ptr<JobRes> lease(int device, int cls, size_t want, cudaError_t* err) {
+        std::unique_ptr<JobRes> r;
+        StreamSet* ss = nullptr;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            for (auto& r : retired_) {                    // finished fan-out parts (retire() may not touch CUDA)
-                r->ev_used = 0; r->dev.used = 0; r->pin.used = 0;
-                pool_[r->device].push_back(std::move(r));
+            for (auto& q : retired_) {                    // finished fan-out parts (retire() may not touch CUDA)
+                q->ev_used = 0; q->dev.used = 0; q->pin.used = 0; q->sealed = false;
+                pool_[q->device].push_back(std::move(q));
             }
             retired_.clear();
             auto& v = pool_[device];
-            if (!v.empty()) { auto r = std::move(v.back()); v.pop_back(); return r; }
+            size_t best = v.size();
+            for (size_t i = 0; i < v.size(); i++) {
+                const bool fits = v[i]->dev.cap >= want;
+                if (best == v.size()) { best = i; continue; }
+                const bool best_fits = v[best]->dev.cap >= want;
+                if ((fits && !best_fits) || (fits == best_fits && (fits ? v[i]->dev.cap < v[best]->dev.cap : v[i]->dev.cap > v[best]->dev.cap))) best = i;
+            }
+            if (best < v.size()) { r = std::move(v[best]); v.erase(v.begin() + (long)best); }
+            size_t& hw = high_water_[device];
+            if (want > hw) hw = want;
+            want_alloc_ = hw;
+            auto& slot = streams_[device];
+            if (!slot) {
+                slot = std::make_unique<StreamSet>();
+                if ((*err = slot->init()) != cudaSuccess) { slot.reset(); return nullptr; }
+            }
+            ss = slot.get();
+            if (!r) {
+                r = std::make_unique<JobRes>();
+                if ((*err = r->init(device)) != cudaSuccess) return nullptr;
+            }
+            r->h2d = ss->h2d[cls & 1];
+            r->d2h = ss->d2h[cls & 1];
+            r->k = ss->k[ss->next_k++ & 3];
         }
-        auto r = std::make_unique<JobRes>();
-        *err = r->init(device);
-        if (*err != cudaSuccess) return nullptr;
         return r;
+    }
+    size_t alloc_hint(int device) {
+        std::lock_guard<std::mutex> lk(mu_);
+        return high_water_[device];
     }
     void give_back(std::unique_ptr<JobRes> r) {          // callers quiesce() first
         if (!r) return;
@@ -132,6 +191,9 @@ private:
     std::vector<std::unique_ptr<JobRes>> retired_;
     std::mutex mu_;
     std::map<int, std::vector<std::unique_ptr<JobRes>>> pool_;
+    std::map<int, std::unique_ptr<StreamSet>> streams_;
+    std::map<int, size_t> high_water_;
+    size_t want_alloc_ = 0;
 };
 
 // A result that lands in the pinned arena and still has to reach pageable caller memory.

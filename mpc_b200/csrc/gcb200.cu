@@ -53,6 +53,11 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
     } while (0)
 
+// The library keeps eight streams per device busy beside the caller's own; the default of 8 hardware work queues
+// per context makes streams share queues (false dependencies between jobs).  Takes effect when the library is
+// loaded before the CUDA context is created and the variable is not set by the user.
+__attribute__((constructor)) static void more_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 // ----------------------------------------------------------------- devices ----
 constexpr size_t kSmemOptin = 232448;           // 227 KiB per CTA on sm_100
 constexpr uint32_t kCounterRing = 1024;
@@ -507,11 +512,17 @@ static int ensure_wires(gcb_stream* s, uint32_t max_id) {
 // Host-pointer garble / eval as asynchronous jobs (async.hpp).
 static ResPool g_res_pool;
 
-static int lease_res(int device, std::unique_ptr<JobRes>* out) {
+static int lease_res(int device, std::unique_ptr<JobRes>* out, int cls = 0, size_t want = 0) {
     cudaError_t e = cudaSuccess;
-    *out = g_res_pool.lease(device, &e);
+    *out = g_res_pool.lease(device, cls, want, &e);
     if (!*out) return cuda_fail(e, "stream creation");
     return GCB_OK;
+}
+// Grows the part's device arena: to the largest request any part of this device has made so far, not just to this one.
+static cudaError_t reserve_dev(JobRes& r) {
+    if (r.dev.used <= r.dev.cap) return cudaSuccess;
+    const size_t hint = g_res_pool.alloc_hint(r.device);
+    return r.dev.reserve(hint > r.dev.used ? hint : r.dev.used);
 }
 
 // One operand of a staged call: `per` bytes per instance at host address `host` (already offset to the
@@ -553,10 +564,12 @@ static int begin_part(bool garble, const Plan& plan, int device, const uint8_t* 
     DeviceInfo* di;
     int rc = use_device(device, &di);
     if (rc) return rc;
-    if ((rc = lease_res(device, &part->res))) return rc;
+    size_t per_inst = 0, want = 512;
+    for (std::vector<Operand>* v : {&ins, &outs})
+        for (Operand& o : *v) if (o.per) want += (((size_t)batch * o.per + 255) & ~(size_t)255);
+    if ((rc = lease_res(device, &part->res, garble ? 0 : 1, want))) return rc;
     JobRes& r = *part->res;
-    r.dev.used = r.pin.used = 0; r.ev_used = 0;
-    size_t per_inst = 0;
+    r.dev.used = r.pin.used = 0; r.ev_used = 0; r.sealed = false;
     const size_t key_pin = r.pin.take(64), key_dev = r.dev.take(64);      // the shared key always goes through pinned staging
     for (std::vector<Operand>* v : {&ins, &outs})
         for (Operand& o : *v) {
@@ -567,7 +580,7 @@ static int begin_part(bool garble, const Plan& plan, int device, const uint8_t* 
             per_inst += o.per;
         }
     cudaError_t e;
-    if ((e = r.dev.reserve(r.dev.used)) != cudaSuccess) return cuda_fail(e, "device staging allocation");
+    if ((e = reserve_dev(r)) != cudaSuccess) return cuda_fail(e, "device staging allocation");
     if ((e = r.pin.reserve(r.pin.used)) != cudaSuccess) return cuda_fail(e, "pinned staging allocation");
     auto copy_in = [&](void* dst, const void* src, size_t n) {
         return peer.home >= 0 ? cudaMemcpyPeerAsync(dst, device, src, peer.home, n, r.h2d)
@@ -632,6 +645,7 @@ static int begin_part(bool garble, const Plan& plan, int device, const uint8_t* 
         CK(r.event(peer.done));
         CK(cudaEventRecord(*peer.done, r.d2h));
     }
+    CK(r.seal());
     return GCB_OK;
 }
 
@@ -811,16 +825,18 @@ struct HostOp {
 static int stage_begin(int device, std::vector<HostOp*> ops, JobPart* part) {
     int rc = use_device(device, nullptr);
     if (rc) return rc;
-    if ((rc = lease_res(device, &part->res))) return rc;
+    size_t want = 0;
+    for (HostOp* o : ops) want += ((o->bytes ? o->bytes : 16) + 255) & ~(size_t)255;
+    if ((rc = lease_res(device, &part->res, 0, want))) return rc;
     JobRes& r = *part->res;
-    r.dev.used = r.pin.used = 0; r.ev_used = 0;
+    r.dev.used = r.pin.used = 0; r.ev_used = 0; r.sealed = false;
     for (HostOp* o : ops) {
         o->pinned = o->host() && is_pinned(o->host());
         o->dev_off = r.dev.take(o->bytes ? o->bytes : 16);
         if (!o->pinned) o->pin_off = r.pin.take(o->bytes ? o->bytes : 16);
     }
     cudaError_t e;
-    if ((e = r.dev.reserve(r.dev.used)) != cudaSuccess) return cuda_fail(e, "device staging allocation");
+    if ((e = reserve_dev(r)) != cudaSuccess) return cuda_fail(e, "device staging allocation");
     if ((e = r.pin.reserve(r.pin.used ? r.pin.used : 16)) != cudaSuccess) return cuda_fail(e, "pinned staging allocation");
     for (HostOp* o : ops) {
         o->dptr = r.dev.base + o->dev_off;
@@ -844,6 +860,7 @@ static int stage_end(std::vector<HostOp*> ops, JobPart* part) {
             part->late.push_back(LateCopy{o->dst, static_cast<const uint8_t*>(h), o->bytes, ready});
         }
     }
+    CK(r.seal());
     return GCB_OK;
 }
 // Runs body(device, lo, hi, part) for every device's block of `units`, then waits for all parts.
@@ -1172,8 +1189,9 @@ int gcb_job_done(gcb_job* job) {
     for (JobPart& part : job->parts) {
         if (!part.res) continue;
         cudaSetDevice(part.res->device);
-        for (cudaStream_t st : {part.res->h2d, part.res->k, part.res->d2h}) {
-            const cudaError_t e = cudaStreamQuery(st);
+        if (!part.res->sealed) continue;
+        for (cudaEvent_t t : part.res->tail) {
+            const cudaError_t e = cudaEventQuery(t);
             if (e == cudaErrorNotReady) return 0;
             if (e != cudaSuccess) return 1;              // gcb_job_wait reports it
         }
@@ -2305,6 +2323,7 @@ int gcb_tables_to_wire(const gcb_plan* plan, uint32_t batch, const gcb_label* ta
         if ((rc = gcb_tables_to_wire_dev(plan, (uint32_t)m, (const gcb_label*)dt.dptr, (uint8_t*)dw.dptr, s16, part->res->k))) return rc;
         // rows of `total` bytes at the caller's stride (pageable or pinned: the 2-D copy handles both)
         CK(cudaMemcpy2DAsync(dst + lo * stride, stride, dw.dptr, s16, total, m, cudaMemcpyDeviceToHost, part->res->k));
+        CK(part->res->seal());
         return GCB_OK;
     });
     GCB_CATCH

@@ -19,7 +19,7 @@ constexpr int64_t kForever = std::numeric_limits<int64_t>::max();
 inline int op_class(uint8_t op) { return op <= OP_XNOR ? 0 : (op == OP_INV ? 2 : 1); }
 }  // namespace
 
-int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin) {
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin, int balance) {
     char msg[160];
     const uint32_t ng = spec.num_gates, nw = spec.num_wires;
     const bool identity = spec.loc.empty();
@@ -106,24 +106,102 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         }
         is_out_def[(size_t)cur_def[l]] = 1;
     }
-    auto alap_levels = [&](bool cipher_asap) {
+    // fixed: cipher levels chosen by the caller (the balanced schedule); the free gates then go as late as their
+    // consumers allow, but never before their own inputs exist under those cipher levels.
+    auto alap_levels = [&](bool cipher_asap, const std::vector<uint32_t>* fixed = nullptr) {
         constexpr uint32_t kNone = 0xffffffffu;
         std::vector<uint32_t> need(ndefs, kNone);          // latest phase in which the definition may appear
         const uint32_t last_phase = n_phases ? n_phases - 1 : 0;
         for (size_t d = 0; d < ndefs; d++) if (is_out_def[d]) need[d] = last_phase;
+        std::vector<uint32_t> earliest;
+        if (fixed) {                                       // when each value exists, front to back
+            std::vector<uint32_t> avail(ndefs, 0);
+            earliest.resize(ng);
+            for (uint32_t i = 0; i < ng; i++) {
+                earliest[i] = std::max(avail[(size_t)def_a[i]], avail[(size_t)def_b[i]]);
+                avail[ninit + i] = spec.gates[i].op >= OP_AND ? (*fixed)[i] + 1 : earliest[i];
+            }
+        }
         std::vector<uint32_t> lv(ng);
         for (uint32_t i = ng; i-- > 0;) {
             const bool cipher = spec.gates[i].op >= OP_AND;
+            const uint32_t lo = fixed ? earliest[i] : asap[i];
             uint32_t l = need[ninit + i];
-            if (cipher) l = (l == kNone || cipher_asap) ? asap[i] : (l == 0 ? 0 : l - 1);
-            else if (l == kNone) l = asap[i];
-            if (l < asap[i]) l = asap[i];
+            if (cipher) l = fixed ? (*fixed)[i] : (l == kNone || cipher_asap) ? asap[i] : (l == 0 ? 0 : l - 1);
+            else if (l == kNone) l = lo;
+            if (l < lo) l = lo;
             lv[i] = l;
             // what this gate demands of its inputs: available in phase lv (free producers) --
             // the kernel runs a phase's free wires before its cipher level
             for (const int64_t d : {def_a[i], def_b[i]}) need[(size_t)d] = std::min(need[(size_t)d], lv[i]);
         }
         return lv;
+    };
+
+    // ---- balanced cipher levels.  A cipher level costs one warp pass per 32 tasks STARTED (4 tasks per AND / OR
+    // and 2 per INV in the garbler, 2 and 1 in the evaluator): a level of 39 tasks pays for 64.  Deep, narrow
+    // circuits (sha256: 2,387 levels of ~39 garbler tasks) have slack -- most gates are not on the critical path --
+    // so the levels are filled front to back: a level takes the gates that can wait no longer (ALAP level reached)
+    // and tops its last pass up with ready gates that could still wait, least slack first.  The depth is unchanged.
+    auto balanced_levels = [&](int mode) {
+        const uint32_t wq = mode == 1 ? 4u : 2u, wi = mode == 1 ? 2u : 1u;       // tasks per AND/OR, per INV
+        const std::vector<uint32_t> alap = alap_levels(false);
+        std::vector<std::vector<uint32_t>> users(ndefs);
+        for (uint32_t i = 0; i < ng; i++) {
+            users[(size_t)def_a[i]].push_back(i);
+            if (def_b[i] != def_a[i]) users[(size_t)def_b[i]].push_back(i);
+        }
+        std::vector<uint32_t> avail(ndefs, 0), lv(ng, 0);
+        std::vector<uint8_t> waiting(ng);
+        for (uint32_t i = 0; i < ng; i++) waiting[i] = def_a[i] == def_b[i] ? 1 : 2;
+        std::vector<std::vector<uint32_t>> ready_at(n_phases + 1);
+        std::vector<size_t> stack;
+        auto resolve = [&](size_t d0) {                        // definition d0 now has its availability level
+            stack.assign(1, d0);
+            while (!stack.empty()) {
+                const size_t d = stack.back();
+                stack.pop_back();
+                for (uint32_t u : users[d]) {
+                    if (--waiting[u]) continue;
+                    const uint32_t e = std::max(avail[(size_t)def_a[u]], avail[(size_t)def_b[u]]);
+                    if (spec.gates[u].op >= OP_AND) ready_at[std::min<uint32_t>(e, n_phases)].push_back(u);
+                    else { avail[ninit + u] = e; stack.push_back(ninit + u); }
+                }
+            }
+        };
+        for (size_t k = 0; k < ninit; k++) resolve(k);
+        using Item = std::pair<uint32_t, uint32_t>;             // (ALAP level, gate): least slack first
+        std::priority_queue<Item, std::vector<Item>, std::greater<Item>> pool;
+        std::vector<uint32_t> chosen;
+        for (uint32_t L = 0; L < n_phases; L++) {
+            for (uint32_t g : ready_at[L]) pool.push(Item{alap[g], g});
+            chosen.clear();
+            uint32_t tasks = 0;
+            while (!pool.empty() && pool.top().first <= L) {       // cannot wait
+                const uint32_t g = pool.top().second;
+                pool.pop();
+                chosen.push_back(g);
+                tasks += spec.gates[g].op == OP_INV ? wi : wq;
+            }
+            // top the last pass up (never open a new one for gates that can wait)
+            const uint32_t cap = (tasks + 31) / 32 * 32;
+            std::vector<Item> skipped;
+            while (!pool.empty() && tasks < cap) {
+                const Item it = pool.top();
+                pool.pop();
+                const uint32_t w = spec.gates[it.second].op == OP_INV ? wi : wq;
+                if (tasks + w > cap) { skipped.push_back(it); continue; }
+                chosen.push_back(it.second);
+                tasks += w;
+            }
+            for (const Item& it : skipped) pool.push(it);
+            for (uint32_t g : chosen) {
+                lv[g] = L;
+                avail[ninit + g] = L + 1;
+            }
+            for (uint32_t g : chosen) resolve(ninit + g);
+        }
+        return alap_levels(false, &lv);
     };
 
     // emit = false: only the figures the policies are compared on (slots, steps); the records (and the
@@ -364,10 +442,19 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             err = msg;
             return GCB_E_TOO_LARGE;
         }
+        uint32_t g_passes = 0, e_passes = 0;
+        for (uint32_t p = 0; p < n_phases; p++) {
+            uint32_t nq = 0, ni = 0;
+            for (uint32_t i : phase_cipher[p]) (spec.gates[i].op == OP_INV ? ni : nq)++;
+            g_passes += (4 * nq + 2 * ni + 31) / 32;
+            e_passes += (2 * nq + ni + 31) / 32;
+        }
         if (!emit) {
             out.info = gcb_plan_info{};
             out.info.num_slots = next_slot;
             out.info.num_steps = (uint32_t)nsteps;
+            out.info.garble_passes = g_passes;
+            out.info.eval_passes = e_passes;
             return GCB_OK;
         }
         out.live_out.clear();
@@ -524,22 +611,31 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         in.num_and = n_and; in.num_or = n_or; in.num_inv = n_inv; in.num_free = n_free;
         in.garble_hashes = 4 * n_and + 4 * n_or + 2 * n_inv;
         in.eval_hashes = 2 * n_and + n_or + n_inv;
+        in.garble_passes = g_passes;
+        in.eval_passes = e_passes;
         return GCB_OK;
     };
 
-    // ---- try the schedules and keep the one that needs the fewest wire slots (the three trials are
-    // independent and run on their own threads: the compiler is on the critical path of the first use of a
-    // circuit, e.g. a streaming evaluator that meets a new sub-circuit)
+    // ---- try the schedules and keep the best (the trials are independent and run on their own threads: the
+    // compiler is on the critical path of the first use of a circuit, e.g. a streaming evaluator that meets a new
+    // sub-circuit).  Policies 0-2 are compared on wire slots.  Policies 3 and 4, the schedules balanced for the
+    // garbler's and for the evaluator's pass size, replace the winner when they save at least 2 % of the warp passes
+    // (garbler + evaluator: the plan serves both) and do not cost resident instances: the instances that fit beside
+    // two T-tables must not drop (narrow circuits are bound by the latency of a level, so resident instances count
+    // as much as passes).
     {
+        auto levels_of = [&](int policy) {
+            return policy == 0 ? asap : policy >= 3 ? balanced_levels(policy - 2) : alap_levels(policy == 2);
+        };
         int best_policy = -1, best_rc = GCB_OK;
         uint32_t best_slots = 0, best_steps = 0;
         std::string first_err;
-        const int n_policies = keep_all ? 1 : 3;          // the full-wire plan keeps the simple schedule
-        Plan cand[3];
-        int rcs[3] = {GCB_OK, GCB_OK, GCB_OK};
-        std::string errs[3];
+        const int n_policies = keep_all ? 1 : (balance ? 5 : 3);          // the full-wire plan keeps the simple schedule
+        Plan cand[5];
+        int rcs[5] = {GCB_OK, GCB_OK, GCB_OK, GCB_OK, GCB_OK};
+        std::string errs[5];
         auto trial = [&](int policy) {
-            rcs[policy] = schedule(policy == 0 ? asap : alap_levels(policy == 2), cand[policy], false, errs[policy]);
+            rcs[policy] = schedule(levels_of(policy), cand[policy], false, errs[policy]);
         };
         {
             // joined on every path out of this scope (an exception in trial(0) or in thread creation must not
@@ -555,7 +651,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             for (int policy = 1; policy < n_policies; policy++) workers.v.emplace_back(guarded, policy);
             guarded(0);
         }
-        for (int policy = 0; policy < n_policies; policy++) {
+        for (int policy = 0; policy < std::min(n_policies, 3); policy++) {
             if (rcs[policy] != GCB_OK) { if (best_policy < 0 && first_err.empty()) { first_err = errs[policy]; best_rc = rcs[policy]; } continue; }
             if (best_policy < 0 || cand[policy].info.num_slots < best_slots ||
                 (cand[policy].info.num_slots == best_slots && cand[policy].info.num_steps < best_steps)) {
@@ -563,11 +659,25 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             }
         }
         if (best_policy < 0) { err = first_err; return best_rc; }
+        if (n_policies == 5) {
+            auto resident = [](uint32_t slots) {                  // instances beside two T-tables (gcb200.cu: teams_that_fit)
+                const size_t n = (232448 - 65536 - 1024) / ((size_t)slots * 16 + 272);
+                return n > 16 ? (n >= 32 ? (size_t)32 : (size_t)16) : n;
+            };
+            const gcb_plan_info b = cand[best_policy].info;
+            uint64_t best_passes = ((uint64_t)b.garble_passes + b.eval_passes) * 98 / 100;     // worth it from 2 % on
+            for (int policy = 3; policy < 5; policy++) {
+                const gcb_plan_info& c = cand[policy].info;
+                if (rcs[policy] != GCB_OK || resident(c.num_slots) < resident(b.num_slots)) continue;
+                if ((uint64_t)c.garble_passes + c.eval_passes <= best_passes) { best_policy = policy; best_passes = (uint64_t)c.garble_passes + c.eval_passes; }
+            }
+        }
         Plan best;
         best.row_off = plan.row_off; best.ops = plan.ops;
-        const int rc = schedule(best_policy == 0 ? asap : alap_levels(best_policy == 2), best, true, err);
+        const int rc = schedule(levels_of(best_policy), best, true, err);
         if (rc != GCB_OK) return rc;
         plan.info = best.info;
+        plan.policy = best_policy;
         plan.phases.swap(best.phases); plan.waves.swap(best.waves); plan.nodes.swap(best.nodes);
         plan.crecs.swap(best.crecs); plan.nout_wire.swap(best.nout_wire); plan.cout_wire.swap(best.cout_wire);
         plan.live_in.swap(best.live_in); plan.live_out.swap(best.live_out);

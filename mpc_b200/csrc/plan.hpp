@@ -121,6 +121,7 @@ struct Plan {
     gcb_plan_info info{};
     uint32_t ilp = 1;                     // AES blocks a thread interleaves (kernel variant)
     uint32_t stagger = 0;                 // SM cycles between the starts of consecutive teams
+    int policy = 0;                       // which schedule won (0 ASAP, 1 ALAP, 2 cipher-ASAP + free-ALAP, 3 / 4 balanced for the garbler's / evaluator's passes)
     std::vector<PhaseRec> phases;
     std::vector<WaveRec> waves;
     std::vector<NodeRec> nodes;           // free-wire nodes in schedule order
@@ -139,7 +140,9 @@ struct Plan {
 // Returns GCB_OK or a negative status; message in err.  max_fanin = NODE_MAX_FANIN
 // for the normal plan; 2 keeps every XOR / XNOR gate as its own node (the
 // wires_full variant, where every wire label has to be produced).
-int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN);
+// balance: 0 = the three slot-minimising schedules only; otherwise also the two schedules that fill the warp
+// passes of the garbler / of the evaluator (plan.cpp: balanced_levels).
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, int balance = 1);
 
 }  // namespace gcb
 

@@ -44,7 +44,7 @@ struct Acc {
 };
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: plan_model file.gates team_threads\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: plan_model file.gates team_threads [balance]\n"); return 2; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 1; }
     uint32_t hdr[4];
@@ -59,7 +59,9 @@ int main(int argc, char** argv) {
     for (uint32_t i = 0; i < hdr[3]; i++) spec.live_out.push_back(hdr[1] - hdr[3] + i);
     Plan plan;
     std::string err;
-    if (int rc = build_plan(spec, plan, err)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
+    const int balance = argc > 3 ? atoi(argv[3]) : 0;      // 0 none, 1 garbler, 2 evaluator (plan.cpp: balanced_levels)
+    if (int rc = build_plan(spec, plan, err, NODE_MAX_FANIN, balance)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
+    printf("balance %d  policy %d  garble_passes %u  eval_passes %u\n", balance, plan.policy, plan.info.garble_passes, plan.info.eval_passes);
     const gcb_plan_info& in = plan.info;
     printf("gates %u  and %u inv %u or %u free %u  slots %u  steps %u  phases %zu  waves %zu  nodes %zu  node_loads %u\n",
            in.num_gates, in.num_and, in.num_inv, in.num_or, in.num_free, in.num_slots, in.num_steps, plan.phases.size(),
