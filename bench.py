@@ -377,45 +377,66 @@ def roofline_of(b: Bench, circ, eng, batch: int, g_ms: float, e_ms: float, nr: i
 
 
 def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinned: bool):
-    """The call a user makes, from ONE host thread: gcb_garble_begin on every part, then per part
-    gcb_job_wait -> gcb_eval_begin, then the eval waits.  Host buffers; copies inside the timed region."""
+    """The call a user makes, from ONE host thread, for a stream of batches: gcb_garble_begin on every part of the
+    step's batch, then per part gcb_job_wait -> gcb_eval_begin; the eval jobs of step k are only waited for when
+    their buffers come round again (two sets of host buffers), so the garbler's tables of step k+1 stream back
+    (D2H) while the evaluator's tables of step k stream in (H2D).  Every step copies its own inputs up and its
+    own results down inside the timed region; the last step is fully drained before the clock stops."""
     from mpc_b200.circuit import host_alloc, host_free
     from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
     nin, nout, rows = circ.num_inputs, circ.num_outputs, circ.num_rows
     r, l0, bits = inputs
     alloc = host_alloc if pinned else (lambda shape, dt: np.zeros(shape, dtype=dt))
-    h_r, h_l0 = alloc((batch,), LABEL_DTYPE), alloc((batch, nin), LABEL_DTYPE)
-    h_tab, h_io = alloc((batch, rows), LABEL_DTYPE), alloc((batch, nin + nout), WIRE_DTYPE)
-    h_in, h_out = alloc((batch, nin), LABEL_DTYPE), alloc((batch, nout), LABEL_DTYPE)
-    h_r[:] = r
-    h_l0[:] = l0
+    n_sets = 2
+    sets = []
+    for _ in range(n_sets):
+        h = {"r": alloc((batch,), LABEL_DTYPE), "l0": alloc((batch, nin), LABEL_DTYPE), "tab": alloc((batch, rows), LABEL_DTYPE),
+             "io": alloc((batch, nin + nout), WIRE_DTYPE), "in": alloc((batch, nin), LABEL_DTYPE), "out": alloc((batch, nout), LABEL_DTYPE)}
+        h["r"][:] = r
+        h["l0"][:] = l0
+        sets.append(h)
     n_parts = max(1, min(E2E_PARTS, batch // 64))
     parts = [slice(k * batch // n_parts, (k + 1) * batch // n_parts) for k in range(n_parts)]
+    pending = [[] for _ in range(n_sets)]          # eval jobs still reading / writing each buffer set
 
-    def step():
-        gj = [eng.garble_begin(KEY, h_r[sl], h_l0[sl], h_tab[sl], h_io[sl]) for sl in parts]
-        ej = []
-        for j, sl in zip(gj, parts):
-            j.wait()                                  # this part's tables are on the host: its evaluation may start
-            ej.append(eng.eval_begin(KEY, h_tab[sl], h_in[sl], h_out[sl]))
-        for j in ej:
+    def drain(k):
+        for j in pending[k]:
             j.wait()
+        pending[k] = []
 
-    step()
-    h_in[:] = np.where(bits.astype(bool), h_io["l1"][:, :nin], h_io["l0"][:, :nin])
-    step()
+    def step(k):
+        h = sets[k % n_sets]
+        drain(k % n_sets)                           # the set's previous step has left its buffers
+        gj = [eng.garble_begin(KEY, h["r"][sl], h["l0"][sl], h["tab"][sl], h["io"][sl]) for sl in parts]
+        for j, sl in zip(gj, parts):
+            j.wait()                                # this part's tables are on the host: its evaluation may start
+            pending[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
+
+    for k in range(n_sets):                         # warm-up: also fills the evaluator's input labels of every set
+        step(k)
+        drain(k)
+        h = sets[k]
+        h["in"][:] = np.where(bits.astype(bool), h["io"]["l1"][:, :nin], h["io"]["l0"][:, :nin])
+    for k in range(n_sets):
+        step(k)
+    for k in range(n_sets):
+        drain(k)
     b.barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
+    for k in range(steps):
+        step(k)
+    for k in range(n_sets):
+        drain(k)
     b.torch.cuda.synchronize()
     sec = (time.perf_counter() - t0) / steps
     d_tab, d_out, _ = ref_dev
-    ok = h_out.tobytes() == d_out.cpu().numpy().tobytes() and h_tab.tobytes() == d_tab.cpu().numpy().tobytes()
-    assert ok, "host-pointer path and device-resident path disagree"
+    for h in sets:
+        ok = h["out"].tobytes() == d_out.cpu().numpy().tobytes() and h["tab"].tobytes() == d_tab.cpu().numpy().tobytes()
+        assert ok, "host-pointer path and device-resident path disagree"
     if pinned:
-        for a in (h_r, h_l0, h_tab, h_io, h_in, h_out):
-            host_free(a)
+        for h in sets:
+            for a in h.values():
+                host_free(a)
     return sec, n_parts
 
 
@@ -620,7 +641,8 @@ def run_gcb(args):
         e2e = {"value": n_and * batch * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(world * h2d), "d2h_bytes_per_step": int(world * d2h), "ms_per_step": e2e_ms,
                "how": f"gcb_garble_begin / gcb_eval_begin / gcb_job_wait on page-locked host buffers (gcb_host_alloc), "
-                      f"{n_parts} parts in flight, ONE host thread per GPU"
+                      f"{n_parts} parts per step, two buffer sets (the tables of step k+1 stream back while those of step k "
+                      f"stream in), ONE host thread per GPU"
                       + (f", ranks bound to their GPU's NUMA node ({b.numa['cpus']} cpus)" if b.numa else "")}
 
     extra = {}

@@ -120,6 +120,8 @@ typedef struct {
     uint32_t eval_hashes;     /* AES blocks per evaluated instance (2/AND, 1/OR, 1/INV) */
     uint32_t garble_passes;   /* warp passes of 32 AES blocks the cipher levels start, garbler ... */
     uint32_t eval_passes;     /* ... and evaluator (>= hashes / 32: a level pays for whole passes) */
+    uint32_t num_hot_slots;   /* of num_slots, the labels held in shared memory; the rest (values that idle for
+                                 hundreds of levels between uses) live in an L2-resident scratch per instance */
 } gcb_plan_info;
 
 /* Replaces: the per-circuit preparation Circuit.Garble does lazily

@@ -28,7 +28,7 @@ class PlanInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "num_gates", "num_wires", "num_inputs", "num_outputs", "num_rows", "num_tweaks", "num_steps",
         "num_slots", "num_and", "num_or", "num_inv", "num_free", "teams_per_sm", "team_threads",
-        "garble_hashes", "eval_hashes", "garble_passes", "eval_passes")]
+        "garble_hashes", "eval_hashes", "garble_passes", "eval_passes", "num_hot_slots")]
 
 
 class Label(C.Structure):

@@ -13,6 +13,8 @@ namespace gcb {
 //   ilp 1, nt 2: deep, narrow circuits (twice the label space, four node rows in flight)
 //   ilp 2, nt 2: wide circuits whose live labels do not fit beside four tables
 //   ilp 2, nt 2, spill: circuits whose live labels do not fit on chip at all (the excess in global memory)
+//   ilp 1, nt 2, spill: hot / cold plans of deep, narrow circuits (plan.cpp): only the hot labels in shared memory,
+//                       so that twice the instances are resident
 struct GcVariant { uint32_t ilp, nt; bool spill; };
 
 cudaError_t gc_opt_in_garble(int smem_bytes);
@@ -24,7 +26,7 @@ void gc_launch_eval(int mode, uint32_t keylen, GcVariant v, dim3 grid, dim3 bloc
 // every (rounds, mode, variant) instantiation
 #define GC_FOR_VARIANT(M, NR, MODE) \
     M(NR, MODE, 2, 512, 4, false) M(NR, MODE, 1, 1024, 4, false) M(NR, MODE, 1, 512, 2, false) M(NR, MODE, 2, 512, 2, false) \
-    M(NR, MODE, 2, 512, 2, true)
+    M(NR, MODE, 2, 512, 2, true) M(NR, MODE, 1, 512, 2, true)
 #define GC_FOR_NR(M, MODE) GC_FOR_VARIANT(M, 10, MODE) GC_FOR_VARIANT(M, 12, MODE) GC_FOR_VARIANT(M, 14, MODE)
 #define GC_FOR_ALL(M) GC_FOR_NR(M, GC_PLAIN) GC_FOR_NR(M, GC_FULL) GC_FOR_NR(M, GC_STREAM)
 

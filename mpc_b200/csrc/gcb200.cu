@@ -59,7 +59,6 @@ static int cuda_fail(cudaError_t e, const char* what) {
 __attribute__((constructor)) static void more_work_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 // ----------------------------------------------------------------- devices ----
-constexpr size_t kSmemOptin = 232448;           // 227 KiB per CTA on sm_100
 constexpr uint32_t kCounterRing = 1024;
 
 struct DeviceInfo {
@@ -82,8 +81,6 @@ __global__ void smem_base_probe(uint32_t* out) {
     extern __shared__ __align__(16) uint8_t smem[];
     if (threadIdx.x == 0) *out = smem_addr(smem);
 }
-constexpr uint32_t kAssumedSmemBase = 1024;
-static uint32_t table_pad(uint32_t smem_base) { return ((smem_base + 0xffffu) & ~0xffffu) - smem_base; }
 
 // Which device(s) a call runs on.  A thread that called gcb_set_device(d >= 0) uses d.  Otherwise the
 // process-wide list of gcb_set_devices applies: calls that can split their work (host-pointer garble /
@@ -247,15 +244,21 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
 // each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
 // GCB_NT / GCB_TEAMS / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
 struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false; };
-static size_t teams_that_fit(uint32_t num_slots, uint32_t smem_base, uint32_t nt) {
-    // teams are packed below the 64 KiB-aligned tables first, then above them
-    const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
-    const size_t pad = table_pad(smem_base);
-    return pad / per_team + (kSmemOptin - pad - (size_t)aes_table_bytes((int)nt)) / per_team;
-}
 // width = AES blocks per cipher level of the garbler (4 per AND / OR, 2 per INV), averaged.
-static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base) {
+// num_hot < num_slots: a hot / cold plan (plan.cpp) -- only the hot labels need shared memory.
+static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base, uint32_t num_hot = 0) {
     Geometry g;
+    if (num_hot && num_hot < num_slots) {
+        size_t n = teams_that_fit(num_hot, smem_base, 2);
+        if (n > 16) n = 16;
+        if (n == 0) return g;
+        if (const char* e = getenv("GCB_TEAMS")) { const int v = atoi(e); if (v >= 1 && (size_t)v <= n) n = (size_t)v; }
+        g.n_teams = (uint32_t)n; g.ilp = 1; g.nt = 2; g.spill = true; g.n_smem = num_hot;
+        g.team_threads = n >= 8 ? 32u : 32u * (uint32_t)(512 / 32 / n > 3 ? 3 : 512 / 32 / n);
+        g.stagger = n > 1 ? 100000 : 0;
+        if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
+        return g;
+    }
     const size_t n4 = teams_that_fit(num_slots, smem_base, 4), n2 = teams_that_fit(num_slots, smem_base, 2);
     // Wide levels keep the shared-memory pipe busy with a few resident instances: four tables.
     // Deep, narrow circuits (sha256: 39 blocks per level) are bound by the latency of each level,
@@ -301,7 +304,7 @@ static uint32_t plan_width(const Plan& plan) {
     return np ? (uint32_t)(plan.info.garble_hashes / np) : 0u;
 }
 void team_geometry(Plan& plan) {                    // what gcb_plan_get_info reports (typical device)
-    const Geometry g = compute_geometry(plan.info.num_slots, plan_width(plan), kAssumedSmemBase);
+    const Geometry g = compute_geometry(plan.info.num_slots, plan_width(plan), kAssumedSmemBase, plan.info.num_hot_slots);
     plan.info.teams_per_sm = g.n_teams; plan.info.team_threads = g.team_threads;
     plan.ilp = g.ilp; plan.stagger = g.stagger;
 }
@@ -347,7 +350,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
                      cudaStream_t stream, const uint32_t* in_ids = nullptr, const uint32_t* out_ids = nullptr,
                      uint4* const* pages = nullptr) {
     const gcb_plan_info& in = plan.info;
-    const Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base);
+    const Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base, in.num_hot_slots);
     if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
     std::shared_ptr<DevicePlan> dp;
     int rc = plan_on_device(plan, device, geo.team_threads, &dp);
@@ -1021,7 +1024,8 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     static std::atomic<uint64_t> next_uid{1};
     pl->uid = next_uid.fetch_add(1);
     std::string err;
-    int rc = build_plan(spec, pl->p, err);
+    pl->p.gates.assign(gates, gates + num_gates);
+    int rc = build_best_plan(spec, pl->p, err);
     if (rc) return fail(rc, "%s", err.c_str());
     team_geometry(pl->p);
     if (pl->p.info.teams_per_sm == 0)
@@ -1496,7 +1500,7 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
             auto ap = std::make_shared<gcb_stream::AliasPlan>();
             ap->plan_uid = plan->uid;
             ap->plan = std::make_unique<Plan>();
-            if ((rc = build_plan(spec, *ap->plan, err))) return fail(rc, "%s", err.c_str());
+            if ((rc = build_best_plan(spec, *ap->plan, err))) return fail(rc, "%s", err.c_str());
             team_geometry(*ap->plan);
             if (ap->plan->info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ap->plan->info.num_slots);
             ap->loc = spec.loc;
@@ -1785,7 +1789,7 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
             if (first_is_read[l]) { spec.live_in.push_back(l); ep->in_ids.push_back(l); }     // canonical locations;
             if (written[l]) { spec.live_out.push_back(l); ep->out_ids.push_back(l); }         // mapped to ids per call
         }
-        if ((rc = build_plan(spec, ep->plan, err))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
+        if ((rc = build_best_plan(spec, ep->plan, err))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
         team_geometry(ep->plan);
         if (ep->plan.info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ep->plan.info.num_slots);
         ep->canon.swap(canon);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstdio>
 #include <functional>
 #include <iterator>
@@ -19,7 +20,7 @@ constexpr int64_t kForever = std::numeric_limits<int64_t>::max();
 inline int op_class(uint8_t op) { return op <= OP_XNOR ? 0 : (op == OP_INV ? 2 : 1); }
 }  // namespace
 
-int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin, int balance) {
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin, int balance, uint32_t hot_cap, int only_policy) {
     char msg[160];
     const uint32_t ng = spec.num_gates, nw = spec.num_wires;
     const bool identity = spec.loc.empty();
@@ -308,8 +309,69 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         for (const int64_t d : out_def) last[(size_t)d] = kForever;
         for (size_t d = 0; d < ndefs; d++) last[d] = std::max(last[d], born[d]);
 
+        // ---- hot / cold.  With hot_cap > 0 at most hot_cap labels may be live in shared memory at any step; the
+        // others are COLD: they live in the team's scratch in global memory (L2-resident) for their whole life and
+        // are read from there by the nodes and gates that use them (gc_kernels.cuh: SlotsSpill).  Deep, narrow
+        // circuits are bound by the latency of a level, so the instances an SM holds count more than an L2 round trip
+        // now and then: sha256 keeps its 768 inputs and its message schedule live for hundreds of levels between
+        // uses.  A value is cold when it idles long per access (lifetime / (reads + 1) above a threshold); the
+        // threshold is the largest one whose hot set fits.
+        std::vector<uint8_t> cold(ndefs, 0);
+        uint64_t cold_accesses = 0;
+        if (hot_cap) {
+            std::vector<uint32_t> nreads(ndefs, 0);
+            for (uint32_t p = 0; p < n_phases; p++) {
+                for (const Node& nd : phase_nodes[p]) for (uint32_t l : nd.leaves) nreads[l]++;
+                for (uint32_t i : phase_cipher[p]) { nreads[(size_t)def_a[i]]++; nreads[(size_t)def_b[i]]++; }
+            }
+            std::vector<int64_t> b0(ndefs), l0(ndefs);
+            std::vector<double> idle(ndefs, 0.0);
+            std::vector<uint8_t> stored(ndefs, 0);                 // values that get a slot at all (not the inlined XORs)
+            for (size_t d = 0; d < ndefs; d++) {
+                stored[d] = d < ninit || born[d] >= 0;
+                if (!stored[d]) continue;
+                b0[d] = std::max<int64_t>(born[d], 0);
+                l0[d] = last[d] == kForever ? nsteps : std::max<int64_t>(last[d], b0[d]);
+                idle[d] = (double)(l0[d] - b0[d] + 1) / (nreads[d] + 1);
+            }
+            // live labels per step, as a max segment tree with lazy range add
+            size_t nleaf = 1;
+            while (nleaf < (size_t)nsteps + 2) nleaf <<= 1;
+            std::vector<int32_t> mx(2 * nleaf, 0), lz(2 * nleaf, 0);
+            std::function<void(size_t, size_t, size_t, size_t, size_t, int32_t)> add = [&](size_t n, size_t l, size_t r, size_t ql, size_t qr, int32_t v) {
+                if (qr < l || r < ql) return;
+                if (ql <= l && r <= qr) { mx[n] += v; lz[n] += v; return; }
+                const size_t m = (l + r) / 2;
+                add(2 * n, l, m, ql, qr, v); add(2 * n + 1, m + 1, r, ql, qr, v);
+                mx[n] = std::max(mx[2 * n], mx[2 * n + 1]) + lz[n];
+            };
+            std::function<int32_t(size_t, size_t, size_t, size_t, size_t)> qmax = [&](size_t n, size_t l, size_t r, size_t ql, size_t qr) -> int32_t {
+                if (qr < l || r < ql) return INT32_MIN / 2;
+                if (ql <= l && r <= qr) return mx[n];
+                const size_t m = (l + r) / 2;
+                return std::max(qmax(2 * n, l, m, ql, qr), qmax(2 * n + 1, m + 1, r, ql, qr)) + lz[n];
+            };
+            std::vector<size_t> order;
+            for (size_t d = 0; d < ndefs; d++)
+                if (stored[d]) { order.push_back(d); add(1, 0, nleaf - 1, (size_t)b0[d], (size_t)l0[d], 1); }
+            // longest idle per access first; a value goes cold only if it is live across a step that is still over the cap
+            std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return idle[x] != idle[y] ? idle[x] > idle[y] : x < y; });
+            for (size_t d : order) {
+                if (mx[1] <= (int32_t)hot_cap) break;
+                if (qmax(1, 0, nleaf - 1, (size_t)b0[d], (size_t)l0[d]) <= (int32_t)hot_cap) continue;
+                cold[d] = 1;
+                cold_accesses += nreads[d] + 1;
+                add(1, 0, nleaf - 1, (size_t)b0[d], (size_t)l0[d], -1);
+            }
+            if (mx[1] > (int32_t)hot_cap) { err = "hot set does not fit"; return GCB_E_TOO_LARGE; }
+        }
+
         // ---- slots: lowest free index first; a slot whose value was last read in step s may
-        // be rewritten from step s+1 on (reads and writes of one step are unordered).
+        // be rewritten from step s+1 on (reads and writes of one step are unordered).  Cold values take slots
+        // from their own pool, numbered from kColdBase while the hot pool grows and renumbered behind it at the end.
+        constexpr uint32_t kColdBase = 0x40000000u;
+        std::set<uint32_t> free_cold;
+        uint32_t next_cold = 0;
         std::vector<std::vector<size_t>> expire((size_t)nsteps + 1);
         std::vector<uint32_t> slot(ndefs, 0);
         // Free slots by bank group (slot & 7: a 16-byte label covers four of the 32 banks).  A
@@ -320,10 +382,16 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         // slot is opened only when no slot is free).
         std::set<uint32_t> free_slots[8];
         uint32_t next_slot = 0;
-        auto release = [&](uint32_t s) { free_slots[s & 7].insert(s); };
+        auto release = [&](uint32_t s) { if (s >= kColdBase) free_cold.insert(s); else free_slots[s & 7].insert(s); };
+        auto take_cold = [&]() {
+            if (free_cold.empty()) return kColdBase + next_cold++;
+            const uint32_t c = *free_cold.begin();
+            free_cold.erase(free_cold.begin());
+            return c;
+        };
         out.live_in.clear();
         for (size_t k = 0; k < ninit; k++) {
-            slot[k] = next_slot++;
+            slot[k] = cold[k] ? take_cold() : next_slot++;
             out.live_in.push_back(SlotRef{slot[k], (uint32_t)k});
             if (last[k] < 0) release(slot[k]);                         // never read, not live-out
             else if (last[k] != kForever) expire[(size_t)last[k]].push_back(k);
@@ -358,6 +426,11 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         uint16_t store_used[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         auto take_slot = [&](size_t d, uint32_t lane) {
             if ((lane & 7) == 0) std::fill(store_used, store_used + 8, (uint16_t)0);
+            if (cold[d]) {
+                slot[d] = take_cold();
+                if (last[d] != kForever) expire[(size_t)last[d]].push_back(d);
+                return;
+            }
             int from = -1;
             uint32_t best = 0xffffffffu;
             for (int b = 0; b < 8; b++) {
@@ -437,11 +510,15 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                 }
             }
         }
-        if (next_slot > 65535) {
-            snprintf(msg, sizeof msg, "circuit needs %u live wire slots (limit 65535)", next_slot);
+        if (next_slot + next_cold > 65535) {
+            snprintf(msg, sizeof msg, "circuit needs %u live wire slots (limit 65535)", next_slot + next_cold);
             err = msg;
             return GCB_E_TOO_LARGE;
         }
+        const uint32_t num_hot = next_slot;
+        for (size_t d = 0; d < ndefs; d++) if (slot[d] >= kColdBase) slot[d] = num_hot + (slot[d] - kColdBase);
+        for (SlotRef& r : out.live_in) if (r.slot >= kColdBase) r.slot = num_hot + (r.slot - kColdBase);
+        next_slot += next_cold;
         uint32_t g_passes = 0, e_passes = 0;
         for (uint32_t p = 0; p < n_phases; p++) {
             uint32_t nq = 0, ni = 0;
@@ -452,7 +529,9 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         if (!emit) {
             out.info = gcb_plan_info{};
             out.info.num_slots = next_slot;
+            out.info.num_hot_slots = num_hot;
             out.info.num_steps = (uint32_t)nsteps;
+            out.cold_accesses = cold_accesses;
             out.info.garble_passes = g_passes;
             out.info.eval_passes = e_passes;
             return GCB_OK;
@@ -608,6 +687,8 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         in.num_tweaks = tweak;
         in.num_steps = (uint32_t)nsteps;
         in.num_slots = next_slot;
+        in.num_hot_slots = num_hot;
+        out.cold_accesses = cold_accesses;
         in.num_and = n_and; in.num_or = n_or; in.num_inv = n_inv; in.num_free = n_free;
         in.garble_hashes = 4 * n_and + 4 * n_or + 2 * n_inv;
         in.eval_hashes = 2 * n_and + n_or + n_inv;
@@ -637,7 +718,8 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         auto trial = [&](int policy) {
             rcs[policy] = schedule(levels_of(policy), cand[policy], false, errs[policy]);
         };
-        {
+        if (only_policy >= 0 && only_policy < n_policies) best_policy = only_policy;      // the caller knows which schedule it wants
+        else {
             // joined on every path out of this scope (an exception in trial(0) or in thread creation must not
             // leave joinable threads behind: that would terminate the process)
             struct Joiner {
@@ -651,7 +733,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             for (int policy = 1; policy < n_policies; policy++) workers.v.emplace_back(guarded, policy);
             guarded(0);
         }
-        for (int policy = 0; policy < std::min(n_policies, 3); policy++) {
+        for (int policy = 0; only_policy < 0 && policy < std::min(n_policies, 3); policy++) {
             if (rcs[policy] != GCB_OK) { if (best_policy < 0 && first_err.empty()) { first_err = errs[policy]; best_rc = rcs[policy]; } continue; }
             if (best_policy < 0 || cand[policy].info.num_slots < best_slots ||
                 (cand[policy].info.num_slots == best_slots && cand[policy].info.num_steps < best_steps)) {
@@ -659,9 +741,9 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             }
         }
         if (best_policy < 0) { err = first_err; return best_rc; }
-        if (n_policies == 5) {
-            auto resident = [](uint32_t slots) {                  // instances beside two T-tables (gcb200.cu: teams_that_fit)
-                const size_t n = (232448 - 65536 - 1024) / ((size_t)slots * 16 + 272);
+        if (n_policies == 5 && only_policy < 0) {
+            auto resident = [](uint32_t slots) {                  // instances beside two T-tables
+                const size_t n = teams_that_fit(slots, kAssumedSmemBase, 2);
                 return n > 16 ? (n >= 32 ? (size_t)32 : (size_t)16) : n;
             };
             const gcb_plan_info b = cand[best_policy].info;
@@ -682,6 +764,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         plan.crecs.swap(best.crecs); plan.nout_wire.swap(best.nout_wire); plan.cout_wire.swap(best.cout_wire);
         plan.live_in.swap(best.live_in); plan.live_out.swap(best.live_out);
         plan.node_loads = best.node_loads;
+        plan.cold_accesses = best.cold_accesses;
     }
     return GCB_OK;
 }
@@ -689,6 +772,42 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 }  // namespace gcb
 
 namespace gcb {
+
+int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin) {
+    int rc = build_plan(spec, plan, err, max_fanin);
+    if (rc != GCB_OK || max_fanin == 2) return rc;
+    int force = -1;
+    if (const char* e = getenv("GCB_HOT_TEAMS")) force = atoi(e);
+    if (force == 0) return GCB_OK;
+    const gcb_plan_info& in = plan.info;
+    const size_t np = plan.phases.size();
+    const uint32_t width = np ? (uint32_t)(in.garble_hashes / np) : 0u;
+    const size_t have = teams_that_fit(in.num_slots, kAssumedSmemBase, 2);
+    if (force < 0 && (width >= 128 || have >= 16 || in.num_slots < 256)) return GCB_OK;    // wide (pipe-bound) or already many
+    // the target: twice the resident instances (at most 16), or what the caller forces
+    for (size_t target = force > 0 ? (size_t)force : std::min<size_t>(16, have ? 2 * have : 2); target > have; target /= 2) {
+        uint32_t lo = 32, hi = in.num_slots;               // largest hot set with which `target` teams fit
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) / 2;
+            if (teams_that_fit(mid, kAssumedSmemBase, 2) >= target) lo = mid; else hi = mid - 1;
+        }
+        if (teams_that_fit(lo, kAssumedSmemBase, 2) < target) continue;
+        Plan cand;
+        std::string e2;
+        if (build_plan(spec, cand, e2, max_fanin, 1, lo, plan.policy) != GCB_OK) continue;
+        // label accesses of an instance: node leaves + node results + three per ciphered gate
+        const uint64_t accesses = (uint64_t)cand.node_loads + cand.nodes.size() + 3ull * cand.crecs.size();
+        if (force <= 0 && cand.cold_accesses * 100 > accesses * 10) continue;           // more than 10 % would go to L2
+        plan.info = cand.info; plan.policy = cand.policy;
+        plan.phases.swap(cand.phases); plan.waves.swap(cand.waves); plan.nodes.swap(cand.nodes); plan.crecs.swap(cand.crecs);
+        plan.nout_wire.swap(cand.nout_wire); plan.cout_wire.swap(cand.cout_wire);
+        plan.live_in.swap(cand.live_in); plan.live_out.swap(cand.live_out);
+        plan.row_off.swap(cand.row_off); plan.ops.swap(cand.ops);
+        plan.node_loads = cand.node_loads; plan.cold_accesses = cand.cold_accesses;
+        break;
+    }
+    return GCB_OK;
+}
 
 int parse_stream(const uint8_t* buf, size_t len, uint32_t ngates, std::vector<StreamGate>& gates,
                  std::vector<uint32_t>& row_pos, size_t* consumed, std::string& err) {

@@ -128,6 +128,7 @@ struct Plan {
     std::vector<GateRec> crecs;           // ciphered gates in schedule order
     std::vector<uint32_t> nout_wire, cout_wire;   // original output wire of nodes[i] / crecs[i]
     uint32_t node_loads = 0;              // sum of node fan-ins (label loads of the free part)
+    uint64_t cold_accesses = 0;           // label reads + writes that go to the global-memory scratch (hot / cold plans)
     std::vector<SlotRef> live_in, live_out;
     std::vector<uint32_t> row_off;        // num_gates+1, original order
     std::vector<uint8_t> ops;             // original order
@@ -137,12 +138,32 @@ struct Plan {
     mutable std::map<std::pair<int, uint32_t>, std::shared_ptr<DevicePlan>> dev;   // (device, team width)
 };
 
+// ---- shared-memory geometry of the gate kernels (gc_kernels.cuh), needed by the compiler's choices too ----
+// [teams below the tables | 64 KiB-aligned T-tables (nt * 32 KiB) | teams above]; a team's block is its round keys
+// (256 B), a claim word (16 B) and its labels.  smem_base: where dynamic shared memory starts in the shared window.
+constexpr size_t kSmemOptin = 232448;                 // 227 KiB per CTA on sm_100
+constexpr uint32_t kAssumedSmemBase = 1024;
+inline size_t table_pad(uint32_t smem_base) { return ((smem_base + 0xffffu) & ~0xffffu) - smem_base; }
+inline size_t teams_that_fit(uint32_t smem_slots, uint32_t smem_base, uint32_t nt) {
+    const size_t per_team = (size_t)smem_slots * 16 + 256 + 16;
+    const size_t pad = table_pad(smem_base);
+    return pad / per_team + (kSmemOptin - pad - (size_t)nt * 32768) / per_team;
+}
+
 // Returns GCB_OK or a negative status; message in err.  max_fanin = NODE_MAX_FANIN
 // for the normal plan; 2 keeps every XOR / XNOR gate as its own node (the
 // wires_full variant, where every wire label has to be produced).
 // balance: 0 = the three slot-minimising schedules only; otherwise also the two schedules that fill the warp
 // passes of the garbler / of the evaluator (plan.cpp: balanced_levels).
-int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, int balance = 1);
+// hot_cap: 0 = every label lives in shared memory; otherwise at most hot_cap do (slots below info.num_hot_slots) and the
+// values that idle longest per access live in the team's global-memory scratch (slots from num_hot_slots up).
+int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, int balance = 1,
+               uint32_t hot_cap = 0, int only_policy = -1);
+
+// build_plan, then -- for deep, narrow circuits that hold fewer than 16 instances per SM -- a second plan that keeps
+// only a hot subset of the labels in shared memory so that more instances fit (hot_cap above), kept when few
+// enough label accesses go cold.  GCB_HOT_TEAMS = 0 switches the second plan off, N forces the target.
+int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN);
 
 }  // namespace gcb
 

@@ -245,6 +245,35 @@ def test_every_kernel_variant_is_bit_exact(variant, monkeypatch):
             assert np.array_equal(decode(g.Wires[-no:], wires[-no:]), circ.compute_bits(bits[0].tolist()))
 
 
+@pytest.mark.parametrize("name,batch,teams", [("sha256", 5, "16"), ("aes_128", 9, "16"), ("sha512", 2, "8"), ("mul64", 6, "32")])
+def test_hot_cold_plans_are_bit_exact(name, batch, teams, monkeypatch):
+    """Plans that keep only a hot subset of the labels in shared memory (the rest in the per-instance L2 scratch), so
+    that more instances are resident per SM: forced here for several circuits and targets, garble and eval against
+    the oracle.  sha256 / sha512 take such a plan by default."""
+    monkeypatch.setenv("GCB_HOT_TEAMS", teams)
+    circ = load_circuit(name)
+    eng = GarbleEngine(circ)
+    if name != "mul64":                                            # mul64 already holds 16 instances: nothing to gain
+        assert eng.info.num_hot_slots < eng.info.num_slots and eng.info.teams_per_sm >= int(teams) // 2
+    keys, rand = garble_inputs(f"hotcold/{name}", batch, circ.num_inputs, 32)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    _, o_tables, o_io = O.garble_batch(circ, keys, rand, threads=4)
+    assert eq(tables, o_tables) and eq(io, o_io)
+    bits = np.random.default_rng(2).integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+    inl = select(io[:, : circ.num_inputs], bits)
+    out = eng.eval_batch(keys, tables, inl)
+    assert eq(out, O.eval_batch(circ, keys, o_tables, inl, threads=4))
+
+
+def test_default_plans_of_narrow_circuits_go_hot_cold():
+    for name in ("sha256", "sha512"):
+        i = GarbleEngine(load_circuit(name)).info
+        assert i.num_hot_slots < i.num_slots, name
+    i = GarbleEngine(load_circuit("aes_128")).info                 # wide levels: bound by the pipe, stays all-hot
+    assert i.num_hot_slots == i.num_slots
+
+
 def _wide_circuit(n_pairs: int):
     """2 * n_pairs inputs, all live until the single AND level: out[i] = in[i] & in[n_pairs + i]."""
     lines = [f"2 1 {i} {n_pairs + i} {2 * n_pairs + i} AND" for i in range(n_pairs)]

@@ -317,6 +317,9 @@ int main() {
     // hybrid: 12 T-table warps and 1 / 2 / 4 bitsliced warps per SM at the same time, as two kernels
     const int smem = 65536 + AES_TABLE_BYTES + 1024;
     CK(cudaFuncSetAttribute(k_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // kernels that ask for different shared-memory carve-outs cannot share an SM
+    CK(cudaFuncSetAttribute(k_tt, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(k_bs_span, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     Span *sp_tt, *sp_bs; long long* cyc2;
     CK(cudaMalloc(&sp_tt, sms * sizeof(Span))); CK(cudaMalloc(&sp_bs, sms * sizeof(Span))); CK(cudaMalloc(&cyc2, sms * 8));
     cudaStream_t s1, s2;

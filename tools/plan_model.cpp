@@ -60,8 +60,11 @@ int main(int argc, char** argv) {
     Plan plan;
     std::string err;
     const int balance = argc > 3 ? atoi(argv[3]) : 0;      // 0 none, 1 garbler, 2 evaluator (plan.cpp: balanced_levels)
-    if (int rc = build_plan(spec, plan, err, NODE_MAX_FANIN, balance)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
-    printf("balance %d  policy %d  garble_passes %u  eval_passes %u\n", balance, plan.policy, plan.info.garble_passes, plan.info.eval_passes);
+    const uint32_t hot_cap = argc > 4 ? (uint32_t)atoi(argv[4]) : 0;   // 0: all labels in shared memory
+    if (int rc = build_plan(spec, plan, err, NODE_MAX_FANIN, balance, hot_cap)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
+    printf("balance %d  policy %d  garble_passes %u  eval_passes %u  hot slots %u of %u  cold accesses %llu (node loads %u, gates %u)\n", balance, plan.policy,
+           plan.info.garble_passes, plan.info.eval_passes, plan.info.num_hot_slots, plan.info.num_slots, (unsigned long long)plan.cold_accesses,
+           plan.node_loads, plan.info.num_and + plan.info.num_inv + plan.info.num_or);
     const gcb_plan_info& in = plan.info;
     printf("gates %u  and %u inv %u or %u free %u  slots %u  steps %u  phases %zu  waves %zu  nodes %zu  node_loads %u\n",
            in.num_gates, in.num_and, in.num_inv, in.num_or, in.num_free, in.num_slots, in.num_steps, plan.phases.size(),
