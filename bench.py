@@ -378,16 +378,17 @@ def roofline_of(b: Bench, circ, eng, batch: int, g_ms: float, e_ms: float, nr: i
 
 def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinned: bool):
     """The call a user makes, from ONE host thread, for a stream of batches: gcb_garble_begin on every part of the
-    step's batch, then per part gcb_job_wait -> gcb_eval_begin; the eval jobs of step k are only waited for when
-    their buffers come round again (two sets of host buffers), so the garbler's tables of step k+1 stream back
-    (D2H) while the evaluator's tables of step k stream in (H2D).  Every step copies its own inputs up and its
-    own results down inside the timed region; the last step is fully drained before the clock stops."""
+    step's batch, then per part gcb_job_wait -> gcb_eval_begin; the eval jobs of a step are only waited for when
+    their buffers come round again (three sets of host buffers) and the garbler is queued one step ahead, so the
+    garbler's tables of step k+1 stream back (D2H) while the evaluator's tables of step k stream in (H2D).  Every
+    step copies its own inputs up and its own results down inside the timed region; the last step is fully
+    drained before the clock stops."""
     from mpc_b200.circuit import host_alloc, host_free
     from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
     nin, nout, rows = circ.num_inputs, circ.num_outputs, circ.num_rows
     r, l0, bits = inputs
     alloc = host_alloc if pinned else (lambda shape, dt: np.zeros(shape, dtype=dt))
-    n_sets = 2
+    n_sets = 3
     sets = []
     for _ in range(n_sets):
         h = {"r": alloc((batch,), LABEL_DTYPE), "l0": alloc((batch, nin), LABEL_DTYPE), "tab": alloc((batch, rows), LABEL_DTYPE),
@@ -397,36 +398,46 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
         sets.append(h)
     n_parts = max(1, min(E2E_PARTS, batch // 64))
     parts = [slice(k * batch // n_parts, (k + 1) * batch // n_parts) for k in range(n_parts)]
-    pending = [[] for _ in range(n_sets)]          # eval jobs still reading / writing each buffer set
+    eval_jobs = [[] for _ in range(n_sets)]        # eval jobs still reading / writing each buffer set
+    garble_jobs = [None] * n_sets
 
     def drain(k):
-        for j in pending[k]:
+        for j in eval_jobs[k]:
             j.wait()
-        pending[k] = []
+        eval_jobs[k] = []
 
-    def step(k):
+    def garble(k):                                  # queue the garbler's jobs of step k (its buffer set is free again)
         h = sets[k % n_sets]
-        drain(k % n_sets)                           # the set's previous step has left its buffers
-        gj = [eng.garble_begin(KEY, h["r"][sl], h["l0"][sl], h["tab"][sl], h["io"][sl]) for sl in parts]
-        for j, sl in zip(gj, parts):
-            j.wait()                                # this part's tables are on the host: its evaluation may start
-            pending[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
+        drain(k % n_sets)
+        garble_jobs[k % n_sets] = [eng.garble_begin(KEY, h["r"][sl], h["l0"][sl], h["tab"][sl], h["io"][sl]) for sl in parts]
+
+    def evaluate(k):                                # each part as soon as its tables are on the host
+        h = sets[k % n_sets]
+        for j, sl in zip(garble_jobs[k % n_sets], parts):
+            j.wait()
+            eval_jobs[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
+
+    def run(n):
+        # the garbler runs one step ahead: its kernels of step k+1 are done long before the tables of step k have
+        # crossed PCIe, so the device->host engine never waits for a kernel, nor the host->device engine for a wait
+        garble(0)
+        for k in range(n):
+            if k + 1 < n:
+                garble(k + 1)
+            evaluate(k)
+        for k in range(n_sets):
+            drain(k)
 
     for k in range(n_sets):                         # warm-up: also fills the evaluator's input labels of every set
-        step(k)
+        garble(k)
+        evaluate(k)
         drain(k)
         h = sets[k]
         h["in"][:] = np.where(bits.astype(bool), h["io"]["l1"][:, :nin], h["io"]["l0"][:, :nin])
-    for k in range(n_sets):
-        step(k)
-    for k in range(n_sets):
-        drain(k)
+    run(n_sets)
     b.barrier()
     t0 = time.perf_counter()
-    for k in range(steps):
-        step(k)
-    for k in range(n_sets):
-        drain(k)
+    run(steps)
     b.torch.cuda.synchronize()
     sec = (time.perf_counter() - t0) / steps
     d_tab, d_out, _ = ref_dev
@@ -641,7 +652,7 @@ def run_gcb(args):
         e2e = {"value": n_and * batch * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(world * h2d), "d2h_bytes_per_step": int(world * d2h), "ms_per_step": e2e_ms,
                "how": f"gcb_garble_begin / gcb_eval_begin / gcb_job_wait on page-locked host buffers (gcb_host_alloc), "
-                      f"{n_parts} parts per step, two buffer sets (the tables of step k+1 stream back while those of step k "
+                      f"{n_parts} parts per step, three buffer sets and the garbler queued one step ahead (the tables of step k+1 stream back while those of step k "
                       f"stream in), ONE host thread per GPU"
                       + (f", ranks bound to their GPU's NUMA node ({b.numa['cpus']} cpus)" if b.numa else "")}
 

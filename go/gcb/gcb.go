@@ -37,6 +37,19 @@ type Gate struct {
 	Level                  uint32
 }
 
+// call runs one C entry point and fetches its error text on the SAME OS thread: gcb_last_error() is
+// thread-local in C, and a goroutine may migrate between two cgo calls unless it is locked.
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != 0 {
+		return errors.New(C.GoString(C.gcb_last_error()))
+	}
+	return nil
+}
+
+// lastError is kept for the one-line wrappers below; they go through call() so that the message is read on the
+// thread that produced it.
 func lastError(rc C.int) error {
 	if rc == 0 {
 		return nil
@@ -60,8 +73,10 @@ func NewPlan(gates []Gate, numWires, numInputs, numOutputs int) (*Plan, error) {
 	if len(gates) > 0 {
 		g = (*C.gcb_gate)(unsafe.Pointer(&gates[0]))
 	}
-	if err := lastError(C.gcb_plan_create(g, C.uint32_t(len(gates)), C.uint32_t(numWires),
-		C.uint32_t(numInputs), C.uint32_t(numOutputs), &p.h)); err != nil {
+	if err := call(func() C.int {
+		return C.gcb_plan_create(g, C.uint32_t(len(gates)), C.uint32_t(numWires),
+			C.uint32_t(numInputs), C.uint32_t(numOutputs), &p.h)
+	}); err != nil {
 		return nil, err
 	}
 	C.gcb_plan_get_info(p.h, &p.Info)
@@ -82,15 +97,21 @@ func HostFree(p unsafe.Pointer) { C.gcb_host_free(p) }
 // l0: batch*numInputs input L0 draws (reader order, garble.go:253-278);
 // tables: batch*rows; ioWires: batch*(in+out) or nil; wiresFull: batch*numWires or nil.
 func (p *Plan) Garble(key []byte, keyStride, batch int, r, l0, tables []Label, ioWires, wiresFull []Wire) error {
-	return lastError(C.gcb_garble(p.h, (*C.uint8_t)(unsafe.Pointer(&key[0])), C.uint32_t(len(key)/max(1, batchIf(keyStride, batch))),
-		C.uint32_t(keyStride), C.uint32_t(batch), lp(r), lp(l0), lp(tables), wp(ioWires), wp(wiresFull), 0))
+	defer runtime.KeepAlive(p) // the finalizer must not free the plan while C still uses it
+	return call(func() C.int {
+		return C.gcb_garble(p.h, (*C.uint8_t)(unsafe.Pointer(&key[0])), C.uint32_t(len(key)/max(1, batchIf(keyStride, batch))),
+			C.uint32_t(keyStride), C.uint32_t(batch), lp(r), lp(l0), lp(tables), wp(ioWires), wp(wiresFull), 0)
+	})
 }
 
 // Eval runs gcb_eval.  tables: batch*rows; in: batch*numInputs; out: batch*numOutputs;
 // wiresFull: batch*numWires or nil.
 func (p *Plan) Eval(key []byte, keyStride, batch int, tables, in, out, wiresFull []Label) error {
-	return lastError(C.gcb_eval(p.h, (*C.uint8_t)(unsafe.Pointer(&key[0])), C.uint32_t(len(key)/max(1, batchIf(keyStride, batch))),
-		C.uint32_t(keyStride), C.uint32_t(batch), lp(tables), lp(in), lp(out), lp(wiresFull), 0))
+	defer runtime.KeepAlive(p)
+	return call(func() C.int {
+		return C.gcb_eval(p.h, (*C.uint8_t)(unsafe.Pointer(&key[0])), C.uint32_t(len(key)/max(1, batchIf(keyStride, batch))),
+			C.uint32_t(keyStride), C.uint32_t(batch), lp(tables), lp(in), lp(out), lp(wiresFull), 0)
+	})
 }
 
 func batchIf(stride, batch int) int {

@@ -133,7 +133,7 @@ public:
     // cls: 0 = garble-like (bulk results), 1 = eval-like (bulk inputs).  want: device staging bytes the part needs;
     // the pooled entry that fits best is taken, and a new arena is sized for the largest request seen so far, so that
     // the pool converges to arenas any part can use (growing one costs a cudaFree, i.e. a device-wide synchronisation).
-    std::unique_ptr<JobRes> lease(int device, int cls, size_t want, cudaError_t* err) {
+    std::unique_ptr<JobRes> lease(int device, int cls, size_t want, cudaError_t* err, size_t want_pin = 0) {
         std::unique_ptr<JobRes> r;
         StreamSet* ss = nullptr;
         {
@@ -146,9 +146,9 @@ public:
             auto& v = pool_[device];
             size_t best = v.size();
             for (size_t i = 0; i < v.size(); i++) {
-                const bool fits = v[i]->dev.cap >= want;
+                const bool fits = v[i]->dev.cap >= want && v[i]->pin.cap >= want_pin;
                 if (best == v.size()) { best = i; continue; }
-                const bool best_fits = v[best]->dev.cap >= want;
+                const bool best_fits = v[best]->dev.cap >= want && v[best]->pin.cap >= want_pin;
                 if ((fits && !best_fits) || (fits == best_fits && (fits ? v[i]->dev.cap < v[best]->dev.cap : v[i]->dev.cap > v[best]->dev.cap))) best = i;
             }
             if (best < v.size()) { r = std::move(v[best]); v.erase(v.begin() + (long)best); }

@@ -515,9 +515,9 @@ static int ensure_wires(gcb_stream* s, uint32_t max_id) {
 // Host-pointer garble / eval as asynchronous jobs (async.hpp).
 static ResPool g_res_pool;
 
-static int lease_res(int device, std::unique_ptr<JobRes>* out, int cls = 0, size_t want = 0) {
+static int lease_res(int device, std::unique_ptr<JobRes>* out, int cls = 0, size_t want = 0, size_t want_pin = 0) {
     cudaError_t e = cudaSuccess;
-    *out = g_res_pool.lease(device, cls, want, &e);
+    *out = g_res_pool.lease(device, cls, want, &e, want_pin);
     if (!*out) return cuda_fail(e, "stream creation");
     return GCB_OK;
 }
@@ -567,17 +567,21 @@ static int begin_part(bool garble, const Plan& plan, int device, const uint8_t* 
     DeviceInfo* di;
     int rc = use_device(device, &di);
     if (rc) return rc;
-    size_t per_inst = 0, want = 512;
+    size_t per_inst = 0, want = 512, want_pin = 512;
     for (std::vector<Operand>* v : {&ins, &outs})
-        for (Operand& o : *v) if (o.per) want += (((size_t)batch * o.per + 255) & ~(size_t)255);
-    if ((rc = lease_res(device, &part->res, garble ? 0 : 1, want))) return rc;
+        for (Operand& o : *v) {
+            if (!o.per) continue;
+            o.pinned = peer.home >= 0 || is_pinned(o.host);
+            want += (((size_t)batch * o.per + 255) & ~(size_t)255);
+            if (!o.pinned) want_pin += (((size_t)batch * o.per + 255) & ~(size_t)255);
+        }
+    if ((rc = lease_res(device, &part->res, garble ? 0 : 1, want, want_pin))) return rc;
     JobRes& r = *part->res;
     r.dev.used = r.pin.used = 0; r.ev_used = 0; r.sealed = false;
     const size_t key_pin = r.pin.take(64), key_dev = r.dev.take(64);      // the shared key always goes through pinned staging
     for (std::vector<Operand>* v : {&ins, &outs})
         for (Operand& o : *v) {
             if (!o.per) continue;
-            o.pinned = peer.home >= 0 || is_pinned(o.host);
             o.dev_off = r.dev.take((size_t)batch * o.per);
             if (!o.pinned) o.pin_off = r.pin.take((size_t)batch * o.per);
             per_inst += o.per;

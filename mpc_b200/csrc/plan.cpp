@@ -207,7 +207,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 
     // emit = false: only the figures the policies are compared on (slots, steps); the records (and the
     // leaf ordering, the expensive part) are produced once, for the schedule that won
-    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out, bool emit, std::string& err) -> int {
+    auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out, bool emit, std::string& err, uint32_t hot_cap) -> int {
         char msg[160];
         // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
         // free gate of a later phase, or by the caller afterwards
@@ -709,14 +709,14 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             return policy == 0 ? asap : policy >= 3 ? balanced_levels(policy - 2) : alap_levels(policy == 2);
         };
         int best_policy = -1, best_rc = GCB_OK;
-        uint32_t best_slots = 0, best_steps = 0;
+        uint32_t best_slots = 0, best_steps = 0, best_cap = hot_cap;
         std::string first_err;
         const int n_policies = keep_all ? 1 : (balance ? 5 : 3);          // the full-wire plan keeps the simple schedule
         Plan cand[5];
         int rcs[5] = {GCB_OK, GCB_OK, GCB_OK, GCB_OK, GCB_OK};
         std::string errs[5];
         auto trial = [&](int policy) {
-            rcs[policy] = schedule(levels_of(policy), cand[policy], false, errs[policy]);
+            rcs[policy] = schedule(levels_of(policy), cand[policy], false, errs[policy], hot_cap);
         };
         if (only_policy >= 0 && only_policy < n_policies) best_policy = only_policy;      // the caller knows which schedule it wants
         else {
@@ -749,14 +749,33 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             const gcb_plan_info b = cand[best_policy].info;
             uint64_t best_passes = ((uint64_t)b.garble_passes + b.eval_passes) * 98 / 100;     // worth it from 2 % on
             for (int policy = 3; policy < 5; policy++) {
-                const gcb_plan_info& c = cand[policy].info;
-                if (rcs[policy] != GCB_OK || resident(c.num_slots) < resident(b.num_slots)) continue;
-                if ((uint64_t)c.garble_passes + c.eval_passes <= best_passes) { best_policy = policy; best_passes = (uint64_t)c.garble_passes + c.eval_passes; }
+                if (rcs[policy] != GCB_OK) continue;
+                gcb_plan_info c = cand[policy].info;
+                if ((uint64_t)c.garble_passes + c.eval_passes > best_passes) continue;
+                uint32_t cap = hot_cap;
+                if (resident(c.num_slots) < resident(b.num_slots) && hot_cap == 0) {
+                    // A few labels too many for the resident instances of the slot-minimal schedule (sha256: 1,272
+                    // against 1,263 for eight): keep those few in the L2 scratch instead of giving up an instance.
+                    uint32_t lo = 32, hi = c.num_slots;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi + 1) / 2;
+                        if (resident(mid) >= resident(b.num_slots)) lo = mid; else hi = mid - 1;
+                    }
+                    Plan capped;
+                    std::string e2;
+                    if (resident(lo) < resident(b.num_slots) || schedule(levels_of(policy), capped, false, e2, lo) != GCB_OK) continue;
+                    // label accesses: about three per stored value; at most 0.5 % of them may go to the scratch
+                    if (capped.cold_accesses * 200 > 3ull * (n_and + n_or + n_inv + n_free / 2)) continue;
+                    c = capped.info;
+                    cap = lo;
+                }
+                if (resident(cap ? c.num_hot_slots : c.num_slots) < resident(b.num_slots)) continue;
+                best_policy = policy; best_passes = (uint64_t)c.garble_passes + c.eval_passes; best_cap = cap;
             }
         }
         Plan best;
         best.row_off = plan.row_off; best.ops = plan.ops;
-        const int rc = schedule(levels_of(best_policy), best, true, err);
+        const int rc = schedule(levels_of(best_policy), best, true, err, best_cap);
         if (rc != GCB_OK) return rc;
         plan.info = best.info;
         plan.policy = best_policy;
@@ -776,9 +795,13 @@ namespace gcb {
 int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin) {
     int rc = build_plan(spec, plan, err, max_fanin);
     if (rc != GCB_OK || max_fanin == 2) return rc;
-    int force = -1;
+    // Measured on B200 (profiles/r02_hot_cold.txt): with synchronous loads from the scratch, 16 resident sha256
+    // instances run 34 % SLOWER than 8 all-hot ones (every cold leaf is an L2 round trip on the dependency chain of its
+    // level); sha512 gains 10 % at 8 instances and chacha20 6 % at 16.  So the second plan is opt-in (GCB_HOT_TEAMS = N);
+    // build_plan itself still moves a handful of labels to the scratch when that keeps an instance resident.
+    int force = 0;
     if (const char* e = getenv("GCB_HOT_TEAMS")) force = atoi(e);
-    if (force == 0) return GCB_OK;
+    if (force <= 0) return GCB_OK;
     const gcb_plan_info& in = plan.info;
     const size_t np = plan.phases.size();
     const uint32_t width = np ? (uint32_t)(in.garble_hashes / np) : 0u;

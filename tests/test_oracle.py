@@ -12,6 +12,8 @@
 import hashlib
 import struct
 
+import os
+
 import numpy as np
 import pytest
 
@@ -565,3 +567,41 @@ def test_iknp_malicious_check_sums_verify():
     key = seed2[0].to_bytes(8, "big") + seed2[1].to_bytes(8, "big")
     blk = P.Aes(key).enc(5)                           # OpenSSL: keystream block 5 of AES-128-CTR with zero IV
     assert lo == x == (blk >> 64, blk & (2**64 - 1)) and hi == (0, 0)
+
+
+REFERENCE_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_garble_fixture.json")
+
+
+def reference_fixture():
+    """The reference's own Garble bytes for sha2pc's deterministic transcript (tools/reference_fixture/): key, reader
+    bytes and SHA-256 digests of the rows and of the I/O wires.  Needs one run of the reference with a Go toolchain;
+    absent here, so the tests that use it skip and the oracle stays pinned by KATs and invariants only."""
+    import json
+    if not os.path.exists(REFERENCE_FIXTURE):
+        pytest.skip("tests/golden/reference_garble_fixture.json not generated (needs Go; see tools/reference_fixture/)")
+    return json.load(open(REFERENCE_FIXTURE))
+
+
+def fixture_digests(tables, io_wires, nin):
+    """SHA-256 of the rows / input wires / output wires in the SendLabel encoding (BE64(D0) || BE64(D1))."""
+    import hashlib
+
+    def be(a):
+        return np.stack([a["d0"].astype(">u8"), a["d1"].astype(">u8")], axis=-1).tobytes()
+
+    def wires(w):
+        return np.stack([w["l0"]["d0"].astype(">u8"), w["l0"]["d1"].astype(">u8"),
+                         w["l1"]["d0"].astype(">u8"), w["l1"]["d1"].astype(">u8")], axis=-1).tobytes()
+
+    return (hashlib.sha256(be(tables)).hexdigest(), hashlib.sha256(wires(io_wires[:nin])).hexdigest(),
+            hashlib.sha256(wires(io_wires[nin:])).hexdigest())
+
+
+def test_reference_garble_fixture():
+    fx = reference_fixture()
+    circ = load_circuit("sha256xor")
+    key, rand = bytes.fromhex(fx["key"]), np.frombuffer(bytes.fromhex(fx["rand"]), dtype=np.uint8)
+    assert len(rand) == 16 * (1 + circ.num_inputs) and fx["rows"] == circ.num_rows
+    _, tables, io = O.garble_batch(circ, key, rand.reshape(1, -1))
+    assert fixture_digests(tables[0], io[0], circ.num_inputs) == (
+        fx["tables_sha256"], fx["input_wires_sha256"], fx["output_wires_sha256"])
