@@ -401,29 +401,43 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
     eval_jobs = [[] for _ in range(n_sets)]        # eval jobs still reading / writing each buffer set
     garble_jobs = [None] * n_sets
 
+    prof = {"drain": 0.0, "issue_g": 0.0, "wait_g": 0.0, "issue_e": 0.0}
+    ahead = int(os.environ.get("GCB_E2E_AHEAD", "1"))
+
     def drain(k):
+        t = time.perf_counter()
         for j in eval_jobs[k]:
             j.wait()
         eval_jobs[k] = []
+        prof["drain"] += time.perf_counter() - t
 
     def garble(k):                                  # queue the garbler's jobs of step k (its buffer set is free again)
         h = sets[k % n_sets]
         drain(k % n_sets)
+        t = time.perf_counter()
         garble_jobs[k % n_sets] = [eng.garble_begin(KEY, h["r"][sl], h["l0"][sl], h["tab"][sl], h["io"][sl]) for sl in parts]
+        prof["issue_g"] += time.perf_counter() - t
 
     def evaluate(k):                                # each part as soon as its tables are on the host
         h = sets[k % n_sets]
         for j, sl in zip(garble_jobs[k % n_sets], parts):
+            t = time.perf_counter()
             j.wait()
+            t1 = time.perf_counter()
             eval_jobs[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
+            prof["wait_g"] += t1 - t
+            prof["issue_e"] += time.perf_counter() - t1
 
     def run(n):
-        # the garbler runs one step ahead: its kernels of step k+1 are done long before the tables of step k have
-        # crossed PCIe, so the device->host engine never waits for a kernel, nor the host->device engine for a wait
-        garble(0)
+        # GCB_E2E_AHEAD=1: the garbler runs one step ahead -- its kernels of step k+1 are done long before the tables of
+        # step k have crossed PCIe, so the device->host engine never waits for a kernel
+        if ahead:
+            garble(0)
         for k in range(n):
-            if k + 1 < n:
+            if ahead and k + 1 < n:
                 garble(k + 1)
+            if not ahead:
+                garble(k)
             evaluate(k)
         for k in range(n_sets):
             drain(k)
@@ -436,10 +450,15 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
         h["in"][:] = np.where(bits.astype(bool), h["io"]["l1"][:, :nin], h["io"]["l0"][:, :nin])
     run(n_sets)
     b.barrier()
+    for k in prof:
+        prof[k] = 0.0
     t0 = time.perf_counter()
     run(steps)
     b.torch.cuda.synchronize()
     sec = (time.perf_counter() - t0) / steps
+    if os.environ.get("GCB_E2E_TRACE") and b.rank == 0:
+        sys.stderr.write(f"e2e trace (pinned={pinned}, ahead={ahead}, {steps} steps, {sec * 1e3:.2f} ms/step): "
+                         + ", ".join(f"{k} {v * 1e3 / steps:.2f} ms/step" for k, v in prof.items()) + "\n")
     d_tab, d_out, _ = ref_dev
     for h in sets:
         ok = h["out"].tobytes() == d_out.cpu().numpy().tobytes() and h["tab"].tobytes() == d_tab.cpu().numpy().tobytes()

@@ -34,6 +34,12 @@
 
 namespace gcb {
 
+// 1: the single-block pass keeps its AES rounds in a loop (48 instructions) instead of unrolling them (430): with
+// many one-warp teams per SM every warp is somewhere else in the kernel and the instruction caches, not the
+// pipes, become the limit (ncu: no_inst 44 % of the stall samples with 16 teams of the unrolled form).
+#ifndef GC_ROLL_SINGLE
+#define GC_ROLL_SINGLE 1
+#endif
 constexpr int GC_MAX_TEAMS = 32;          // 32 one-warp teams, or <= 16 named-barrier teams
 constexpr int GC_RK_BYTES = 256;          // 60 round-key words, padded
 // Node rows a thread keeps in flight ahead of the one it runs: the single-block 512-thread variant
@@ -66,6 +72,7 @@ struct GcParams {
     uint4* wires_full;                    // optional
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
+    uint32_t hdr_split;                   // shared-memory layout: team headers kept together (1) or in front of each label block (0)
     uint32_t stagger;                     // SM cycles by which consecutive teams start apart
     long long* trace;                     // optional: phase timestamps of block 0 / team 0 (tools/trace_phases.py)
     // streaming mode (GC_STREAM): live-in / live-out labels come from and go to
@@ -135,7 +142,7 @@ __device__ __forceinline__ void aes_hash_multi(const AesLane& a, const uint32_t*
             s[j][0] = K[j].w0 ^ k.x; s[j][1] = K[j].w1 ^ k.y; s[j][2] = K[j].w2 ^ k.z; s[j][3] = K[j].w3 ^ k.w;
         }
     }
-    if (UU == 1) {
+    if (UU == 1 && !GC_ROLL_SINGLE) {
 #pragma unroll
         for (int r = 1; r < NR; r++) aes_round<NT>(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
     } else {
@@ -165,22 +172,25 @@ struct TeamCtx {
     uint32_t team, ttid;
 };
 
-// Shared-memory map of the gate kernels: [region A | 64 KiB-aligned tables | region B].
-// Region A is the pad below the tables; teams are packed into A first, then B.  A team's
-// block is: round keys (GC_RK_BYTES), claim word (16 B), wire labels (n_slots * 16).
-__device__ __forceinline__ uint32_t team_block_bytes(uint32_t n_slots) { return GC_RK_BYTES + 16 + n_slots * 16; }
+// Shared-memory map of the gate kernels (plan.hpp): [blocks | 64 KiB-aligned tables | blocks], packed below the tables
+// first.  A team has a header (round keys, GC_RK_BYTES, and a claim word, 16 B) and n_smem * 16 bytes of labels; the
+// headers sit in front of their label blocks or all together at the start, whichever layout holds more teams.
 template <int NT>
 __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     TeamCtx c;
     c.tables = aes_align_tables(smem);
     c.team = threadIdx.x / p.team_threads;
     c.ttid = threadIdx.x - c.team * p.team_threads;
-    const uint32_t tb = team_block_bytes(p.n_smem);
-    const uint32_t in_a = (uint32_t)(c.tables - smem) / tb;               // teams that fit below the tables
-    uint8_t* q = c.team < in_a ? smem + c.team * tb : c.tables + aes_table_bytes(NT) + (c.team - in_a) * tb;
-    c.rk = reinterpret_cast<uint32_t*>(q);
-    c.claim = reinterpret_cast<volatile uint32_t*>(q + GC_RK_BYTES);
-    c.slots = reinterpret_cast<uint4*>(q + GC_RK_BYTES + 16);
+    constexpr uint32_t H = GC_RK_BYTES + 16;
+    const uint32_t split = p.hdr_split;                                   // 1: headers together at the start, 0: in front of each block
+    const uint32_t tb = p.n_smem * 16 + (split ? 0u : H), hdr = split ? p.n_teams * H : 0u;
+    const uint32_t pad = (uint32_t)(c.tables - smem);
+    const uint32_t in_a = (tb && pad > hdr) ? (pad - hdr) / tb : 0u;      // teams whose block fits below the tables
+    uint8_t* blk = c.team < in_a ? smem + hdr + c.team * tb : c.tables + aes_table_bytes(NT) + (c.team - in_a) * tb;
+    uint8_t* h = split ? smem + c.team * H : blk;
+    c.rk = reinterpret_cast<uint32_t*>(h);
+    c.claim = reinterpret_cast<volatile uint32_t*>(h + GC_RK_BYTES);
+    c.slots = reinterpret_cast<uint4*>(split ? blk : blk + H);
     return c;
 }
 

@@ -243,13 +243,13 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
 // Team geometry for a plan: how many instances one SM keeps resident, how many threads work on
 // each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
 // GCB_NT / GCB_TEAMS / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
-struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false; };
+struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false, split = false; };
 // width = AES blocks per cipher level of the garbler (4 per AND / OR, 2 per INV), averaged.
 // num_hot < num_slots: a hot / cold plan (plan.cpp) -- only the hot labels need shared memory.
 static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base, uint32_t num_hot = 0) {
     Geometry g;
     if (num_hot && num_hot < num_slots) {
-        size_t n = teams_that_fit(num_hot, smem_base, 2);
+        size_t n = teams_that_fit(num_hot, smem_base, 2, &g.split);
         if (n > 16) n = 16;
         if (n == 0) return g;
         if (const char* e = getenv("GCB_TEAMS")) { const int v = atoi(e); if (v >= 1 && (size_t)v <= n) n = (size_t)v; }
@@ -259,22 +259,24 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
         if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
         return g;
     }
-    const size_t n4 = teams_that_fit(num_slots, smem_base, 4), n2 = teams_that_fit(num_slots, smem_base, 2);
+    bool split4 = false, split2 = false;
+    const size_t n4 = teams_that_fit(num_slots, smem_base, 4, &split4), n2 = teams_that_fit(num_slots, smem_base, 2, &split2);
     // Wide levels keep the shared-memory pipe busy with a few resident instances: four tables.
     // Deep, narrow circuits (sha256: 39 blocks per level) are bound by the latency of each level,
     // so the number of resident instances is what counts: two tables, twice the label space.
     uint32_t nt = (n4 == 0 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
     if (const char* e = getenv("GCB_NT")) { const int v = atoi(e); if (v == 2 || v == 4) nt = (uint32_t)v; }
     size_t n = nt == 2 ? n2 : n4;
+    g.split = nt == 2 ? split2 : split4;
     g.n_smem = num_slots;
     if (n == 0) {
         // More live labels than one team's share of shared memory holds even beside two tables: one team
         // per SM keeps the low (hot) slots in the region above the tables and spills the rest to a
         // global-memory scratch (gc_kernels.cuh: SlotsSpill).
         const size_t pad = table_pad(smem_base);
-        const size_t above = kSmemOptin - pad - (size_t)aes_table_bytes(2), region = above > pad ? above : pad;
-        g.n_teams = 1; g.team_threads = 256; g.ilp = 2; g.nt = 2; g.stagger = 0; g.spill = true;
-        g.n_smem = (uint32_t)((region - GC_RK_BYTES - 16) / 16);
+        const size_t above = kSmemOptin - pad - (size_t)aes_table_bytes(2), below = pad - kTeamHeaderBytes;
+        g.n_teams = 1; g.team_threads = 256; g.ilp = 2; g.nt = 2; g.stagger = 0; g.spill = true; g.split = true;
+        g.n_smem = (uint32_t)((above > below ? above : below) / 16);
         return g;
     }
     if (n >= 32) n = 32; else if (n > 16) n = 16;
@@ -308,9 +310,9 @@ void team_geometry(Plan& plan) {                    // what gcb_plan_get_info re
     plan.info.teams_per_sm = g.n_teams; plan.info.team_threads = g.team_threads;
     plan.ilp = g.ilp; plan.stagger = g.stagger;
 }
-size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams, uint32_t nt, uint32_t smem_base) {
-    const size_t per_team = (size_t)num_slots * 16 + GC_RK_BYTES + 16;
-    const size_t pad = table_pad(smem_base), in_a = pad / per_team;
+size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams, uint32_t nt, uint32_t smem_base, bool split) {
+    const size_t per_team = team_block_bytes(num_slots, split);
+    const size_t pad = table_pad(smem_base), in_a = teams_below(num_slots, n_teams, smem_base, split);
     return pad + (size_t)aes_table_bytes((int)nt) + (n_teams > in_a ? (n_teams - in_a) * per_team : 0);
 }
 
@@ -380,7 +382,8 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const uint32_t want = (batch + p.n_teams - 1) / p.n_teams;
     const dim3 grid(want < (uint32_t)di->sm_count ? want : (uint32_t)di->sm_count);
     const dim3 block(p.n_teams * p.team_threads);
-    const size_t smem = gc_smem_bytes(geo.n_smem, p.n_teams, geo.nt, di->smem_base);
+    const size_t smem = gc_smem_bytes(geo.n_smem, p.n_teams, geo.nt, di->smem_base, geo.split);
+    p.hdr_split = geo.split ? 1u : 0u;
     const bool full = wires_full != nullptr;
     const int mode = pages ? GC_STREAM : full ? GC_FULL : GC_PLAIN;
     const GcVariant var{geo.ilp, geo.nt, geo.spill};
@@ -1034,7 +1037,7 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     team_geometry(pl->p);
     if (pl->p.info.teams_per_sm == 0)
         return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; at most %zu fit on chip",
-                    pl->p.info.num_slots, (kSmemOptin - table_pad(kAssumedSmemBase) - (size_t)aes_table_bytes(2) - GC_RK_BYTES - 16) / 16);
+                    pl->p.info.num_slots, (kSmemOptin - table_pad(kAssumedSmemBase) - (size_t)aes_table_bytes(2)) / 16);
     pl->p.gates.assign(gates, gates + num_gates);
     *out = pl.release();
     return GCB_OK;

@@ -700,10 +700,8 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
     // ---- try the schedules and keep the best (the trials are independent and run on their own threads: the
     // compiler is on the critical path of the first use of a circuit, e.g. a streaming evaluator that meets a new
     // sub-circuit).  Policies 0-2 are compared on wire slots.  Policies 3 and 4, the schedules balanced for the
-    // garbler's and for the evaluator's pass size, replace the winner when they save at least 2 % of the warp passes
-    // (garbler + evaluator: the plan serves both) and do not cost resident instances: the instances that fit beside
-    // two T-tables must not drop (narrow circuits are bound by the latency of a level, so resident instances count
-    // as much as passes).
+    // garbler's and for the evaluator's pass size, replace the winner when they lower the warp passes (garbler +
+    // evaluator: the plan serves both) per instance resident beside two T-tables by at least 2 %.
     {
         auto levels_of = [&](int policy) {
             return policy == 0 ? asap : policy >= 3 ? balanced_levels(policy - 2) : alap_levels(policy == 2);
@@ -741,36 +739,26 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             }
         }
         if (best_policy < 0) { err = first_err; return best_rc; }
+        if (getenv("GCB_PLAN_DEBUG"))
+            for (int policy = 0; policy < n_policies; policy++)
+                fprintf(stderr, "plan policy %d: rc %d slots %u steps %u passes %u + %u\n", policy, rcs[policy], cand[policy].info.num_slots,
+                        cand[policy].info.num_steps, cand[policy].info.garble_passes, cand[policy].info.eval_passes);
         if (n_policies == 5 && only_policy < 0) {
             auto resident = [](uint32_t slots) {                  // instances beside two T-tables
                 const size_t n = teams_that_fit(slots, kAssumedSmemBase, 2);
                 return n > 16 ? (n >= 32 ? (size_t)32 : (size_t)16) : n;
             };
-            const gcb_plan_info b = cand[best_policy].info;
-            uint64_t best_passes = ((uint64_t)b.garble_passes + b.eval_passes) * 98 / 100;     // worth it from 2 % on
+            // cost of a schedule: warp passes per resident instance (deep circuits are bound by the latency of a level,
+            // so an instance more per SM is worth as much as proportionally fewer passes)
+            auto cost = [&](const gcb_plan_info& i) {
+                const size_t r = resident(hot_cap ? i.num_hot_slots : i.num_slots);
+                return r ? ((double)i.garble_passes + i.eval_passes) / (double)r : 1e30;
+            };
+            double best_cost = cost(cand[best_policy].info) * 0.98;                             // worth it from 2 % on
             for (int policy = 3; policy < 5; policy++) {
                 if (rcs[policy] != GCB_OK) continue;
-                gcb_plan_info c = cand[policy].info;
-                if ((uint64_t)c.garble_passes + c.eval_passes > best_passes) continue;
-                uint32_t cap = hot_cap;
-                if (resident(c.num_slots) < resident(b.num_slots) && hot_cap == 0) {
-                    // A few labels too many for the resident instances of the slot-minimal schedule (sha256: 1,272
-                    // against 1,263 for eight): keep those few in the L2 scratch instead of giving up an instance.
-                    uint32_t lo = 32, hi = c.num_slots;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi + 1) / 2;
-                        if (resident(mid) >= resident(b.num_slots)) lo = mid; else hi = mid - 1;
-                    }
-                    Plan capped;
-                    std::string e2;
-                    if (resident(lo) < resident(b.num_slots) || schedule(levels_of(policy), capped, false, e2, lo) != GCB_OK) continue;
-                    // label accesses: about three per stored value; at most 0.5 % of them may go to the scratch
-                    if (capped.cold_accesses * 200 > 3ull * (n_and + n_or + n_inv + n_free / 2)) continue;
-                    c = capped.info;
-                    cap = lo;
-                }
-                if (resident(cap ? c.num_hot_slots : c.num_slots) < resident(b.num_slots)) continue;
-                best_policy = policy; best_passes = (uint64_t)c.garble_passes + c.eval_passes; best_cap = cap;
+                const double c = cost(cand[policy].info);
+                if (c <= best_cost) { best_policy = policy; best_cost = c; }
             }
         }
         Plan best;

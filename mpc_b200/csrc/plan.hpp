@@ -139,15 +139,33 @@ struct Plan {
 };
 
 // ---- shared-memory geometry of the gate kernels (gc_kernels.cuh), needed by the compiler's choices too ----
-// [teams below the tables | 64 KiB-aligned T-tables (nt * 32 KiB) | teams above]; a team's block is its round keys
-// (256 B), a claim word (16 B) and its labels.  smem_base: where dynamic shared memory starts in the shared window.
+// [team headers | label blocks of the first teams | 64 KiB-aligned T-tables (nt * 32 KiB) | label blocks of the rest].
+// A header is a team's round keys (256 B) and claim word (16 B); keeping the headers together, away from the label
+// blocks, can let the blocks fill the two regions either side of the tables better (sha256's balanced schedule needs
+// 1,272 labels: eight such blocks fit only this way).  smem_base: where dynamic shared memory starts in the shared window.
 constexpr size_t kSmemOptin = 232448;                 // 227 KiB per CTA on sm_100
 constexpr uint32_t kAssumedSmemBase = 1024;
+constexpr size_t kTeamHeaderBytes = 256 + 16;
 inline size_t table_pad(uint32_t smem_base) { return ((smem_base + 0xffffu) & ~0xffffu) - smem_base; }
-inline size_t teams_that_fit(uint32_t smem_slots, uint32_t smem_base, uint32_t nt) {
-    const size_t per_team = (size_t)smem_slots * 16 + 256 + 16;
-    const size_t pad = table_pad(smem_base);
-    return pad / per_team + (kSmemOptin - pad - (size_t)nt * 32768) / per_team;
+// Two layouts, whichever holds more teams: split (below) or inline (each team's header directly in front of its labels).
+// teams_below: team blocks that fit below the tables.
+inline size_t team_block_bytes(uint32_t smem_slots, bool split) { return (size_t)smem_slots * 16 + (split ? 0 : kTeamHeaderBytes); }
+inline size_t teams_below(uint32_t smem_slots, uint32_t n_teams, uint32_t smem_base, bool split) {
+    const size_t per = team_block_bytes(smem_slots, split), pad = table_pad(smem_base), hdr = split ? (size_t)n_teams * kTeamHeaderBytes : 0;
+    return (per && pad > hdr) ? (pad - hdr) / per : 0;
+}
+inline size_t teams_that_fit_layout(uint32_t smem_slots, uint32_t smem_base, uint32_t nt, bool split) {
+    const size_t per = team_block_bytes(smem_slots, split), pad = table_pad(smem_base);
+    if (!per) return 32;
+    const size_t above = (kSmemOptin - pad - (size_t)nt * 32768) / per;
+    for (uint32_t n = 32; n >= 1; n--)
+        if ((!split || (size_t)n * kTeamHeaderBytes <= pad) && teams_below(smem_slots, n, smem_base, split) + above >= n) return n;
+    return 0;
+}
+inline size_t teams_that_fit(uint32_t smem_slots, uint32_t smem_base, uint32_t nt, bool* split = nullptr) {
+    const size_t a = teams_that_fit_layout(smem_slots, smem_base, nt, false), b = teams_that_fit_layout(smem_slots, smem_base, nt, true);
+    if (split) *split = b > a;
+    return b > a ? b : a;
 }
 
 // Returns GCB_OK or a negative status; message in err.  max_fanin = NODE_MAX_FANIN
