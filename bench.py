@@ -396,7 +396,7 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
         h["r"][:] = r
         h["l0"][:] = l0
         sets.append(h)
-    n_parts = max(1, min(E2E_PARTS, batch // 64))
+    n_parts = max(1, min(int(os.environ.get("GCB_E2E_PARTS", E2E_PARTS)), batch // 64))
     parts = [slice(k * batch // n_parts, (k + 1) * batch // n_parts) for k in range(n_parts)]
     eval_jobs = [[] for _ in range(n_sets)]        # eval jobs still reading / writing each buffer set
     garble_jobs = [None] * n_sets
@@ -411,42 +411,46 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
         eval_jobs[k] = []
         prof["drain"] += time.perf_counter() - t
 
-    def garble(k):                                  # queue the garbler's jobs of step k (its buffer set is free again)
-        h = sets[k % n_sets]
-        drain(k % n_sets)
+    def garble_part(k, i):                          # queue part i of the garbler's step k
+        h, sl = sets[k % n_sets], parts[i]
+        if i == 0:
+            drain(k % n_sets)                       # the set's previous step (k - n_sets) has left its buffers
+            garble_jobs[k % n_sets] = []
         t = time.perf_counter()
-        garble_jobs[k % n_sets] = [eng.garble_begin(KEY, h["r"][sl], h["l0"][sl], h["tab"][sl], h["io"][sl]) for sl in parts]
+        garble_jobs[k % n_sets].append(eng.garble_begin(KEY, h["r"][sl], h["l0"][sl], h["tab"][sl], h["io"][sl]))
         prof["issue_g"] += time.perf_counter() - t
 
-    def evaluate(k):                                # each part as soon as its tables are on the host
-        h = sets[k % n_sets]
-        for j, sl in zip(garble_jobs[k % n_sets], parts):
-            t = time.perf_counter()
-            j.wait()
-            t1 = time.perf_counter()
-            eval_jobs[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
-            prof["wait_g"] += t1 - t
-            prof["issue_e"] += time.perf_counter() - t1
-
     def run(n):
-        # GCB_E2E_AHEAD=1: the garbler runs one step ahead -- its kernels of step k+1 are done long before the tables of
-        # step k have crossed PCIe, so the device->host engine never waits for a kernel
+        # The garbler is queued one step ahead, part by part: after part i of step k has been handed to the evaluator,
+        # part i of step k+1 is queued.  Its kernel has long run when the tables of step k have crossed PCIe, so the
+        # device->host engine never waits for a kernel or for the host, and the evaluator's kernels are never queued
+        # behind a whole step of garbling.  GCB_E2E_AHEAD=0: queue a step's garbling when the step starts.
         if ahead:
-            garble(0)
+            for i in range(n_parts):
+                garble_part(0, i)
         for k in range(n):
-            if ahead and k + 1 < n:
-                garble(k + 1)
             if not ahead:
-                garble(k)
-            evaluate(k)
+                for i in range(n_parts):
+                    garble_part(k, i)
+            h = sets[k % n_sets]
+            for i, sl in enumerate(parts):
+                t = time.perf_counter()
+                garble_jobs[k % n_sets][i].wait()   # this part's tables are on the host: its evaluation may start
+                t1 = time.perf_counter()
+                eval_jobs[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
+                prof["wait_g"] += t1 - t
+                prof["issue_e"] += time.perf_counter() - t1
+                if ahead and k + 1 < n:
+                    garble_part(k + 1, i)
         for k in range(n_sets):
             drain(k)
 
     for k in range(n_sets):                         # warm-up: also fills the evaluator's input labels of every set
-        garble(k)
-        evaluate(k)
-        drain(k)
-        h = sets[k]
+        ahead, keep = 0, ahead
+        run(1)
+        ahead = keep
+        sets.append(sets.pop(0))                    # run(1) uses set 0: rotate so that every set gets its turn
+        h = sets[-1]
         h["in"][:] = np.where(bits.astype(bool), h["io"]["l1"][:, :nin], h["io"]["l0"][:, :nin])
     run(n_sets)
     b.barrier()
@@ -671,7 +675,7 @@ def run_gcb(args):
         e2e = {"value": n_and * batch * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(world * h2d), "d2h_bytes_per_step": int(world * d2h), "ms_per_step": e2e_ms,
                "how": f"gcb_garble_begin / gcb_eval_begin / gcb_job_wait on page-locked host buffers (gcb_host_alloc), "
-                      f"{n_parts} parts per step, three buffer sets and the garbler queued one step ahead (the tables of step k+1 stream back while those of step k "
+                      f"{n_parts} parts per step, three buffer sets and the garbler queued one step ahead part by part (the tables of step k+1 stream back while those of step k "
                       f"stream in), ONE host thread per GPU"
                       + (f", ranks bound to their GPU's NUMA node ({b.numa['cpus']} cpus)" if b.numa else "")}
 

@@ -783,20 +783,23 @@ namespace gcb {
 int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin) {
     int rc = build_plan(spec, plan, err, max_fanin);
     if (rc != GCB_OK || max_fanin == 2) return rc;
-    // Measured on B200 (profiles/r02_hot_cold.txt): with synchronous loads from the scratch, 16 resident sha256
-    // instances run 34 % SLOWER than 8 all-hot ones (every cold leaf is an L2 round trip on the dependency chain of its
-    // level); sha512 gains 10 % at 8 instances and chacha20 6 % at 16.  So the second plan is opt-in (GCB_HOT_TEAMS = N);
-    // build_plan itself still moves a handful of labels to the scratch when that keeps an instance resident.
-    int force = 0;
+    // Measured on B200 (profiles/r02_hot_cold.txt), single-block AES rounds rolled (with them unrolled, 16 one-warp teams
+    // spent 44 % of their stall samples waiting for instructions):
+    //   sha512  3 all-hot instances per SM  869 M AND/s   ->  8 instances, 1,280 hot labels  1,153 M AND/s  (+33 %)
+    //   sha256  8 all-hot instances       1,826 M AND/s   -> 12 / 16 instances               1,456 / 1,620 M AND/s (slower)
+    // Every cold leaf is an L2 round trip on the dependency chain of its level, so the second plan pays only while the
+    // SM is nearly empty: it is built when fewer than 8 instances fit, with 8 as the target.  GCB_HOT_TEAMS = 0 switches
+    // it off, N forces a target.
+    int force = -1;
     if (const char* e = getenv("GCB_HOT_TEAMS")) force = atoi(e);
-    if (force <= 0) return GCB_OK;
+    if (force == 0) return GCB_OK;
     const gcb_plan_info& in = plan.info;
     const size_t np = plan.phases.size();
     const uint32_t width = np ? (uint32_t)(in.garble_hashes / np) : 0u;
     const size_t have = teams_that_fit(in.num_slots, kAssumedSmemBase, 2);
-    if (force < 0 && (width >= 128 || have >= 16 || in.num_slots < 256)) return GCB_OK;    // wide (pipe-bound) or already many
-    // the target: twice the resident instances (at most 16), or what the caller forces
-    for (size_t target = force > 0 ? (size_t)force : std::min<size_t>(16, have ? 2 * have : 2); target > have; target /= 2) {
+    if (force < 0 && (width >= 128 || have >= 8 || in.num_slots < 256)) return GCB_OK;    // wide (pipe-bound) or enough resident
+    // the target: 8 resident instances, or what the caller forces (halved until the hot set fits)
+    for (size_t target = force > 0 ? (size_t)force : 8; target > have; target /= 2) {
         uint32_t lo = 32, hi = in.num_slots;               // largest hot set with which `target` teams fit
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) / 2;

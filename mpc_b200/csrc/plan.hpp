@@ -178,8 +178,9 @@ inline size_t teams_that_fit(uint32_t smem_slots, uint32_t smem_base, uint32_t n
 int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, int balance = 1,
                uint32_t hot_cap = 0, int only_policy = -1);
 
-// build_plan; with GCB_HOT_TEAMS = N in the environment also a second plan that keeps only a hot subset of the
-// labels in shared memory so that N instances fit per SM (hot_cap above).  Opt-in: see the measurement in plan.cpp.
+// build_plan; for deep, narrow circuits of which fewer than 8 instances fit per SM (sha512: 3) also a second plan that
+// keeps only a hot subset of the labels in shared memory so that 8 fit (hot_cap above), kept when at most a tenth of the
+// label accesses go to the scratch.  GCB_HOT_TEAMS = 0 switches it off, N forces a target; see the measurement in plan.cpp.
 int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN);
 
 }  // namespace gcb
