@@ -318,8 +318,31 @@ size_t gc_smem_bytes(uint32_t num_slots, uint32_t n_teams, uint32_t nt, uint32_t
 
 // The plan a call runs on: the flattened one, or -- when the caller wants every wire
 // label (Garbled.Wires / Eval's in-place wires) -- one that keeps every XOR gate.
-static int plan_for(const gcb_plan* plan, bool full, const Plan** out) {
-    if (!full) { *out = &plan->p; return GCB_OK; }
+static int plan_for(const gcb_plan* plan, bool full, const Plan** out, uint64_t batch = 0) {
+    if (!full) {
+        *out = &plan->p;
+        const Plan& base = plan->p;
+        // a batch that overflows the resident instances of the all-hot plan may run faster on a plan that holds more
+        // instances with only a hot subset of the labels in shared memory (plan.cpp: build_best_plan)
+        if (batch > (uint64_t)base.info.teams_per_sm * 148 && base.info.teams_per_sm < 8) {
+            std::lock_guard<std::mutex> lk(plan->many_mu);
+            if (!plan->many_tried) {
+                plan->many_tried = true;
+                PlanSpec spec;
+                spec.gates = base.gates.data(); spec.num_gates = (uint32_t)base.gates.size(); spec.num_wires = base.info.num_wires;
+                for (uint32_t i = 0; i < base.info.num_inputs; i++) spec.live_in.push_back(i);
+                for (uint32_t i = 0; i < base.info.num_outputs; i++) spec.live_out.push_back(base.info.num_wires - base.info.num_outputs + i);
+                auto mp = std::make_unique<Plan>();
+                std::string err;
+                if (build_best_plan(spec, *mp, err) == GCB_OK && mp->info.num_hot_slots < mp->info.num_slots) {
+                    team_geometry(*mp);
+                    if (mp->info.teams_per_sm > base.info.teams_per_sm) plan->many = std::move(mp);
+                }
+            }
+            if (plan->many) *out = plan->many.get();
+        }
+        return GCB_OK;
+    }
     std::lock_guard<std::mutex> lk(plan->full_mu);
     if (!plan->full) {
         const Plan& base = plan->p;
@@ -688,11 +711,11 @@ static int garble_begin_impl(const gcb_plan* plan, const uint8_t* keys, uint32_t
                              const gcb_label* r, const gcb_label* in_l0, gcb_label* tables, gcb_wire* io_wires,
                              gcb_wire* wires_full, gcb_job* job) {
     const Plan* use;
-    int rc = plan_for(plan, wires_full != nullptr, &use);
+    std::vector<int> devs = call_devices();
+    int rc = plan_for(plan, wires_full != nullptr, &use, batch / (devs.empty() ? 1 : devs.size()));
     if (rc) return rc;
     const gcb_plan_info& in = use->info;
     const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
-    std::vector<int> devs = call_devices();
     const uint32_t nd = (uint32_t)std::min<size_t>(devs.size(), batch);
     job->parts.resize(nd);
     for (uint32_t d = 0; d < nd; d++) {
@@ -714,11 +737,11 @@ static int eval_begin_impl(const gcb_plan* plan, const uint8_t* keys, uint32_t k
                            const gcb_label* tables, const gcb_label* in_labels, gcb_label* out_labels, gcb_label* wires_full,
                            gcb_job* job) {
     const Plan* use;
-    int rc = plan_for(plan, wires_full != nullptr, &use);
+    std::vector<int> devs = call_devices();
+    int rc = plan_for(plan, wires_full != nullptr, &use, batch / (devs.empty() ? 1 : devs.size()));
     if (rc) return rc;
     const gcb_plan_info& in = use->info;
     const size_t nin = in.num_inputs, nout = in.num_outputs, rows = in.num_rows, nw = in.num_wires;
-    std::vector<int> devs = call_devices();
     const uint32_t nd = (uint32_t)std::min<size_t>(devs.size(), batch);
     job->parts.resize(nd);
     for (uint32_t d = 0; d < nd; d++) {
@@ -1032,7 +1055,10 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     pl->uid = next_uid.fetch_add(1);
     std::string err;
     pl->p.gates.assign(gates, gates + num_gates);
-    int rc = build_best_plan(spec, pl->p, err);
+    // GCB_HOT_TEAMS = N (experiments, tests): the plan itself is the hot / cold one; otherwise that plan is built on
+    // demand for batches that overflow this one (plan_for)
+    const char* forced = getenv("GCB_HOT_TEAMS");
+    int rc = (forced && atoi(forced) > 0) ? build_best_plan(spec, pl->p, err) : build_plan(spec, pl->p, err);
     if (rc) return fail(rc, "%s", err.c_str());
     team_geometry(pl->p);
     if (pl->p.info.teams_per_sm == 0)
@@ -1073,7 +1099,7 @@ int gcb_garble_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, u
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
     const Plan* use;
-    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
+    if ((rc = plan_for(plan, wires_full != nullptr, &use, batch))) return rc;
     if (flags & GCB_FLAG_FANOUT) {
         if (wires_full) return fail(GCB_E_ARG, "GCB_FLAG_FANOUT does not produce wires_full");
         const size_t nin = use->info.num_inputs, nout = use->info.num_outputs, rows = use->info.num_rows;
@@ -1104,7 +1130,7 @@ int gcb_eval_dev(const gcb_plan* plan, const uint8_t* keys, uint32_t keylen, uin
     DeviceInfo* di;
     if ((rc = select_device(&di))) return rc;
     const Plan* use;
-    if ((rc = plan_for(plan, wires_full != nullptr, &use))) return rc;
+    if ((rc = plan_for(plan, wires_full != nullptr, &use, batch))) return rc;
     if (flags & GCB_FLAG_FANOUT) {
         if (wires_full) return fail(GCB_E_ARG, "GCB_FLAG_FANOUT does not produce wires_full");
         const size_t nin = use->info.num_inputs, nout = use->info.num_outputs, rows = use->info.num_rows;
@@ -1507,7 +1533,7 @@ static int stream_garble_impl(gcb_stream* s, const gcb_plan* plan, const uint32_
             auto ap = std::make_shared<gcb_stream::AliasPlan>();
             ap->plan_uid = plan->uid;
             ap->plan = std::make_unique<Plan>();
-            if ((rc = build_best_plan(spec, *ap->plan, err))) return fail(rc, "%s", err.c_str());
+            if ((rc = build_best_plan(spec, *ap->plan, err, NODE_MAX_FANIN, s->batch))) return fail(rc, "%s", err.c_str());
             team_geometry(*ap->plan);
             if (ap->plan->info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ap->plan->info.num_slots);
             ap->loc = spec.loc;
@@ -1796,7 +1822,7 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
             if (first_is_read[l]) { spec.live_in.push_back(l); ep->in_ids.push_back(l); }     // canonical locations;
             if (written[l]) { spec.live_out.push_back(l); ep->out_ids.push_back(l); }         // mapped to ids per call
         }
-        if ((rc = build_best_plan(spec, ep->plan, err))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
+        if ((rc = build_best_plan(spec, ep->plan, err, NODE_MAX_FANIN, s->batch))) return fail(rc == GCB_E_WIRE ? GCB_E_CORRUPT : rc, "corrupted circuit: %s", err.c_str());
         team_geometry(ep->plan);
         if (ep->plan.info.teams_per_sm == 0) return fail(GCB_E_TOO_LARGE, "sub-circuit keeps %u wire labels live", ep->plan.info.num_slots);
         ep->canon.swap(canon);

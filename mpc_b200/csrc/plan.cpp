@@ -780,9 +780,13 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 
 namespace gcb {
 
-int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin) {
+int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin, uint64_t batch_hint) {
     int rc = build_plan(spec, plan, err, max_fanin);
     if (rc != GCB_OK || max_fanin == 2) return rc;
+    // The second plan trades the latency of one instance (narrower teams, L2 round trips) for resident instances:
+    // it only pays when the batch does not fit the all-hot plan in one wave (148 SMs assumed).
+    const char* forced = getenv("GCB_HOT_TEAMS");
+    if (!(forced && atoi(forced) > 0) && batch_hint <= teams_that_fit(plan.info.num_slots, kAssumedSmemBase, 2) * 148) return GCB_OK;
     // Measured on B200 (profiles/r02_hot_cold.txt), single-block AES rounds rolled (with them unrolled, 16 one-warp teams
     // spent 44 % of their stall samples waiting for instructions):
     //   sha512  3 all-hot instances per SM  869 M AND/s   ->  8 instances, 1,280 hot labels  1,153 M AND/s  (+33 %)

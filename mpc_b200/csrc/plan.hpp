@@ -181,7 +181,9 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 // build_plan; for deep, narrow circuits of which fewer than 8 instances fit per SM (sha512: 3) also a second plan that
 // keeps only a hot subset of the labels in shared memory so that 8 fit (hot_cap above), kept when at most a tenth of the
 // label accesses go to the scratch.  GCB_HOT_TEAMS = 0 switches it off, N forces a target; see the measurement in plan.cpp.
-int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN);
+// batch_hint: instances the plan will run on at once; the second plan is only considered when they do not fit the first
+// plan's resident instances in one wave.
+int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, uint64_t batch_hint = ~0ull);
 
 }  // namespace gcb
 
@@ -204,6 +206,9 @@ struct gcb_plan {
     mutable std::map<int, std::shared_ptr<gcb::DevWireLayout>> wire_dev;   // per device
     mutable std::mutex full_mu;
     mutable std::unique_ptr<gcb::Plan> full;  // every wire materialised (wires_full requests), built on demand
+    mutable std::mutex many_mu;
+    mutable std::unique_ptr<gcb::Plan> many;  // hot / cold plan for batches that overflow `p`'s resident instances, on demand
+    mutable bool many_tried = false;
 };
 
 namespace gcb {

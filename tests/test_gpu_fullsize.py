@@ -122,3 +122,25 @@ def test_stream_program_over_1e8_gates():
     res = sp.run_program(steps, batch=3, check=2, warm=2, oracle_steps=2)
     assert res["gates_per_instance"] >= 100_000_000
     assert res["checks_ok"]
+
+
+def test_sha512_batch_that_overflows_the_resident_instances():
+    """A batch larger than one wave of the all-hot sha512 plan (3 instances per SM) runs on the plan that keeps only a
+    hot subset of the labels in shared memory (8 instances per SM), built on demand: sampled instances equal the oracle,
+    every instance decodes to the plaintext function."""
+    from mpc_b200.circuit import HostCircuit
+    circ = load_circuit("sha512")
+    eng = GarbleEngine(circ)
+    batch, nin = 470, circ.num_inputs
+    assert batch > eng.info.teams_per_sm * 148
+    rng = np.random.default_rng(512)
+    rand = rng.integers(0, 256, (batch, 16 * (1 + nin)), dtype=np.uint8)
+    key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    r, l0 = rand_to_labels(rand, nin)
+    tables, io = eng.garble_batch(key, r, l0)
+    bits = rng.integers(0, 2, (batch, nin), dtype=np.uint8)
+    out = eng.eval_batch(key, tables, select(io[:, :nin], bits))
+    assert np.array_equal(decode(io[:, nin:], out), HostCircuit(circ).compute_bits(bits))
+    sample = [0, 147, 148, 469]
+    _, o_tables, o_io = O.garble_batch(circ, key, rand[sample])
+    assert eq(tables[sample], o_tables) and eq(io[sample], o_io)
