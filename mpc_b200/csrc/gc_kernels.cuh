@@ -72,6 +72,7 @@ struct GcParams {
     uint4* wires_full;                    // optional
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
+    uint32_t twin;                        // one-warp teams run as lock-step pairs (team_ctx)
     uint32_t hdr_split;                   // shared-memory layout: team headers kept together (1) or in front of each label block (0)
     uint32_t stagger;                     // SM cycles by which consecutive teams start apart
     long long* trace;                     // optional: phase timestamps of block 0 / team 0 (tools/trace_phases.py)
@@ -94,8 +95,10 @@ __device__ __forceinline__ uint4* wf_slot(uint4* const* pages, uint32_t id, uint
     return pages[id >> WF_PAGE_SHIFT] + ((size_t)inst << WF_PAGE_SHIFT) + (id & (WF_PAGE_IDS - 1));
 }
 
+// team: the team's barrier number, or -- for TWIN teams, see team_ctx -- 0x80000000 | the pair's barrier number.
 __device__ __forceinline__ void team_barrier(uint32_t team, uint32_t team_threads) {
-    if (team_threads == 32) __syncwarp();
+    if (team & 0x80000000u) asm volatile("bar.sync %0, 64;" ::"r"(team & 0xffu) : "memory");
+    else if (team_threads == 32) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(team), "r"(team_threads) : "memory");
 }
 
@@ -170,6 +173,8 @@ struct TeamCtx {
     uint4* slots;          // this team's wire labels
     volatile uint32_t* claim;
     uint32_t team, ttid;
+    uint32_t bar;          // what team_barrier takes: the team, or the twin pair
+    uint32_t sub;          // twin teams: 0 / 1 within the pair
 };
 
 // Shared-memory map of the gate kernels (plan.hpp): [blocks | 64 KiB-aligned tables | blocks], packed below the tables
@@ -186,11 +191,25 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     const uint32_t tb = p.n_smem * 16 + (split ? 0u : H), hdr = split ? p.n_teams * H : 0u;
     const uint32_t pad = (uint32_t)(c.tables - smem);
     const uint32_t in_a = (tb && pad > hdr) ? (pad - hdr) / tb : 0u;      // teams whose block fits below the tables
-    uint8_t* blk = c.team < in_a ? smem + hdr + c.team * tb : c.tables + aes_table_bytes(NT) + (c.team - in_a) * tb;
-    uint8_t* h = split ? smem + c.team * H : blk;
+    auto block_of = [&](uint32_t t) { return t < in_a ? smem + hdr + t * tb : c.tables + aes_table_bytes(NT) + (t - in_a) * tb; };
+    auto header_of = [&](uint32_t t) { return split ? smem + t * H : block_of(t); };
+    uint8_t* blk = block_of(c.team);
+    uint8_t* h = header_of(c.team);
     c.rk = reinterpret_cast<uint32_t*>(h);
     c.claim = reinterpret_cast<volatile uint32_t*>(h + GC_RK_BYTES);
     c.slots = reinterpret_cast<uint4*>(split ? blk : blk + H);
+    c.bar = c.team;
+    c.sub = 0;
+    // TWIN teams: with 16 one-warp teams every warp scheduler holds four warps that are each somewhere else in a 60 KB
+    // kernel, and its instruction cache thrashes (ncu: no_inst 26-44 % of the stall samples).  The plan drives the control
+    // flow, not the data, so two instances started together stay together if their barriers are shared: warps w and w ^ 4
+    // (same scheduler: warp w runs on scheduler w % 4) form a pair, claim two consecutive instances at once and replace
+    // __syncwarp by a 64-thread named barrier.  The pair shares the leader's claim word.
+    if (p.twin) {
+        c.sub = (c.team >> 2) & 1u;
+        c.bar = 0x80000000u | (1u + (c.team & 3u) + ((c.team >> 3) << 2));
+        c.claim = reinterpret_cast<volatile uint32_t*>(header_of(c.team & ~4u) + GC_RK_BYTES);
+    }
     return c;
 }
 
@@ -493,16 +512,18 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
         if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
-        team_barrier(tc.team, TT);
+        team_barrier(tc.bar, TT);
     }
     const auto slots = team_slots<SPILL>(tc, p);
-    stagger_start(tc.team, p.stagger);
+    stagger_start(p.twin ? (tc.bar & 0xffu) : tc.team, p.stagger);
 
     for (;;) {
-        if (ttid == 0) *tc.claim = atomicAdd(p.counter, 1u);
-        team_barrier(tc.team, TT);
-        const uint32_t inst = *tc.claim;
-        if (inst >= p.batch) break;
+        // the next instance (twin teams: the pair's next two; an odd tail is run twice, by both warps, with the same result)
+        if (ttid == 0 && tc.sub == 0) *tc.claim = atomicAdd(p.counter, p.twin ? 2u : 1u);
+        team_barrier(tc.bar, TT);
+        const uint32_t claimed = *tc.claim;
+        if (claimed >= p.batch) break;
+        const uint32_t inst = claimed + tc.sub < p.batch ? claimed + tc.sub : p.batch - 1;
         if (p.key_stride != 0 && ttid == 0)
             aes_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Label R = label_from_mem(__ldg(p.r + inst));
@@ -531,7 +552,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                 w[1] = label_to_mem(label_from_mem(m) ^ R);
             }
         }
-        team_barrier(tc.team, TT);
+        team_barrier(tc.bar, TT);
         const GarbleEnv<decltype(slots)> env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, R, inst};
         // first-pass gate records: requested one phase ahead where the registers allow it (single-block
         // variants), at the top of their own phase -- behind the node rows -- in the two-block variants
@@ -547,7 +568,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
-            run_rows<true, FULL, D>(p, slots, R, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
+            run_rows<true, FULL, D>(p, slots, R, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
             if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
             const uint32_t ntask = task_count<true>(ph);
@@ -575,7 +596,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                     for (int j = 0; j < ILP; j++) cur[j] = nxt[j];
                 }
                 if (tracing) p.trace[4 * pi + 3] = clock64();
-                team_barrier(tc.team, TT);
+                team_barrier(tc.bar, TT);
             }
             ph = ph_n; ph_n = ph_nn;
             if (AHEAD) {
@@ -598,7 +619,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                 w[1] = label_to_mem(l0 ^ R);
             }
         }
-        team_barrier(tc.team, TT);
+        team_barrier(tc.bar, TT);
     }
 }
 
@@ -717,16 +738,18 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
         if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
-        team_barrier(tc.team, TT);
+        team_barrier(tc.bar, TT);
     }
     const auto slots = team_slots<SPILL>(tc, p);
-    stagger_start(tc.team, p.stagger);
+    stagger_start(p.twin ? (tc.bar & 0xffu) : tc.team, p.stagger);
 
     for (;;) {
-        if (ttid == 0) *tc.claim = atomicAdd(p.counter, 1u);
-        team_barrier(tc.team, TT);
-        const uint32_t inst = *tc.claim;
-        if (inst >= p.batch) break;
+        // the next instance (twin teams: the pair's next two; an odd tail is run twice, by both warps, with the same result)
+        if (ttid == 0 && tc.sub == 0) *tc.claim = atomicAdd(p.counter, p.twin ? 2u : 1u);
+        team_barrier(tc.bar, TT);
+        const uint32_t claimed = *tc.claim;
+        if (claimed >= p.batch) break;
+        const uint32_t inst = claimed + tc.sub < p.batch ? claimed + tc.sub : p.batch - 1;
         if (p.key_stride != 0 && ttid == 0)
             aes_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
@@ -742,7 +765,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             slots.stm(ref.x, m);
             if (FULL) p.wires_full[(size_t)inst * p.n_wires + ref.y] = m;
         }
-        team_barrier(tc.team, TT);
+        team_barrier(tc.bar, TT);
         const EvalEnv<decltype(slots)> env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, inst};
         uint4 cur[ILP];
         prefetch_cipher<false, ILP>(p, ph, 0, ttid, TT, cur);
@@ -763,7 +786,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             }
             uint4 cur_n[ILP];
             prefetch_cipher<false, ILP>(p, ph_n, 0, ttid, TT, cur_n);
-            run_rows<false, FULL, D>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.team, ttid, TT, pipe, row);
+            run_rows<false, FULL, D>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);
@@ -790,7 +813,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
 #pragma unroll
                     for (int j = 0; j < ILP; j++) cur[j] = nxt[j];
                 }
-                team_barrier(tc.team, TT);
+                team_barrier(tc.bar, TT);
             }
             ph = ph_n; ph_n = ph_nn;
 #pragma unroll
@@ -801,7 +824,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             if (STREAM) *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots.ldm(ref.x);   // StreamEval.Set
             else p.io[(size_t)inst * p.n_out + ref.y] = slots.ldm(ref.x);
         }
-        team_barrier(tc.team, TT);
+        team_barrier(tc.bar, TT);
     }
 }
 

@@ -243,7 +243,7 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
 // Team geometry for a plan: how many instances one SM keeps resident, how many threads work on
 // each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
 // GCB_NT / GCB_TEAMS / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
-struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false, split = false; };
+struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false, split = false, twin = false; };
 // width = AES blocks per cipher level of the garbler (4 per AND / OR, 2 per INV), averaged.
 // num_hot < num_slots: a hot / cold plan (plan.cpp) -- only the hot labels need shared memory.
 static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base, uint32_t num_hot = 0) {
@@ -257,6 +257,9 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
         g.team_threads = n >= 8 ? 32u : 32u * (uint32_t)(512 / 32 / n > 3 ? 3 : 512 / 32 / n);
         g.stagger = n > 1 ? 100000 : 0;
         if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
+        // 16 one-warp teams run as 8 lock-step pairs (gc_kernels.cuh: team_ctx)
+        g.twin = g.team_threads == 32 && (n == 16 || n == 8) && n > 8;
+        if (const char* e = getenv("GCB_TWIN")) g.twin = atoi(e) != 0 && g.team_threads == 32 && n % 8 == 0;
         return g;
     }
     bool split4 = false, split2 = false;
@@ -299,6 +302,7 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
     g.n_teams = (uint32_t)n; g.team_threads = tt; g.ilp = ilp; g.nt = nt;
     g.stagger = n > 1 ? 100000 : 0;                 // teams start ~50 us apart
     if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
+    if (const char* e = getenv("GCB_TWIN")) g.twin = atoi(e) != 0 && tt == 32 && n % 8 == 0 && n <= 16;
     return g;
 }
 static uint32_t plan_width(const Plan& plan) {
@@ -407,6 +411,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     const dim3 block(p.n_teams * p.team_threads);
     const size_t smem = gc_smem_bytes(geo.n_smem, p.n_teams, geo.nt, di->smem_base, geo.split);
     p.hdr_split = geo.split ? 1u : 0u;
+    p.twin = geo.twin ? 1u : 0u;
     const bool full = wires_full != nullptr;
     const int mode = pages ? GC_STREAM : full ? GC_FULL : GC_PLAIN;
     const GcVariant var{geo.ilp, geo.nt, geo.spill};

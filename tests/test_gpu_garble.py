@@ -266,6 +266,28 @@ def test_hot_cold_plans_are_bit_exact(name, batch, teams, monkeypatch):
     assert eq(out, O.eval_batch(circ, keys, o_tables, inl, threads=4))
 
 
+@pytest.mark.parametrize("batch", [1, 2, 7, 300])
+def test_twin_teams_are_bit_exact(batch, monkeypatch):
+    """One-warp teams run as lock-step pairs (two instances claimed at once, shared 64-thread barriers); an odd tail is
+    run by both warps of the last pair.  Forced here on sha256's eight all-hot teams."""
+    monkeypatch.setenv("GCB_TWIN", "1")
+    circ = load_circuit("sha256")
+    eng = GarbleEngine(circ)
+    keys, rand = garble_inputs(f"twin/{batch}", batch, circ.num_inputs, 16)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    sample = sorted({0, batch // 2, batch - 1})
+    _, o_tables, o_io = O.garble_batch(circ, keys[sample], rand[sample], threads=4)
+    assert eq(tables[sample], o_tables) and eq(io[sample], o_io)
+    bits = np.random.default_rng(4).integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+    inl = select(io[:, : circ.num_inputs], bits)
+    out = eng.eval_batch(keys, tables, inl)
+    assert eq(out[sample], O.eval_batch(circ, keys[sample], o_tables, inl[sample], threads=4))
+    got = decode(io[:, circ.num_inputs:], out)
+    assert got.max() <= 1
+    assert np.array_equal(got[batch - 1], circ.compute_bits(bits[batch - 1].tolist()))
+
+
 def test_default_plan_of_sha256_keeps_eight_instances_with_the_balanced_schedule():
     """The schedule that fills the warp passes needs 1,272 live labels per instance; eight such label blocks fit either
     side of the T-tables because the team headers are kept apart from them.  Everything stays in shared memory."""

@@ -60,8 +60,9 @@ int main(int argc, char** argv) {
     Plan plan;
     std::string err;
     const int balance = argc > 3 ? atoi(argv[3]) : 0;      // 0 none, 1 garbler, 2 evaluator (plan.cpp: balanced_levels)
-    const uint32_t hot_cap = argc > 4 ? (uint32_t)atoi(argv[4]) : 0;   // 0: all labels in shared memory
-    if (int rc = build_plan(spec, plan, err, NODE_MAX_FANIN, balance, hot_cap)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
+    const uint32_t hot_cap = argc > 4 ? (uint32_t)atoi(argv[4]) : 0;
+    const int max_fanin_arg = argc > 5 ? atoi(argv[5]) : NODE_MAX_FANIN;   // 0: all labels in shared memory
+    if (int rc = build_plan(spec, plan, err, max_fanin_arg, balance, hot_cap)) { fprintf(stderr, "plan: %d %s\n", rc, err.c_str()); return 1; }
     printf("balance %d  policy %d  garble_passes %u  eval_passes %u  hot slots %u of %u  cold accesses %llu (node loads %u, gates %u)\n", balance, plan.policy,
            plan.info.garble_passes, plan.info.eval_passes, plan.info.num_hot_slots, plan.info.num_slots, (unsigned long long)plan.cold_accesses,
            plan.node_loads, plan.info.num_and + plan.info.num_inv + plan.info.num_or);
