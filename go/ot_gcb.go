@@ -121,3 +121,78 @@ func (s *IKNPSender) checkSums(seed2 Label, result, choiceVector []Label) (q0, q
 	q1 = Label{D0: a[1].D0 ^ b[1].D0, D1: a[1].D1 ^ b[1].D1}
 	return
 }
+
+// ReceiveBits (ot/iknp.go:554-620): the same U exchange as receive; the result is Bit(0) of every label, packed.
+func (r *IKNPReceiver) ReceiveBits(choices []uint64, result []uint64, n int) error {
+	if (n+63)/64 > len(choices) {
+		return fmt.Errorf("choices buffer len=%d too short for n=%d", len(choices), n)
+	}
+	u := make([]byte, gcb.IKNPUSize(n))
+	err := gcb.IKNPReceiverExpandBits((*[128]gcb.Label)(unsafe.Pointer(&r.k0)), (*[128]gcb.Label)(unsafe.Pointer(&r.k1)),
+		r.pos, choices, n, u, result)
+	if err != nil {
+		return err
+	}
+	r.pos += gcb.IKNPStreamAdvance(n)
+	for ofs := 0; ofs < len(u); {
+		end := ofs + chunkSize
+		if end > len(u) {
+			end = len(u)
+		}
+		if err := r.io.SendData(u[ofs:end]); err != nil {
+			return err
+		}
+		ofs = end
+	}
+	return r.io.Flush()
+}
+
+// SendBits (ot/iknp.go:259-310): column 0 of the matrix, packed LSB-first.
+func (s *IKNPSender) SendBits(result []uint64, n int) error {
+	u := make([]byte, 0, gcb.IKNPUSize(n))
+	for ofs := 0; ofs < n; {
+		chunk, err := s.io.ReceiveData()
+		if err != nil {
+			return err
+		}
+		if len(chunk)%K != 0 {
+			return fmt.Errorf("invalid chunk size: %v", len(chunk))
+		}
+		u = append(u, chunk...)
+		ofs += len(chunk) / K * 8
+	}
+	err := gcb.IKNPSenderExpandBits((*[128]gcb.Label)(unsafe.Pointer(&s.k0)), (*gcb.Label)(unsafe.Pointer(&s.Delta)), s.pos, u, n, result)
+	s.pos += gcb.IKNPStreamAdvance(n)
+	return err
+}
+
+// Receive (ot/cot.go:184-235): the extension, then one call instead of the per-batch MiTCCRH loop; the 2n messages
+// are read off the connection in the SendLabel encoding with one ReceiveBytes.
+func (cot *COT) Receive(flags []bool, result []Label) error {
+	if cot.iknpR == nil {
+		return fmt.Errorf("not initialized as receiver")
+	}
+	if err := cot.iknpR.Receive(flags, result, cot.malicious); err != nil {
+		return err
+	}
+	var ld LabelData
+	var seed Label
+	if err := cot.io.ReceiveLabel(&seed, &ld); err != nil {
+		return err
+	}
+	msgs := make([]byte, 32*len(result))
+	if err := cot.io.ReceiveBytes(msgs); err != nil {
+		return err
+	}
+	return gcb.COTReceive((*gcb.Label)(unsafe.Pointer(&seed)), flags, msgs,
+		unsafe.Slice((*gcb.Label)(unsafe.Pointer(&result[0])), len(result)))
+}
+
+// ROT.Send / ROT.Receive after the extension (ot/rot.go:155-172, 192-197).
+func (rot *ROT) hashSend(seed Label, q []Label, wires []Wire) error {
+	return gcb.ROTSend((*gcb.Label)(unsafe.Pointer(&seed)), (*gcb.Label)(unsafe.Pointer(&rot.iknpS.Delta)),
+		unsafe.Slice((*gcb.Label)(unsafe.Pointer(&q[0])), len(q)), unsafe.Slice((*gcb.Wire)(unsafe.Pointer(&wires[0])), len(wires)))
+}
+func (rot *ROT) hashReceive(seed Label, result []Label) error {
+	return gcb.ROTReceive((*gcb.Label)(unsafe.Pointer(&seed)), unsafe.Slice((*gcb.Label)(unsafe.Pointer(&result[0])), len(result)))
+}

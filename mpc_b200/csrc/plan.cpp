@@ -787,13 +787,15 @@ int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_
     // it only pays when the batch does not fit the all-hot plan in one wave (148 SMs assumed).
     const char* forced = getenv("GCB_HOT_TEAMS");
     if (!(forced && atoi(forced) > 0) && batch_hint <= teams_that_fit(plan.info.num_slots, kAssumedSmemBase, 2) * 148) return GCB_OK;
-    // Measured on B200 (profiles/r02_hot_cold.txt), single-block AES rounds rolled (with them unrolled, 16 one-warp teams
-    // spent 44 % of their stall samples waiting for instructions):
-    //   sha512  3 all-hot instances per SM  869 M AND/s   ->  8 instances, 1,280 hot labels  1,153 M AND/s  (+33 %)
-    //   sha256  8 all-hot instances       1,826 M AND/s   -> 12 / 16 instances               1,456 / 1,620 M AND/s (slower)
-    // Every cold leaf is an L2 round trip on the dependency chain of its level, so the second plan pays only while the
-    // SM is nearly empty: it is built when fewer than 8 instances fit, with 8 as the target.  GCB_HOT_TEAMS = 0 switches
-    // it off, N forces a target.
+    // Measured on B200 (profiles/r02_hot_cold.txt), single-block AES rounds rolled, 16 one-warp teams run as lock-step
+    // pairs ("twin": without both, 16 teams spent 26-44 % of their stall samples waiting for instructions):
+    //   sha512  3 all-hot instances per SM  870 M AND/s  ->  8 instances 1,000-1,150  ->  16 instances (626 hot labels) 1,666
+    //   sha256  8 all-hot instances       1,826 M AND/s  -> 12 / 16 instances 1,456 / 1,729 (slower)
+    //   chacha20 / sha256xor  9-10 all-hot  1,661 / 1,825 ->  16 instances 1,506 / 1,718 (slower)
+    // Every cold leaf is an L2 round trip on the dependency chain of its level and the dual-path label access costs
+    // 17 % more instructions, so the second plan pays only while the SM is nearly empty: it is built when fewer than 8
+    // instances fit, with 16 as the target (halved until the hot set fits and at most a fifth of the label accesses go
+    // to the scratch).  GCB_HOT_TEAMS = 0 switches it off, N forces a target.
     int force = -1;
     if (const char* e = getenv("GCB_HOT_TEAMS")) force = atoi(e);
     if (force == 0) return GCB_OK;
@@ -802,8 +804,8 @@ int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_
     const uint32_t width = np ? (uint32_t)(in.garble_hashes / np) : 0u;
     const size_t have = teams_that_fit(in.num_slots, kAssumedSmemBase, 2);
     if (force < 0 && (width >= 128 || have >= 8 || in.num_slots < 256)) return GCB_OK;    // wide (pipe-bound) or enough resident
-    // the target: 8 resident instances, or what the caller forces (halved until the hot set fits)
-    for (size_t target = force > 0 ? (size_t)force : 8; target > have; target /= 2) {
+    // the target: 16 resident instances, or what the caller forces (halved until the hot set fits)
+    for (size_t target = force > 0 ? (size_t)force : 16; target > have; target /= 2) {
         uint32_t lo = 32, hi = in.num_slots;               // largest hot set with which `target` teams fit
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) / 2;
@@ -815,7 +817,7 @@ int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_
         if (build_plan(spec, cand, e2, max_fanin, 1, lo, plan.policy) != GCB_OK) continue;
         // label accesses of an instance: node leaves + node results + three per ciphered gate
         const uint64_t accesses = (uint64_t)cand.node_loads + cand.nodes.size() + 3ull * cand.crecs.size();
-        if (force <= 0 && cand.cold_accesses * 100 > accesses * 10) continue;           // more than 10 % would go to L2
+        if (force <= 0 && cand.cold_accesses * 100 > accesses * 20) continue;           // more than 20 % would go to L2
         plan.info = cand.info; plan.policy = cand.policy;
         plan.phases.swap(cand.phases); plan.waves.swap(cand.waves); plan.nodes.swap(cand.nodes); plan.crecs.swap(cand.crecs);
         plan.nout_wire.swap(cand.nout_wire); plan.cout_wire.swap(cand.cout_wire);
