@@ -379,10 +379,10 @@ def roofline_of(b: Bench, circ, eng, batch: int, g_ms: float, e_ms: float, nr: i
 def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinned: bool):
     """The call a user makes, from ONE host thread, for a stream of batches: gcb_garble_begin on every part of the
     step's batch, then per part gcb_job_wait -> gcb_eval_begin; the eval jobs of a step are only waited for when
-    their buffers come round again (three sets of host buffers) and the garbler is queued one step ahead, so the
-    garbler's tables of step k+1 stream back (D2H) while the evaluator's tables of step k stream in (H2D).  Every
-    step copies its own inputs up and its own results down inside the timed region; the last step is fully
-    drained before the clock stops."""
+    their buffers come round again (three sets of host buffers) and the first parts of the next step's garbling are
+    queued behind this step's last, so the garbler's tables of step k+1 stream back (D2H) while the evaluator's
+    tables of step k stream in (H2D).  Every step copies its own inputs up and its own results down inside the
+    timed region; the last step is fully drained before the clock stops."""
     from mpc_b200.circuit import host_alloc, host_free
     from mpc_b200.circuit_io import LABEL_DTYPE, WIRE_DTYPE
     nin, nout, rows = circ.num_inputs, circ.num_outputs, circ.num_rows
@@ -402,7 +402,7 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
     garble_jobs = [None] * n_sets
 
     prof = {"drain": 0.0, "issue_g": 0.0, "wait_g": 0.0, "issue_e": 0.0}
-    ahead = int(os.environ.get("GCB_E2E_AHEAD", "1"))
+    ahead = min(int(os.environ.get("GCB_E2E_AHEAD", "3")), max(1, batch // 64))   # parts of the next step queued ahead
 
     def drain(k):
         t = time.perf_counter()
@@ -421,17 +421,16 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
         prof["issue_g"] += time.perf_counter() - t
 
     def run(n):
-        # The garbler is queued one step ahead, part by part: after part i of step k has been handed to the evaluator,
-        # part i of step k+1 is queued.  Its kernel has long run when the tables of step k have crossed PCIe, so the
-        # device->host engine never waits for a kernel or for the host, and the evaluator's kernels are never queued
-        # behind a whole step of garbling.  GCB_E2E_AHEAD=0: queue a step's garbling when the step starts.
-        if ahead:
-            for i in range(n_parts):
-                garble_part(0, i)
+        # A step queues its garbling, then hands each part to the evaluator as soon as its tables are on the host.
+        # The first `ahead` parts of the NEXT step's garbling are queued behind the last parts of this step, so that
+        # their kernels have run when this step's last tables have crossed PCIe: the device->host engine never waits
+        # for the host to queue a step or for its first kernel.  (Queuing the whole next step ahead measured slower:
+        # 24.4 against 23.3 ms.)
+        issued = 0                                  # parts of step k already queued ahead
         for k in range(n):
-            if not ahead:
-                for i in range(n_parts):
-                    garble_part(k, i)
+            for i in range(issued, n_parts):
+                garble_part(k, i)
+            issued = 0
             h = sets[k % n_sets]
             for i, sl in enumerate(parts):
                 t = time.perf_counter()
@@ -440,8 +439,9 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
                 eval_jobs[k % n_sets].append(eng.eval_begin(KEY, h["tab"][sl], h["in"][sl], h["out"][sl]))
                 prof["wait_g"] += t1 - t
                 prof["issue_e"] += time.perf_counter() - t1
-                if ahead and k + 1 < n:
-                    garble_part(k + 1, i)
+                if k + 1 < n and i >= n_parts - ahead:
+                    garble_part(k + 1, issued)
+                    issued += 1
         for k in range(n_sets):
             drain(k)
 
@@ -474,12 +474,15 @@ def e2e_loop(b: Bench, circ, eng, batch: int, inputs, ref_dev, steps: int, pinne
     return sec, n_parts
 
 
-def pcie_probe(b: Bench, h2d_bytes: int, d2h_bytes: int, reps: int = 5):
-    """Copy-only floor of the e2e step on this box: every rank moves the step's bytes host->device and
-    device->host at the same time (page-locked memory, two streams), all ranks at once."""
+def pcie_probe(b: Bench, h2d_bytes: int, d2h_bytes: int, reps: int = 5, parts: int = E2E_PARTS, sets: int = 3):
+    """Copy-only floors of the e2e step on this box, every rank at once, page-locked memory, two streams:
+    `both_ms`     the step's bytes up and down as two single copies between fixed buffers (the best the links can do);
+    `pattern_ms`  the same bytes in the e2e path's pattern: `parts` copies per direction per step, the device->host copy
+                  of part i finished before the host->device copy of part i is queued FROM THE SAME HOST MEMORY (the
+                  evaluator reads what the garbler wrote), rotating over `sets` sets of host buffers."""
     torch = b.torch
-    h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    h_in = [torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory() for _ in range(sets)]
+    h_out = [torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory() for _ in range(sets)]
     d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=b.dev)
     d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=b.dev)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
@@ -490,21 +493,50 @@ def pcie_probe(b: Bench, h2d_bytes: int, d2h_bytes: int, reps: int = 5):
         for _ in range(reps):
             if up:
                 with torch.cuda.stream(s1):
-                    d_in.copy_(h_in, non_blocking=True)
+                    d_in.copy_(h_in[0], non_blocking=True)
             if down:
                 with torch.cuda.stream(s2):
-                    h_out.copy_(d_out, non_blocking=True)
+                    h_out[0].copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    def pattern():
+        cu = [(k * h2d_bytes // parts, (k + 1) * h2d_bytes // parts) for k in range(parts)]
+        cd = [(k * d2h_bytes // parts, (k + 1) * d2h_bytes // parts) for k in range(parts)]
+        b.barrier()
+        t0 = time.perf_counter()
+        evs = []
+        with torch.cuda.stream(s2):                       # step 0's results start down
+            for lo, hi in cd:
+                h_out[0][lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+                e = torch.cuda.Event(); e.record(s2); evs.append(e)
+        for k in range(reps):
+            nxt = []
+            for i in range(parts):
+                evs[i].synchronize()                      # part i is on the host ...
+                with torch.cuda.stream(s1):               # ... and goes up again
+                    lo, hi = cu[i]
+                    d_in[lo:hi].copy_(h_out[k % sets][lo:hi], non_blocking=True)   # the bytes that just came down
+                if k + 1 < reps:
+                    with torch.cuda.stream(s2):           # the next step's part i comes down behind this step's
+                        lo, hi = cd[i]
+                        h_out[(k + 1) % sets][lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+                        e = torch.cuda.Event(); e.record(s2); nxt.append(e)
+            evs = nxt
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / reps
 
     run(True, True)
     both, up, down = run(True, True), run(True, False), run(False, True)
-    both, up, down = b.max_over_ranks([both, up, down])
-    return {"both_ms": both * 1e3, "h2d_alone_gbs_per_gpu": h2d_bytes / up / 1e9, "d2h_alone_gbs_per_gpu": d2h_bytes / down / 1e9,
+    pattern()
+    pat = pattern()
+    both, up, down, pat = b.max_over_ranks([both, up, down, pat])
+    return {"both_ms": both * 1e3, "pattern_ms": pat * 1e3,
+            "h2d_alone_gbs_per_gpu": h2d_bytes / up / 1e9, "d2h_alone_gbs_per_gpu": d2h_bytes / down / 1e9,
             "both_gbs_per_gpu_each_way": (h2d_bytes + d2h_bytes) / 2 / both / 1e9,
             "box_total_gbs": (h2d_bytes + d2h_bytes) * b.world / both / 1e9,
-            "how": f"{b.world} rank(s) at once, {h2d_bytes / 1e9:.2f} GB up + {d2h_bytes / 1e9:.2f} GB down per rank, "
-                   f"pinned memory, two streams, mean of {reps}"}
+            "how": f"{b.world} rank(s) at once, {h2d_bytes / 1e9:.2f} GB up + {d2h_bytes / 1e9:.2f} GB down per rank, pinned memory, "
+                   f"two streams, mean of {reps}; pattern: {parts} copies per direction per step, up after down per part, {sets} buffer sets"}
 
 
 def extra_iknp(b: Bench, n: int = 1 << 24):
@@ -675,7 +707,7 @@ def run_gcb(args):
         e2e = {"value": n_and * batch * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(world * h2d), "d2h_bytes_per_step": int(world * d2h), "ms_per_step": e2e_ms,
                "how": f"gcb_garble_begin / gcb_eval_begin / gcb_job_wait on page-locked host buffers (gcb_host_alloc), "
-                      f"{n_parts} parts per step, three buffer sets and the garbler queued one step ahead part by part (the tables of step k+1 stream back while those of step k "
+                      f"{n_parts} parts per step, three buffer sets, the first parts of the next step's garbling queued behind this step's last (the tables of step k+1 stream back while those of step k "
                       f"stream in), ONE host thread per GPU"
                       + (f", ranks bound to their GPU's NUMA node ({b.numa['cpus']} cpus)" if b.numa else "")}
 
@@ -687,6 +719,8 @@ def run_gcb(args):
         if e2e:
             e2e["pcie_floor_ms"] = probe["both_ms"]
             e2e["frac_of_pcie_floor"] = probe["both_ms"] / e2e["ms_per_step"]
+            e2e["pcie_pattern_ms"] = probe["pattern_ms"]
+            e2e["frac_of_pcie_pattern"] = probe["pattern_ms"] / e2e["ms_per_step"]
             sec, _ = e2e_loop(b, circ, eng, batch, head["inputs"], head["dev"], 2, pinned=False)
             p_ms = b.max_over_ranks([sec * 1e3])[0]
             extra["e2e_pageable"] = {"value": n_and * batch * world / (p_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": p_ms,

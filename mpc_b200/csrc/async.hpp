@@ -12,6 +12,7 @@
 // wait).  Streams, events and arenas are pooled per device and reused by later calls.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -165,8 +166,10 @@ public:
                 r = std::make_unique<JobRes>();
                 if ((*err = r->init(device)) != cudaSuccess) return nullptr;
             }
-            r->h2d = ss->h2d[cls & 1];
-            r->d2h = ss->d2h[cls & 1];
+            // GCB_COPY_STREAMS=1: one stream per direction for both job classes (experiments)
+            static const bool one = [] { const char* e = getenv("GCB_COPY_STREAMS"); return e && atoi(e) == 1; }();
+            r->h2d = ss->h2d[one ? 0 : (cls & 1)];
+            r->d2h = ss->d2h[one ? 0 : (cls & 1)];
             r->k = ss->k[ss->next_k++ & 3];
         }
         return r;
