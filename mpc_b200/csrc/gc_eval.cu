@@ -14,12 +14,13 @@ cudaError_t gc_opt_in_eval(int smem_bytes) {
 
 template <int NR, int MODE>
 static void launch(GcVariant v, dim3 grid, dim3 block, size_t smem, cudaStream_t s, const GcParams& p) {
-    if (v.spill && v.ilp == 1) eval_kernel<NR, MODE, 1, 512, 2, true><<<grid, block, smem, s>>>(p);
-    else if (v.spill) eval_kernel<NR, MODE, 2, 512, 2, true><<<grid, block, smem, s>>>(p);
-    else if (v.nt == 2 && v.ilp == 1) eval_kernel<NR, MODE, 1, 512, 2, false><<<grid, block, smem, s>>>(p);
-    else if (v.nt == 2) eval_kernel<NR, MODE, 2, 512, 2, false><<<grid, block, smem, s>>>(p);
-    else if (v.ilp == 1) eval_kernel<NR, MODE, 1, 1024, 4, false><<<grid, block, smem, s>>>(p);
-    else eval_kernel<NR, MODE, 2, 512, 4, false><<<grid, block, smem, s>>>(p);
+    if (v.spill == 2) eval_kernel<NR, MODE, 1, 512, 2, 2><<<grid, block, smem, s>>>(p);
+    else if (v.spill && v.ilp == 1) eval_kernel<NR, MODE, 1, 512, 2, 1><<<grid, block, smem, s>>>(p);
+    else if (v.spill) eval_kernel<NR, MODE, 2, 512, 2, 1><<<grid, block, smem, s>>>(p);
+    else if (v.nt == 2 && v.ilp == 1) eval_kernel<NR, MODE, 1, 512, 2, 0><<<grid, block, smem, s>>>(p);
+    else if (v.nt == 2) eval_kernel<NR, MODE, 2, 512, 2, 0><<<grid, block, smem, s>>>(p);
+    else if (v.ilp == 1) eval_kernel<NR, MODE, 1, 1024, 4, 0><<<grid, block, smem, s>>>(p);
+    else eval_kernel<NR, MODE, 2, 512, 4, 0><<<grid, block, smem, s>>>(p);
 }
 template <int MODE>
 static void launch_nr(uint32_t keylen, GcVariant v, dim3 g, dim3 b, size_t sm, cudaStream_t s, const GcParams& p) {

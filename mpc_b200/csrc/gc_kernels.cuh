@@ -73,6 +73,8 @@ struct GcParams {
     uint32_t* counter;                    // next instance to claim
     uint32_t team_threads, n_teams;
     uint32_t twin;                        // one-warp teams run as lock-step pairs (team_ctx)
+    const uint32_t* copies;               // SPILL == 2: evict / reload records, src | dst << 16 (DevPhaseRec::copy_first indexes it)
+    uint32_t n_live_in;                   // entries of live_in (an input of a split plan may be loaded into a hot slot AND the scratch)
     uint32_t hdr_split;                   // shared-memory layout: team headers kept together (1) or in front of each label block (0)
     uint32_t stagger;                     // SM cycles by which consecutive teams start apart
     long long* trace;                     // optional: phase timestamps of block 0 / team 0 (tools/trace_phases.py)
@@ -213,9 +215,12 @@ __device__ __forceinline__ TeamCtx team_ctx(uint8_t* smem, const GcParams& p) {
     return c;
 }
 
-template <bool SPILL>
+// SPILL: 0 = every label in shared memory; 1 = slots from n_smem up in the instance's global scratch, read and written in
+// place (SlotsSpill); 2 = live-range splitting (plan.cpp): every access is shared memory, and the plan's per-phase copy
+// lists move values to the scratch after a burst of uses and back, asynchronously, before the next
+template <int SPILL>
 __device__ __forceinline__ auto team_slots(const TeamCtx& tc, const GcParams& p) {
-    if constexpr (SPILL) {
+    if constexpr (SPILL == 1) {
         const size_t team_index = (size_t)blockIdx.x * p.n_teams + tc.team;
         return SlotsSpill{tc.slots, p.spill + team_index * (p.n_slots - p.n_smem), p.n_smem};
     } else {
@@ -338,6 +343,34 @@ __device__ __forceinline__ void stagger_start(uint32_t team, uint32_t stagger) {
     const long long until = clock64() + (long long)team * stagger;
     while (clock64() < until) __nanosleep(2000);
 }
+
+// ---- live-range splitting: the copies queued at the top of a phase (SPILL == 2) ------------------------------------
+__device__ __forceinline__ void cp_async16(uint4* smem_dst, const uint4* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+// What a thread keeps of a phase's copy lists: the header and its own first record of each list, requested a phase ahead.
+struct CopyRegs { uint32_t first, counts, ev, rl; };          // counts = evicts | reloads << 16
+__device__ __forceinline__ CopyRegs load_copies(const GcParams& p, uint32_t pi, uint32_t ttid) {
+    const uint4 h = __ldg(p.phases + 2 * pi + 1);             // (row_first, copy_first, counts, -)
+    CopyRegs c{h.y, h.z, 0u, 0u};
+    const uint32_t n_ev = c.counts & 0xffffu, n_rl = c.counts >> 16;
+    if (ttid < n_ev) c.ev = __ldg(p.copies + c.first + ttid);
+    if (ttid < n_rl) c.rl = __ldg(p.copies + c.first + n_ev + ttid);
+    return c;
+}
+// Evicts: hot slot -> scratch (the value was produced in the previous phase; a barrier lies between).  Reloads: scratch ->
+// hot slot, asynchronously; they are complete when the phase ends (copies_done before its last barrier) and the cluster
+// of uses starts in the next phase.  Returns the number of reloads queued.
+__device__ __forceinline__ uint32_t run_copies(const GcParams& p, uint4* sm, uint4* scratch, const CopyRegs& c, uint32_t ttid, uint32_t TT) {
+    const uint32_t n_ev = c.counts & 0xffffu, n_rl = c.counts >> 16;
+    if (ttid < n_ev) scratch[c.ev >> 16] = sm[c.ev & 0xffffu];
+    for (uint32_t k = TT + ttid; k < n_ev; k += TT) { const uint32_t r = __ldg(p.copies + c.first + k); scratch[r >> 16] = sm[r & 0xffffu]; }
+    if (ttid < n_rl) cp_async16(sm + (c.rl >> 16), scratch + (c.rl & 0xffffu));
+    for (uint32_t k = TT + ttid; k < n_rl; k += TT) { const uint32_t r = __ldg(p.copies + c.first + n_ev + k); cp_async16(sm + (r >> 16), scratch + (r & 0xffffu)); }
+    if (n_rl) asm volatile("cp.async.commit_group;" ::: "memory");
+    return n_rl;
+}
+__device__ __forceinline__ void copies_done() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ------------------------------------------------------------------ garble ----
 template <class SL>
@@ -499,7 +532,7 @@ __device__ __forceinline__ void garble_pass(const AesLane& lane, const GarbleEnv
     }
 }
 
-template <int NR, int MODE, int ILP, int MAXT, int NT, bool SPILL>
+template <int NR, int MODE, int ILP, int MAXT, int NT, int SPILL>
 __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     constexpr uint32_t D = node_pipe(ILP, MAXT, true);
     constexpr bool FULL = MODE == GC_FULL;
@@ -515,6 +548,8 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         team_barrier(tc.bar, TT);
     }
     const auto slots = team_slots<SPILL>(tc, p);
+    constexpr bool COPIES = SPILL == 2;
+    uint4* const scratch = COPIES ? p.spill + ((size_t)blockIdx.x * p.n_teams + tc.team) * (p.n_slots - p.n_smem) : nullptr;
     stagger_start(p.twin ? (tc.bar & 0xffu) : tc.team, p.stagger);
 
     for (;;) {
@@ -534,20 +569,25 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         uint32_t row = 0;
 #pragma unroll
         for (uint32_t d = 0; d < D; d++) pipe[d] = load_row(p, d, ttid);
+        CopyRegs cp_cur{0, 0, 0, 0};
+        if (COPIES) cp_cur = load_copies(p, 0, ttid);
         // input wires: L0 from the caller's reader bytes, L1 = L0 ^ R (garble.go:271-278)
-        for (uint32_t k = ttid; k < p.n_in; k += TT) {
+        for (uint32_t k = ttid; k < p.n_live_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
+            const uint32_t src = ref.y & 0x7fffffffu;          // bit 31: the second entry of an input that goes to a hot slot and the scratch
             uint4 m;
-            if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + ref.y), inst);
-            else m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
-            slots.stm(ref.x, m);
+            if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + src), inst);
+            else m = __ldg(p.in_labels + (size_t)inst * p.n_in + src);
+            if (COPIES && ref.x >= p.n_smem) scratch[ref.x - p.n_smem] = m;
+            else slots.stm(ref.x, m);
+            if (ref.y >> 31) continue;
             if (!STREAM && p.io) {
-                uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + ref.y) * 2;
+                uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + src) * 2;
                 w[0] = m;
                 w[1] = label_to_mem(label_from_mem(m) ^ R);
             }
             if (FULL) {
-                uint4* w = p.wires_full + ((size_t)inst * p.n_wires + ref.y) * 2;
+                uint4* w = p.wires_full + ((size_t)inst * p.n_wires + src) * 2;
                 w[0] = m;
                 w[1] = label_to_mem(label_from_mem(m) ^ R);
             }
@@ -565,6 +605,11 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             uint4 cur_n[AHEAD ? ILP : 1];
             if (AHEAD) prefetch_cipher<true, ILP>(p, ph_n, 0, ttid, TT, reinterpret_cast<uint4 (&)[ILP]>(cur_n));
             else prefetch_cipher<true, ILP>(p, ph, 0, ttid, TT, cur);
+            uint32_t n_reload = 0;
+            if (COPIES) {                                      // this phase's evicts and reloads; the next phase's records are requested
+                n_reload = run_copies(p, tc.slots, scratch, cp_cur, ttid, TT);
+                cp_cur = load_copies(p, pi + 1, ttid);
+            }
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
@@ -596,6 +641,10 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
                     for (int j = 0; j < ILP; j++) cur[j] = nxt[j];
                 }
                 if (tracing) p.trace[4 * pi + 3] = clock64();
+                if (COPIES && n_reload) copies_done();
+                team_barrier(tc.bar, TT);
+            } else if (COPIES && n_reload) {
+                copies_done();
                 team_barrier(tc.bar, TT);
             }
             ph = ph_n; ph_n = ph_nn;
@@ -608,12 +657,12 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         if (STREAM) {                                          // Streaming.Set, stream_garble.go:144-157
             for (uint32_t k = ttid; k < p.n_out; k += TT) {
                 const uint2 ref = __ldg(p.live_out + k);
-                *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots.ldm(ref.x);
+                *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = (COPIES && ref.x >= p.n_smem) ? scratch[ref.x - p.n_smem] : slots.ldm(ref.x);
             }
         } else if (p.io) {
             for (uint32_t k = ttid; k < p.n_out; k += TT) {
                 const uint2 ref = __ldg(p.live_out + k);
-                const Label l0 = lds_label(slots, ref.x);
+                const Label l0 = label_from_mem((COPIES && ref.x >= p.n_smem) ? scratch[ref.x - p.n_smem] : slots.ldm(ref.x));
                 uint4* w = p.io + ((size_t)inst * (p.n_in + p.n_out) + p.n_in + ref.y) * 2;
                 w[0] = label_to_mem(l0);
                 w[1] = label_to_mem(l0 ^ R);
@@ -725,7 +774,7 @@ __device__ __forceinline__ void eval_pass(const AesLane& lane, const EvalEnv<SL>
     }
 }
 
-template <int NR, int MODE, int ILP, int MAXT, int NT, bool SPILL>
+template <int NR, int MODE, int ILP, int MAXT, int NT, int SPILL>
 __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     constexpr uint32_t D = node_pipe(ILP, MAXT, false);
     constexpr bool FULL = MODE == GC_FULL;
@@ -741,6 +790,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         team_barrier(tc.bar, TT);
     }
     const auto slots = team_slots<SPILL>(tc, p);
+    constexpr bool COPIES = SPILL == 2;
+    uint4* const scratch = COPIES ? p.spill + ((size_t)blockIdx.x * p.n_teams + tc.team) * (p.n_slots - p.n_smem) : nullptr;
     stagger_start(p.twin ? (tc.bar & 0xffu) : tc.team, p.stagger);
 
     for (;;) {
@@ -757,13 +808,17 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         uint32_t row = 0;
 #pragma unroll
         for (uint32_t d = 0; d < D; d++) pipe[d] = load_row(p, d, ttid);
-        for (uint32_t k = ttid; k < p.n_in; k += TT) {
+        CopyRegs cp_cur{0, 0, 0, 0};
+        if (COPIES) cp_cur = load_copies(p, 0, ttid);
+        for (uint32_t k = ttid; k < p.n_live_in; k += TT) {
             const uint2 ref = __ldg(p.live_in + k);
+            const uint32_t src = ref.y & 0x7fffffffu;
             uint4 m;
-            if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + ref.y), inst);    // StreamEval.Get, stream_evaluator.go:57-66
-            else m = __ldg(p.in_labels + (size_t)inst * p.n_in + ref.y);
-            slots.stm(ref.x, m);
-            if (FULL) p.wires_full[(size_t)inst * p.n_wires + ref.y] = m;
+            if (STREAM) m = *wf_slot(p.pages, __ldg(p.in_ids + src), inst);      // StreamEval.Get, stream_evaluator.go:57-66
+            else m = __ldg(p.in_labels + (size_t)inst * p.n_in + src);
+            if (COPIES && ref.x >= p.n_smem) scratch[ref.x - p.n_smem] = m;
+            else slots.stm(ref.x, m);
+            if (FULL && !(ref.y >> 31)) p.wires_full[(size_t)inst * p.n_wires + src] = m;
         }
         team_barrier(tc.bar, TT);
         const EvalEnv<decltype(slots)> env{&p, slots, tc.rk, p.tables + (size_t)inst * p.n_rows, inst};
@@ -786,6 +841,11 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
             }
             uint4 cur_n[ILP];
             prefetch_cipher<false, ILP>(p, ph_n, 0, ttid, TT, cur_n);
+            uint32_t n_reload = 0;
+            if (COPIES) {
+                n_reload = run_copies(p, tc.slots, scratch, cp_cur, ttid, TT);
+                cp_cur = load_copies(p, pi + 1, ttid);
+            }
             run_rows<false, FULL, D>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
@@ -813,6 +873,10 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
 #pragma unroll
                     for (int j = 0; j < ILP; j++) cur[j] = nxt[j];
                 }
+                if (COPIES && n_reload) copies_done();
+                team_barrier(tc.bar, TT);
+            } else if (COPIES && n_reload) {
+                copies_done();
                 team_barrier(tc.bar, TT);
             }
             ph = ph_n; ph_n = ph_nn;
@@ -821,8 +885,9 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         }
         for (uint32_t k = ttid; k < p.n_out; k += TT) {
             const uint2 ref = __ldg(p.live_out + k);
-            if (STREAM) *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = slots.ldm(ref.x);   // StreamEval.Set
-            else p.io[(size_t)inst * p.n_out + ref.y] = slots.ldm(ref.x);
+            const uint4 v = (COPIES && ref.x >= p.n_smem) ? scratch[ref.x - p.n_smem] : slots.ldm(ref.x);
+            if (STREAM) *wf_slot(p.pages, __ldg(p.out_ids + ref.y), inst) = v;   // StreamEval.Set
+            else p.io[(size_t)inst * p.n_out + ref.y] = v;
         }
         team_barrier(tc.bar, TT);
     }

@@ -171,6 +171,7 @@ DevicePlan::~DevicePlan() {
     if (cout_wire) cudaFree(cout_wire);
     if (live_in) cudaFree(live_in);
     if (live_out) cudaFree(live_out);
+    if (copies) cudaFree(copies);
 }
 
 template <class T>
@@ -223,6 +224,12 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
         }
         d.n_rows = (uint32_t)(rows.size() / TT) - d.row_first;
         if (src.n_waves & 0x80000000u) d.n_rows |= 0x80000000u;
+        if (!plan.phase_copy.empty()) {                     // live-range splitting: this phase's evict / reload lists
+            const auto& c = plan.phase_copy[ph.size()];
+            d.copy_first = c[0];
+            d.n_evict = c[1] | (c[2] << 16);                // the kernels read (copy_first, evicts | reloads << 16)
+            d.n_reload = 0;
+        }
         ph.push_back(d);
     }
     ph.push_back(DevPhaseRec{});                        // the kernels read two records ahead
@@ -235,6 +242,12 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
     CK(upload(&dp->cout_wire, plan.cout_wire));
     CK(upload(&dp->live_in, plan.live_in));
     CK(upload(&dp->live_out, plan.live_out));
+    {
+        std::vector<uint32_t> packed;                       // (src, dst) pairs -> src | dst << 16, plus one spare (read-ahead)
+        for (size_t i = 0; i + 1 < plan.copies.size(); i += 2) packed.push_back(plan.copies[i] | (plan.copies[i + 1] << 16));
+        packed.push_back(0);
+        CK(upload(&dp->copies, packed));
+    }
     plan.dev[key] = dp;
     *out = dp;
     return GCB_OK;
@@ -243,17 +256,18 @@ int plan_on_device(const Plan& plan, int device, uint32_t team_threads, std::sha
 // Team geometry for a plan: how many instances one SM keeps resident, how many threads work on
 // each, which kernel variant runs (AES blocks a thread interleaves, resident T-tables).
 // GCB_NT / GCB_TEAMS / GCB_ILP / GCB_TEAM_THREADS / GCB_STAGGER override the choice (tuning experiments).
-struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; bool spill = false, split = false, twin = false; };
+struct Geometry { uint32_t n_teams = 0, team_threads = 0, ilp = 1, nt = 4, stagger = 0, n_smem = 0; int spill = 0; bool split = false, twin = false; };
 // width = AES blocks per cipher level of the garbler (4 per AND / OR, 2 per INV), averaged.
 // num_hot < num_slots: a hot / cold plan (plan.cpp) -- only the hot labels need shared memory.
-static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base, uint32_t num_hot = 0) {
+// copies: the hot / cold plan moves its values with copy lists (live-range splitting) instead of in-place scratch access.
+static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t smem_base, uint32_t num_hot = 0, bool copies = false) {
     Geometry g;
     if (num_hot && num_hot < num_slots) {
         size_t n = teams_that_fit(num_hot, smem_base, 2, &g.split);
         if (n > 16) n = 16;
         if (n == 0) return g;
         if (const char* e = getenv("GCB_TEAMS")) { const int v = atoi(e); if (v >= 1 && (size_t)v <= n) n = (size_t)v; }
-        g.n_teams = (uint32_t)n; g.ilp = 1; g.nt = 2; g.spill = true; g.n_smem = num_hot;
+        g.n_teams = (uint32_t)n; g.ilp = 1; g.nt = 2; g.spill = copies ? 2 : 1; g.n_smem = num_hot;
         g.team_threads = n >= 8 ? 32u : 32u * (uint32_t)(512 / 32 / n > 3 ? 3 : 512 / 32 / n);
         g.stagger = n > 1 ? 100000 : 0;
         if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
@@ -278,7 +292,7 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
         // global-memory scratch (gc_kernels.cuh: SlotsSpill).
         const size_t pad = table_pad(smem_base);
         const size_t above = kSmemOptin - pad - (size_t)aes_table_bytes(2), below = pad - kTeamHeaderBytes;
-        g.n_teams = 1; g.team_threads = 256; g.ilp = 2; g.nt = 2; g.stagger = 0; g.spill = true; g.split = true;
+        g.n_teams = 1; g.team_threads = 256; g.ilp = 2; g.nt = 2; g.stagger = 0; g.spill = 1; g.split = true;
         g.n_smem = (uint32_t)((above > below ? above : below) / 16);
         return g;
     }
@@ -310,7 +324,7 @@ static uint32_t plan_width(const Plan& plan) {
     return np ? (uint32_t)(plan.info.garble_hashes / np) : 0u;
 }
 void team_geometry(Plan& plan) {                    // what gcb_plan_get_info reports (typical device)
-    const Geometry g = compute_geometry(plan.info.num_slots, plan_width(plan), kAssumedSmemBase, plan.info.num_hot_slots);
+    const Geometry g = compute_geometry(plan.info.num_slots, plan_width(plan), kAssumedSmemBase, plan.info.num_hot_slots, !plan.phase_copy.empty());
     plan.info.teams_per_sm = g.n_teams; plan.info.team_threads = g.team_threads;
     plan.ilp = g.ilp; plan.stagger = g.stagger;
 }
@@ -379,7 +393,7 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
                      cudaStream_t stream, const uint32_t* in_ids = nullptr, const uint32_t* out_ids = nullptr,
                      uint4* const* pages = nullptr) {
     const gcb_plan_info& in = plan.info;
-    const Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base, in.num_hot_slots);
+    const Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base, in.num_hot_slots, !plan.phase_copy.empty());
     if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
     std::shared_ptr<DevicePlan> dp;
     int rc = plan_on_device(plan, device, geo.team_threads, &dp);
@@ -392,6 +406,8 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     p.cout_wire = dp->cout_wire;
     p.live_in = reinterpret_cast<const uint2*>(dp->live_in);
     p.live_out = reinterpret_cast<const uint2*>(dp->live_out);
+    p.copies = dp->copies;
+    p.n_live_in = (uint32_t)plan.live_in.size();
     p.n_phases = (uint32_t)plan.phases.size(); p.n_in = in.num_inputs; p.n_out = in.num_outputs;
     p.n_slots = in.num_slots; p.n_rows = in.num_rows; p.n_wires = in.num_wires;
     p.keys = keys; p.keylen = keylen; p.key_stride = key_stride; p.batch = batch;

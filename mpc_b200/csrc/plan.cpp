@@ -107,13 +107,20 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         }
         is_out_def[(size_t)cur_def[l]] = 1;
     }
+    // GCB_HOT_MODE = 1: hot / cold by whole-life classification with synchronous scratch reads (the first form, kept for
+    // comparison); default: live-range splitting with asynchronous reloads
+    static const bool split_mode = [] { const char* e = getenv("GCB_HOT_MODE"); return !(e && atoi(e) == 1); }();
     // fixed: cipher levels chosen by the caller (the balanced schedule); the free gates then go as late as their
     // consumers allow, but never before their own inputs exist under those cipher levels.
     auto alap_levels = [&](bool cipher_asap, const std::vector<uint32_t>* fixed = nullptr) {
         constexpr uint32_t kNone = 0xffffffffu;
         std::vector<uint32_t> need(ndefs, kNone);          // latest phase in which the definition may appear
         const uint32_t last_phase = n_phases ? n_phases - 1 : 0;
-        for (size_t d = 0; d < ndefs; d++) if (is_out_def[d]) need[d] = last_phase;
+        // Values the caller reads afterwards may wait until the last phase -- unless live ranges are split (hot_cap): then
+        // sha256's 256 outputs and the 769 values they are made of would all be hot at the very end (the peak of the whole
+        // schedule); computed when their inputs are there, they are evicted and read from the scratch at the end.
+        if (!(hot_cap && split_mode))
+            for (size_t d = 0; d < ndefs; d++) if (is_out_def[d]) need[d] = last_phase;
         std::vector<uint32_t> earliest;
         if (fixed) {                                       // when each value exists, front to back
             std::vector<uint32_t> avail(ndefs, 0);
@@ -209,6 +216,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
     // leaf ordering, the expensive part) are produced once, for the schedule that won
     auto schedule = [&](const std::vector<uint32_t>& phase_of, Plan& out, bool emit, std::string& err, uint32_t hot_cap) -> int {
         char msg[160];
+        size_t ndefs = ninit + ng;                          // grows when live ranges are split (reload segments)
         // ---- pass 2: which free wires must exist in a slot: read by a ciphered gate, by a
         // free gate of a later phase, or by the caller afterwards
         std::vector<uint8_t> required(ng, keep_all ? 1 : 0);
@@ -309,6 +317,165 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         for (const int64_t d : out_def) last[(size_t)d] = kForever;
         for (size_t d = 0; d < ndefs; d++) last[d] = std::max(last[d], born[d]);
 
+        // ---- hot / cold by LIVE-RANGE SPLITTING (hot_cap > 0, the default mode).  Deep circuits keep most labels idle
+        // for hundreds of levels between bursts of use (sha256: its 768 inputs, the message schedule, the state words):
+        // 1,272 labels are live at the peak but fewer than 330 are within 16 phases of a use.  A value therefore
+        // leaves shared memory after a cluster of uses (EVICT: one copy to the instance's L2 scratch, queued a phase
+        // after it was produced) and comes back before the next cluster (RELOAD: an asynchronous copy queued one phase
+        // ahead, gc_kernels.cuh: cp.async) when more than `gap` phases lie between them.  Every read and write of the
+        // gate kernels stays a plain shared-memory access; the scratch traffic is off the dependency chain.  `gap` is
+        // the largest value whose hot set fits hot_cap (fewest copies).  Consumers name the hot SEGMENT they read: every
+        // reload cluster is a new definition with its own slot.
+        const size_t ndefs0 = ndefs;
+        std::vector<std::vector<uint32_t>> reload_at(n_phases), evict_at(n_phases);
+        std::vector<uint32_t> seg_parent;                        // reload segment (def id - ndefs0) -> the value it reloads
+        std::vector<std::vector<std::pair<int64_t, uint32_t>>> seg_map;   // value -> (last step of cluster, def id), ascending
+        std::vector<uint8_t> hot_input(ninit, 1), cold_input(ninit, 0), out_cold(ndefs0, 0), is_out(ndefs0, 0);
+        std::vector<uint32_t> cold_until(ndefs0, 0);             // last phase in which the cold copy is read
+        std::vector<uint32_t> ga(ng), gb(ng);                    // the definitions (segments) the ciphered gates read
+        for (uint32_t i = 0; i < ng; i++) { ga[i] = (uint32_t)def_a[i]; gb[i] = (uint32_t)def_b[i]; }
+        for (const int64_t d : out_def) is_out[(size_t)d] = 1;
+        const bool use_split = hot_cap != 0 && split_mode;
+        uint64_t n_reloads = 0, n_evicts = 0;
+        if (use_split) {
+            std::vector<uint32_t> step_phase((size_t)nsteps + 1, n_phases ? n_phases - 1 : 0);
+            std::vector<int64_t> phase_start(n_phases + 1, nsteps);
+            std::vector<uint8_t> phase_has_steps(n_phases, 0);
+            for (uint32_t p = 0; p < n_phases; p++) {
+                const int64_t s0 = wave_step0[p], s1 = (int64_t)cipher_step[p] + (phase_cipher[p].empty() ? 0 : 1);
+                for (int64_t q = s0; q < s1; q++) step_phase[(size_t)q] = p;
+                phase_start[p] = s0;
+                phase_has_steps[p] = s1 > s0;
+            }
+            std::vector<std::vector<int64_t>> ev(ndefs0);
+            for (uint32_t p = 0; p < n_phases; p++) {
+                for (const Node& nd : phase_nodes[p]) for (uint32_t l : nd.leaves) ev[l].push_back((int64_t)wave_step0[p] + nd.wave);
+                for (uint32_t i : phase_cipher[p]) { ev[(size_t)def_a[i]].push_back(cipher_step[p]); ev[(size_t)def_b[i]].push_back(cipher_step[p]); }
+            }
+            for (auto& e : ev) { std::sort(e.begin(), e.end()); e.erase(std::unique(e.begin(), e.end()), e.end()); }
+            struct Cluster { int64_t lo, hi; uint32_t first_phase; };
+            // the clusters of one value for a gap; c0 = true: the first cluster starts at the value's birth (or load)
+            auto clusters_of = [&](size_t d, uint32_t gap, std::vector<Cluster>& cl, bool& c0, bool& hot_end, bool& needs_cold) {
+                cl.clear();
+                const bool input = d < ninit;
+                const int64_t b = std::max<int64_t>(born[d], 0);
+                const uint32_t pb = input ? 0u : step_phase[(size_t)b];
+                uint32_t last_phase = pb;
+                c0 = !input;
+                if (!input) cl.push_back(Cluster{b, b, pb});
+                for (int64_t st : ev[d]) {
+                    const uint32_t ph = step_phase[(size_t)st];
+                    if (cl.empty()) {
+                        if (ph <= gap) { c0 = true; cl.push_back(Cluster{0, st, 0}); }        // an input used early stays hot from the load
+                        else cl.push_back(Cluster{st, st, ph});
+                    } else if (ph > last_phase + gap && ph >= 1) cl.push_back(Cluster{st, st, ph});
+                    else cl.back().hi = st;
+                    last_phase = ph;
+                }
+                // a live-out value is read by the caller after the last phase: from its hot slot if its last cluster is
+                // recent, else from the scratch
+                hot_end = is_out[d] && !cl.empty() && n_phases - 1 - std::min(last_phase, n_phases - 1) <= gap;
+                const size_t n_reload_clusters = cl.size() - (c0 ? 1 : 0);
+                needs_cold = n_reload_clusters > 0 || (is_out[d] && !hot_end);
+                if (!input && needs_cold) {
+                    // the evict runs at the start of the phase after the birth: the value must still be hot there.  A value born
+                    // in the last phase is hot at the end by construction (gap >= 1).
+                    const uint32_t pe = std::min(pb + 1, n_phases - 1);
+                    cl[0].hi = std::max(cl[0].hi, phase_start[pe]);
+                }
+                if (hot_end) cl.back().hi = nsteps;
+            };
+            auto reload_phase = [&](uint32_t first_phase) {                 // the phase at whose start the reload is queued
+                uint32_t p = first_phase - 1;
+                while (p > 0 && !phase_has_steps[p]) p--;
+                return p;
+            };
+            std::vector<Cluster> cl;
+            auto peak_for = [&](uint32_t gap) {
+                std::vector<int32_t> diff((size_t)nsteps + 3, 0);
+                for (size_t d = 0; d < ndefs0; d++) {
+                    if (!(d < ninit || born[d] >= 0)) continue;
+                    bool c0, hot_end, needs_cold;
+                    clusters_of(d, gap, cl, c0, hot_end, needs_cold);
+                    for (size_t k = 0; k < cl.size(); k++) {
+                        const int64_t lo = (k == 0 && c0) ? cl[k].lo : phase_start[reload_phase(cl[k].first_phase)];
+                        diff[(size_t)lo]++; diff[(size_t)std::min<int64_t>(cl[k].hi, nsteps) + 1]--;
+                    }
+                }
+                int32_t cur = 0, peak = 0;
+                size_t at = 0;
+                for (size_t q = 0; q < diff.size(); q++) { cur += diff[q]; if (cur > peak) { peak = cur; at = q; } }
+                if (getenv("GCB_PLAN_DEBUG") && gap == 64) {
+                    size_t n_in = 0, n_c0 = 0, n_rel = 0, n_end = 0;
+                    for (size_t d = 0; d < ndefs0; d++) {
+                        if (!(d < ninit || born[d] >= 0)) continue;
+                        bool c0, hot_end, needs_cold;
+                        clusters_of(d, gap, cl, c0, hot_end, needs_cold);
+                        for (size_t k = 0; k < cl.size(); k++) {
+                            const int64_t lo = (k == 0 && c0) ? cl[k].lo : phase_start[reload_phase(cl[k].first_phase)];
+                            if (lo <= (int64_t)at && (int64_t)at <= std::min<int64_t>(cl[k].hi, nsteps)) {
+                                if (d < ninit) n_in++; else if (k == 0) n_c0++; else n_rel++;
+                                if (hot_end && k + 1 == cl.size()) n_end++;
+                            }
+                        }
+                    }
+                    fprintf(stderr, "split peak at step %zu of %lld: inputs %zu, birth clusters %zu, reload clusters %zu, of them hot to the end %zu\n",
+                            at, (long long)nsteps, n_in, n_c0, n_rel, n_end);
+                }
+                return (uint32_t)peak;
+            };
+            static const uint32_t kGaps[] = {0xffffffffu, 512, 256, 128, 96, 64, 48, 32, 24, 16, 12, 8, 6, 4, 3, 2};
+            uint32_t gap = 0;
+            for (uint32_t g : kGaps) {
+                const uint32_t pk = peak_for(g);
+                if (getenv("GCB_PLAN_DEBUG")) fprintf(stderr, "split: gap %u -> hot peak %u (cap %u)\n", g, pk, hot_cap);
+                if (pk <= hot_cap) { gap = g; break; }
+            }
+            if (gap == 0) { err = "hot set does not fit"; return GCB_E_TOO_LARGE; }
+            seg_map.assign(ndefs0, {});
+            for (size_t d = 0; d < ndefs0; d++) {
+                if (!(d < ninit || born[d] >= 0)) continue;
+                bool c0, hot_end, needs_cold;
+                clusters_of(d, gap, cl, c0, hot_end, needs_cold);
+                const bool input = d < ninit;
+                if (input) { hot_input[d] = c0; cold_input[d] = needs_cold; }
+                if (!needs_cold && cl.size() <= 1 && c0) continue;                    // an ordinary value: one hot segment, as before
+                uint32_t last_reload = 0;
+                for (size_t k = 0; k < cl.size(); k++) {
+                    uint32_t id = (uint32_t)d;
+                    if (k == 0 && c0) last[d] = cl[k].hi >= nsteps ? kForever : cl[k].hi;
+                    else {
+                        id = (uint32_t)(ndefs0 + seg_parent.size());
+                        seg_parent.push_back((uint32_t)d);
+                        const uint32_t pr = reload_phase(cl[k].first_phase);
+                        born.push_back(phase_start[pr]);
+                        last.push_back(cl[k].hi >= nsteps ? kForever : cl[k].hi);
+                        reload_at[pr].push_back(id);
+                        last_reload = std::max(last_reload, pr);
+                        n_reloads++;
+                    }
+                    seg_map[d].push_back({cl[k].hi, id});
+                }
+                if (!c0 && input) last[d] = -1;                                       // no hot slot of its own
+                if (needs_cold) {
+                    out_cold[d] = is_out[d] && !hot_end;
+                    cold_until[d] = out_cold[d] ? n_phases + 1 : last_reload;
+                    if (!input) { evict_at[std::min(step_phase[(size_t)std::max<int64_t>(born[d], 0)] + 1, n_phases - 1)].push_back((uint32_t)d); n_evicts++; }
+                }
+            }
+            ndefs = born.size();
+            // consumers read the segment that is hot at their step
+            auto seg_for = [&](uint32_t d, int64_t step) {
+                if (d >= seg_map.size() || seg_map[d].empty()) return d;
+                for (const auto& s : seg_map[d]) if (step <= s.first) return s.second;
+                return seg_map[d].back().second;
+            };
+            for (uint32_t p = 0; p < n_phases; p++) {
+                for (Node& nd : phase_nodes[p]) for (uint32_t& l : nd.leaves) l = seg_for(l, (int64_t)wave_step0[p] + nd.wave);
+                for (uint32_t i : phase_cipher[p]) { ga[i] = seg_for(ga[i], cipher_step[p]); gb[i] = seg_for(gb[i], cipher_step[p]); }
+            }
+        }
+
         // ---- hot / cold.  With hot_cap > 0 at most hot_cap labels may be live in shared memory at any step; the
         // others are COLD: they live in the team's scratch in global memory (L2-resident) for their whole life and
         // are read from there by the nodes and gates that use them (gc_kernels.cuh: SlotsSpill).  Deep, narrow
@@ -318,7 +485,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         // threshold is the largest one whose hot set fits.
         std::vector<uint8_t> cold(ndefs, 0);
         uint64_t cold_accesses = 0;
-        if (hot_cap) {
+        if (hot_cap && !use_split) {
             std::vector<uint32_t> nreads(ndefs, 0);
             for (uint32_t p = 0; p < n_phases; p++) {
                 for (const Node& nd : phase_nodes[p]) for (uint32_t l : nd.leaves) nreads[l]++;
@@ -389,8 +556,22 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             free_cold.erase(free_cold.begin());
             return c;
         };
+        // scratch slots of evicted values (live-range splitting): by phase, freed two phases after the last reload
+        std::vector<uint32_t> cold_slot(ndefs0, 0);
+        std::vector<std::vector<uint32_t>> cold_expire(n_phases + 4);
+        struct CopyOp { uint32_t src, dst; };
+        std::vector<CopyOp> copies;
+        std::vector<std::array<uint32_t, 3>> phase_copy(n_phases, std::array<uint32_t, 3>{0, 0, 0});   // first, evicts, reloads
         out.live_in.clear();
         for (size_t k = 0; k < ninit; k++) {
+            if (use_split) {
+                if (cold_input[k]) {
+                    cold_slot[k] = take_cold();
+                    cold_expire[std::min<size_t>(cold_until[k] + 2, n_phases + 3)].push_back((uint32_t)k);
+                    out.live_in.push_back(SlotRef{cold_slot[k], (uint32_t)k | (hot_input[k] ? 0x80000000u : 0u)});
+                }
+                if (!hot_input[k]) continue;
+            }
             slot[k] = cold[k] ? take_cold() : next_slot++;
             out.live_in.push_back(SlotRef{slot[k], (uint32_t)k});
             if (last[k] < 0) release(slot[k]);                         // never read, not live-out
@@ -468,7 +649,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                         size_t pick = 0;
                         int best = 1 << 30;
                         for (size_t c = 0; c < rest.size() && best > 0; c++) {
-                            const uint32_t a = slot[(size_t)def_a[rest[c]]], b = slot[(size_t)def_b[rest[c]]];
+                            const uint32_t a = slot[ga[rest[c]]], b = slot[gb[rest[c]]];
                             int cost = 0;
                             for (size_t q = 0; q < n; q++) {
                                 cost += (sa[q] != a && (sa[q] & 7) == (a & 7));
@@ -476,7 +657,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                             }
                             if (cost < best) { best = cost; pick = c; }
                         }
-                        sa[n] = slot[(size_t)def_a[rest[pick]]]; sb[n] = slot[(size_t)def_b[rest[pick]]];
+                        sa[n] = slot[ga[rest[pick]]]; sb[n] = slot[gb[rest[pick]]];
                         n++;
                         done.push_back(rest[pick]);
                         rest.erase(rest.begin() + (long)pick);
@@ -495,6 +676,25 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                 }
             };
             for (uint32_t p = 0; p < n_phases; p++) {
+                if (use_split) {
+                    // the copies queued at the top of this phase: evicts of values produced in the previous phase (their hot slot
+                    // stays theirs through this step), reloads into hot slots taken now for the clusters that start next phase
+                    advance();
+                    for (uint32_t d : cold_expire[p]) release(cold_slot[d]);
+                    phase_copy[p][0] = (uint32_t)copies.size();
+                    for (uint32_t d : evict_at[p]) {
+                        cold_slot[d] = take_cold();
+                        cold_expire[std::min<size_t>(cold_until[d] + 2, n_phases + 3)].push_back(d);
+                        copies.push_back(CopyOp{slot[d], cold_slot[d]});
+                    }
+                    phase_copy[p][1] = (uint32_t)evict_at[p].size();
+                    uint32_t lane = 0;
+                    for (uint32_t id : reload_at[p]) {
+                        take_slot(id, lane++);
+                        copies.push_back(CopyOp{cold_slot[seg_parent[id - ndefs0]], slot[id]});
+                    }
+                    phase_copy[p][2] = (uint32_t)reload_at[p].size();
+                }
                 size_t pos = 0;
                 for (uint32_t w = 0; w < n_waves[p]; w++, s++) {
                     advance();
@@ -516,8 +716,13 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             return GCB_E_TOO_LARGE;
         }
         const uint32_t num_hot = next_slot;
-        for (size_t d = 0; d < ndefs; d++) if (slot[d] >= kColdBase) slot[d] = num_hot + (slot[d] - kColdBase);
+        for (size_t d = 0; d < slot.size(); d++) if (slot[d] >= kColdBase) slot[d] = num_hot + (slot[d] - kColdBase);
+        for (uint32_t& c : cold_slot) if (c >= kColdBase) c = num_hot + (c - kColdBase);
         for (SlotRef& r : out.live_in) if (r.slot >= kColdBase) r.slot = num_hot + (r.slot - kColdBase);
+        for (CopyOp& c : copies) {                                   // scratch side: index into the instance's scratch
+            if (c.src >= kColdBase) c.src -= kColdBase;
+            if (c.dst >= kColdBase) c.dst -= kColdBase;
+        }
         next_slot += next_cold;
         uint32_t g_passes = 0, e_passes = 0;
         for (uint32_t p = 0; p < n_phases; p++) {
@@ -531,14 +736,20 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             out.info.num_slots = next_slot;
             out.info.num_hot_slots = num_hot;
             out.info.num_steps = (uint32_t)nsteps;
-            out.cold_accesses = cold_accesses;
+            out.cold_accesses = use_split ? n_reloads + n_evicts : cold_accesses;
             out.info.garble_passes = g_passes;
             out.info.eval_passes = e_passes;
             return GCB_OK;
         }
         out.live_out.clear();
         for (size_t k = 0; k < spec.live_out.size(); k++)
-            out.live_out.push_back(SlotRef{slot[(size_t)out_def[k]], (uint32_t)k});
+        {
+            const size_t d = (size_t)out_def[k];
+            uint32_t from = slot[d];
+            if (use_split && d < ndefs0 && !seg_map[d].empty()) from = out_cold[d] ? cold_slot[d] : slot[seg_map[d].back().second];
+            else if (use_split && d < ndefs0 && out_cold[d]) from = cold_slot[d];
+            out.live_out.push_back(SlotRef{from, (uint32_t)k});
+        }
 
         // ---- leaf order.  The eight nodes of a quarter warp read leaf j in the same instruction; XOR
         // commutes, so each node's leaves are permuted to put labels of different bank groups side by
@@ -668,7 +879,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
             ph.cipher_first = (uint32_t)out.crecs.size();
             for (uint32_t i : phase_cipher[p]) {
                 const gcb_gate& g = spec.gates[i];
-                out.crecs.push_back(GateRec{(uint16_t)slot[(size_t)def_a[i]], (uint16_t)slot[(size_t)def_b[i]],
+                out.crecs.push_back(GateRec{(uint16_t)slot[ga[i]], (uint16_t)slot[gb[i]],
                                              (uint16_t)slot[ninit + i], g.op, 0, tweak_of[i], plan.row_off[i]});
                 out.cout_wire.push_back(g.out);
                 (g.op == OP_INV ? ph.n_inv : ph.n_quad)++;
@@ -688,7 +899,13 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         in.num_steps = (uint32_t)nsteps;
         in.num_slots = next_slot;
         in.num_hot_slots = num_hot;
-        out.cold_accesses = cold_accesses;
+        out.cold_accesses = use_split ? n_reloads + n_evicts : cold_accesses;
+        out.copies.clear();
+        out.phase_copy.clear();
+        if (use_split) {
+            for (const CopyOp& c : copies) { out.copies.push_back(c.src); out.copies.push_back(c.dst); }
+            out.phase_copy = phase_copy;
+        }
         in.num_and = n_and; in.num_or = n_or; in.num_inv = n_inv; in.num_free = n_free;
         in.garble_hashes = 4 * n_and + 4 * n_or + 2 * n_inv;
         in.eval_hashes = 2 * n_and + n_or + n_inv;
@@ -772,6 +989,7 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
         plan.live_in.swap(best.live_in); plan.live_out.swap(best.live_out);
         plan.node_loads = best.node_loads;
         plan.cold_accesses = best.cold_accesses;
+        plan.copies.swap(best.copies); plan.phase_copy.swap(best.phase_copy);
     }
     return GCB_OK;
 }
@@ -824,6 +1042,7 @@ int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_
         plan.live_in.swap(cand.live_in); plan.live_out.swap(cand.live_out);
         plan.row_off.swap(cand.row_off); plan.ops.swap(cand.ops);
         plan.node_loads = cand.node_loads; plan.cold_accesses = cand.cold_accesses;
+        plan.copies.swap(cand.copies); plan.phase_copy.swap(cand.phase_copy);
         break;
     }
     return GCB_OK;

@@ -5,6 +5,7 @@
 // offsets in ORIGINAL gate order (circuit/garble.go:285-299,357-359,419-420,
 // 451-452), and on-chip wire slots assigned from liveness.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -88,7 +89,7 @@ struct DevPhaseRec {
     uint32_t cipher_first, n_quad;    // range in the GateRec array: n_quad AND/OR gates ...
     uint32_t n_inv;                   // ... then n_inv INV gates
     uint32_t row_first;               // first node row of the phase
-    uint32_t pad[3];
+    uint32_t copy_first, n_evict, n_reload;   // copies queued at the top of the phase (hot / cold plans)
 };
 static_assert(sizeof(DevPhaseRec) == 32, "DevPhaseRec must be 32 bytes");
 constexpr uint32_t GC_NODE_PIPE_MAX = 4;  // most rows any kernel variant keeps in flight ahead of the one it runs
@@ -114,6 +115,7 @@ struct DevicePlan {                   // per (device, team width) copy of the ta
     uint32_t* cout_wire = nullptr;
     SlotRef* live_in = nullptr;
     SlotRef* live_out = nullptr;
+    uint32_t* copies = nullptr;       // (src, dst) pairs of the evict / reload lists
     ~DevicePlan();
 };
 
@@ -129,6 +131,10 @@ struct Plan {
     std::vector<uint32_t> nout_wire, cout_wire;   // original output wire of nodes[i] / crecs[i]
     uint32_t node_loads = 0;              // sum of node fan-ins (label loads of the free part)
     uint64_t cold_accesses = 0;           // label reads + writes that go to the global-memory scratch (hot / cold plans)
+    // live-range splitting (plan.cpp): per phase (first copy, evicts, reloads); copies = (src, dst) pairs -- an evict copies
+    // hot slot src to scratch index dst, a reload scratch index src to hot slot dst
+    std::vector<uint32_t> copies;
+    std::vector<std::array<uint32_t, 3>> phase_copy;
     std::vector<SlotRef> live_in, live_out;
     std::vector<uint32_t> row_off;        // num_gates+1, original order
     std::vector<uint8_t> ops;             // original order

@@ -66,6 +66,12 @@ int main(int argc, char** argv) {
     printf("balance %d  policy %d  garble_passes %u  eval_passes %u  hot slots %u of %u  cold accesses %llu (node loads %u, gates %u)\n", balance, plan.policy,
            plan.info.garble_passes, plan.info.eval_passes, plan.info.num_hot_slots, plan.info.num_slots, (unsigned long long)plan.cold_accesses,
            plan.node_loads, plan.info.num_and + plan.info.num_inv + plan.info.num_or);
+    if (!plan.phase_copy.empty()) {
+        uint64_t ev = 0, rl = 0;
+        for (const auto& c : plan.phase_copy) { ev += c[1]; rl += c[2]; }
+        printf("live-range splitting: %llu evicts, %llu reloads per instance, scratch %u labels\n", (unsigned long long)ev, (unsigned long long)rl,
+               plan.info.num_slots - plan.info.num_hot_slots);
+    }
     const gcb_plan_info& in = plan.info;
     printf("gates %u  and %u inv %u or %u free %u  slots %u  steps %u  phases %zu  waves %zu  nodes %zu  node_loads %u\n",
            in.num_gates, in.num_and, in.num_inv, in.num_or, in.num_free, in.num_slots, in.num_steps, plan.phases.size(),
