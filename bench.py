@@ -14,7 +14,7 @@ cores.  Prints ONE JSON line on rank 0.
 
 `extra` in the same line carries the other BASELINE.json configurations, each
 timed at this N with its own algorithmic bytes and HBM fraction: aes_128 with
-per-instance 32-byte keys (the production key shape), sha256.circ x 1184,
+per-instance 32-byte keys (the production key shape), sha256.circ x 2368,
 IKNP 2^24 (sender + receiver), one streaming sha256 step, the >= 10^8-gate
 streaming program (config 5 stand-in), a copy-only PCIe probe (the floor of the
 e2e figure on this box with N ranks copying at once) and, at N = 1, the latency
@@ -46,8 +46,8 @@ E2E_PARTS = 16
 KEY = b"0123456789abcdef"            # circuit/garble_bench_test.go:34
 CIRCUIT_DIR = os.path.join(ROOT, "tests", "golden", "circuits")
 # --circuit: the headline workload (aes_128, BASELINE.json configs[1]) or the second circuit BASELINE's
-# target names (sha256: 22,573 AND; batch = 8 resident instances x 148 SMs)
-WORKLOADS = {"aes_128": ("AES-128 circuit", 4096), "sha256": ("SHA-256 circuit", 1184)}
+# target names (sha256: 22,573 AND; batch = 16 resident instances x 148 SMs)
+WORKLOADS = {"aes_128": ("AES-128 circuit", 4096), "sha256": ("SHA-256 circuit", 2368)}
 
 
 def load_circuit(name: str = "aes_128"):
@@ -365,7 +365,9 @@ def device_loop(b: Bench, circ, eng, batch: int, keys, steps: int, warmup: int, 
 def roofline_of(b: Bench, circ, eng, batch: int, g_ms: float, e_ms: float, nr: int):
     gb, eb = algorithmic_bytes(circ)
     ach_g, ach_e = gb * batch / (g_ms * 1e-3) / 1e9, eb * batch / (e_ms * 1e-3) / 1e9
-    geo = f"{eng.info.teams_per_sm} teams x {eng.info.team_threads} threads per SM"
+    info = eng.info_for(batch)
+    geo = f"{info.teams_per_sm} teams x {info.team_threads} threads per SM" + (
+        f", split live ranges: {info.num_hot_slots} of {info.num_slots} labels in shared memory" if info.num_hot_slots < info.num_slots else "")
     return {"bound": "hbm", "achieved": ach_g, "peak": b.peak, "unit": "GB/s", "frac": ach_g / b.peak,
             "traffic": ncu_traffic(circ.name, "garble_kernel"), "algorithmic_bytes": gb * batch,
             "kernel": f"garble_kernel<NR={nr},PLAIN> ({geo})", "kernel_ms": g_ms,
@@ -798,7 +800,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gcb", choices=["gcb", "reference"])
     ap.add_argument("--circuit", default="aes_128", choices=sorted(WORKLOADS), help="aes_128 = the headline workload")
-    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: 4096 for aes_128, 1184 for sha256)")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: 4096 for aes_128, 2368 for sha256)")
     ap.add_argument("--program-batch", type=int, default=148, help="instances per GPU of the streaming program in `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: device-resident loop only")

@@ -130,6 +130,11 @@ int gcb_plan_create(const gcb_gate *gates, uint32_t num_gates, uint32_t num_wire
                     uint32_t num_inputs, uint32_t num_outputs, gcb_plan **out);
 void gcb_plan_destroy(gcb_plan *plan);
 int gcb_plan_get_info(const gcb_plan *plan, gcb_plan_info *info);
+/* The same for the plan a call with `batch` instances per device runs on: deep, narrow circuits whose batch
+ * overflows the resident instances of the default plan get a second plan with split live ranges (more instances
+ * per SM, num_hot_slots < num_slots), built on first use.  The output bytes never depend on the plan.
+ * Replaces nothing in the reference (diagnostics: bench.py names the kernel geometry it timed). */
+int gcb_plan_get_info_for_batch(const gcb_plan *plan, uint64_t batch, gcb_plan_info *info);
 /* Static slab offset of every gate's first row (num_gates+1 entries): lets the
  * Go side rebuild Garbled.Gates [][]ot.Label slice headers over the slab. */
 int gcb_plan_row_offsets(const gcb_plan *plan, uint32_t *row_off);

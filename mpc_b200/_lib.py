@@ -57,6 +57,7 @@ SYMBOLS = {
     "gcb_plan_create": (_int, [_vp, _u32, _u32, _u32, _u32, C.POINTER(_vp)]),
     "gcb_plan_destroy": (None, [_vp]),
     "gcb_plan_get_info": (_int, [_vp, C.POINTER(PlanInfo)]),
+    "gcb_plan_get_info_for_batch": (_int, [_vp, C.c_uint64, C.POINTER(PlanInfo)]),
     "gcb_plan_row_offsets": (_int, [_vp, _vp]),
     "gcb_garble": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _u32]),
     "gcb_eval": (_int, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32]),

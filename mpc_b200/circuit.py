@@ -181,6 +181,12 @@ class GarbleEngine:
         self.row_off = np.zeros(circ.num_gates + 1, dtype=np.uint32)
         check(_lib.lib().gcb_plan_row_offsets(self._h, ptr(self.row_off)))
 
+    def info_for(self, batch: int) -> PlanInfo:
+        """Geometry of the plan a call with ``batch`` instances per device runs on (gcb_plan_get_info_for_batch)."""
+        info = PlanInfo()
+        check(_lib.lib().gcb_plan_get_info_for_batch(self._h, int(batch), C.byref(info)))
+        return info
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:

@@ -342,7 +342,9 @@ static int plan_for(const gcb_plan* plan, bool full, const Plan** out, uint64_t 
         const Plan& base = plan->p;
         // a batch that overflows the resident instances of the all-hot plan may run faster on a plan that holds more
         // instances with only a hot subset of the labels in shared memory (plan.cpp: build_best_plan)
-        if (batch > (uint64_t)base.info.teams_per_sm * 148 && base.info.teams_per_sm < 8) {
+        // (narrow circuits only: wide cipher levels are bound by the shared-memory pipe, not by resident instances)
+        if (batch > (uint64_t)base.info.teams_per_sm * 148 && base.info.teams_per_sm < 16 && plan_width(base) < 128 &&
+            base.info.num_slots >= 256) {
             std::lock_guard<std::mutex> lk(plan->many_mu);
             if (!plan->many_tried) {
                 plan->many_tried = true;
@@ -1095,6 +1097,16 @@ int gcb_plan_get_info(const gcb_plan* plan, gcb_plan_info* info) {
     GCB_TRY
     if (!plan || !info) return fail(GCB_E_ARG, "null argument");
     *info = plan->p.info;
+    return GCB_OK;
+    GCB_CATCH
+}
+int gcb_plan_get_info_for_batch(const gcb_plan* plan, uint64_t batch, gcb_plan_info* info) {
+    GCB_TRY
+    if (!plan || !info) return fail(GCB_E_ARG, "null argument");
+    const Plan* use;
+    int rc = plan_for(plan, false, &use, batch);
+    if (rc) return rc;
+    *info = use->info;
     return GCB_OK;
     GCB_CATCH
 }

@@ -1005,15 +1005,18 @@ int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_
     // it only pays when the batch does not fit the all-hot plan in one wave (148 SMs assumed).
     const char* forced = getenv("GCB_HOT_TEAMS");
     if (!(forced && atoi(forced) > 0) && batch_hint <= teams_that_fit(plan.info.num_slots, kAssumedSmemBase, 2) * 148) return GCB_OK;
-    // Measured on B200 (profiles/r02_hot_cold.txt), single-block AES rounds rolled, 16 one-warp teams run as lock-step
-    // pairs ("twin": without both, 16 teams spent 26-44 % of their stall samples waiting for instructions):
-    //   sha512  3 all-hot instances per SM  870 M AND/s  ->  8 instances 1,000-1,150  ->  16 instances (626 hot labels) 1,666
-    //   sha256  8 all-hot instances       1,826 M AND/s  -> 12 / 16 instances 1,456 / 1,729 (slower)
-    //   chacha20 / sha256xor  9-10 all-hot  1,661 / 1,825 ->  16 instances 1,506 / 1,718 (slower)
-    // Every cold leaf is an L2 round trip on the dependency chain of its level and the dual-path label access costs
-    // 17 % more instructions, so the second plan pays only while the SM is nearly empty: it is built when fewer than 8
-    // instances fit, with 16 as the target (halved until the hot set fits and at most a fifth of the label accesses go
-    // to the scratch).  GCB_HOT_TEAMS = 0 switches it off, N forces a target.
+    // Measured on B200 (profiles/r02_hot_cold.txt, profiles/r02_split.txt), M AND/s garble + eval on batches of 16 x 148:
+    //                                    all-hot          whole-life hot / cold, synchronous     live-range splitting,
+    //                                                     scratch reads (GCB_HOT_MODE=1)         asynchronous reloads (default)
+    //   sha512     3 instances per SM      870            16 instances: 1,718                    16 instances: 2,497
+    //   sha256     8                     1,788            16: 1,705                              16: 2,440
+    //   sha256xor  9                     1,825            16: 1,718                              16: 2,462
+    //   chacha20  10                     1,661            16: 1,506                              16: 2,021
+    // With whole-life classification every cold leaf is an L2 round trip on the dependency chain of its level; with split
+    // live ranges a value is evicted once after its birth and reloaded (cp.async, one phase ahead) before each cluster of
+    // uses, so every gate and node access stays in shared memory and the extra instances pay.  The second plan is built
+    // when fewer than 16 instances fit, with 16 as the target (halved until the hot set fits and the evicts + reloads
+    // stay below a fifth of the label accesses).  GCB_HOT_TEAMS = 0 switches it off, N forces a target.
     int force = -1;
     if (const char* e = getenv("GCB_HOT_TEAMS")) force = atoi(e);
     if (force == 0) return GCB_OK;
@@ -1021,7 +1024,7 @@ int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_
     const size_t np = plan.phases.size();
     const uint32_t width = np ? (uint32_t)(in.garble_hashes / np) : 0u;
     const size_t have = teams_that_fit(in.num_slots, kAssumedSmemBase, 2);
-    if (force < 0 && (width >= 128 || have >= 8 || in.num_slots < 256)) return GCB_OK;    // wide (pipe-bound) or enough resident
+    if (force < 0 && (width >= 128 || have >= 16 || in.num_slots < 256)) return GCB_OK;    // wide (pipe-bound) or enough resident
     // the target: 16 resident instances, or what the caller forces (halved until the hot set fits)
     for (size_t target = force > 0 ? (size_t)force : 16; target > have; target /= 2) {
         uint32_t lo = 32, hi = in.num_slots;               // largest hot set with which `target` teams fit

@@ -184,9 +184,9 @@ inline size_t teams_that_fit(uint32_t smem_slots, uint32_t smem_base, uint32_t n
 int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, int balance = 1,
                uint32_t hot_cap = 0, int only_policy = -1);
 
-// build_plan; for deep, narrow circuits of which fewer than 8 instances fit per SM (sha512: 3) also a second plan that
+// build_plan; for deep, narrow circuits of which fewer than 16 instances fit per SM (sha512: 3, sha256: 8) also a second plan that
 // keeps only a hot subset of the labels in shared memory so that 16 fit (hot_cap above), kept when at most a fifth of the
-// label accesses go to the scratch.  GCB_HOT_TEAMS = 0 switches it off, N forces a target; see the measurement in plan.cpp.
+// label accesses are evicts / reloads.  GCB_HOT_TEAMS = 0 switches it off, N forces a target; see the measurement in plan.cpp.
 // batch_hint: instances the plan will run on at once; the second plan is only considered when they do not fit the first
 // plan's resident instances in one wave.
 int build_best_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin = NODE_MAX_FANIN, uint64_t batch_hint = ~0ull);

@@ -144,3 +144,25 @@ def test_sha512_batch_that_overflows_the_resident_instances():
     sample = [0, 147, 148, 469]
     _, o_tables, o_io = O.garble_batch(circ, key, rand[sample])
     assert eq(tables[sample], o_tables) and eq(io[sample], o_io)
+
+
+def test_sha256_batch_that_overflows_the_resident_instances():
+    """sha256 keeps 8 all-hot instances per SM; a batch beyond 8 x 148 runs on the plan with split live ranges (16
+    instances per SM, labels evicted to / reloaded from the per-instance scratch by per-phase copy lists), built on
+    demand: every instance decodes to SHA-256's compression function, sampled instances equal the oracle."""
+    from mpc_b200.circuit import HostCircuit
+    circ = load_circuit("sha256")
+    eng = GarbleEngine(circ)
+    batch, nin = 16 * 148 + 5, circ.num_inputs
+    assert batch > eng.info.teams_per_sm * 148
+    rng = np.random.default_rng(256)
+    rand = rng.integers(0, 256, (batch, 16 * (1 + nin)), dtype=np.uint8)
+    key = rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+    r, l0 = rand_to_labels(rand, nin)
+    tables, io = eng.garble_batch(key, r, l0)
+    bits = rng.integers(0, 2, (batch, nin), dtype=np.uint8)
+    out = eng.eval_batch(key, tables, select(io[:, :nin], bits))
+    assert np.array_equal(decode(io[:, nin:], out), HostCircuit(circ).compute_bits(bits))
+    sample = [0, 1183, 1184, 2367, batch - 1]
+    _, o_tables, o_io = O.garble_batch(circ, key, rand[sample])
+    assert eq(tables[sample], o_tables) and eq(io[sample], o_io)
