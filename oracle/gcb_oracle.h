@@ -18,12 +18,19 @@
  *   (circuit/circuit_test.go:14-19), functional digest of sha2pc
  *   (sha2pc/sha2pc_test.go:124) and the plaintext KATs of the shipped
  *   circuits; AES / CTR by FIPS-197 App. C and SP 800-38A F.5.
- *   PARITY UNPINNED at the byte level for Circuit.Garble / Streaming.Garble
- *   table bytes and IKNP label bytes: the only reference test that pins
- *   them (sha2pc TestDeterministicTranscript) draws its randomness from Go's
- *   math/rand, which cannot be reproduced without a Go toolchain.  Those
- *   outputs are cross-checked against an independent Python restatement that
- *   uses OpenSSL's AES (tests/pyref.py) and by protocol invariants.
+ *   Circuit.Garble's bytes (garbled rows in gate order, input and output wire
+ *   labels; 32-byte key) are pinned by the reference's golden transcript
+ *   hashes (sha2pc/sha2pc_test.go:74-131, TestDeterministicTranscript): the
+ *   test's math/rand streams, crypto/rand.Int, P-256 and the round encodings
+ *   are restated in tests/gostd.py + tests/sha2pc_transcript.py, and
+ *   tests/test_reference_transcript.py reproduces all four hashes with
+ *   orc_garble / orc_eval in the middle (and with the CUDA path on the GPU).
+ *   PARITY UNPINNED at the byte level for IKNP label bytes and for the
+ *   Streaming.Garble record stream: the reference holds no vector for them.
+ *   The stream shares garbleGate's arithmetic with the pinned Garble; IKNP
+ *   rests on its pinned parts (AES-CTR by SP 800-38A, MiTCCRH golden blocks),
+ *   an independent Python restatement on OpenSSL's AES (tests/pyref.py) and
+ *   the protocol invariant t = q ^ b * Delta.
  */
 #ifndef GCB_ORACLE_H
 #define GCB_ORACLE_H
