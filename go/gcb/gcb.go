@@ -86,6 +86,15 @@ func NewPlan(gates []Gate, numWires, numInputs, numOutputs int) (*Plan, error) {
 	return p, nil
 }
 
+// InfoForBatch reports the plan a call with `batch` instances per device runs on: deep, narrow circuits get a second
+// plan with split live ranges (more resident instances per SM) when the batch overflows the default one.
+func (p *Plan) InfoForBatch(batch int) (C.gcb_plan_info, error) {
+	defer runtime.KeepAlive(p)
+	var info C.gcb_plan_info
+	err := call(func() C.int { return C.gcb_plan_get_info_for_batch(p.h, C.uint64_t(batch), &info) })
+	return info, err
+}
+
 // HostAlloc returns page-locked memory for slabs that are pooled per circuit
 // (replaces garbleScratchPool); such buffers are DMA'd in place.
 func HostAlloc(n int) unsafe.Pointer { return C.gcb_host_alloc(C.size_t(n)) }
