@@ -281,9 +281,15 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
     // Wide levels keep the shared-memory pipe busy with a few resident instances: four tables.
     // Deep, narrow circuits (sha256: 39 blocks per level) are bound by the latency of each level,
     // so the number of resident instances is what counts: two tables, twice the label space.
-    uint32_t nt = (n4 == 0 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
+    // Wide levels of which fewer than eight instances fit beside four tables but eight beside two (aes_128: 5 / 9): eight
+    // two-warp teams on two tables beat five three-warp teams on four (measured, profiles/r02_geometry_p.txt: garble
+    // 3.85 -> 3.73 ms, eval 2.50 -> 2.47 ms) -- smaller teams wait less at their barriers, and the eight extra PRMTs per
+    // round fit the ALU pipe's slack.
+    const bool wide8 = width >= 128 && n4 < 8 && n2 >= 8 && !getenv("GCB_TEAMS") && !getenv("GCB_TEAM_THREADS");
+    uint32_t nt = (n4 == 0 || wide8 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
     if (const char* e = getenv("GCB_NT")) { const int v = atoi(e); if (v == 2 || v == 4) nt = (uint32_t)v; }
     size_t n = nt == 2 ? n2 : n4;
+    if (wide8 && nt == 2) n = 8;
     g.split = nt == 2 ? split2 : split4;
     g.n_smem = num_slots;
     if (n == 0) {
@@ -314,7 +320,9 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
         if (v >= 32 && v % 32 == 0 && (size_t)v * n <= maxt && (v == 32 || n <= 16)) tt = (uint32_t)v;
     }
     g.n_teams = (uint32_t)n; g.team_threads = tt; g.ilp = ilp; g.nt = nt;
-    g.stagger = n > 1 ? 100000 : 0;                 // teams start ~50 us apart
+    // one-warp teams start ~50 us apart (in lock step they collide in the same phases: sha256 x 16 teams 13.7 instead of
+    // 11.2-12.4 ms); multi-warp teams drift apart on their own, a start offset only idles the SM (aes_128: +2.7 % without)
+    g.stagger = n > 1 && tt == 32 ? 100000 : 0;
     if (const char* e = getenv("GCB_STAGGER")) g.stagger = (uint32_t)atoi(e);
     if (const char* e = getenv("GCB_TWIN")) g.twin = atoi(e) != 0 && tt == 32 && n % 8 == 0 && n <= 16;
     return g;

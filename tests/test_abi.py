@@ -138,3 +138,22 @@ def test_plan_limits_of_live_labels():
     _lib.lib().gcb_plan_destroy(h)
     rc, h = plan(22000)                                  # 66,000 > 65,535
     assert rc == _lib.E_TOO_LARGE and b"65535" in _lib.lib().gcb_last_error()
+
+
+def test_plan_choice_by_batch():
+    """gcb_plan_get_info_for_batch (host only): a deep, narrow circuit whose batch overflows the resident instances of
+    its all-hot plan runs on the plan with split live ranges (16 instances per SM, a hot subset of the labels in shared
+    memory); a batch that fits, a wide circuit and a circuit of which 16 instances already fit stay on the default plan."""
+    eng = GarbleEngine(load_circuit("sha256"))
+    base = eng.info
+    assert base.teams_per_sm == 8 and base.num_hot_slots == base.num_slots
+    fits = eng.info_for(8 * 148)
+    assert (fits.teams_per_sm, fits.num_slots, fits.num_hot_slots) == (8, base.num_slots, base.num_slots)
+    many = eng.info_for(8 * 148 + 1)
+    assert many.teams_per_sm == 16 and many.team_threads == 32 and many.num_hot_slots < many.num_slots
+    assert many.num_rows == base.num_rows and many.num_and == base.num_and        # the same tables whatever the plan
+    aes = GarbleEngine(load_circuit("aes_128"))
+    wide = aes.info_for(1 << 20)
+    assert wide.teams_per_sm == aes.info.teams_per_sm and wide.num_hot_slots == wide.num_slots
+    mul = GarbleEngine(load_circuit("mul64"))
+    assert mul.info_for(1 << 20).num_hot_slots == mul.info.num_slots

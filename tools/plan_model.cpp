@@ -77,6 +77,29 @@ int main(int argc, char** argv) {
            in.num_gates, in.num_and, in.num_inv, in.num_or, in.num_free, in.num_slots, in.num_steps, plan.phases.size(),
            plan.waves.size(), plan.nodes.size(), plan.node_loads);
 
+    // what lane splitting would cost: a wave whose nodes fill at most TT / f lanes gives each node f adjacent lanes
+    // (leaves dealt round robin), combined with log2(f) shuffle steps (counted as one loop iteration each)
+    {
+        uint64_t now = 0, split = 0, rows = 0;
+        for (const WaveRec& wr : plan.waves) {
+            const uint32_t nrow = (wr.count + TT - 1) / TT;
+            uint32_t f = 1;
+            while (f < 4 && (wr.count * f * 2 + TT - 1) / TT == nrow) f *= 2;
+            for (uint32_t base = 0; base < wr.count; base += 32 / f) {
+                uint32_t kmax = 0;
+                for (uint32_t l = 0; l < 32 / f && base + l < wr.count; l++) kmax = std::max<uint32_t>(kmax, plan.nodes[wr.first + base + l].k);
+                split += (kmax + f - 1) / f + (f == 4 ? 2 : f == 2 ? 1 : 0);
+                rows++;
+            }
+            for (uint32_t base = 0; base < wr.count; base += 32) {
+                uint32_t kmax = 0;
+                for (uint32_t l = 0; l < 32 && base + l < wr.count; l++) kmax = std::max<uint32_t>(kmax, plan.nodes[wr.first + base + l].k);
+                now += kmax;
+            }
+        }
+        printf("node row loop iterations per instance: now %llu, with lane splitting %llu (%llu warp rows)\n", (unsigned long long)now,
+               (unsigned long long)split, (unsigned long long)rows);
+    }
     Acc node_ld, node_st, g_ld, g_st, e_ld, e_st;
     uint64_t barriers = 0, garble_passes = 0, eval_passes = 0, node_iters = 0, node_floor = 0;
     std::vector<int> ls(32);
