@@ -403,8 +403,18 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
                      cudaStream_t stream, const uint32_t* in_ids = nullptr, const uint32_t* out_ids = nullptr,
                      uint4* const* pages = nullptr) {
     const gcb_plan_info& in = plan.info;
-    const Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base, in.num_hot_slots, !plan.phase_copy.empty());
+    Geometry geo = compute_geometry(in.num_slots, plan_width(plan), di->smem_base, in.num_hot_slots, !plan.phase_copy.empty());
     if (geo.n_teams == 0) return fail(GCB_E_TOO_LARGE, "circuit keeps %u wire labels live; they do not fit on chip", in.num_slots);
+    // A batch smaller than one wave is spread over the SMs instead of filling a few of them: a CTA then carries only as
+    // many teams as it needs (256 aes_128 instances: 2 teams on each of 128 SMs instead of 8 on each of 32), and every
+    // instance gets a larger share of its SM's shared-memory pipe.
+    static const bool spread = [] { const char* e = getenv("GCB_SPREAD"); return !(e && atoi(e) == 0); }();
+    if (spread && (uint64_t)batch < (uint64_t)geo.n_teams * di->sm_count) {
+        geo.n_teams = (batch + di->sm_count - 1) / di->sm_count;
+        if (geo.n_teams == 0) geo.n_teams = 1;
+        geo.twin = geo.twin && geo.n_teams % 8 == 0;
+        if (geo.n_teams == 1) geo.stagger = 0;
+    }
     std::shared_ptr<DevicePlan> dp;
     int rc = plan_on_device(plan, device, geo.team_threads, &dp);
     if (rc) return rc;
