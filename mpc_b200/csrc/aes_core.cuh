@@ -156,6 +156,28 @@ __device__ __forceinline__ void aes_round(const AesLane& a, uint32_t& s0, uint32
     s0 = t0; s1 = t1; s2 = t2; s3 = t3;
 }
 
+// The same round for NT == 2 with a PRE-ROTATED round key kr = rot16(k) (aes_rotate_mid_keys).  T2 = rot16(T0),
+// T3 = rot16(T1), and XOR commutes with the byte rotation, so a column is
+//     T0[a] ^ T1[b] ^ rot16(T0[c] ^ T1[d] ^ rot16(k)):
+// one rotation per column instead of one per T2 / T3 lookup, with the key folded into the first LOP3 -- 7 ALU
+// instructions per column (4 address PRMTs, LOP3, PRMT, LOP3) instead of 8.
+__device__ __forceinline__ uint32_t col_rot2(const AesLane& a, uint32_t x3, uint32_t x2, uint32_t x1, uint32_t x0, uint32_t kr) {
+    const uint32_t u = te<0, 1, 2>(a, x1) ^ te<1, 0, 2>(a, x0) ^ kr;
+    return te<0, 3, 2>(a, x3) ^ te<1, 2, 2>(a, x2) ^ __byte_perm(u, 0, 0x1032);
+}
+__device__ __forceinline__ void aes_round_rot2(const AesLane& a, uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3,
+                                               const uint4 kr) {
+    const uint32_t t0 = col_rot2(a, s0, s1, s2, s3, kr.x);
+    const uint32_t t1 = col_rot2(a, s1, s2, s3, s0, kr.y);
+    const uint32_t t2 = col_rot2(a, s2, s3, s0, s1, kr.z);
+    const uint32_t t3 = col_rot2(a, s3, s0, s1, s2, kr.w);
+    s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+}
+// Round keys 1 .. nr-1 of an expanded schedule -> rot16 of themselves (round 0 and the final round keep theirs).
+__device__ __forceinline__ void aes_rotate_mid_keys(uint32_t* rk, int nr) {
+    for (int i = 4; i < 4 * nr; i++) rk[i] = __byte_perm(rk[i], 0, 0x1032);
+}
+
 // Final round (SubBytes + ShiftRows + AddRoundKey).  S[x] sits in two byte lanes
 // of every T-table entry; T2 = (S,3S,2S,S) and T3 = (S,S,3S,2S) have it in the
 // top and bottom bytes, so two PRMTs gather the four S-box bytes of a column.

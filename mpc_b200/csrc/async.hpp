@@ -63,10 +63,10 @@ inline bool is_pinned(const void* p) {
 // one another -- with three private streams per job, a result copy waiting for its kernel held up the input
 // copies of other jobs queued behind it.  Bulk copies of the two directions have their own streams per job
 // class (garble: small inputs up, tables down; eval: tables up, small results down), so neither class waits
-// behind the other's bulk transfers; kernels rotate over four streams so that short launches overlap.
+// behind the other's bulk transfers; kernels rotate over two streams per class.
 struct StreamSet {
     cudaStream_t h2d[2] = {nullptr, nullptr}, d2h[2] = {nullptr, nullptr}, k[4] = {nullptr, nullptr, nullptr, nullptr};
-    uint32_t next_k = 0;
+    uint32_t next_k = 0, next_kc[2] = {0, 0};
     cudaError_t init() {
         cudaError_t e;
         for (cudaStream_t* s : {&h2d[0], &h2d[1], &d2h[0], &d2h[1], &k[0], &k[1], &k[2], &k[3]})
@@ -170,7 +170,11 @@ public:
             static const bool one = [] { const char* e = getenv("GCB_COPY_STREAMS"); return e && atoi(e) == 1; }();
             r->h2d = ss->h2d[one ? 0 : (cls & 1)];
             r->d2h = ss->d2h[one ? 0 : (cls & 1)];
-            r->k = ss->k[ss->next_k++ & 3];
+            // kernels: two streams per job class.  With one rotation for both classes a garbling kernel could sit behind an
+            // evaluation kernel that is still waiting for its tables to cross PCIe, and the device->host engine ran dry at
+            // every step boundary of a pipelined caller (bench.py e2e).  GCB_KERNEL_STREAMS=shared restores the rotation.
+            static const bool shared_k = [] { const char* e = getenv("GCB_KERNEL_STREAMS"); return e && !strcmp(e, "shared"); }();
+            r->k = shared_k ? ss->k[ss->next_k++ & 3] : ss->k[(cls & 1) * 2 + (ss->next_kc[cls & 1]++ & 1)];
         }
         return r;
     }

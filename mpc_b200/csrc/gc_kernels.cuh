@@ -134,6 +134,13 @@ __device__ __forceinline__ Label shfl_label(Label h, int src) {
 }
 __device__ __forceinline__ uint32_t mask_of(uint32_t bit) { return 0u - (bit & 1u); }
 
+// A team's round keys (one thread): FIPS-197 schedule; with two resident tables the middle round keys are kept rotated.
+template <int NT>
+__device__ __forceinline__ void gate_expand_key(const AesLane& a, const uint8_t* key, int keylen, uint32_t* rk) {
+    aes_expand_key<NT>(a, key, keylen, rk);
+    if (NT == 2) aes_rotate_mid_keys(rk, (keylen >> 2) + 6);
+}
+
 // H(K) = AES(K) ^ K for UU independent blocks, rounds interleaved.
 template <int NR, int UU, int NT>
 __device__ __forceinline__ void aes_hash_multi(const AesLane& a, const uint32_t* __restrict__ rk, const Label (&K)[UU],
@@ -147,15 +154,22 @@ __device__ __forceinline__ void aes_hash_multi(const AesLane& a, const uint32_t*
             s[j][0] = K[j].w0 ^ k.x; s[j][1] = K[j].w1 ^ k.y; s[j][2] = K[j].w2 ^ k.z; s[j][3] = K[j].w3 ^ k.w;
         }
     }
+    // NT == 2: the team's middle round keys are stored pre-rotated (gate_expand_key), see aes_round_rot2
     if (UU == 1 && !GC_ROLL_SINGLE) {
 #pragma unroll
-        for (int r = 1; r < NR; r++) aes_round<NT>(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
+        for (int r = 1; r < NR; r++) {
+            if (NT == 2) aes_round_rot2(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
+            else aes_round<NT>(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
+        }
     } else {
 #pragma unroll 1
         for (int r = 1; r < NR; r++) {
             const uint4 k = k4[r];
 #pragma unroll
-            for (int j = 0; j < UU; j++) aes_round<NT>(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
+            for (int j = 0; j < UU; j++) {
+                if (NT == 2) aes_round_rot2(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
+                else aes_round<NT>(a, s[j][0], s[j][1], s[j][2], s[j][3], k);
+            }
         }
     }
     {
@@ -544,7 +558,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
     const AesLane lane = aes_lane(tc.tables);
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
-        if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
+        if (ttid == 0) gate_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.bar, TT);
     }
     const auto slots = team_slots<SPILL>(tc, p);
@@ -560,7 +574,7 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
         if (claimed >= p.batch) break;
         const uint32_t inst = claimed + tc.sub < p.batch ? claimed + tc.sub : p.batch - 1;
         if (p.key_stride != 0 && ttid == 0)
-            aes_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+            gate_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Label R = label_from_mem(__ldg(p.r + inst));
         R.w0 |= 0x80000000u;                                   // r.SetS(true), garble.go:258
         // plan records of the first phases load while the inputs do
@@ -786,7 +800,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
     const AesLane lane = aes_lane(tc.tables);
     const uint32_t TT = p.team_threads, ttid = tc.ttid;
     if (p.key_stride == 0) {
-        if (ttid == 0) aes_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
+        if (ttid == 0) gate_expand_key<NT>(lane, p.keys, (int)p.keylen, tc.rk);
         team_barrier(tc.bar, TT);
     }
     const auto slots = team_slots<SPILL>(tc, p);
@@ -802,7 +816,7 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
         if (claimed >= p.batch) break;
         const uint32_t inst = claimed + tc.sub < p.batch ? claimed + tc.sub : p.batch - 1;
         if (p.key_stride != 0 && ttid == 0)
-            aes_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
+            gate_expand_key<NT>(lane, p.keys + (size_t)inst * p.key_stride, (int)p.keylen, tc.rk);
         Phase ph = load_phase(p.phases, 0), ph_n = load_phase(p.phases, 1);
         NodeRegs pipe[D];
         uint32_t row = 0;

@@ -408,12 +408,26 @@ static int launch_gc(bool garble, const Plan& plan, DeviceInfo* di, int device, 
     // A batch smaller than one wave is spread over the SMs instead of filling a few of them: a CTA then carries only as
     // many teams as it needs (256 aes_128 instances: 2 teams on each of 128 SMs instead of 8 on each of 32), and every
     // instance gets a larger share of its SM's shared-memory pipe.
-    static const bool spread = [] { const char* e = getenv("GCB_SPREAD"); return !(e && atoi(e) == 0); }();
+    const char* spread_env = getenv("GCB_SPREAD");                       // GCB_SPREAD=0: tests that want full CTAs for tiny batches
+    const bool spread = !(spread_env && atoi(spread_env) == 0);
     if (spread && (uint64_t)batch < (uint64_t)geo.n_teams * di->sm_count) {
+        const uint32_t had = geo.n_teams;
         geo.n_teams = (batch + di->sm_count - 1) / di->sm_count;
         if (geo.n_teams == 0) geo.n_teams = 1;
         geo.twin = geo.twin && geo.n_teams % 8 == 0;
         if (geo.n_teams == 1) geo.stagger = 0;
+        // ... and the threads the absent teams would have had go to the present ones: an instance alone on its SM is
+        // bound by the latency of its levels.  Measured (profiles/r02_small_batch.txt): aes_128 x 148, garble + eval
+        // 1.70 ms in full CTAs on 19 SMs, 0.95 ms spread with 64-thread teams, 0.54 ms with one 256-thread team per SM
+        // (480 threads: no better); sha256 / sha512 x 148: 64-thread teams 5 % / 12 % faster than one warp, 96 no better.
+        if (!geo.spill && !getenv("GCB_TEAM_THREADS")) {
+            const uint32_t maxt = (geo.ilp == 1 && geo.nt == 4) ? 1024u : 512u;
+            uint32_t tt = geo.team_threads;
+            if (plan_width(plan) >= 128) tt = 256;
+            else if (geo.n_teams * 2 <= had && tt < 64) tt = 64;
+            while (tt > 32 && tt * geo.n_teams > maxt) tt -= 32;
+            if (tt > geo.team_threads) { geo.team_threads = tt; geo.stagger = 0; geo.twin = false; }
+        }
     }
     std::shared_ptr<DevicePlan> dp;
     int rc = plan_on_device(plan, device, geo.team_threads, &dp);

@@ -34,7 +34,10 @@ CASES = [("and", 70, 16), ("not", 33, 32), ("add64", 40, 16), ("sub64", 17, 24),
 
 @pytest.mark.parametrize("per_instance_keys", [False, True])
 @pytest.mark.parametrize("name,batch,klen", CASES)
-def test_garble_eval_batch_bit_exact(name, batch, klen, per_instance_keys):
+def test_garble_eval_batch_bit_exact(name, batch, klen, per_instance_keys, monkeypatch):
+    # per-instance keys: the library's own launch shape (a small batch is spread over the SMs, one team per CTA);
+    # shared key: full CTAs, every team of an SM racing for the instances
+    monkeypatch.setenv("GCB_SPREAD", "1" if per_instance_keys else "0")
     circ, eng = get(name)
     keys, rand = garble_inputs(f"gpu/{name}/{klen}", batch, circ.num_inputs, klen)
     if not per_instance_keys:
@@ -214,6 +217,7 @@ def test_every_kernel_variant_is_bit_exact(variant, monkeypatch):
     """The geometry (resident T-tables, AES blocks per thread, team width, node rows in flight) must not change
     a bit: every kernel variant, plain and full-wire mode, against the oracle on a circuit with all gate types
     and on mul64 (deep carry chains: many waves per phase)."""
+    monkeypatch.setenv("GCB_SPREAD", "0")                # full CTAs (every team of an SM) although the batch is small
     for k, v in variant.items():
         monkeypatch.setenv(k, v)
     for circ, batch in ((mixed_circuit(7, 2500, 48, 24), 7), (load_circuit("mul64"), 3)):
@@ -251,6 +255,7 @@ def test_hot_cold_plans_are_bit_exact(name, batch, teams, monkeypatch):
     by per-phase evict / reload lists), so that more instances are resident per SM: forced here for several circuits
     and targets, garble and eval against the oracle."""
     monkeypatch.setenv("GCB_HOT_TEAMS", teams)
+    monkeypatch.setenv("GCB_SPREAD", "0")
     circ = load_circuit(name)
     eng = GarbleEngine(circ)
     if name != "mul64":                                            # mul64 already holds 16 instances: nothing to gain
@@ -271,6 +276,7 @@ def test_twin_teams_are_bit_exact(batch, monkeypatch):
     """One-warp teams run as lock-step pairs (two instances claimed at once, shared 64-thread barriers); an odd tail is
     run by both warps of the last pair.  Forced here on sha256's eight all-hot teams."""
     monkeypatch.setenv("GCB_TWIN", "1")
+    monkeypatch.setenv("GCB_SPREAD", "0")
     circ = load_circuit("sha256")
     eng = GarbleEngine(circ)
     keys, rand = garble_inputs(f"twin/{batch}", batch, circ.num_inputs, 16)
