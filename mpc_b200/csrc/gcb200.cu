@@ -160,6 +160,8 @@ static int fresh_counter(DeviceInfo* di, cudaStream_t stream, uint32_t** out) {
 // written by block 0 / team 0 of the next garble launches; nullptr switches it off.
 static long long* g_trace = nullptr;
 extern "C" void gcb_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+// Developer hook (not in the public header): the staging copier of async.hpp, so that it can be tested without a device.
+extern "C" void gcb_debug_host_copy(void* dst, const void* src, size_t n) { host_copy(dst, src, n); }
 
 // ------------------------------------------------------------- plan upload ----
 DevicePlan::~DevicePlan() {
@@ -693,7 +695,7 @@ static int begin_part(bool garble, const Plan& plan, int device, const uint8_t* 
             if (!o.per) continue;
             const size_t off = (size_t)b0 * o.per, n = (size_t)nb * o.per;
             const uint8_t* src = o.host + off;
-            if (!o.pinned) { memcpy(r.pin.base + o.pin_off + off, src, n); src = r.pin.base + o.pin_off + off; }
+            if (!o.pinned) { host_copy(r.pin.base + o.pin_off + off, src, n); src = r.pin.base + o.pin_off + off; }
             CK(copy_in(r.dev.base + o.dev_off + off, src, n));
         }
         cudaEvent_t ev_in, ev_k;
@@ -748,7 +750,7 @@ static int finish_job(gcb_job* job) {
         for (const LateCopy& c : part.late) {
             cudaError_t e = cudaEventSynchronize(c.ready);
             if (e != cudaSuccess) { if (!rc) rc = cuda_fail(e, "result copy"); break; }
-            memcpy(c.dst, c.src, c.bytes);
+            host_copy(c.dst, c.src, c.bytes);
         }
         cudaError_t e = r.quiesce();
         if (e != cudaSuccess && !rc) rc = cuda_fail(e, "job completion");
@@ -930,7 +932,7 @@ static int stage_begin(int device, std::vector<HostOp*> ops, JobPart* part) {
         o->dptr = r.dev.base + o->dev_off;
         if (!o->src || !o->bytes) continue;
         const void* h = o->src;
-        if (!o->pinned) { memcpy(r.pin.base + o->pin_off, o->src, o->bytes); h = r.pin.base + o->pin_off; }
+        if (!o->pinned) { host_copy(r.pin.base + o->pin_off, o->src, o->bytes); h = r.pin.base + o->pin_off; }
         CK(cudaMemcpyAsync(o->dptr, h, o->bytes, cudaMemcpyHostToDevice, r.k));
     }
     return GCB_OK;

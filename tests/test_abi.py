@@ -157,3 +157,27 @@ def test_plan_choice_by_batch():
     assert wide.teams_per_sm == aes.info.teams_per_sm and wide.num_hot_slots == wide.num_slots
     mul = GarbleEngine(load_circuit("mul64"))
     assert mul.info_for(1 << 20).num_hot_slots == mul.info.num_slots
+
+
+def test_staging_copier_moves_every_byte():
+    """The parallel staging copier behind pageable host buffers (async.hpp: 2 MB pieces pulled by a few workers and the
+    caller): sizes around the piece and threshold boundaries, and four callers at once."""
+    import ctypes as C
+    import threading
+    fn = _lib.lib().gcb_debug_host_copy
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    fn.restype = None
+    rng = np.random.default_rng(5)
+    for n in (0, 1, (8 << 20) - 1, 8 << 20, (8 << 20) + 1, (32 << 20) + 12345):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        dst = np.zeros(n + 64, dtype=np.uint8)
+        fn(dst.ctypes.data + 32, src.ctypes.data, n)
+        assert np.array_equal(dst[32:32 + n], src) and not dst[:32].any() and not dst[32 + n:].any()
+    srcs = [rng.integers(0, 256, (24 << 20) + 7 * k, dtype=np.uint8) for k in range(4)]
+    dsts = [np.zeros_like(s) for s in srcs]
+    ts = [threading.Thread(target=lambda s=s, d=d: [fn(d.ctypes.data, s.ctypes.data, s.size) for _ in range(3)]) for s, d in zip(srcs, dsts)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert all(np.array_equal(s, d) for s, d in zip(srcs, dsts))
