@@ -42,7 +42,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "million AND-gates/sec garble+eval (AES-128 circuit)"
 UNIT = "M AND-gates/s"
-E2E_PARTS = 16
+E2E_PARTS = 8
 KEY = b"0123456789abcdef"            # circuit/garble_bench_test.go:34
 CIRCUIT_DIR = os.path.join(ROOT, "tests", "golden", "circuits")
 # --circuit: the headline workload (aes_128, BASELINE.json configs[1]) or the second circuit BASELINE's
