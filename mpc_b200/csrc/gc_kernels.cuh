@@ -37,6 +37,9 @@ namespace gcb {
 // 1: the single-block pass keeps its AES rounds in a loop (48 instructions) instead of unrolling them (430): with
 // many one-warp teams per SM every warp is somewhere else in the kernel and the instruction caches, not the
 // pipes, become the limit (ncu: no_inst 44 % of the stall samples with 16 teams of the unrolled form).
+#ifndef GC_ROUNDS_UNROLL
+#define GC_ROUNDS_UNROLL 1
+#endif
 #ifndef GC_ROLL_SINGLE
 #define GC_ROLL_SINGLE 1
 #endif
@@ -162,7 +165,10 @@ __device__ __forceinline__ void aes_hash_multi(const AesLane& a, const uint32_t*
             else aes_round<NT>(a, s[0][0], s[0][1], s[0][2], s[0][3], k4[r]);
         }
     } else {
-#pragma unroll 1
+        // rolled: with 8-16 teams per SM every warp is somewhere else in the kernel and unrolled rounds thrash the
+        // instruction caches (GC_ROUNDS_UNROLL: rounds per loop iteration of the two-block form, for experiments)
+        constexpr int U = UU == 2 ? GC_ROUNDS_UNROLL : 1;
+#pragma unroll U
         for (int r = 1; r < NR; r++) {
             const uint4 k = k4[r];
 #pragma unroll
