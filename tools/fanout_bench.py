@@ -123,7 +123,8 @@ def main():
         gc.set_devices(list(range(n)))
         rcv, snd = IKNPReceiver(k0, k1), IKNPSender(k0, delta)
         u, t = rcv.receive(choice)
-        rcv.pos = 0
+        q = snd.send(u, n_ot)                        # warm both sides: staging arenas of every device, result arrays
+        rcv.pos = snd.pos = 0
         t0 = time.perf_counter()
         u, t = rcv.receive(choice)
         q = snd.send(u, n_ot)
