@@ -369,3 +369,26 @@ def test_reference_garble_fixture_gpu():
     tables, io = eng.garble_batch(key, r, l0)
     assert fixture_digests(tables[0], io[0], circ.num_inputs) == (
         fx["tables_sha256"], fx["input_wires_sha256"], fx["output_wires_sha256"])
+
+
+@pytest.mark.parametrize("name,batch,klen", [("aes_128", 149, 16), ("aes_128", 300, 32), ("aes_128", 700, 16),
+                                             ("sha256", 300, 16), ("mul64", 700, 24), ("sha512", 150, 32)])
+def test_batches_below_one_wave_are_spread_over_the_sms(name, batch, klen):
+    """A batch smaller than one wave runs with fewer, wider teams per CTA (2-5 teams of up to 256 threads for aes_128,
+    64-thread teams for the narrow circuits) on all SMs: sampled instances against the oracle, every instance decoded."""
+    circ, eng = get(name)
+    assert batch < eng.info.teams_per_sm * 148
+    keys, rand = garble_inputs(f"spread/{name}/{batch}", batch, circ.num_inputs, klen)
+    r, l0 = rand_to_labels(rand, circ.num_inputs)
+    tables, io = eng.garble_batch(keys, r, l0)
+    sample = sorted({0, 1, 147, 148, batch // 2, batch - 1})
+    _, o_tables, o_io = O.garble_batch(circ, keys[sample], rand[sample], threads=4)
+    assert eq(tables[sample], o_tables) and eq(io[sample], o_io)
+    bits = np.random.default_rng(batch).integers(0, 2, (batch, circ.num_inputs), dtype=np.uint8)
+    inl = select(io[:, : circ.num_inputs], bits)
+    out = eng.eval_batch(keys, tables, inl)
+    assert eq(out[sample], O.eval_batch(circ, keys[sample], o_tables, inl[sample], threads=4))
+    got = decode(io[:, circ.num_inputs:], out)
+    assert got.max() <= 1
+    for i in (0, batch - 1):
+        assert np.array_equal(got[i], circ.compute_bits(bits[i].tolist()))
