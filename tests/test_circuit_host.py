@@ -127,3 +127,30 @@ def test_parser_errors(text, msg):
         c_parse(text.encode(), 0)
     with pytest.raises(GcbError):
         c_parse(b"\x00\x01", 1)                           # truncated MPCLC header
+
+
+REFERENCE = "/root/reference"
+REF_FILES = {"aes_128": "pkg/crypto/aes/aes_128.circ", "sha256": "pkg/crypto/sha256/sha256.circ", "mul64": "pkg/math/mul64.circ",
+             "sha256xor": "sha2pc/sha256xor.mpclc", "chacha20block": "pkg/crypto/chacha20/chacha20block.mpclc",
+             "and": "apps/circuit/and.circ"}
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REFERENCE), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("name", sorted(REF_FILES))
+def test_cpp_parsers_read_the_reference_files(name):
+    """The C++ front end on the reference's own circuit files, byte for byte as shipped (Bristol text and the MPCLC
+    binary format of circuit/parser.go:71-211 / Circuit.Marshal): gates, wires and I/O sizes equal the golden fixture
+    (whose sha256xor reading reproduces the reference's transcript hashes, tests/test_reference_transcript.py)."""
+    import os
+    path = os.path.join(REFERENCE, REF_FILES[name])
+    data = open(path, "rb").read()
+    h = c_parse(data, 1 if path.endswith(".mpclc") else 0)
+    try:
+        info, gates, ins, outs = c_view(h)
+        want = load_circuit(name)
+        assert (info.num_gates, info.num_wires) == (want.num_gates, want.num_wires)
+        assert ins == list(want.inputs) and outs == list(want.outputs)
+        for f in ("in0", "in1", "out", "op"):
+            assert np.array_equal(gates[f], want.gates[f]), f
+    finally:
+        _lib.lib().gcb_circuit_destroy(h)
