@@ -100,6 +100,34 @@ int main(int argc, char** argv) {
         printf("node row loop iterations per instance: now %llu, with lane splitting %llu (%llu warp rows)\n", (unsigned long long)now,
                (unsigned long long)split, (unsigned long long)rows);
     }
+    // warp-level hash calls of the two-block kernels (gc_kernels.cuh: the cipher pass loop) and what they would be with other team widths
+    for (uint32_t tt : {32u, 64u, 96u, 128u}) {
+        for (int garble = 1; garble >= 0; garble--) {
+            uint64_t dbl = 0, sgl = 0, rounds = 0;
+            std::vector<uint32_t> hist(9, 0);
+            for (const PhaseRec& ph : plan.phases) {
+                const uint32_t ntask = garble ? 4 * ph.n_quad + 2 * ph.n_inv : 2 * ph.n_quad + ph.n_inv;
+                if (!ntask) continue;
+                hist[std::min<uint32_t>(8, (ntask + 31) / 32)]++;
+                const uint32_t per_thread = (ntask + tt - 1) / tt;
+                for (uint32_t k0 = 0; k0 < per_thread;) {
+                    const uint32_t uu = per_thread - k0 >= 2 ? 2 : 1;
+                    bool any2 = false;
+                    for (uint32_t w = 0; w < tt / 32; w++) {
+                        if (uu == 2 && (k0 + 1) * tt + 32 * w < ntask) { dbl++; any2 = true; }
+                        else if (k0 * tt + 32 * w < ntask) sgl++;
+                    }
+                    rounds += 1;   // serial steps of the team (a double call costs about 1.3 single calls of latency)
+                    (void)any2;
+                    k0 += uu;
+                }
+            }
+            printf("%s TT=%u: double calls %llu, single calls %llu, serial call rounds %llu", garble ? "garble" : "eval  ", tt,
+                   (unsigned long long)dbl, (unsigned long long)sgl, (unsigned long long)rounds);
+            if (tt == 32) { printf("  | phases by 32-block passes 1..8+:"); for (int i = 1; i <= 8; i++) printf(" %u", hist[i]); }
+            printf("\n");
+        }
+    }
     Acc node_ld, node_st, g_ld, g_st, e_ld, e_st;
     uint64_t barriers = 0, garble_passes = 0, eval_passes = 0, node_iters = 0, node_floor = 0;
     std::vector<int> ls(32);
