@@ -283,15 +283,29 @@ static Geometry compute_geometry(uint32_t num_slots, uint32_t width, uint32_t sm
     // Wide levels keep the shared-memory pipe busy with a few resident instances: four tables.
     // Deep, narrow circuits (sha256: 39 blocks per level) are bound by the latency of each level,
     // so the number of resident instances is what counts: two tables, twice the label space.
-    // Wide levels of which fewer than eight instances fit beside four tables but eight beside two (aes_128: 5 / 9): eight
-    // two-warp teams on two tables beat five three-warp teams on four (measured, profiles/r02_geometry_p.txt: garble
-    // 3.85 -> 3.73 ms, eval 2.50 -> 2.47 ms) -- smaller teams wait less at their barriers, and the eight extra PRMTs per
-    // round fit the ALU pipe's slack.
-    const bool wide8 = width >= 128 && n4 < 8 && n2 >= 8 && !getenv("GCB_TEAMS") && !getenv("GCB_TEAM_THREADS");
-    uint32_t nt = (n4 == 0 || wide8 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
+    // Wide levels: what counts is warps per SM (the 512-thread variants hold 16), then teams -- smaller teams wait less
+    // at their barriers, one-warp teams have none -- and two resident tables only cost eight PRMTs per round, which fit
+    // the ALU pipe's slack.  For each table count the team count n <= fit that gives the most warps (n teams of
+    // min(3, 16 / n) warps), ties to the larger n; two tables when that is strictly better.  Measured
+    // (profiles/r02_geometry_p.txt, r02_geometry_z.txt): aes_128 5 x 96 on four tables 4,126 M AND/s, 8 x 64 on two 4,222;
+    // mul64 10 x 32 on four 3,257, 8 x 64 on four 3,307, 16 x 32 on two 3,756.
+    auto best_teams = [](size_t fit, uint32_t* warps) {
+        size_t best = 0;
+        *warps = 0;
+        for (size_t k = 1; k <= fit && k <= 16; k++) {
+            const uint32_t w = (uint32_t)(k * std::min<size_t>(3, 16 / k));
+            if (w >= *warps) { *warps = w; best = k; }
+        }
+        return best;
+    };
+    uint32_t w4 = 0, w2 = 0;
+    const size_t b4 = best_teams(n4, &w4), b2 = best_teams(n2, &w2);
+    const bool tuned = width >= 128 && n4 < 16 && !getenv("GCB_TEAMS") && !getenv("GCB_TEAM_THREADS");
+    const bool wide2 = tuned && (w2 > w4 || (w2 == w4 && b2 > b4));
+    uint32_t nt = (n4 == 0 || wide2 || (width < 128 && n2 > n4 && n4 < 16)) ? 2u : 4u;
     if (const char* e = getenv("GCB_NT")) { const int v = atoi(e); if (v == 2 || v == 4) nt = (uint32_t)v; }
     size_t n = nt == 2 ? n2 : n4;
-    if (wide8 && nt == 2) n = 8;
+    if (tuned && !getenv("GCB_NT")) n = nt == 2 ? b2 : b4;
     g.split = nt == 2 ? split2 : split4;
     g.n_smem = num_slots;
     if (n == 0) {
