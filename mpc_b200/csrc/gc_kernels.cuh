@@ -297,7 +297,11 @@ __device__ __forceinline__ NodeRegs load_node(const uint4* nodes, uint32_t i) {
 // One node per thread: dst = XOR of the leaves (^ R for an odd number of XNORs on the way).
 // words: lo.x = dst | k<<16 | flags<<24 (NODE_PARITY / NODE_WAVE_END / NODE_ACTIVE); then 14 leaf
 // slots, two per word.
-template <bool GARBLE, bool FULL, class SL>
+// PAIR: two leaves (one record word) per step, both loads in flight before the first XOR needs its operand.  One-warp teams
+// are bound by the latency of their rows and gain (sha256 x 2368: 2,644 -> 2,724 M AND/s, mul64: 3,756 -> 4,008); the
+// multi-warp teams of wide circuits are bound by the shared-memory pipe, where the bursts of 128-bit loads delay the
+// other teams' table lookups (aes_128 garble 3.61 -> 3.85 ms): they keep one leaf per step.
+template <bool GARBLE, bool FULL, bool PAIR, class SL>
 __device__ __forceinline__ void run_node(const GcParams& p, const SL& slots, const Label R, uint32_t inst, uint32_t index,
                                          const NodeRegs& n) {
     const bool active = (n.lo.x >> 24) & NODE_ACTIVE;
@@ -305,13 +309,26 @@ __device__ __forceinline__ void run_node(const GcParams& p, const SL& slots, con
     Label acc = Label{0, 0, 0, 0};
     if (GARBLE) acc = label_and_mask(R, mask_of(n.lo.x >> 24));
     const uint32_t kmax = __reduce_max_sync(0xffffffffu, k);
+    if (PAIR) {
 #pragma unroll
-    for (int j = 0; j < NODE_MAX_FANIN; j++) {
-        if ((uint32_t)j >= kmax) break;                        // warp-uniform
-        const uint32_t w = j < 2 ? n.lo.y : j < 4 ? n.lo.z : j < 6 ? n.lo.w : j < 8 ? n.hi.x
-                         : j < 10 ? n.hi.y : j < 12 ? n.hi.z : n.hi.w;
-        const uint32_t s = (j & 1) ? (w >> 16) : (w & 0xffff);
-        if ((uint32_t)j < k) acc = acc ^ lds_label(slots, s);
+        for (int j = 0; j < NODE_MAX_FANIN; j += 2) {
+            if ((uint32_t)j >= kmax) break;                    // warp-uniform
+            const uint32_t w = j < 2 ? n.lo.y : j < 4 ? n.lo.z : j < 6 ? n.lo.w : j < 8 ? n.hi.x
+                             : j < 10 ? n.hi.y : j < 12 ? n.hi.z : n.hi.w;
+            Label l0 = Label{0, 0, 0, 0}, l1 = Label{0, 0, 0, 0};
+            if ((uint32_t)j < k) l0 = lds_label(slots, w & 0xffff);
+            if ((uint32_t)j + 1 < k) l1 = lds_label(slots, w >> 16);
+            acc = acc ^ l0 ^ l1;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NODE_MAX_FANIN; j++) {
+            if ((uint32_t)j >= kmax) break;                    // warp-uniform
+            const uint32_t w = j < 2 ? n.lo.y : j < 4 ? n.lo.z : j < 6 ? n.lo.w : j < 8 ? n.hi.x
+                             : j < 10 ? n.hi.y : j < 12 ? n.hi.z : n.hi.w;
+            const uint32_t s = (j & 1) ? (w >> 16) : (w & 0xffff);
+            if ((uint32_t)j < k) acc = acc ^ lds_label(slots, s);
+        }
     }
     if (!active) return;
     sts_label(slots, n.lo.x & 0xffff, acc);
@@ -337,7 +354,7 @@ __device__ __forceinline__ NodeRegs load_row(const GcParams& p, uint32_t row, ui
 // statically -- rows run in aligned groups of D with warp-uniform guards -- because a pipeline that
 // shifts registers would copy the newest load right after issuing it and wait for it there.  A
 // team barrier follows the last row of a wave.
-template <bool GARBLE, bool FULL, uint32_t D, class SL>
+template <bool GARBLE, bool FULL, uint32_t D, bool PAIR, class SL>
 __device__ __forceinline__ void run_rows(const GcParams& p, const SL& slots, const Label R, uint32_t inst, uint32_t n_rows,
                                          uint32_t team, uint32_t ttid, uint32_t TT, NodeRegs (&pipe)[D], uint32_t& row) {
     static_assert((D & (D - 1)) == 0, "pipeline depth must be a power of two");
@@ -349,7 +366,7 @@ __device__ __forceinline__ void run_rows(const GcParams& p, const SL& slots, con
             if (k >= k0 && row < end) {
                 const NodeRegs cur = pipe[k];
                 pipe[k] = load_row(p, row + D, ttid);
-                run_node<GARBLE, FULL>(p, slots, R, inst, row * TT + ttid, cur);
+                run_node<GARBLE, FULL, PAIR>(p, slots, R, inst, row * TT + ttid, cur);
                 row++;
                 if ((cur.lo.x >> 24) & NODE_WAVE_END) team_barrier(team, TT);
             }
@@ -633,7 +650,9 @@ __global__ void __launch_bounds__(MAXT, 1) garble_kernel(const GcParams p) {
             const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0 && inst < gridDim.x * p.n_teams;
             if (tracing) p.trace[4 * pi] = clock64();
             // ---- free wires: waves of independent XOR nodes, one thread per node
-            run_rows<true, FULL, D>(p, slots, R, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
+            // (the single-block variants always pair: their circuits are narrow; the two-block variants decide by team width)
+            if (ILP == 1 || TT == 32) run_rows<true, FULL, D, true>(p, slots, R, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
+            else run_rows<true, FULL, D, ILP == 1>(p, slots, R, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
             if (tracing) p.trace[4 * pi + 1] = p.trace[4 * pi + 2] = clock64();
             // ---- ciphered gates: one AES block per task, up to ILP tasks per thread at once
             const uint32_t ntask = task_count<true>(ph);
@@ -866,7 +885,8 @@ __global__ void __launch_bounds__(MAXT, 1) eval_kernel(const GcParams p) {
                 n_reload = run_copies(p, tc.slots, scratch, cp_cur, ttid, TT);
                 cp_cur = load_copies(p, pi + 1, ttid);
             }
-            run_rows<false, FULL, D>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
+            if (ILP == 1 || TT == 32) run_rows<false, FULL, D, true>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
+            else run_rows<false, FULL, D, ILP == 1>(p, slots, Label{0, 0, 0, 0}, inst, ph.n_rows, tc.bar, ttid, TT, pipe, row);
             // ciphered gates: AND = 2 tasks (a with j0, b with j1); OR/INV = 1 hash.
             // OR shares the 2-task slot of its class (second task idle).
             const uint32_t ntask = task_count<false>(ph);
