@@ -1,6 +1,5 @@
 #!/bin/bash
-# Round-2 GPU pass T (1 GPU): pre-rotated round keys on two tables (7 instead of 8 ALU instructions per column):
-# parity, timings, then the profile set of the final kernels (launch list, ncu --set full of the headline and sha256 kernels).
+# Round-2 GPU pass T (1 GPU): parity, timings, then the profile set of the final kernels (launch list, ncu --set full of the headline and sha256 kernels).
 set -u
 mkdir -p gpurun_out /tmp/prof
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_pytest.log
@@ -28,8 +27,4 @@ for K in garble eval; do
   ncu -i /tmp/prof/sha_$K.ncu-rep --page raw --csv > gpurun_out/t_sha256_${K}_raw.csv 2>/dev/null
   ncu -i /tmp/prof/sha_$K.ncu-rep --page source --csv > gpurun_out/t_sha256_${K}_src.csv 2>/dev/null
 done
-for P in 4 6 8 12 16; do
-GCB_E2E_PARTS=$P GCB_E2E_TRACE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/t_bench_p$P.json 2>> gpurun_out/t_bench.err
-done
-grep "e2e trace" gpurun_out/t_bench.err
 tail -4 gpurun_out/t_pytest.log; cat gpurun_out/t_times.txt; head -6 gpurun_out/t_launches.csv | cut -c1-200
