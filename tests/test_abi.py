@@ -181,3 +181,16 @@ def test_staging_copier_moves_every_byte():
     for t in ts:
         t.join()
     assert all(np.array_equal(s, d) for s, d in zip(srcs, dsts))
+
+
+def test_geometry_choices_of_the_shipped_circuits():
+    """Team geometry the plan reports (host-only; `compute_geometry`): wide circuits take the table count that gives the
+    most warps, then the most teams (aes_128 / aes_256: 8 two-warp teams on two tables, mul64: 16 one-warp teams);
+    deep, narrow ones keep as many one-warp instances as fit (sha256 8, chacha20 10), sha512's 2,401 labels leave room
+    for three 96-thread teams."""
+    want = {"aes_128": (8, 64), "aes_256": (8, 64), "mul64": (16, 32), "sha256": (8, 32), "chacha20block": (10, 32),
+            "sha512": (3, 96), "add64": (16, 32)}
+    for name, geo in want.items():
+        i = GarbleEngine(load_circuit(name)).info
+        assert (i.teams_per_sm, i.team_threads) == geo, (name, i.teams_per_sm, i.team_threads)
+        assert i.teams_per_sm * i.team_threads <= 512
