@@ -363,12 +363,24 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
                 uint32_t last_phase = pb;
                 c0 = !input;
                 if (!input) cl.push_back(Cluster{b, b, pb});
+                // A reload is queued at the top of the last phase with steps before its cluster; the value reaches the scratch
+                // at the top of the phase after its birth.  Both run unordered within their phase, so the reload must be queued
+                // in a LATER phase than the evict: a cluster that would start sooner (tiny gaps, empty phases in between) stays
+                // part of the previous one.  (Found by tools/plan_check.cpp: add64 with a cap just below its all-hot need
+                // reloaded values before they were born.)  Inputs are in the scratch before phase 0.
+                const uint32_t evict_phase = std::min(pb + 1, n_phases - 1);
+                auto reload_after_evict = [&](uint32_t first_phase) {
+                    if (input) return true;
+                    uint32_t p = first_phase - 1;
+                    while (p > 0 && !phase_has_steps[p]) p--;
+                    return p > evict_phase;
+                };
                 for (int64_t st : ev[d]) {
                     const uint32_t ph = step_phase[(size_t)st];
                     if (cl.empty()) {
                         if (ph <= gap) { c0 = true; cl.push_back(Cluster{0, st, 0}); }        // an input used early stays hot from the load
                         else cl.push_back(Cluster{st, st, ph});
-                    } else if (ph > last_phase + gap && ph >= 1) cl.push_back(Cluster{st, st, ph});
+                    } else if (ph > last_phase + gap && ph >= 1 && reload_after_evict(ph)) cl.push_back(Cluster{st, st, ph});
                     else cl.back().hi = st;
                     last_phase = ph;
                 }
