@@ -248,6 +248,13 @@ static int check_circuit(const Circuit& c, uint64_t* plans) {
             run(NODE_MAX_FANIN, 1, cap, -1, "hot cap");
             run(NODE_MAX_FANIN, 1, cap, 3, "hot cap, balanced schedule");
         }
+    {   // what the library itself picks for a batch that overflows the all-hot plan (plan.cpp: build_best_plan)
+        Plan plan;
+        std::string e;
+        const int rc = build_best_plan(spec, plan, e, NODE_MAX_FANIN, ~0ull);
+        if (rc) { fprintf(stderr, "%s: build_best_plan failed: %d %s\n", c.name.c_str(), rc, e.c_str()); errors++; }
+        else { (*plans)++; errors += check_plan(c, plan, "the library's plan for large batches"); }
+    }
     return errors;
 }
 
