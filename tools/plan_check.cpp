@@ -91,7 +91,8 @@ static int check_plan(const Circuit& c, const Plan& plan, const char* what) {
     if (split && plan.phase_copy.size() < plan.phases.size()) err("copy lists for %zu of %zu phases", plan.phase_copy.size(), plan.phases.size());
     std::vector<uint8_t> mark(n_slots, 0);
     std::vector<std::pair<uint32_t, uint64_t>> pending;
-    std::vector<uint8_t> seen(ng, 0);
+    std::vector<uint32_t> evict_src;                              // hot slots the evicts of this phase read: no barrier lies
+    std::vector<uint8_t> seen(ng, 0);                             // between them and the first step of the phase
     for (size_t pi = 0; pi < plan.phases.size(); pi++) {
         const PhaseRec& ph = plan.phases[pi];
         pending.clear();
@@ -100,12 +101,14 @@ static int check_plan(const Circuit& c, const Plan& plan, const char* what) {
             const uint32_t first = pc[0], n_ev = pc[1], n_rl = pc[2];
             if ((size_t)2 * (first + n_ev + n_rl) > plan.copies.size()) { err("phase %zu: copy list out of range", pi); break; }
             std::vector<uint32_t> evicted;
+            evict_src.clear();
             for (uint32_t k = 0; k < n_ev; k++) {
                 const uint32_t src = plan.copies[2 * (first + k)], dst = plan.copies[2 * (first + k) + 1];
                 if (src >= n_hot || dst >= G.size()) { err("phase %zu: evict %u -> %u out of range", pi, src, dst); continue; }
                 if (S[src] == kPoison) err("phase %zu: evict of empty slot %u", pi, src);
                 G[dst] = S[src];
                 evicted.push_back(dst);
+                evict_src.push_back(src);
             }
             for (uint32_t k = 0; k < n_rl; k++) {
                 const uint32_t src = plan.copies[2 * (first + n_ev + k)], dst = plan.copies[2 * (first + n_ev + k) + 1];
@@ -116,7 +119,10 @@ static int check_plan(const Circuit& c, const Plan& plan, const char* what) {
                 S[dst] = kPoison;                              // in flight until the phase ends
             }
         }
+        if (!split) evict_src.clear();
         auto is_pending = [&](uint32_t s) { for (auto& q : pending) if (q.first == s) return true; return false; };
+        bool first_step = true;
+        auto evict_reads = [&](uint32_t s) { if (first_step) for (uint32_t e : evict_src) if (e == s) return true; return false; };
         const uint32_t nw = ph.n_waves & 0x7fffffffu;
         for (uint32_t w = 0; w < nw; w++) {
             const WaveRec& wr = plan.waves[ph.wave_first + w];
@@ -131,12 +137,14 @@ static int check_plan(const Circuit& c, const Plan& plan, const char* what) {
                 if (acc != fp[wire]) err("phase %zu wave %u: node %u does not produce wire %u", pi, w, j, wire);
                 if (nd.dst >= direct) { err("node dst %u", nd.dst); continue; }
                 if (is_pending(nd.dst)) err("phase %zu: node writes slot %u with a reload in flight", pi, nd.dst);
+                if (evict_reads(nd.dst)) err("phase %zu: node of the first wave writes slot %u that an evict of the phase reads", pi, nd.dst);
                 writes.push_back({nd.dst, acc});
             }
             for (auto& q : writes) if (mark[q.first]) err("phase %zu wave %u: slot %u read and written in one wave", pi, w, q.first);
             for (uint32_t j = 0; j < wr.count; j++)
                 for (uint32_t k = 0; k < plan.nodes[wr.first + j].k; k++) { const uint32_t l = plan.nodes[wr.first + j].leaf[k]; if (l < n_slots) mark[l] = 0; }
             for (auto& q : writes) S[q.first] = q.second;
+            if (wr.count) first_step = false;
         }
         std::vector<std::pair<uint32_t, uint64_t>> writes;
         std::vector<uint32_t> reads;
@@ -157,6 +165,7 @@ static int check_plan(const Circuit& c, const Plan& plan, const char* what) {
             else if (g.b >= direct) err("INV gate %u names slot %u", o, g.b);      // the kernel loads it (unused)
             if (g.c >= direct) { err("gate dst %u", g.c); continue; }
             if (is_pending(g.c)) err("phase %zu: gate writes slot %u with a reload in flight", pi, g.c);
+            if (evict_reads(g.c)) err("phase %zu: gate writes slot %u that an evict of the phase reads", pi, g.c);
             writes.push_back({g.c, fp[wire]});
         }
         for (uint32_t r : reads) if (r < n_slots) mark[r] = 1;
