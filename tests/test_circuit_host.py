@@ -154,3 +154,38 @@ def test_cpp_parsers_read_the_reference_files(name):
             assert np.array_equal(gates[f], want.gates[f]), f
     finally:
         _lib.lib().gcb_circuit_destroy(h)
+
+
+def test_parsers_survive_mutated_files():
+    """Circuit files can come from a peer: thousands of mutations (flipped bytes, truncations, insertions, huge 32-bit
+    fields) of a valid Bristol file and a valid MPCLC file must each be either refused with an error or parsed into a
+    circuit that also plans (or is refused there) -- never a crash, a hang or an allocation sized by the peer."""
+    circ = mixed_circuit(11, 120, 12, 5)
+    good = {0: circ.to_bristol().encode(), 1: to_mpclc(circ)}
+    rng = np.random.default_rng(1)
+    parsed = 0
+    for fmt, data in good.items():
+        for _ in range(1500):
+            b = bytearray(data)
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                for _ in range(int(rng.integers(1, 6))):
+                    b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            elif kind == 1:
+                b = b[: int(rng.integers(0, len(b)))]
+            elif kind == 2:
+                i = int(rng.integers(0, len(b)))
+                b[i:i] = bytes(rng.integers(0, 256, int(rng.integers(1, 9)), dtype=np.uint8))
+            else:
+                i = int(rng.integers(0, max(1, len(b) - 4)))
+                b[i:i + 4] = struct.pack(">I", int(rng.choice([0xffffffff, 0x7fffffff, 0x80000000, 1 << 20])))
+            h = C.c_void_p()
+            buf = np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, np.uint8)
+            if _lib.lib().gcb_circuit_parse(ptr(buf) if len(buf) else None, len(buf), fmt, C.byref(h)) != 0:
+                continue
+            parsed += 1
+            ph = C.c_void_p()
+            if _lib.lib().gcb_circuit_plan(h, C.byref(ph)) == 0:
+                _lib.lib().gcb_plan_destroy(ph)
+            _lib.lib().gcb_circuit_destroy(h)
+    assert parsed > 0
