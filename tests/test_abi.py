@@ -194,3 +194,34 @@ def test_geometry_choices_of_the_shipped_circuits():
         i = GarbleEngine(load_circuit(name)).info
         assert (i.teams_per_sm, i.team_threads) == geo, (name, i.teams_per_sm, i.team_threads)
         assert i.teams_per_sm * i.team_threads <= 512
+
+
+def test_plan_create_survives_corrupted_gate_arrays():
+    """gcb_plan_create on gate arrays with corrupted fields (wires out of range, reads before assignment, invalid ops)
+    and wire / input / output counts up to 2^32 - 1: refused or planned, quickly -- never a crash or an allocation sized
+    by the corrupted count (a wire count of 0xffffffff once cost 32 GB and a minute before it was refused)."""
+    import ctypes as C
+    import time
+    base = mixed_circuit(5, 400, 20, 8)
+    rng = np.random.default_rng(3)
+    t0 = time.time()
+    planned = 0
+    for _ in range(1200):
+        g = np.ascontiguousarray(base.gates).copy()
+        nw, nin, nout = base.num_wires, base.num_inputs, base.num_outputs
+        for _ in range(int(rng.integers(1, 5))):
+            i = int(rng.integers(0, len(g)))
+            f = ["in0", "in1", "out", "op"][int(rng.integers(0, 4))]
+            g[f][i] = int(rng.integers(0, 9)) if f == "op" else int(rng.choice([0, 1, nw - 1, nw, nw + 5, 0xffffffff, 7, 255]))
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            nw = int(rng.choice([0, 1, nw - 1, nw + 1, 70000, 0xffffffff]))
+        elif kind == 1:
+            nin = int(rng.choice([0, nw, nw + 1, 0xffffffff]))
+        elif kind == 2:
+            nout = int(rng.choice([0, nw, nw + 1, 0xffffffff]))
+        h = C.c_void_p()
+        if _lib.lib().gcb_plan_create(_lib.ptr(g), len(g), nw, nin, nout, C.byref(h)) == 0:
+            planned += 1
+            _lib.lib().gcb_plan_destroy(h)
+    assert planned > 0 and time.time() - t0 < 120
