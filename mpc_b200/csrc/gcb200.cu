@@ -587,10 +587,20 @@ static int grow(DevBuf& b, size_t& cap, size_t bytes) {
 }
 
 // ensureWires (stream_garble.go:78-100): pages up to max_id exist, zero-filled.
+constexpr uint32_t kMaxStreamWires = 1u << 28;
 static int ensure_wires(gcb_stream* s, uint32_t max_id) {
     const size_t need = ((size_t)max_id >> WF_PAGE_SHIFT) + 1;
     if (need <= s->pages.size()) return GCB_OK;
     const size_t page_bytes = (size_t)s->batch * WF_PAGE_IDS * 16;
+    {   // the highest wire id can come from the peer (the OpCircuit header of a record stream): a wire file that cannot
+        // fit is refused before the first page is allocated instead of after a hundred thousand of them
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t want = (need - s->pages.size()) * page_bytes;
+        if (want > free_b)
+            return fail(GCB_E_TOO_LARGE, "wire file up to id %u needs %zu more bytes of device memory for %u instances; %zu are free",
+                        max_id, want, s->batch, free_b);
+    }
     while (s->pages.size() < need) {
         uint4* p = nullptr;
         CK(cudaMalloc(&p, page_bytes));
@@ -1117,6 +1127,10 @@ int gcb_plan_create(const gcb_gate* gates, uint32_t num_gates, uint32_t num_wire
     *out = nullptr;
     if (!gates && num_gates) return fail(GCB_E_ARG, "null gate array");
     if (num_inputs > num_wires || num_outputs > num_wires) return fail(GCB_E_ARG, "more I/O wires than wires");
+    // every wire is an input or is assigned by a gate (circuit/parser.go:199 rejects files with unassigned wires): a wire
+    // count beyond that is refused before anything is sized by it (0xffffffff used to cost 32 GB and a minute)
+    if ((uint64_t)num_wires > (uint64_t)num_inputs + num_gates)
+        return fail(GCB_E_WIRE, "corrupted circuit: wire %llu not assigned", (unsigned long long)num_inputs + num_gates);
     PlanSpec spec;
     spec.gates = gates; spec.num_gates = num_gates; spec.num_wires = num_wires;
     for (uint32_t i = 0; i < num_inputs; i++) spec.live_in.push_back(i);
@@ -1846,7 +1860,10 @@ int gcb_seval_circuit(gcb_seval* s, const uint8_t* src, size_t src_stride, size_
     if ((rc = parse_stream(src, len, ngates, sg, row_pos, &used, err))) return fail(rc, "%s", err.c_str());
     if (consumed) *consumed = used;
     if (ngates == 0) return GCB_OK;
-    // InitCircuit (stream_evaluator.go:86-96): wires up to nwires exist
+    // InitCircuit (stream_evaluator.go:86-96): wires up to nwires exist.  The count comes from the peer; the reference
+    // would size a Go slice by it.  Here: at most 2^28 wire ids per evaluator (4 GiB of labels per instance).
+    if (nwires > kMaxStreamWires)
+        return fail(GCB_E_TOO_LARGE, "record stream declares %u wires; at most %u are supported", nwires, kMaxStreamWires);
     if (nwires) { if ((rc = ensure_wires(s, nwires - 1))) return rc; }
     // wire space of the recovered circuit: [permanent ids in order of first use | tmp wires].  The
     // plan depends only on this canonical form, not on the actual ids, so the steps of a program

@@ -33,13 +33,6 @@ int build_plan(const PlanSpec& spec, Plan& plan, std::string& err, int max_fanin
 
     const size_t ninit = spec.live_in.size();
     const size_t ndefs = ninit + ng;
-    // every location holds a live-in value or is assigned by a gate (circuit/parser.go rejects files with unassigned
-    // wires): a wire count beyond that is refused before anything is sized by it (0xffffffff used to cost 32 GB and a minute)
-    if (identity && (uint64_t)nloc > (uint64_t)ninit + ng) {
-        snprintf(msg, sizeof msg, "wire %llu not assigned", (unsigned long long)(ninit + ng));
-        err = msg;
-        return GCB_E_WIRE;
-    }
     // A definition is one value of one location: the initial value of a live-in
     // location, or the output of one gate.  Re-assigned locations (legal in the
     // file formats, and the norm for aliased streaming wires) get a new

@@ -295,3 +295,20 @@ def test_streaming_step_that_spills_labels():
     ow = st.get_inputs(out_ids)[0]
     dec = np.where(got == ow["l1"], 1, np.where(got == ow["l0"], 0, 2))
     assert np.array_equal(dec, circ.compute_bits(bits.astype(np.uint8).tolist()))
+
+
+def test_stream_eval_refuses_wire_counts_it_cannot_hold():
+    """The wire count of an OpCircuit comes from the peer (the reference sizes a slice by it): counts beyond 2^28, or
+    beyond the free device memory, are refused at once -- not after allocating page by page towards them."""
+    import time
+    from mpc_b200 import _lib
+    circ = load_circuit("sub64")
+    key = DRBG("big/key").read(16)
+    sev = StreamEval(key, 1)
+    stream = np.zeros((1, 64), dtype=np.uint8)
+    t0 = time.time()
+    for nwires in (0xffffffff, (1 << 28) + 1):
+        with pytest.raises(_lib.GcbError) as e:
+            sev.circuit(stream, 1, circ.num_wires, nwires)
+        assert e.value.rc in (_lib.E_TOO_LARGE, _lib.E_BUFFER, _lib.E_BADOP, _lib.E_WIRE)
+    assert time.time() - t0 < 5
